@@ -1,0 +1,770 @@
+// extern "C" entry points (include/basic_b200.h) and the host-side orchestration of the kernels.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace basic {
+
+// ---- implemented in the other translation units -----------------------------------------------------
+int rans_tables_from_freqs(RansTables &, const int32_t *, int, int, const int32_t *, const int32_t *, int, cudaStream_t);
+int rans_tables_from_cdfs(RansTables &, const int32_t *, int, int, const int32_t *, const int32_t *, int, cudaStream_t);
+int pmf_to_cdf_device(const float *, int, int, int32_t *);
+int launch_rans64_encode(const RansTables &, const int32_t *, const int32_t *, int64_t, int, int, uint32_t *, int64_t,
+                         long long *, int *, cudaStream_t);
+int launch_rans64_decode(const RansTables &, const uint32_t *, int64_t, void *, int, const int32_t *, int64_t, int, int,
+                         int32_t *, int *, cudaStream_t);
+int launch_bls_encode(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, int, int, uint16_t *, int,
+                      uint32_t *, uint32_t *, unsigned char *, long long *, int *, int, cudaStream_t);
+int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64_t, const int32_t *, int64_t, int, int,
+                      int32_t *, int *, int, cudaStream_t);
+int launch_estimate_bits(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, float *, cudaStream_t);
+int launch_quantize_index(const float *, const float *, const int32_t *, int64_t, int, int, int, const float *, int, int32_t *,
+                          int32_t *, float *, int, cudaStream_t);
+int launch_dequantize(const int32_t *, const float *, const int32_t *, int64_t, int, int, int, float *, int, cudaStream_t);
+
+struct CtxModel;
+CtxModel *ctx_new(int C, int G, int k, int device, int sm_count);
+void ctx_delete(CtxModel *);
+int ctx_set_weights(CtxModel &, const float *, const float *, const float *, const float *, const float *, const float *,
+                    const float *, const float *);
+int ctx_set_map(CtxModel &, const int32_t *, int, int);
+int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t);
+int ctx_num_stages(const CtxModel &);
+int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
+int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
+
+struct TansTables;
+TansTables *tans_new();
+void tans_delete(TansTables *);
+int tans_init(TansTables &, const int32_t *, int, int, const int32_t *, const int32_t *, unsigned, int, unsigned, int role,
+              cudaStream_t);
+int tans_encode(TansTables &, const int32_t *d_sym, const int32_t *d_idx, int64_t n, uint8_t *d_out, int64_t cap,
+                long long *d_len, int *d_status, cudaStream_t);
+int tans_decode(TansTables &, const uint8_t *d_enc, int64_t len, const int32_t *d_idx, int64_t n, int32_t *d_out, int *d_status,
+                cudaStream_t);
+
+static thread_local std::string t_error;
+void set_error(const std::string &msg) { t_error = msg; }
+int64_t g_launches = 0;
+
+static constexpr double kAutoBudget = 0.004;  // target container overhead in auto mode (bar: 0.5 %)
+static constexpr int kChunkOverhead = 132;    // 32 states + directory entry
+
+}  // namespace basic
+
+using namespace basic;
+
+struct basic_coder {
+    int kind = 0, role = 0;
+    unsigned precision = 16, max_symbol_value = 255, bypass_precision = 4;
+    int bypass = 1, device = 0, sm_count = 148;
+    RansTables rt;
+    TansTables *tt = nullptr;
+    bool initialized = false;
+    // Gaussian conditional
+    std::vector<float> h_scale;
+    DevBuf d_scale;
+    // scratch
+    DevBuf in_a, in_b, out_i32, words, first, states, segs, small, stream_dev, y_dev, prior_dev, buf, params, sym_all, idx_all,
+        yhat_stage;
+    void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
+    // cache for cache=1 / flush()
+    std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
+    std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
+    // streaming decode state
+    int stream_lanes = 1;
+    std::vector<uint8_t> h_stream;
+    int64_t stream_pos = 0;
+    bool stream_set = false;
+};
+
+struct basic_ctx {
+    CtxModel *m;
+    int device;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Returns a device pointer for `p` (copying host data into `staging` when needed).
+template <class T>
+int to_device(const T *p, size_t count, DevBuf &staging, cudaStream_t s, const T **out)
+{
+    if (!p || count == 0) { *out = p; return BASIC_OK; }
+    if (is_device_ptr(p)) { *out = p; return BASIC_OK; }
+    BASIC_TRY(staging.reserve(count * sizeof(T) + 16));
+    BASIC_CUDA(cudaMemcpyAsync(staging.p, p, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    *out = staging.as<T>();
+    return BASIC_OK;
+}
+
+int status_error(int st)
+{
+    if (st & 1) return value_error("index out of range of the coder tables");
+    if (st & 2) return value_error("symbol out of table range and bypass_coding is disabled");
+    if (st & 4) { set_error("malformed or truncated stream"); return BASIC_ERR_STREAM; }
+    return BASIC_OK;
+}
+
+struct Small {  // layout of coder->small (device) and coder->pinned (host mirror)
+    long long len[4];
+    int status;
+    float bits;
+};
+
+int need_init(basic_coder *c)
+{
+    if (!c) return value_error("null coder");
+    if (!c->initialized) return value_error("ANS not initialized!");
+    return BASIC_OK;
+}
+
+void chunking(int64_t n, int64_t want_chunks, int *chunk_syms, int *n_chunks)
+{
+    if (want_chunks < 1) want_chunks = 1;
+    int64_t cs = (n + want_chunks - 1) / want_chunks;
+    cs = ((cs + 127) / 128) * 128;
+    if (cs < 128) cs = 128;
+    *chunk_syms = (int)cs;
+    *n_chunks = (int)((n + cs - 1) / cs);
+}
+
+// lanes = 1: reference stream of (d_sym, d_idx) into c->segs; returns byte length via *len (host, synchronised).
+int encode_compat(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, int64_t n, cudaStream_t s, const uint8_t **d_bytes,
+                  int64_t *len)
+{
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int64_t cap_words = attempt == 0 ? n + n / 4 + 64 : 12 * n + 64;
+        BASIC_TRY(c->segs.reserve((size_t)cap_words * 4));
+        BASIC_TRY(c->small.reserve(sizeof(Small)));
+        BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
+        Small *ds = c->small.as<Small>();
+        BASIC_TRY(launch_rans64_encode(c->rt, d_sym, d_idx, n, c->bypass, (int)c->bypass_precision, c->segs.as<uint32_t>(),
+                                       cap_words, &ds->len[0], &ds->status, s));
+        Small *hs = reinterpret_cast<Small *>(c->pinned);
+        BASIC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        if ((hs->status & 4) && !(hs->status & 3) && attempt == 0) continue;  // escape-heavy input: retry, worst-case size
+        BASIC_TRY(status_error(hs->status));
+        *d_bytes = reinterpret_cast<const uint8_t *>(c->segs.as<uint32_t>() + hs->len[0]);
+        *len = (cap_words - hs->len[0]) * 4;
+        return BASIC_OK;
+    }
+    return BASIC_ERR_CUDA;
+}
+
+// One multi-lane segment into c->segs at byte offset `at` (must be 4-aligned); *seg_len host value (synchronised).
+int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, int64_t n, int lanes, size_t at, cudaStream_t s,
+                   int64_t *seg_len)
+{
+    Small *ds = c->small.as<Small>();
+    Small *hs = reinterpret_cast<Small *>(c->pinned);
+    int64_t want_chunks;
+    if (lanes == BASIC_LANES_AUTO) {
+        BASIC_CUDA(cudaMemsetAsync(&ds->bits, 0, sizeof(float), s));
+        BASIC_TRY(launch_estimate_bits(c->rt, c->bypass, (int)c->bypass_precision, d_sym, d_idx, n, &ds->bits, s));
+        BASIC_CUDA(cudaMemcpyAsync(&hs->bits, &ds->bits, sizeof(float), cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        const double est_bytes = (double)hs->bits / 8.0;
+        want_chunks = (int64_t)(kAutoBudget * est_bytes / kChunkOverhead);
+    } else {
+        want_chunks = (lanes + kLanes - 1) / kLanes;
+    }
+    int chunk_syms, n_chunks;
+    chunking(n, want_chunks, &chunk_syms, &n_chunks);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int cap_words = attempt == 0 ? chunk_syms + chunk_syms / 4 + 64 : 12 * chunk_syms + 64;
+        cap_words = (cap_words + 7) & ~7;
+        const size_t seg_bound = 8 + (size_t)n_chunks * 132 + (size_t)n_chunks * cap_words * 2 + 8;
+        BASIC_TRY(c->words.reserve((size_t)n_chunks * cap_words * 2 + 16));
+        BASIC_TRY(c->first.reserve((size_t)n_chunks * 4 + 16));
+        BASIC_TRY(c->states.reserve((size_t)n_chunks * 128 + 16));
+        if (c->segs.cap < at + seg_bound) {  // grow, keeping what earlier segments wrote
+            DevBuf bigger;
+            BASIC_TRY(bigger.reserve((at + seg_bound) * 2));
+            if (at) BASIC_CUDA(cudaMemcpyAsync(bigger.p, c->segs.p, at, cudaMemcpyDeviceToDevice, s));
+            BASIC_CUDA(cudaStreamSynchronize(s));
+            c->segs.release();
+            c->segs = bigger;
+        }
+        BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
+        BASIC_TRY(launch_bls_encode(c->rt, c->bypass, (int)c->bypass_precision, d_sym, d_idx, n, chunk_syms, n_chunks,
+                                    c->words.as<uint16_t>(), cap_words, c->first.as<uint32_t>(), c->states.as<uint32_t>(),
+                                    c->segs.as<unsigned char>() + at, &ds->len[0], &ds->status, c->sm_count, s));
+        BASIC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        if ((hs->status & 4) && !(hs->status & 3) && attempt == 0) continue;
+        BASIC_TRY(status_error(hs->status));
+        *seg_len = hs->len[0];
+        return BASIC_OK;
+    }
+    return BASIC_ERR_CUDA;
+}
+
+int copy_out(const void *d_src, int64_t len, uint8_t *out, int64_t cap, cudaStream_t s)
+{
+    if (len > cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    if (len > 0) BASIC_CUDA(cudaMemcpyAsync(out, d_src, (size_t)len, cudaMemcpyDefault, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return BASIC_OK;
+}
+
+// Parses a segment header that lives in host memory.
+int parse_segment(const uint8_t *p, int64_t avail, int64_t n, int *chunk_syms, int *n_chunks, int64_t *seg_len)
+{
+    if (avail < 8) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
+    uint32_t nc, cs;
+    memcpy(&nc, p, 4);
+    memcpy(&cs, p + 4, 4);
+    if (cs == 0 || cs % 128 || (int64_t)nc != (n + cs - 1) / cs) { set_error("multi-lane segment does not match the number of indexes"); return BASIC_ERR_STREAM; }
+    const int64_t hdr = 8 + (int64_t)nc * 132;
+    if (avail < hdr) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
+    uint32_t total_words = 0;
+    if (nc) memcpy(&total_words, p + 8 + 4 * (int64_t)(nc - 1), 4);
+    int64_t len = hdr + 2 * (int64_t)total_words;
+    len = (len + 3) & ~(int64_t)3;
+    if (len > avail) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
+    *chunk_syms = (int)cs;
+    *n_chunks = (int)nc;
+    *seg_len = len;
+    return BASIC_OK;
+}
+
+}  // namespace
+
+// ============================================================================================== C ABI
+extern "C" {
+
+const char *basic_last_error(void) { return t_error.c_str(); }
+
+int basic_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int64_t basic_launch_count(int reset)
+{
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int basic_coder_create(int kind, unsigned precision, unsigned max_symbol_value, int bypass_coding, unsigned bypass_precision,
+                       int device, basic_coder **out)
+{
+    if (!out) return value_error("null out pointer");
+    const int base_kind = kind & 0xf;
+    if (base_kind != BASIC_KIND_RANS64 && base_kind != BASIC_KIND_TANS) return value_error("unknown coder kind");
+    if (bypass_precision < 1 || bypass_precision > 8) return value_error("bypass_precision must be in [1, 8]");
+    int ndev = 0;
+    BASIC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return BASIC_ERR_CUDA; }
+    DeviceGuard guard(device);
+    basic_coder *c = new basic_coder();
+    c->kind = base_kind;
+    c->role = kind >> 4;
+    c->precision = precision;
+    c->max_symbol_value = max_symbol_value;
+    c->bypass = bypass_coding ? 1 : 0;
+    c->bypass_precision = bypass_precision;
+    c->device = device;
+    cudaDeviceProp prop;
+    BASIC_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    BASIC_CUDA(cudaHostAlloc(&c->pinned, 256, cudaHostAllocDefault));
+    BASIC_TRY(c->small.reserve(sizeof(Small)));
+    if (c->kind == BASIC_KIND_TANS) c->tt = tans_new();
+    *out = c;
+    return BASIC_OK;
+}
+
+void basic_coder_destroy(basic_coder *c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
+                      &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
+                      &c->idx_all, &c->yhat_stage};
+    for (DevBuf *b : bufs) b->release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->tt) tans_delete(c->tt);
+    delete c;
+}
+
+int basic_coder_init_params(basic_coder *c, const int32_t *freqs, int T, int M, const int32_t *num_symbols, const int32_t *offsets)
+{
+    if (!c) return value_error("null coder");
+    DeviceGuard guard(c->device);
+    c->initialized = false;
+    if (c->kind == BASIC_KIND_RANS64)
+        BASIC_TRY(rans_tables_from_freqs(c->rt, freqs, T, M, num_symbols, offsets, (int)c->precision, 0));
+    else
+        BASIC_TRY(tans_init(*c->tt, freqs, T, M, num_symbols, offsets, c->precision, c->bypass, c->bypass_precision, c->role, 0));
+    c->initialized = true;
+    return BASIC_OK;
+}
+
+int basic_coder_init_cdf_params(basic_coder *c, const int32_t *cdfs, int T, int M, const int32_t *cdf_sizes, const int32_t *offsets)
+{
+    if (!c) return value_error("null coder");
+    if (c->kind != BASIC_KIND_RANS64) return value_error("init_cdf_params is a rANS call");
+    DeviceGuard guard(c->device);
+    c->initialized = false;
+    BASIC_TRY(rans_tables_from_cdfs(c->rt, cdfs, T, M, cdf_sizes, offsets, (int)c->precision, 0));
+    c->initialized = true;
+    return BASIC_OK;
+}
+
+int basic_coder_cdfs_shape(basic_coder *c, int *T, int *M)
+{
+    if (!c || c->kind != BASIC_KIND_RANS64 || !c->initialized) { *T = 0; *M = 0; return BASIC_OK; }
+    *T = c->rt.T;
+    *M = *std::max_element(c->rt.h_sizes.begin(), c->rt.h_sizes.end());
+    return BASIC_OK;
+}
+
+int basic_coder_get_cdfs(basic_coder *c, int32_t *out)
+{
+    BASIC_TRY(need_init(c));
+    DeviceGuard guard(c->device);
+    int T, M;
+    basic_coder_cdfs_shape(c, &T, &M);
+    BASIC_CUDA(cudaMemcpy2D(out, (size_t)M * 4, c->rt.cdf32.p, (size_t)c->rt.stride * 4, (size_t)M * 4, T, cudaMemcpyDeviceToHost));
+    return BASIC_OK;
+}
+
+int basic_pmf_to_quantized_cdf(const float *pmf, int n, int precision, int device, int32_t *cdf_out)
+{
+    DeviceGuard guard(device);
+    return pmf_to_cdf_device(pmf, n, precision, cdf_out);
+}
+
+int64_t basic_coder_encode_bound(basic_coder *c, int64_t n, int lanes)
+{
+    if (c && c->kind == BASIC_KIND_TANS) return n * (int64_t)c->precision / 8 + 16;
+    if (lanes == BASIC_LANES_REFERENCE) return (12 * n + 64) * 4;
+    return 16 + ((n + 127) / 128) * 132 + 24 * n + 64;
+}
+
+int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, int lanes, int cache,
+                       uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (n < 0 || lanes < 0) return value_error("negative size");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (out_len) *out_len = 0;
+    const int32_t *d_sym, *d_idx;
+    if (cache && (c->kind == BASIC_KIND_TANS || lanes == BASIC_LANES_REFERENCE)) {
+        // reference cache mode (rans64.cpp:327-345): operands are kept, the stream is produced by flush()
+        std::vector<int32_t> hs((size_t)n), hi((size_t)n);
+        BASIC_CUDA(cudaMemcpyAsync(hs.data(), symbols, (size_t)n * 4, cudaMemcpyDefault, s));
+        BASIC_CUDA(cudaMemcpyAsync(hi.data(), indexes, (size_t)n * 4, cudaMemcpyDefault, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        c->cache_sym.insert(c->cache_sym.end(), hs.begin(), hs.end());
+        c->cache_idx.insert(c->cache_idx.end(), hi.begin(), hi.end());
+        return BASIC_OK;
+    }
+    BASIC_TRY(to_device(symbols, (size_t)n, c->in_a, s, &d_sym));
+    BASIC_TRY(to_device(indexes, (size_t)n, c->in_b, s, &d_idx));
+    if (c->kind == BASIC_KIND_TANS) {
+        const int64_t cap = n * (int64_t)c->precision / 8;
+        BASIC_TRY(c->segs.reserve((size_t)cap + 64));
+        BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
+        Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+        BASIC_TRY(tans_encode(*c->tt, d_sym, d_idx, n, c->segs.as<uint8_t>(), cap, &ds->len[0], &ds->status, s));
+        BASIC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        if (hs->status & 8) return value_error("Destination buffer is too small");
+        BASIC_TRY(status_error(hs->status));
+        BASIC_TRY(copy_out(c->segs.p, hs->len[0], out, out_cap, s));
+        if (out_len) *out_len = hs->len[0];
+        return BASIC_OK;
+    }
+    if (lanes == BASIC_LANES_REFERENCE) {
+        const uint8_t *d_bytes;
+        int64_t len;
+        BASIC_TRY(encode_compat(c, d_sym, d_idx, n, s, &d_bytes, &len));
+        BASIC_TRY(copy_out(d_bytes, len, out, out_cap, s));
+        if (out_len) *out_len = len;
+        return BASIC_OK;
+    }
+    // multi-lane container: magic | segment
+    BASIC_TRY(c->segs.reserve(64));
+    int64_t seg_len = 0;
+    BASIC_TRY(encode_segment(c, d_sym, d_idx, n, lanes, 4, s, &seg_len));
+    if (cache) {
+        std::vector<uint8_t> seg((size_t)seg_len);
+        BASIC_CUDA(cudaMemcpyAsync(seg.data(), c->segs.as<unsigned char>() + 4, (size_t)seg_len, cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        c->cache_segments.push_back(std::move(seg));
+        return BASIC_OK;
+    }
+    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
+    BASIC_TRY(copy_out(c->segs.p, 4 + seg_len, out, out_cap, s));
+    if (out_len) *out_len = 4 + seg_len;
+    return BASIC_OK;
+}
+
+int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    DeviceGuard guard(c->device);
+    if (out_len) *out_len = 0;
+    if (c->kind == BASIC_KIND_TANS || lanes == BASIC_LANES_REFERENCE) {
+        std::vector<int32_t> sym, idx;
+        sym.swap(c->cache_sym);
+        idx.swap(c->cache_idx);
+        return basic_coder_encode(c, sym.data(), idx.data(), (int64_t)sym.size(), BASIC_LANES_REFERENCE, 0, out, out_cap, out_len,
+                                  stream);
+    }
+    int64_t total = 4;
+    for (auto &sg : c->cache_segments) total += (int64_t)sg.size();
+    if (total > out_cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    std::vector<uint8_t> all((size_t)total);
+    memcpy(all.data(), &kMagic, 4);
+    size_t at = 4;
+    for (auto &sg : c->cache_segments) { memcpy(all.data() + at, sg.data(), sg.size()); at += sg.size(); }
+    c->cache_segments.clear();
+    BASIC_CUDA(cudaMemcpy(out, all.data(), (size_t)total, cudaMemcpyDefault));
+    if (out_len) *out_len = total;
+    return BASIC_OK;
+}
+
+int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, int lanes, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind == BASIC_KIND_TANS) { c->stream_set = true; return BASIC_OK; }  // tans.cpp:824-836: stores the string only
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (len < 0) return value_error("negative length");
+    c->h_stream.resize((size_t)len);
+    if (len) BASIC_CUDA(cudaMemcpyAsync(c->h_stream.data(), encoded, (size_t)len, cudaMemcpyDefault, s));
+    BASIC_TRY(c->stream_dev.reserve((size_t)len + 64));
+    BASIC_CUDA(cudaMemsetAsync(c->stream_dev.p, 0, (size_t)len + 64, s));
+    if (len) BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyDefault, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    c->stream_lanes = lanes;
+    c->stream_set = true;
+    if (lanes == BASIC_LANES_REFERENCE) {
+        c->stream_pos = -1;  // state is initialised by the first decode_stream launch
+    } else {
+        uint32_t magic = 0;
+        if (len >= 4) memcpy(&magic, c->h_stream.data(), 4);
+        if (magic != kMagic) { c->stream_set = false; set_error("not a multi-lane (BLS1) container"); return BASIC_ERR_STREAM; }
+        c->stream_pos = 4;
+    }
+    return BASIC_OK;
+}
+
+int basic_coder_decode_stream(basic_coder *c, const int32_t *indexes, int64_t n, int32_t *out, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind == BASIC_KIND_TANS) return value_error("decode_stream is not implemented for tANS (reference stub, tans.cpp:838-915)");
+    if (!c->stream_set) return value_error("set_stream has not been called");
+    if (n < 0) return value_error("negative size");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int32_t *d_idx;
+    BASIC_TRY(to_device(indexes, (size_t)n, c->in_b, s, &d_idx));
+    int32_t *d_out = out;
+    const bool out_dev = is_device_ptr(out);
+    if (!out_dev) { BASIC_TRY(c->out_i32.reserve((size_t)n * 4 + 16)); d_out = c->out_i32.as<int32_t>(); }
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    if (c->stream_lanes == BASIC_LANES_REFERENCE) {
+        const int init = c->stream_pos < 0;
+        BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), (int64_t)c->h_stream.size() / 4, &ds->len[2], init, d_idx,
+                                       n, c->bypass, (int)c->bypass_precision, d_out, &ds->status, s));
+        c->stream_pos = 0;
+    } else {
+        int chunk_syms = 128, n_chunks = 0;
+        int64_t seg_len = 0;
+        if (n > 0 || c->stream_pos < (int64_t)c->h_stream.size()) {
+            BASIC_TRY(parse_segment(c->h_stream.data() + c->stream_pos, (int64_t)c->h_stream.size() - c->stream_pos, n, &chunk_syms,
+                                    &n_chunks, &seg_len));
+            BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
+                                        seg_len, d_idx, n, chunk_syms, n_chunks, d_out, &ds->status, c->sm_count, s));
+            c->stream_pos += seg_len;
+        }
+    }
+    BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!out_dev && n) BASIC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return status_error(hs->status);
+}
+
+int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, const int32_t *indexes, int64_t n, int lanes,
+                       int32_t *out, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind == BASIC_KIND_TANS) {
+        DeviceGuard guard(c->device);
+        cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+        if (len < 1) return value_error("Src size incorrect");
+        const int32_t *d_idx;
+        BASIC_TRY(to_device(indexes, (size_t)n, c->in_b, s, &d_idx));
+        BASIC_TRY(c->stream_dev.reserve((size_t)len + 64));
+        BASIC_CUDA(cudaMemsetAsync(c->stream_dev.p, 0, (size_t)len + 64, s));
+        BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + 16, encoded, (size_t)len, cudaMemcpyDefault, s));
+        int32_t *d_out = out;
+        const bool out_dev = is_device_ptr(out);
+        if (!out_dev) { BASIC_TRY(c->out_i32.reserve((size_t)n * 4 + 16)); d_out = c->out_i32.as<int32_t>(); }
+        Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+        BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+        BASIC_TRY(tans_decode(*c->tt, c->stream_dev.as<uint8_t>() + 16, len, d_idx, n, d_out, &ds->status, s));
+        BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (!out_dev && n) BASIC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        if (hs->status & 8) return value_error("Error (generic)");  // end mark not present
+        return status_error(hs->status);
+    }
+    BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
+    return basic_coder_decode_stream(c, indexes, n, out, stream);
+}
+
+// ------------------------------------------------------------------------------- Gaussian conditional
+int basic_coder_set_scale_table(basic_coder *c, const float *scale_table, int n_scales)
+{
+    if (!c) return value_error("null coder");
+    if (n_scales < 1 || n_scales > 256) return value_error("scale table must have 1..256 entries");
+    DeviceGuard guard(c->device);
+    c->h_scale.assign(scale_table, scale_table + n_scales);
+    for (int i = 1; i < n_scales; ++i)
+        if (!(c->h_scale[i] > c->h_scale[i - 1])) return value_error("scale table must be strictly increasing");
+    BASIC_TRY(c->d_scale.reserve(sizeof(float) * n_scales));
+    BASIC_CUDA(cudaMemcpy(c->d_scale.p, c->h_scale.data(), sizeof(float) * n_scales, cudaMemcpyHostToDevice));
+    return BASIC_OK;
+}
+
+int basic_gauss_quantize_index(basic_coder *c, const float *y, const float *params, const int32_t *positions, int64_t n_pos, int B,
+                               int C, int HW, int32_t *symbols, int32_t *indexes, float *yhat_buf, void *stream)
+{
+    if (!c || c->h_scale.empty()) return value_error("scale table not set");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!is_device_ptr(params) || (y && !is_device_ptr(y)) || !is_device_ptr(indexes) || (positions && !is_device_ptr(positions)) ||
+        (y && !is_device_ptr(symbols)) || (yhat_buf && !is_device_ptr(yhat_buf)))
+        return value_error("basic_gauss_quantize_index works on device memory");
+    return launch_quantize_index(y, params, positions, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(), symbols,
+                                 indexes, yhat_buf, c->sm_count, s);
+}
+
+int basic_gauss_dequantize(basic_coder *c, const int32_t *symbols, const float *params, const int32_t *positions, int64_t n_pos,
+                           int B, int C, int HW, float *yhat_buf, void *stream)
+{
+    if (!c) return value_error("null coder");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!is_device_ptr(params) || !is_device_ptr(symbols) || !is_device_ptr(yhat_buf) || (positions && !is_device_ptr(positions)))
+        return value_error("basic_gauss_dequantize works on device memory");
+    return launch_dequantize(symbols, params, positions, n_pos, B, C, HW, yhat_buf, c->sm_count, s);
+}
+
+// ------------------------------------------------------------------------------------- context model
+int basic_ctx_create(int C, int G, int kernel_size, int device, basic_ctx **out)
+{
+    if (!out) return value_error("null out pointer");
+    if (C < 1 || G < 1 || C % G) return value_error("in_channels must be a positive multiple of channel_groups");
+    if (kernel_size != 5 && kernel_size != 3 && kernel_size != 1) return value_error("kernel_size must be 1, 3 or 5");
+    int ndev = 0;
+    BASIC_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return BASIC_ERR_CUDA; }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    BASIC_CUDA(cudaGetDeviceProperties(&prop, device));
+    basic_ctx *m = new basic_ctx();
+    m->m = ctx_new(C, G, kernel_size, device, prop.multiProcessorCount);
+    m->device = device;
+    *out = m;
+    return BASIC_OK;
+}
+
+void basic_ctx_destroy(basic_ctx *m)
+{
+    if (!m) return;
+    DeviceGuard guard(m->device);
+    ctx_delete(m->m);
+    delete m;
+}
+
+int basic_ctx_set_weights(basic_ctx *m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b, const float *m2_w,
+                          const float *m2_b, const float *m3_w, const float *m3_b)
+{
+    if (!m) return value_error("null model");
+    DeviceGuard guard(m->device);
+    return ctx_set_weights(*m->m, ctx_w, ctx_b, m1_w, m1_b, m2_w, m2_b, m3_w, m3_b);
+}
+
+int basic_ctx_set_map(basic_ctx *m, const int32_t *tg, int H, int W)
+{
+    if (!m) return value_error("null model");
+    if (H < 1 || W < 1) return value_error("empty map");
+    DeviceGuard guard(m->device);
+    return ctx_set_map(*m->m, tg, H, W);
+}
+
+int basic_ctx_num_stages(basic_ctx *m) { return m ? ctx_num_stages(*m->m) : 0; }
+
+int basic_ctx_stage_positions(basic_ctx *m, int g, const int32_t **positions_dev, int64_t *n_pos)
+{
+    if (!m) return value_error("null model");
+    return ctx_stage_positions(*m->m, g, positions_dev, n_pos);
+}
+
+int basic_ctx_stage_params(basic_ctx *m, int g, const float *buf, const float *prior, int B, float *params, void *stream)
+{
+    if (!m) return value_error("null model");
+    DeviceGuard guard(m->device);
+    if (!is_device_ptr(buf) || !is_device_ptr(prior) || !is_device_ptr(params)) return value_error("basic_ctx_stage_params works on device memory");
+    return ctx_stage_params(*m->m, g, buf, prior, B, params, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------------------------- whole y path
+int64_t basic_ypath_encode_bound(basic_coder *c, int B, int C, int H, int W, int lanes)
+{
+    const int64_t n = (int64_t)B * C * H * W;
+    return basic_coder_encode_bound(c, n, lanes) + 64 + 16 * (int64_t)H * W * 33;  // + per-stage headers (scanline worst case)
+}
+
+static int ypath_setup(basic_coder *c, basic_ctx *model, int B, int C, int H, int W, int *S)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind != BASIC_KIND_RANS64) return value_error("the y path codes with rANS");
+    if (c->h_scale.empty()) return value_error("scale table not set");
+    if (B < 1 || C < 1 || H < 1 || W < 1) return value_error("empty input");
+    *S = 1;
+    if (model) {
+        int mc, mg, mh, mw;
+        ctx_dims(*model->m, &mc, &mg, &mh, &mw);
+        if (mc != C) return value_error("context model channel count does not match the input");
+        if (mh != H || mw != W) return value_error("group map not set for this spatial size (basic_ctx_set_map)");
+        if (model->device != c->device) return value_error("coder and context model live on different devices");
+        *S = ctx_num_stages(*model->m);
+    }
+    const size_t n = (size_t)B * C * H * W;
+    BASIC_TRY(c->buf.reserve(n * 4));
+    BASIC_TRY(c->params.reserve(n * 8));
+    BASIC_TRY(c->sym_all.reserve(n * 4 + 16));
+    BASIC_TRY(c->idx_all.reserve(n * 4 + 16));
+    return BASIC_OK;
+}
+
+int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const float *prior, int B, int C, int H, int W, int lanes,
+                       uint8_t *out, int64_t out_cap, int64_t *out_len, float *yhat_out, void *stream)
+{
+    int S;
+    BASIC_TRY(ypath_setup(c, model, B, C, H, W, &S));
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int HW = H * W;
+    const size_t n = (size_t)B * C * HW;
+    const float *d_y, *d_prior;
+    BASIC_TRY(to_device(y, n, c->y_dev, s, &d_y));
+    BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
+    float *buf = c->buf.as<float>(), *params = c->params.as<float>();
+    int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
+    BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
+    const float *params_src = params;
+    std::vector<int64_t> seg_at, seg_len;
+    size_t at = 4, done = 0;
+    if (lanes != BASIC_LANES_REFERENCE) BASIC_TRY(c->segs.reserve(64));
+    for (int g = 0; g < S; ++g) {
+        const int32_t *pos = nullptr;
+        int64_t n_pos = (int64_t)C * HW;
+        if (model) {
+            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
+            BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
+        } else {
+            params_src = d_prior;
+        }
+        const int64_t cnt = (int64_t)B * n_pos;
+        if (cnt == 0) continue;
+        BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
+                                        sym + done, idx + done, buf, c->sm_count, s));
+        if (lanes != BASIC_LANES_REFERENCE) {
+            int64_t len = 0;
+            BASIC_TRY(encode_segment(c, sym + done, idx + done, cnt, lanes, at, s, &len));
+            at += (size_t)len;
+        }
+        done += (size_t)cnt;
+    }
+    if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
+    if (lanes == BASIC_LANES_REFERENCE) {
+        const uint8_t *d_bytes;
+        int64_t len;
+        BASIC_TRY(encode_compat(c, sym, idx, (int64_t)done, s, &d_bytes, &len));
+        BASIC_TRY(copy_out(d_bytes, len, out, out_cap, s));
+        if (out_len) *out_len = len;
+        return BASIC_OK;
+    }
+    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
+    BASIC_TRY(copy_out(c->segs.p, (int64_t)at, out, out_cap, s));
+    if (out_len) *out_len = (int64_t)at;
+    return BASIC_OK;
+}
+
+int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded, int64_t len, const float *prior, int B, int C, int H,
+                       int W, int lanes, float *yhat_out, void *stream)
+{
+    int S;
+    BASIC_TRY(ypath_setup(c, model, B, C, H, W, &S));
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int HW = H * W;
+    const size_t n = (size_t)B * C * HW;
+    const float *d_prior;
+    BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
+    BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
+    float *buf = c->buf.as<float>(), *params = c->params.as<float>();
+    int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
+    BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
+    const float *params_src = params;
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    for (int g = 0; g < S; ++g) {
+        const int32_t *pos = nullptr;
+        int64_t n_pos = (int64_t)C * HW;
+        if (model) {
+            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
+            BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
+        } else {
+            params_src = d_prior;
+        }
+        const int64_t cnt = (int64_t)B * n_pos;
+        if (cnt == 0) continue;
+        BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
+                                        nullptr, idx, nullptr, c->sm_count, s));
+        if (lanes == BASIC_LANES_REFERENCE) {
+            const int init = c->stream_pos < 0;
+            BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), (int64_t)c->h_stream.size() / 4, &ds->len[2], init, idx,
+                                           cnt, c->bypass, (int)c->bypass_precision, sym, &ds->status, s));
+            c->stream_pos = 0;
+        } else {
+            int chunk_syms, n_chunks;
+            int64_t seg_len;
+            BASIC_TRY(parse_segment(c->h_stream.data() + c->stream_pos, (int64_t)c->h_stream.size() - c->stream_pos, cnt, &chunk_syms,
+                                    &n_chunks, &seg_len));
+            BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
+                                        seg_len, idx, cnt, chunk_syms, n_chunks, sym, &ds->status, c->sm_count, s));
+            c->stream_pos += seg_len;
+        }
+        BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
+    }
+    BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return status_error(hs->status);
+}
+
+}  // extern "C"

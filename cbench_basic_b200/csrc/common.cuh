@@ -1,0 +1,121 @@
+// Shared definitions of the sm_100a entropy-coding library (see include/basic_b200.h for the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/basic_b200.h"
+
+namespace basic {
+
+void set_error(const std::string &msg);
+extern int64_t g_launches;
+
+#define BASIC_CUDA(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            basic::set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+            return BASIC_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+#define BASIC_TRY(expr)          \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != BASIC_OK) return _rc; \
+    } while (0)
+
+#define BASIC_LAUNCHED()                         \
+    do {                                         \
+        ++basic::g_launches;                     \
+        BASIC_CUDA(cudaGetLastError());          \
+    } while (0)
+
+inline int value_error(const std::string &msg)
+{
+    set_error(msg);
+    return BASIC_ERR_VALUE;
+}
+
+// Grow-only device buffer (scratch that lives as long as the coder object: no cudaMalloc on the hot path).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return BASIC_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        BASIC_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return BASIC_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+inline bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Per-table metadata, one 16-byte record (a single LDS.128 / LDG.128 in the kernels).
+struct __align__(16) TableMeta {
+    uint32_t cdf_base;  // first entry of this table inside the packed u16 CDF array
+    uint32_t lut_base;  // first entry of this table's bucket LUT
+    uint16_t cdf_size;  // number of CDF entries = coded symbols + 1 (reference _cdfs_sizes)
+    uint8_t lut_shift;  // bucket = cum >> lut_shift
+    uint8_t pad;
+    int32_t offset;     // reference _offsets[t]
+};
+
+// Device-resident rANS tables (built by tables.cu).
+struct RansTables {
+    int T = 0, stride = 0, precision = 16;
+    std::vector<int32_t> h_sizes, h_offsets;  // host mirrors (sizes are known without a device round trip)
+    DevBuf cdf32;                              // int32 [T, stride], the reference's _cdfs (zero padded)
+    DevBuf blob;                               // packed: TableMeta[T] | u16 cdf[...] | u16 lut[...]
+    size_t blob_bytes = 0, meta_bytes = 0, cdf16_bytes = 0, lut_bytes = 0;
+    uint32_t total_cdf = 0, total_lut = 0;
+    bool ready = false;
+};
+
+// Views into `blob` (either the global copy or its shared-memory image).
+struct TableView {
+    const TableMeta *meta;
+    const uint16_t *cdf;
+    const uint16_t *lut;
+};
+
+__host__ __device__ inline TableView make_view(const void *blob, size_t meta_bytes, size_t cdf16_bytes)
+{
+    const char *b = reinterpret_cast<const char *>(blob);
+    TableView v;
+    v.meta = reinterpret_cast<const TableMeta *>(b);
+    v.cdf = reinterpret_cast<const uint16_t *>(b + meta_bytes);
+    v.lut = reinterpret_cast<const uint16_t *>(b + meta_bytes + cdf16_bytes);
+    return v;
+}
+
+static constexpr int kLanes = 32;             // lanes of one chunk = one warp
+static constexpr uint32_t kRansL = 1u << 16;  // multi-lane state lower bound
+static constexpr uint32_t kMagic = 0x31534C42u;  // "BLS1"
+static constexpr int kMaxSmemTables = 200 * 1024;
+
+}  // namespace basic

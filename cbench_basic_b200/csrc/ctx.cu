@@ -1,0 +1,522 @@
+// Grouped / checkerboard autoregressive context model, exact-FP32 path.
+//
+// Reference semantics (cbench/nn/layers/masked_conv.py:102-228,287-305):
+//   ctx    = conv5x5(y_hat)         tap (c, dh, dw) visible to out-group go iff tg[gc(c), h+dh, w+dw] <  tg[go, h, w]
+//   m1     = conv1x1([ctx, prior])  ctx in-group j visible iff tg[j, h, w] <= tg[go, h, w]; prior always
+//   m2     = conv1x1(lrelu(m1)), params = conv1x1(lrelu(m2)) with the same "<=" rule.
+// The reference recomputes every position for every group; here each (channel-group, position) CELL is
+// computed exactly once, at the stage its own group id says, and the intermediate activations stay in HBM
+// for the later stages that are allowed to see them.  One launch per layer per stage: a tiled FP32 GEMM whose
+// A operand is gathered on the fly (im2col rows of the stage's cells, masked taps skipped per tile).
+// Deterministic (fixed K order, no atomics): the decoder recomputes bit-identical parameters.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace basic {
+
+struct CtxModel {
+    int C = 0, G = 1, k = 5, device = 0, sm_count = 148;
+    bool has_conv = false, has_merger = false;
+    int c_ctx = 0, c_m1 = 0, c_m2 = 0;  // 2C, 10C/3, 8C/3
+    // weights, K-major ("transposed"): wt[kk][o]
+    DevBuf w_ctx, b_ctx;                // conv: kk = tap * C + c
+    DevBuf w_m1, b_m1, w_m2, b_m2, w_m3, b_m3;
+    // map
+    int H = 0, W = 0, S = 0;
+    std::vector<int32_t> h_tg;
+    struct Stage {
+        std::vector<int> cell_off;       // [G + 1] offsets into the stage's cell arrays
+        size_t cells_at = 0;             // offset of this stage inside d_cells (in cells)
+        size_t pos_at = 0;               // offset inside d_positions
+        int64_t n_pos = 0;
+        uint32_t tap_or = 0;             // OR of all tap masks of the stage (0 -> conv contributes bias only)
+    };
+    std::vector<Stage> stages;
+    DevBuf d_cell_hw;    // int32 [ncells]            cell -> h*W+w
+    DevBuf d_cell_tap;   // uint32 [ncells][G]        visible 5x5 taps per input channel group
+    DevBuf d_cell_grp;   // uint32 [ncells]           bit j: in-group j visible through "<="
+    DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
+    // activations (grow-only)
+    DevBuf a_ctx, a_m1, a_m2;
+    int act_B = 0;
+};
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
+constexpr float kSlope = 0.01f;  // nn.LeakyReLU default negative_slope
+
+struct Source {          // one block of K coming from an NCHW activation tensor
+    const float *ptr;    // [B, channels, H, W]
+    int channels;        // channels of this tensor
+    int groups;          // channel groups subject to the visibility rule (0 = always visible)
+};
+
+struct LayerArgs {
+    // rows = B x cells(stage, out-group)
+    const int32_t *cell_hw;
+    const uint32_t *cell_tap;   // conv only
+    const uint32_t *cell_grp;   // dense only
+    int ncells, cell_base;      // cells of this (stage, out-group) start at cell_base
+    int B, HW, W_img, H_img, G;
+    // K
+    int is_conv, ksize, Cin;    // conv: Cin input channels of `src0`
+    Source src0, src1;          // dense: K = src0.channels + src1.channels
+    const float *wt;            // [K][Ntot] K-major
+    const float *bias;          // [Ntot]
+    int Ntot, n_begin, n_count; // this out-group's output channels [n_begin, n_begin + n_count)
+    // epilogue
+    float *out;                 // [B, Ntot, H, W]
+    const float *add;           // optional [B, Ntot, H, W] added in the epilogue (merger-less: + prior)
+    int lrelu;
+    uint32_t tap_or;            // stage-level OR of the tap masks (conv)
+};
+
+__global__ void __launch_bounds__(NT)
+k_layer(LayerArgs a)
+{
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Ws[BK][BN];
+    __shared__ int s_off[BM];        // b * HW_total offset helper: b
+    __shared__ int s_hw[BM];
+    __shared__ uint32_t s_mask[BM];  // dense: group bits; conv: tap mask of the current input group
+    __shared__ uint32_t s_or;
+
+    const int tid = threadIdx.x;
+    const int rows = a.B * a.ncells;
+    const int row0 = blockIdx.x * BM;
+    if (row0 >= rows) return;
+    const int n0 = blockIdx.y * BN;  // relative to n_begin
+    if (n0 >= a.n_count) return;
+
+    for (int r = tid; r < BM; r += NT) {
+        const int row = row0 + r;
+        if (row < rows) {
+            const int b = row / a.ncells, cell = a.cell_base + (row - b * a.ncells);
+            s_off[r] = b;
+            s_hw[r] = a.cell_hw[cell];
+        } else {
+            s_off[r] = -1;
+            s_hw[r] = 0;
+        }
+    }
+    const int tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty*8..+7, cols tx*4..+3
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int lr = tid & (BM - 1), lk0 = tid >> 7;  // A loader: row lr, k = lk0 + 2 * i  (8 loads)
+    const int wn = tid & (BN - 1), wk0 = tid >> 6;  // W loader: col wn, k = wk0 + 4 * i  (4 loads)
+
+    auto mma_tile = [&]() {
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            const float4 w4 = *reinterpret_cast<const float4 *>(&Ws[kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
+    };
+
+    if (a.is_conv) {
+        const int kh = a.ksize, pad = kh / 2, cpg = a.Cin / a.G;
+        const long long chw = (long long)a.Cin * a.HW;
+        for (int g = 0; g < a.G; ++g) {
+            __syncthreads();
+            if (tid == 0) s_or = 0;
+            __syncthreads();
+            for (int r = tid; r < BM; r += NT) {
+                const int row = row0 + r;
+                uint32_t mk = 0;
+                if (row < rows) {
+                    const int b = row / a.ncells, cell = a.cell_base + (row - b * a.ncells);
+                    mk = a.cell_tap[(size_t)cell * a.G + g];
+                }
+                s_mask[r] = mk;
+                if (mk) atomicOr(&s_or, mk);
+            }
+            __syncthreads();
+            const uint32_t tile_or = s_or;
+            for (int tap = 0; tap < kh * kh; ++tap) {
+                if (!((tile_or >> tap) & 1u)) continue;  // nobody in this tile sees the tap: skip its K block
+                const int dh = tap / kh - pad, dw = tap % kh - pad;
+                const int shift = dh * a.W_img + dw;
+                for (int c0 = g * cpg; c0 < (g + 1) * cpg; c0 += BK) {
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int kk = lk0 + 2 * i, c = c0 + kk;
+                        float v = 0.f;
+                        const int b = s_off[lr];
+                        if (b >= 0 && c < (g + 1) * cpg && ((s_mask[lr] >> tap) & 1u))
+                            v = a.src0.ptr[(long long)b * chw + (long long)c * a.HW + s_hw[lr] + shift];
+                        As[kk][lr] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int kk = wk0 + 4 * i, c = c0 + kk, n = n0 + wn;
+                        float v = 0.f;
+                        if (c < (g + 1) * cpg && n < a.n_count)
+                            v = a.wt[((size_t)tap * a.Cin + c) * a.Ntot + a.n_begin + n];
+                        Ws[kk][wn] = v;
+                    }
+                    __syncthreads();
+                    mma_tile();
+                }
+            }
+        }
+    } else {
+        __syncthreads();
+        if (tid == 0) s_or = 0;
+        __syncthreads();
+        for (int r = tid; r < BM; r += NT) {
+            const int row = row0 + r;
+            uint32_t mk = 0;
+            if (row < rows) {
+                const int b = row / a.ncells, cell = a.cell_base + (row - b * a.ncells);
+                mk = a.cell_grp[cell];
+            }
+            s_mask[r] = mk;
+            if (mk) atomicOr(&s_or, mk);
+        }
+        __syncthreads();
+        const uint32_t tile_or = s_or;
+        int kbase = 0;
+        for (int si = 0; si < 2; ++si) {
+            const Source s = si == 0 ? a.src0 : a.src1;
+            if (!s.ptr || s.channels == 0) continue;
+            const int ngroups = s.groups > 0 ? s.groups : 1;
+            const int cpg = s.channels / ngroups;
+            const long long chw = (long long)s.channels * a.HW;
+            for (int g = 0; g < ngroups; ++g) {
+                if (s.groups > 0 && !((tile_or >> g) & 1u)) continue;
+                for (int c0 = g * cpg; c0 < (g + 1) * cpg; c0 += BK) {
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int kk = lk0 + 2 * i, c = c0 + kk;
+                        float v = 0.f;
+                        const int b = s_off[lr];
+                        if (b >= 0 && c < (g + 1) * cpg && (s.groups == 0 || ((s_mask[lr] >> g) & 1u)))
+                            v = s.ptr[(long long)b * chw + (long long)c * a.HW + s_hw[lr]];
+                        As[kk][lr] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int kk = wk0 + 4 * i, c = c0 + kk, n = n0 + wn;
+                        float v = 0.f;
+                        if (c < (g + 1) * cpg && n < a.n_count) v = a.wt[((size_t)kbase + c) * a.Ntot + a.n_begin + n];
+                        Ws[kk][wn] = v;
+                    }
+                    __syncthreads();
+                    mma_tile();
+                }
+            }
+            kbase += s.channels;
+        }
+    }
+
+    // epilogue: rows ty*8.., cols tx*4..
+    const long long ohw = (long long)a.Ntot * a.HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n >= a.n_count) continue;
+        const int ch = a.n_begin + n;
+        const float bias = a.bias ? a.bias[ch] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = ty * 8 + i;
+            const int b = s_off[r];
+            if (b < 0) continue;
+            const long long o = (long long)b * ohw + (long long)ch * a.HW + s_hw[r];
+            float v = acc[i][j] + bias;
+            if (a.add) v += a.add[o];
+            if (a.lrelu) v = v > 0.f ? v : v * kSlope;
+            a.out[o] = v;
+        }
+    }
+}
+
+// params = prior + bias (no context model weights at all, or a stage that sees nothing and has no merger)
+__global__ void __launch_bounds__(256)
+k_bias_prior(const float *__restrict__ prior, const float *__restrict__ bias, long long total, int HW, int C2,
+             float *__restrict__ params)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)((e / HW) % C2);
+        params[e] = prior[e] + (bias ? bias[ch] : 0.f);
+    }
+}
+
+// weight re-layout: src [N][K] (state_dict, conv flattened as c*k2+tap) -> dst K-major [K'][N]
+__global__ void k_transpose_w(const float *__restrict__ src, float *__restrict__ dst, int N, int Cin, int k2)
+{
+    const long long total = (long long)N * Cin * k2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e / ((long long)Cin * k2));
+        const int rem = (int)(e - (long long)n * Cin * k2);
+        const int c = rem / k2, tap = rem - c * k2;
+        dst[((size_t)tap * Cin + c) * N + n] = src[e];
+    }
+}
+
+int upload(DevBuf &dst, const float *src, size_t count, cudaStream_t s)
+{
+    BASIC_TRY(dst.reserve(count * sizeof(float)));
+    BASIC_CUDA(cudaMemcpyAsync(dst.p, src, count * sizeof(float), cudaMemcpyDefault, s));
+    return BASIC_OK;
+}
+
+int upload_transposed(DevBuf &dst, const float *src, int N, int Cin, int k2, cudaStream_t s)
+{
+    const size_t count = (size_t)N * Cin * k2;
+    DevBuf tmp;
+    BASIC_TRY(tmp.reserve(count * sizeof(float)));
+    BASIC_CUDA(cudaMemcpyAsync(tmp.p, src, count * sizeof(float), cudaMemcpyDefault, s));
+    BASIC_TRY(dst.reserve(count * sizeof(float)));
+    k_transpose_w<<<256, 256, 0, s>>>(tmp.as<float>(), dst.as<float>(), N, Cin, k2);
+    BASIC_LAUNCHED();
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    tmp.release();
+    return BASIC_OK;
+}
+
+}  // namespace
+
+int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b,
+                    const float *m2_w, const float *m2_b, const float *m3_w, const float *m3_b)
+{
+    cudaStream_t s = 0;
+    const int C = m.C;
+    m.c_ctx = 2 * C;
+    m.c_m1 = m.c_ctx * 5 / 3;
+    m.c_m2 = m.c_ctx * 4 / 3;
+    m.has_conv = ctx_w != nullptr;
+    m.has_merger = m1_w != nullptr;
+    if (m.has_merger && !(m1_b && m2_w && m2_b && m3_w && m3_b)) return value_error("merger weights incomplete");
+    if (m.has_merger && !m.has_conv) return value_error("param merger needs the context convolution weights");
+    if (m.has_merger && (m.c_m1 % m.G || m.c_m2 % m.G)) return value_error("2C*5/3 and 2C*4/3 must be divisible by channel_groups");
+    if (C % m.G) return value_error("in_channels must be divisible by channel_groups");
+    if (m.has_conv) BASIC_TRY(upload_transposed(m.w_ctx, ctx_w, m.c_ctx, C, m.k * m.k, s));
+    if (ctx_b) BASIC_TRY(upload(m.b_ctx, ctx_b, m.c_ctx, s)); else m.b_ctx.release();
+    if (m.has_merger) {
+        BASIC_TRY(upload_transposed(m.w_m1, m1_w, m.c_m1, 2 * m.c_ctx, 1, s));
+        BASIC_TRY(upload(m.b_m1, m1_b, m.c_m1, s));
+        BASIC_TRY(upload_transposed(m.w_m2, m2_w, m.c_m2, m.c_m1, 1, s));
+        BASIC_TRY(upload(m.b_m2, m2_b, m.c_m2, s));
+        BASIC_TRY(upload_transposed(m.w_m3, m3_w, m.c_ctx, m.c_m2, 1, s));
+        BASIC_TRY(upload(m.b_m3, m3_b, m.c_ctx, s));
+    }
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return BASIC_OK;
+}
+
+// Builds the per-stage cell lists, visibility masks and coded-position lists on the host (the map is tiny:
+// G*H*W integers) and uploads them.
+int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
+{
+    const int G = m.G, HW = H * W, C = m.C, cpg = C / G, k = m.k, pad = k / 2;
+    std::vector<int32_t> tg((size_t)G * HW);
+    BASIC_CUDA(cudaMemcpy(tg.data(), tg_any, tg.size() * sizeof(int32_t), cudaMemcpyDefault));
+    if (m.H == H && m.W == W && m.h_tg == tg && !m.stages.empty()) return BASIC_OK;  // same map as last time
+    if (G > 32) return value_error("channel_groups > 32 not supported");
+    int S = 0;
+    for (int32_t v : tg) {
+        if (v < 0) return value_error("negative topo group id");
+        S = std::max(S, v + 1);
+    }
+    m.H = H; m.W = W; m.S = S; m.h_tg = tg;
+    m.stages.assign(S, CtxModel::Stage());
+    // bucket cells by stage, ordered by (out-group, hw)
+    std::vector<std::vector<int>> per_stage_count(S, std::vector<int>(G, 0));
+    for (int g = 0; g < G; ++g)
+        for (int p = 0; p < HW; ++p) per_stage_count[tg[(size_t)g * HW + p]][g]++;
+    size_t cells_total = 0, pos_total = 0;
+    for (int s = 0; s < S; ++s) {
+        auto &st = m.stages[s];
+        st.cell_off.assign(G + 1, 0);
+        for (int g = 0; g < G; ++g) st.cell_off[g + 1] = st.cell_off[g] + per_stage_count[s][g];
+        st.cells_at = cells_total;
+        st.pos_at = pos_total;
+        st.n_pos = (int64_t)st.cell_off[G] * cpg;
+        cells_total += (size_t)st.cell_off[G];
+        pos_total += (size_t)st.n_pos;
+    }
+    std::vector<int32_t> cell_hw(cells_total), positions(pos_total);
+    std::vector<uint32_t> cell_tap(cells_total * G), cell_grp(cells_total);
+    std::vector<int> fill(S * G, 0);
+    for (int g = 0; g < G; ++g)
+        for (int p = 0; p < HW; ++p) {
+            const int s = tg[(size_t)g * HW + p];
+            auto &st = m.stages[s];
+            const size_t cell = st.cells_at + st.cell_off[g] + fill[s * G + g]++;
+            cell_hw[cell] = p;
+            const int h = p / W, w = p % W;
+            uint32_t grp = 0;
+            for (int j = 0; j < G; ++j) {
+                if (tg[(size_t)j * HW + p] <= s) grp |= 1u << j;
+                uint32_t taps = 0;
+                for (int t = 0; t < k * k; ++t) {
+                    const int hh = h + t / k - pad, ww = w + t % k - pad;
+                    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+                    if (tg[(size_t)j * HW + hh * W + ww] < s) taps |= 1u << t;
+                }
+                cell_tap[cell * G + j] = taps;
+                st.tap_or |= taps;
+            }
+            cell_grp[cell] = grp;
+        }
+    // coded positions: stage-major, then (c, hw) row-major inside an image == boolean-mask order
+    for (int s = 0; s < S; ++s) {
+        auto &st = m.stages[s];
+        size_t at = st.pos_at;
+        for (int g = 0; g < G; ++g)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+                for (int i = st.cell_off[g]; i < st.cell_off[g + 1]; ++i)
+                    positions[at++] = c * HW + cell_hw[st.cells_at + i];
+    }
+    BASIC_TRY(m.d_cell_hw.reserve(cell_hw.size() * 4 + 16));
+    BASIC_TRY(m.d_cell_tap.reserve(cell_tap.size() * 4 + 16));
+    BASIC_TRY(m.d_cell_grp.reserve(cell_grp.size() * 4 + 16));
+    BASIC_TRY(m.d_positions.reserve(positions.size() * 4 + 16));
+    BASIC_CUDA(cudaMemcpy(m.d_cell_hw.p, cell_hw.data(), cell_hw.size() * 4, cudaMemcpyHostToDevice));
+    BASIC_CUDA(cudaMemcpy(m.d_cell_tap.p, cell_tap.data(), cell_tap.size() * 4, cudaMemcpyHostToDevice));
+    BASIC_CUDA(cudaMemcpy(m.d_cell_grp.p, cell_grp.data(), cell_grp.size() * 4, cudaMemcpyHostToDevice));
+    BASIC_CUDA(cudaMemcpy(m.d_positions.p, positions.data(), positions.size() * 4, cudaMemcpyHostToDevice));
+    return BASIC_OK;
+}
+
+static int launch_layer(const CtxModel &m, LayerArgs a, cudaStream_t stream)
+{
+    const int rows = a.B * a.ncells;
+    if (rows == 0 || a.n_count == 0) return BASIC_OK;
+    dim3 grid((rows + BM - 1) / BM, (a.n_count + BN - 1) / BN);
+    k_layer<<<grid, NT, 0, stream>>>(a);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+// One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).
+int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, int B, float *params, cudaStream_t stream)
+{
+    if (g < 0 || g >= m.S) return value_error("stage out of range");
+    const int HW = m.H * m.W, G = m.G;
+    const auto &st = m.stages[g];
+    if (!m.has_conv) {  // params = prior (+ bias): elementwise over the whole tensor, only needed once (stage 0)
+        if (g == 0) {
+            const long long total = (long long)B * m.c_ctx * HW;
+            k_bias_prior<<<m.sm_count * 8, 256, 0, stream>>>(prior, m.b_ctx.p ? m.b_ctx.as<float>() : nullptr, total, HW,
+                                                            m.c_ctx, params);
+            BASIC_LAUNCHED();
+        }
+        return BASIC_OK;
+    }
+    if (m.act_B < B || !m.a_ctx.p) {
+        BASIC_TRY(m.a_ctx.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
+        if (m.has_merger) {
+            BASIC_TRY(m.a_m1.reserve((size_t)B * m.c_m1 * HW * sizeof(float)));
+            BASIC_TRY(m.a_m2.reserve((size_t)B * m.c_m2 * HW * sizeof(float)));
+        }
+        m.act_B = B;
+    }
+    for (int og = 0; og < G; ++og) {
+        const int ncells = st.cell_off[og + 1] - st.cell_off[og];
+        if (ncells == 0) continue;
+        LayerArgs a = {};
+        a.cell_hw = m.d_cell_hw.as<int32_t>();
+        a.cell_tap = m.d_cell_tap.as<uint32_t>();
+        a.cell_grp = m.d_cell_grp.as<uint32_t>();
+        a.ncells = ncells;
+        a.cell_base = (int)(st.cells_at + st.cell_off[og]);
+        a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = G;
+        a.is_conv = 1; a.ksize = m.k; a.Cin = m.C;
+        a.src0 = Source{buf, m.C, G};
+        a.src1 = Source{nullptr, 0, 0};
+        a.wt = m.w_ctx.as<float>(); a.bias = m.b_ctx.as<float>();
+        a.Ntot = m.c_ctx; a.n_begin = og * (m.c_ctx / G); a.n_count = m.c_ctx / G;
+        a.out = m.has_merger ? m.a_ctx.as<float>() : params;
+        a.add = m.has_merger ? nullptr : prior;
+        a.lrelu = 0;
+        a.tap_or = st.tap_or;
+        BASIC_TRY(launch_layer(m, a, stream));
+    }
+    if (!m.has_merger) return BASIC_OK;
+    // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
+    // same stage at the same position, hence one launch wave per layer
+    for (int layer = 1; layer <= 3; ++layer) {
+        for (int og = 0; og < G; ++og) {
+            const int ncells = st.cell_off[og + 1] - st.cell_off[og];
+            if (ncells == 0) continue;
+            LayerArgs a = {};
+            a.cell_hw = m.d_cell_hw.as<int32_t>();
+            a.cell_tap = m.d_cell_tap.as<uint32_t>();
+            a.cell_grp = m.d_cell_grp.as<uint32_t>();
+            a.ncells = ncells;
+            a.cell_base = (int)(st.cells_at + st.cell_off[og]);
+            a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = G;
+            a.is_conv = 0;
+            if (layer == 1) {
+                a.src0 = Source{m.a_ctx.as<float>(), m.c_ctx, G};
+                a.src1 = Source{prior, m.c_ctx, 0};
+                a.wt = m.w_m1.as<float>(); a.bias = m.b_m1.as<float>();
+                a.Ntot = m.c_m1; a.out = m.a_m1.as<float>(); a.lrelu = 1;
+            } else if (layer == 2) {
+                a.src0 = Source{m.a_m1.as<float>(), m.c_m1, G};
+                a.wt = m.w_m2.as<float>(); a.bias = m.b_m2.as<float>();
+                a.Ntot = m.c_m2; a.out = m.a_m2.as<float>(); a.lrelu = 1;
+            } else {
+                a.src0 = Source{m.a_m2.as<float>(), m.c_m2, G};
+                a.wt = m.w_m3.as<float>(); a.bias = m.b_m3.as<float>();
+                a.Ntot = m.c_ctx; a.out = params; a.lrelu = 0;
+            }
+            a.n_begin = og * (a.Ntot / G);
+            a.n_count = a.Ntot / G;
+            BASIC_TRY(launch_layer(m, a, stream));
+        }
+    }
+    return BASIC_OK;
+}
+
+CtxModel *ctx_new(int C, int G, int k, int device, int sm_count)
+{
+    CtxModel *m = new CtxModel();
+    m->C = C; m->G = G; m->k = k; m->device = device; m->sm_count = sm_count;
+    m->c_ctx = 2 * C;
+    return m;
+}
+
+void ctx_delete(CtxModel *m)
+{
+    if (!m) return;
+    DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
+                      &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2};
+    for (DevBuf *b : bufs) b->release();
+    delete m;
+}
+
+int ctx_num_stages(const CtxModel &m) { return m.S; }
+
+int ctx_stage_positions(const CtxModel &m, int g, const int32_t **positions_dev, int64_t *n_pos)
+{
+    if (g < 0 || g >= m.S) return value_error("stage out of range");
+    *positions_dev = m.d_positions.as<int32_t>() + m.stages[g].pos_at;
+    *n_pos = m.stages[g].n_pos;
+    return BASIC_OK;
+}
+
+int ctx_dims(const CtxModel &m, int *C, int *G, int *H, int *W)
+{
+    *C = m.C; *G = m.G; *H = m.H; *W = m.W;
+    return BASIC_OK;
+}
+
+}  // namespace basic

@@ -1,0 +1,96 @@
+// Gaussian-conditional quantisation + scale index (reference: pgm_coder.py:802-821 _select_best_indexes,
+// torch_ans.py:105-159 _data_preprocess "uniform" quantiser, pgm_coder.py:927-941 / :965-978 the per-group
+// gather / scatter).  Elementwise, HBM-bound: one thread per coded element, coalesced along the position list.
+#include "common.cuh"
+
+namespace basic {
+
+namespace {
+
+// argmin_t |sigma - table[t]| in float32, first minimum (torch.argmin on CPU returns the first).
+__device__ inline int scale_index(float sigma, const float *__restrict__ tab, int n)
+{
+    if (!(fabsf(sigma) <= 3.402823466e38f)) return 0;  // NaN / inf: every distance is NaN / inf -> index 0
+    int lo = 0, hi = n;                                // first t with tab[t] >= sigma
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] < sigma) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0;
+    if (lo == n) return n - 1;
+    const float d0 = fabsf(__fsub_rn(sigma, tab[lo - 1])), d1 = fabsf(__fsub_rn(sigma, tab[lo]));
+    return d0 <= d1 ? lo - 1 : lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, const int32_t *__restrict__ positions,
+                 long long n_pos, int B, int C, int HW, const float *__restrict__ scale_table, int n_scales,
+                 int32_t *__restrict__ symbols, int32_t *__restrict__ indexes, float *__restrict__ yhat)
+{
+    __shared__ float tab[256];
+    for (int i = threadIdx.x; i < n_scales; i += blockDim.x) tab[i] = scale_table[i];
+    __syncthreads();
+    const long long total = (long long)B * n_pos;
+    const long long chw = (long long)C * HW;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / n_pos;
+        const long long k = e - b * n_pos;
+        const int p = positions ? positions[k] : (int)k;
+        const int c = p / HW;
+        const long long po = b * 2 * chw + p + (long long)c * HW;  // channel 2c (mean); scale is HW further
+        const float mean = params[po], sigma = params[po + HW];
+        indexes[e] = scale_index(sigma, tab, n_scales);
+        if (y) {
+            const float s = rintf(__fsub_rn(y[b * chw + p], mean));  // torch.round: half to even
+            symbols[e] = (int32_t)s;
+            if (yhat) yhat[b * chw + p] = __fadd_rn(s, mean);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ params, const int32_t *__restrict__ positions,
+             long long n_pos, int B, int C, int HW, float *__restrict__ yhat)
+{
+    const long long total = (long long)B * n_pos;
+    const long long chw = (long long)C * HW;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / n_pos;
+        const long long k = e - b * n_pos;
+        const int p = positions ? positions[k] : (int)k;
+        const int c = p / HW;
+        const float mean = params[b * 2 * chw + p + (long long)c * HW];
+        // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
+        yhat[b * chw + p] = __fadd_rn(__fadd_rn((float)symbols[e], mean), 0.0f);
+    }
+}
+
+}  // namespace
+
+int launch_quantize_index(const float *y, const float *params, const int32_t *positions, int64_t n_pos, int B, int C, int HW,
+                          const float *d_scale_table, int n_scales, int32_t *symbols, int32_t *indexes, float *yhat,
+                          int sm_count, cudaStream_t stream)
+{
+    const long long total = (long long)B * n_pos;
+    if (total == 0) return BASIC_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    k_quantize_index<<<(int)blocks, 256, 0, stream>>>(y, params, positions, n_pos, B, C, HW, d_scale_table, n_scales, symbols,
+                                                      indexes, yhat);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+int launch_dequantize(const int32_t *symbols, const float *params, const int32_t *positions, int64_t n_pos, int B, int C,
+                      int HW, float *yhat, int sm_count, cudaStream_t stream)
+{
+    const long long total = (long long)B * n_pos;
+    if (total == 0) return BASIC_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+}  // namespace basic

@@ -1,0 +1,242 @@
+// lanes = 1 compatibility coder: reproduces the reference rANS64 bitstream byte for byte
+// (cbench/csrc/ans/rans64.cpp:203-361 encode, :389-598 decode; ryg rans64.h:59-142).
+// The state recurrence is strictly serial, so one thread walks the stream while the rest of the CTA does
+// the parallel part: symbol -> (start, freq, exact reciprocal) lookup and operand staging through shared
+// memory.  This mode exists for bitstream parity; the throughput path is rans_lanes.cu.
+#include "common.cuh"
+
+namespace basic {
+
+namespace {
+
+constexpr int kTile = 2048;     // decode staging tile (2 x 8 KB of shared memory)
+constexpr int kEncTile = 1024;  // encode staging tile (32 KB of EncSym)
+constexpr int kThreads = 256;
+constexpr unsigned long long kL64 = 1ull << 31;
+
+struct EncSym {            // per-symbol operands prepared in parallel
+    unsigned long long rcp;  // Alverson reciprocal (rans64.h:167-245)
+    uint32_t bias, cmpl;     // x_new = x + bias + q * cmpl
+    uint32_t freq;           // for x_max
+    uint32_t shift_esc;      // bits 0..7 rcp_shift, bit 8 escape flag
+    uint32_t raw;            // escape payload
+    uint32_t pad;
+};
+
+__device__ inline void enc_sym_init(EncSym &s, uint32_t start, uint32_t freq, uint32_t prec)
+{
+    s.freq = freq;
+    s.cmpl = (1u << prec) - freq;
+    if (freq < 2) {
+        s.rcp = ~0ull;
+        s.shift_esc = 0;
+        s.bias = start + (1u << prec) - 1;
+    } else {
+        uint32_t shift = 0;
+        while (freq > (1u << shift)) shift++;
+        unsigned long long x0 = freq - 1, x1 = 1ull << (shift + 31);
+        unsigned long long t1 = x1 / freq;
+        x0 += (x1 % freq) << 32;
+        unsigned long long t0 = x0 / freq;
+        s.rcp = t0 + (t1 << 32);
+        s.shift_esc = shift - 1;
+        s.bias = start;
+    }
+}
+
+// One CTA.  Words are written back-to-front into out_words[cap_words]; *first_word receives the index of
+// the first word, status: bit0 = index out of range, bit1 = symbol out of range with bypass off,
+// bit2 = capacity exceeded.  state_io: running state for cached/segmented encodes (nullptr = fresh).
+__global__ void __launch_bounds__(kThreads)
+k_rans64_encode(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, long long n,
+                const void *__restrict__ blob, size_t meta_bytes, size_t cdf16_bytes, int T, int precision, int bypass,
+                int bypass_precision, uint32_t *__restrict__ out_words, long long cap_words, long long *first_word,
+                int *status)
+{
+    __shared__ EncSym sm[kEncTile];
+    const TableView tv = make_view(blob, meta_bytes, cdf16_bytes);
+    const int tid = threadIdx.x;
+    unsigned long long x = kL64;
+    long long p = cap_words;
+    int st = 0;
+    const uint32_t bp = (uint32_t)bypass_precision, maxb = (1u << bp) - 1;
+    const unsigned long long xmax_bits = ((kL64 >> 16) << 32) * (unsigned long long)(1u << (16 - bp));  // rans64.cpp:37-38
+    for (long long hi = n; hi > 0; hi -= kEncTile) {
+        const long long lo = hi - kEncTile > 0 ? hi - kEncTile : 0;
+        const int cnt = (int)(hi - lo);
+        __syncthreads();
+        for (int k = tid; k < cnt; k += kThreads) {
+            int32_t c = indexes[lo + k];
+            if ((uint32_t)c >= (uint32_t)T) { st |= 1; c = 0; }
+            const TableMeta m = tv.meta[c];
+            const int32_t maxv = (int32_t)m.cdf_size - 2;
+            int32_t v = symbols[lo + k] - m.offset;
+            uint32_t raw = 0, esc = 0;
+            if (bypass) {
+                if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = maxv; }
+                else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
+                esc = v == maxv;
+            } else if (v < 0 || v > maxv) { st |= 2; v = 0; }
+            const uint32_t start = tv.cdf[m.cdf_base + v];
+            const uint32_t freq = (uint16_t)(tv.cdf[m.cdf_base + v + 1] - start);
+            EncSym s;
+            enc_sym_init(s, start, freq, (uint32_t)precision);
+            s.shift_esc |= esc << 8;
+            s.raw = raw;
+            s.pad = 0;
+            sm[k] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = cnt - 1; k >= 0; --k) {
+                const EncSym s = sm[k];
+                if (s.shift_esc & 0x100) {  // escape tokens, pushed last to first (rans64.cpp:293-335)
+                    const uint32_t raw = s.raw;
+                    int nd = 0;
+                    while (nd * (int)bp < 32 && (raw >> (nd * bp)) != 0) ++nd;
+                    const int ncnt = nd / (int)maxb + 1, ntok = ncnt + nd;
+                    for (int u = ntok - 1; u >= 0; --u) {
+                        uint32_t tok;
+                        if (u >= ncnt) tok = (raw >> ((u - ncnt) * bp)) & maxb;
+                        else tok = u < ncnt - 1 ? maxb : (uint32_t)(nd - (ncnt - 1) * (int)maxb);
+                        if (x >= xmax_bits) {
+                            if (p > 0) out_words[--p] = (uint32_t)x; else st |= 4;
+                            x >>= 32;
+                        }
+                        x = (x << bp) | tok;
+                    }
+                }
+                const unsigned long long x_max = ((kL64 >> precision) << 32) * (unsigned long long)s.freq;
+                if (x >= x_max) {
+                    if (p > 0) out_words[--p] = (uint32_t)x; else st |= 4;
+                    x >>= 32;
+                }
+                const unsigned long long q = __umul64hi(x, s.rcp) >> (s.shift_esc & 0xff);
+                x = x + s.bias + q * s.cmpl;
+            }
+        }
+    }
+    if (st) atomicOr(status, st);
+    if (tid == 0) {
+        if (p >= 2) {
+            p -= 2;
+            out_words[p] = (uint32_t)x;
+            out_words[p + 1] = (uint32_t)(x >> 32);
+        } else atomicOr(status, 4);
+        *first_word = p;
+    }
+}
+
+struct DecState {
+    unsigned long long x;
+    long long pos;  // next word to read
+};
+
+__device__ inline uint32_t getbits64(unsigned long long &x, const uint32_t *__restrict__ w, long long &pos,
+                                     long long nwords, uint32_t nb, int &st)
+{  // rans64.cpp:49-65
+    const uint32_t v = (uint32_t)(x & ((1u << nb) - 1));
+    x >>= nb;
+    if (x < kL64) {
+        uint32_t word = 0;
+        if (pos < nwords) word = w[pos]; else st |= 4;
+        ++pos;
+        x = (x << 32) | word;
+    }
+    return v;
+}
+
+// One CTA: thread 0 walks the stream, everybody stages indexes in / symbols out through shared memory.
+__global__ void __launch_bounds__(kThreads)
+k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, DecState *state, int init_state,
+                const int32_t *__restrict__ indexes, long long n, const void *__restrict__ blob, size_t meta_bytes,
+                size_t cdf16_bytes, int T, int precision, int bypass, int bypass_precision, int32_t *__restrict__ out,
+                int *status)
+{
+    __shared__ int32_t s_idx[kTile];
+    __shared__ int32_t s_out[kTile];
+    const TableView tv = make_view(blob, meta_bytes, cdf16_bytes);
+    const int tid = threadIdx.x;
+    unsigned long long x = 0;
+    long long pos = 0;
+    int st = 0;
+    if (tid == 0) {
+        if (init_state) {  // set_stream: rans64.hpp:104-111, Rans64DecInit rans64.h:106-115
+            if (nwords >= 2) { x = (unsigned long long)words[0] | ((unsigned long long)words[1] << 32); pos = 2; }
+            else st |= 4;
+        } else { x = state->x; pos = state->pos; }
+    }
+    const uint32_t bp = (uint32_t)bypass_precision, maxb = (1u << bp) - 1;
+    const uint32_t pmask = (1u << precision) - 1;
+    for (long long lo = 0; lo < n; lo += kTile) {
+        const int cnt = (int)(n - lo < kTile ? n - lo : kTile);
+        __syncthreads();
+        for (int k = tid; k < cnt; k += kThreads) {
+            int32_t c = indexes[lo + k];
+            if ((uint32_t)c >= (uint32_t)T) { st |= 1; c = 0; }
+            s_idx[k] = c;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < cnt; ++k) {
+                const TableMeta m = tv.meta[s_idx[k]];
+                const uint16_t *cd = tv.cdf + m.cdf_base;
+                const int nsyms = (int)m.cdf_size - 1, maxv = nsyms - 1;
+                const uint32_t cum = (uint32_t)x & pmask;
+                int s = tv.lut[m.lut_base + (cum >> m.lut_shift)];
+                while (s + 1 < nsyms && cd[s + 1] <= cum) ++s;
+                const uint32_t start = cd[s], freq = (uint16_t)(cd[s + 1] - start);
+                x = (unsigned long long)freq * (x >> precision) + cum - start;
+                if (x < kL64) {
+                    uint32_t word = 0;
+                    if (pos < nwords) word = words[pos]; else st |= 4;
+                    ++pos;
+                    x = (x << 32) | word;
+                }
+                int32_t value = s;
+                if (bypass && s == maxv) {
+                    uint32_t val = getbits64(x, words, pos, nwords, bp, st), nb = val;
+                    while (val == maxb && nb < 64) { val = getbits64(x, words, pos, nwords, bp, st); nb += val; }
+                    uint32_t raw = 0;
+                    for (uint32_t j = 0; j < nb; ++j) {
+                        val = getbits64(x, words, pos, nwords, bp, st);
+                        if (j * bp < 32) raw |= val << (j * bp);
+                    }
+                    value = (int32_t)(raw >> 1);
+                    value = (raw & 1) ? -value - 1 : value + maxv;
+                }
+                s_out[k] = value + m.offset;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < cnt; k += kThreads) out[lo + k] = s_out[k];
+    }
+    if (st) atomicOr(status, st);
+    if (tid == 0) { state->x = x; state->pos = pos; }
+}
+
+}  // namespace
+
+int launch_rans64_encode(const RansTables &tb, const int32_t *d_sym, const int32_t *d_idx, int64_t n, int bypass,
+                         int bypass_precision, uint32_t *d_words, int64_t cap_words, long long *d_first, int *d_status,
+                         cudaStream_t stream)
+{
+    k_rans64_encode<<<1, kThreads, 0, stream>>>(d_sym, d_idx, n, tb.blob.p, tb.meta_bytes, tb.cdf16_bytes, tb.T,
+                                                tb.precision, bypass, bypass_precision, d_words, cap_words, d_first,
+                                                d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+int launch_rans64_decode(const RansTables &tb, const uint32_t *d_words, int64_t nwords, void *d_state, int init_state,
+                         const int32_t *d_idx, int64_t n, int bypass, int bypass_precision, int32_t *d_out, int *d_status,
+                         cudaStream_t stream)
+{
+    k_rans64_decode<<<1, kThreads, 0, stream>>>(d_words, nwords, reinterpret_cast<DecState *>(d_state), init_state, d_idx,
+                                                n, tb.blob.p, tb.meta_bytes, tb.cdf16_bytes, tb.T, tb.precision, bypass,
+                                                bypass_precision, d_out, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+}  // namespace basic

@@ -1,0 +1,458 @@
+// Multi-lane interleaved rANS ("BLS1" segments) -- the throughput coder.
+//
+// Format (CPU specification: oracle/ans_oracle.c section 4; DESIGN.md "Multi-lane stream"):
+//   a segment of n symbols is cut into chunks of `chunk_syms` (multiple of 128) symbols.  One chunk = one
+//   warp = 32 interleaved lanes (32-bit states, L = 2^16, 16-bit renormalisation words) sharing one word
+//   stream; local symbol j belongs to lane (j % 128) / 4 and is coded at step (j / 128) * 4 + (j % 4), so
+//   every lane moves its operands with one 128-bit load / store per 128-symbol block.  Within one event
+//   (a coding step, or one escape sub-step) the lanes that renormalise take consecutive words in lane
+//   order: a warp ballot + popc prefix gives each lane its word, no atomics, no divergence.
+//   Segment bytes: u32 n_chunks | u32 chunk_syms | u32 end_word[n_chunks] (cumulative) | u32 state[n_chunks][32] |
+//   u16 words | zero pad to 4 bytes.
+//
+// Tables (u16 CDFs + bucket LUTs, tables.cu) are staged once per CTA into shared memory.
+#include "common.cuh"
+
+namespace basic {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSegHdr = 8;  // u32 n_chunks | u32 chunk_syms
+
+__device__ inline const TableView stage_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
+                                                bool to_smem, unsigned char *smem)
+{
+    if (!to_smem) return make_view(blob, meta_bytes, cdf16_bytes);
+    const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return make_view(smem, meta_bytes, cdf16_bytes);
+}
+
+struct LaneParams {
+    const void *blob;
+    size_t blob_bytes, meta_bytes, cdf16_bytes;
+    int tables_in_smem;
+    int T, precision, bypass, bypass_precision;
+    long long n;            // symbols in the segment
+    int chunk_syms;         // multiple of 128
+    const int *n_chunks_dev;  // device scalar (the auto mode decides it on the device); nullptr -> n_chunks
+    int n_chunks;
+};
+
+// ------------------------------------------------------------------------------------------------ encode
+// scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
+// Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
+__global__ void __launch_bounds__(kWarps * 32)
+k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
+             uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
+             uint32_t *__restrict__ states, int *status)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
+    const int prec = P.precision;
+    const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
+    const uint32_t xmax_bits = 1u << (32 - bp);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
+    int st = 0;
+    for (int k = blockIdx.x * kWarps + warp; k < n_chunks; k += gridDim.x * kWarps) {
+        const long long base = (long long)k * P.chunk_syms;
+        const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
+        uint16_t *wbuf = scratch + (size_t)k * cap_words;
+        int pos = cap_words;  // warp-uniform
+        uint32_t x = kRansL;
+        const int nblocks = (m + 127) >> 7;
+        for (int blk = nblocks - 1; blk >= 0; --blk) {
+            const int j0 = blk * 128 + lane * 4;
+            int32_t sy[4], ix[4];
+            if (vec_ok && j0 + 3 < m) {
+                const int4 a = *reinterpret_cast<const int4 *>(symbols + base + j0);
+                const int4 b = *reinterpret_cast<const int4 *>(indexes + base + j0);
+                sy[0] = a.x; sy[1] = a.y; sy[2] = a.z; sy[3] = a.w;
+                ix[0] = b.x; ix[1] = b.y; ix[2] = b.z; ix[3] = b.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = j0 + q < m;
+                    sy[q] = ok ? symbols[base + j0 + q] : 0;
+                    ix[q] = ok ? indexes[base + j0 + q] : 0;
+                }
+            }
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {
+                const bool active = j0 + q < m;
+                int32_t c = ix[q];
+                if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
+                const TableMeta mt = tv.meta[c];
+                const int32_t maxv = (int32_t)mt.cdf_size - 2;
+                int32_t v = sy[q] - mt.offset;
+                uint32_t raw = 0;
+                bool esc = false;
+                if (P.bypass) {
+                    if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = maxv; }
+                    else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
+                    esc = active && v == maxv;
+                } else if (v < 0 || v > maxv) { if (active) st |= 2; v = 0; }
+                const uint32_t start = tv.cdf[mt.cdf_base + v];
+                const uint32_t freq = (uint16_t)(tv.cdf[mt.cdf_base + v + 1] - start);
+                // --- escape tokens: sub-steps last to first (oracle: bls_encode_chunk)
+                if (__any_sync(kFull, esc)) {
+                    int nd = 0, ncnt = 0, ntok = 0;
+                    if (esc) {
+                        nd = raw ? (int)((32 - __clz(raw) + bp - 1) / bp) : 0;
+                        ncnt = nd / (int)maxb + 1;
+                        ntok = ncnt + nd;
+                    }
+                    int maxtok = ntok;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) maxtok = max(maxtok, __shfl_xor_sync(kFull, maxtok, o));
+                    for (int u = maxtok - 1; u >= 0; --u) {
+                        const bool part = ntok > u;
+                        const bool emit = part && x >= xmax_bits;
+                        const unsigned em = __ballot_sync(kFull, emit);
+                        pos -= __popc(em);
+                        if (emit) {
+                            const int at = pos + __popc(em & lt_mask);
+                            if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
+                            x >>= 16;
+                        }
+                        if (part) {
+                            uint32_t tok;
+                            if (u >= ncnt) tok = (raw >> ((u - ncnt) * bp)) & maxb;
+                            else tok = u < ncnt - 1 ? maxb : (uint32_t)(nd - (ncnt - 1) * (int)maxb);
+                            x = (x << bp) | tok;
+                        }
+                    }
+                }
+                // --- the symbol itself
+                const unsigned long long x_max = ((unsigned long long)(kRansL >> prec) << 16) * freq;
+                const bool emit = active && x >= x_max;
+                const unsigned em = __ballot_sync(kFull, emit);
+                pos -= __popc(em);
+                if (emit) {
+                    const int at = pos + __popc(em & lt_mask);
+                    if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
+                    x >>= 16;
+                }
+                if (active) {
+                    const uint32_t qt = x / freq;
+                    x = (qt << prec) + (x - qt * freq) + start;
+                }
+            }
+        }
+        states[(size_t)k * 32 + lane] = x;
+        if (lane == 0) first_word[k] = (uint32_t)(pos < 0 ? 0 : pos);
+    }
+    if (st) atomicOr(status, st);
+}
+
+// One CTA: cumulative word counts -> directory, plus the total segment size in bytes.
+__global__ void __launch_bounds__(1024)
+k_bls_scan(const int *n_chunks_dev, int n_chunks_arg, int chunk_syms, const uint32_t *__restrict__ first_word, int cap_words,
+           uint32_t *__restrict__ seg /* segment header in the output buffer */, long long *seg_bytes)
+{
+    __shared__ uint32_t part[1024];
+    const int n_chunks = n_chunks_dev ? *n_chunks_dev : n_chunks_arg;
+    const int tid = threadIdx.x;
+    const int per = (n_chunks + 1023) / 1024;
+    uint32_t s = 0;
+    for (int i = 0; i < per; ++i) {
+        const int k = tid * per + i;
+        if (k < n_chunks) s += (uint32_t)cap_words - first_word[k];
+    }
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        seg[0] = (uint32_t)n_chunks;
+        seg[1] = (uint32_t)chunk_syms;
+        const long long words_at = kSegHdr + 4ll * n_chunks + 128ll * n_chunks;
+        long long total = words_at + 2ll * run;
+        total = (total + 3) & ~3ll;
+        *seg_bytes = total;
+    }
+    __syncthreads();
+    uint32_t run = part[tid];
+    for (int i = 0; i < per; ++i) {
+        const int k = tid * per + i;
+        if (k < n_chunks) {
+            run += (uint32_t)cap_words - first_word[k];
+            seg[2 + k] = run;  // cumulative END of chunk k, in words
+        }
+    }
+}
+
+// Gather: states + words of every chunk into the contiguous segment.
+__global__ void __launch_bounds__(256)
+k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, const uint16_t *__restrict__ scratch, int cap_words,
+             const uint32_t *__restrict__ first_word, const uint32_t *__restrict__ states, unsigned char *__restrict__ seg)
+{
+    const int n_chunks = n_chunks_dev ? *n_chunks_dev : n_chunks_arg;
+    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2;
+    uint32_t *out_states = reinterpret_cast<uint32_t *>(seg) + 2 + n_chunks;
+    uint16_t *out_words = reinterpret_cast<uint16_t *>(seg + kSegHdr + 4ll * n_chunks + 128ll * n_chunks);
+    for (int k = blockIdx.x; k < n_chunks; k += gridDim.x) {
+        if (threadIdx.x < 32) out_states[(size_t)k * 32 + threadIdx.x] = states[(size_t)k * 32 + threadIdx.x];
+        const uint32_t end = end_word[k], beg = k ? end_word[k - 1] : 0;
+        const uint16_t *src = scratch + (size_t)k * cap_words + first_word[k];
+        for (uint32_t i = threadIdx.x; i < end - beg; i += blockDim.x) out_words[beg + i] = src[i];
+        if (k == n_chunks - 1 && threadIdx.x == 0 && (end & 1)) out_words[end] = 0;  // pad to 4 bytes
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+__global__ void __launch_bounds__(kWarps * 32)
+k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
+             int32_t *__restrict__ out, int *status)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem, smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int n_chunks = P.n_chunks;
+    const int prec = P.precision;
+    const uint32_t pmask = (1u << prec) - 1;
+    const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
+    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2;
+    const uint32_t *states = end_word + n_chunks;
+    const long long words_at = kSegHdr + 4ll * n_chunks + 128ll * n_chunks;
+    const uint16_t *words = reinterpret_cast<const uint16_t *>(seg + words_at);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
+    int st = 0;
+    for (int k = blockIdx.x * kWarps + warp; k < n_chunks; k += gridDim.x * kWarps) {
+        const long long base = (long long)k * P.chunk_syms;
+        const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
+        uint32_t wend = end_word[k], wbeg = k ? end_word[k - 1] : 0;
+        if (wend < wbeg || words_at + 2ll * wend > seg_cap) { st |= 4; wend = wbeg = 0; }  // corrupt directory
+        const uint16_t *w = words + wbeg;
+        const uint32_t nw = wend - wbeg;
+        uint32_t wp = 0;  // warp-uniform
+        uint32_t x = states[(size_t)k * 32 + lane];
+        const int nblocks = (m + 127) >> 7;
+        for (int blk = 0; blk < nblocks; ++blk) {
+            const int j0 = blk * 128 + lane * 4;
+            int32_t ix[4], res[4];
+            const bool full4 = vec_ok && j0 + 3 < m;
+            if (full4) {
+                const int4 b = *reinterpret_cast<const int4 *>(indexes + base + j0);
+                ix[0] = b.x; ix[1] = b.y; ix[2] = b.z; ix[3] = b.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ix[q] = j0 + q < m ? indexes[base + j0 + q] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool active = j0 + q < m;
+                int32_t c = ix[q];
+                if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
+                const TableMeta mt = tv.meta[c];
+                const uint16_t *cd = tv.cdf + mt.cdf_base;
+                const int nsyms = (int)mt.cdf_size - 1, maxv = nsyms - 1;
+                const uint32_t cum = x & pmask;
+                int s = tv.lut[mt.lut_base + (cum >> mt.lut_shift)];
+                while (s + 1 < nsyms && cd[s + 1] <= cum) ++s;
+                const uint32_t start = cd[s], freq = (uint16_t)(cd[s + 1] - start);
+                if (active) x = freq * (x >> prec) + cum - start;
+                {
+                    const bool need = active && x < kRansL;
+                    const unsigned nm = __ballot_sync(kFull, need);
+                    if (need) {
+                        const uint32_t at = wp + __popc(nm & lt_mask);
+                        uint32_t word = 0;
+                        if (at < nw) word = w[at]; else st |= 4;
+                        x = (x << 16) | word;
+                    }
+                    wp += __popc(nm);
+                }
+                int32_t value = s;
+                const bool esc = active && P.bypass && s == maxv;
+                if (__any_sync(kFull, esc)) {
+                    bool in = esc;
+                    int phase = 0;
+                    uint32_t nb = 0, raw = 0, jj = 0;
+                    while (__any_sync(kFull, in)) {
+                        uint32_t val = 0;
+                        if (in) { val = x & maxb; x >>= bp; }
+                        const bool need = in && x < kRansL;
+                        const unsigned nm = __ballot_sync(kFull, need);
+                        if (need) {
+                            const uint32_t at = wp + __popc(nm & lt_mask);
+                            uint32_t word = 0;
+                            if (at < nw) word = w[at]; else st |= 4;
+                            x = (x << 16) | word;
+                        }
+                        wp += __popc(nm);
+                        if (in) {
+                            if (phase == 0) {
+                                nb += val;
+                                if (val != maxb) { phase = 1; if (nb == 0) in = false; }
+                                else if (nb > 64) { in = false; st |= 4; }
+                            } else {
+                                if (jj * bp < 32) raw |= val << (jj * bp);
+                                if (++jj == nb) in = false;
+                            }
+                        }
+                    }
+                    if (esc) {
+                        const int32_t v2 = (int32_t)(raw >> 1);
+                        value = (raw & 1) ? -v2 - 1 : v2 + maxv;
+                    }
+                }
+                res[q] = value + mt.offset;
+            }
+            if (full4) {
+                *reinterpret_cast<int4 *>(out + base + j0) = make_int4(res[0], res[1], res[2], res[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (j0 + q < m) out[base + j0 + q] = res[q];
+            }
+        }
+        if (wp != nw && lane == 0) st |= 4;
+    }
+    if (st) atomicOr(status, st);
+}
+
+
+// Sampled size estimate for the auto lane count: mean cost in bits of up to `max_samples` (symbol, index)
+// pairs taken at a regular stride; *out_bits = estimated bits of the whole segment (float accumulation is fine:
+// the estimate only picks the chunk count, which is stored in the stream).
+__global__ void __launch_bounds__(256)
+k_estimate_bits(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, long long stride,
+                long long samples, float *out_bits)
+{
+    __shared__ float red[8];
+    const TableView tv = make_view(P.blob, P.meta_bytes, P.cdf16_bytes);
+    const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
+    float bits = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < samples; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i * stride;
+        int32_t c = indexes[j];
+        if ((uint32_t)c >= (uint32_t)P.T) c = 0;
+        const TableMeta mt = tv.meta[c];
+        const int32_t maxv = (int32_t)mt.cdf_size - 2;
+        int32_t v = symbols[j] - mt.offset;
+        uint32_t raw = 0;
+        float extra = 0.f;
+        if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = maxv; }
+        else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
+        if (P.bypass && v == maxv) {
+            const int nd = raw ? (int)((32 - __clz(raw) + bp - 1) / bp) : 0;
+            extra = (float)((nd / (int)maxb + 1 + nd) * (int)bp);
+        }
+        const uint32_t start = tv.cdf[mt.cdf_base + v];
+        const uint32_t freq = (uint16_t)(tv.cdf[mt.cdf_base + v + 1] - start);
+        bits += (float)P.precision - __log2f((float)(freq ? freq : 1)) + extra;
+    }
+    for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(kFull, bits, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out_bits, t * (float)((double)P.n / (double)samples));
+    }
+}
+
+}  // namespace
+
+static int smem_for(const RansTables &tb) { return tb.blob_bytes <= (size_t)kMaxSmemTables ? (int)tb.blob_bytes : 0; }
+
+static LaneParams make_params(const RansTables &tb, int bypass, int bypass_precision, int64_t n, int chunk_syms, int n_chunks,
+                              const int *n_chunks_dev)
+{
+    LaneParams P;
+    P.blob = tb.blob.p;
+    P.blob_bytes = tb.blob_bytes;
+    P.meta_bytes = tb.meta_bytes;
+    P.cdf16_bytes = tb.cdf16_bytes;
+    P.tables_in_smem = smem_for(tb) > 0;
+    P.T = tb.T;
+    P.precision = tb.precision;
+    P.bypass = bypass;
+    P.bypass_precision = bypass_precision;
+    P.n = n;
+    P.chunk_syms = chunk_syms;
+    P.n_chunks = n_chunks;
+    P.n_chunks_dev = n_chunks_dev;
+    return P;
+}
+
+static int grid_for(int n_chunks, int sm_count)
+{
+    int g = (n_chunks + kWarps - 1) / kWarps;
+    if (g > sm_count) g = sm_count;
+    return g < 1 ? 1 : g;
+}
+
+// Encodes one segment into `seg_out` (device).  *d_seg_bytes (device) receives its size.
+int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, const int32_t *d_sym, const int32_t *d_idx,
+                      int64_t n, int chunk_syms, int n_chunks, uint16_t *d_scratch, int cap_words, uint32_t *d_first,
+                      uint32_t *d_states, unsigned char *d_seg_out, long long *d_seg_bytes, int *d_status, int sm_count,
+                      cudaStream_t stream)
+{
+    const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, nullptr);
+    const int smem = smem_for(tb);
+    static bool attr_done = false;
+    if (!attr_done) {
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        attr_done = true;
+    }
+    if (n_chunks > 0) {
+        k_bls_encode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words,
+                                                                                 d_first, d_states, d_status);
+        BASIC_LAUNCHED();
+    }
+    k_bls_scan<<<1, 1024, 0, stream>>>(nullptr, n_chunks, chunk_syms, d_first, cap_words, reinterpret_cast<uint32_t *>(d_seg_out),
+                                       d_seg_bytes);
+    BASIC_LAUNCHED();
+    if (n_chunks > 0) {
+        int g = n_chunks < 4 * sm_count ? n_chunks : 4 * sm_count;
+        k_bls_gather<<<g, 256, 0, stream>>>(nullptr, n_chunks, d_scratch, cap_words, d_first, d_states, d_seg_out);
+        BASIC_LAUNCHED();
+    }
+    return BASIC_OK;
+}
+
+int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, const unsigned char *d_seg, int64_t seg_cap,
+                      const int32_t *d_idx, int64_t n, int chunk_syms, int n_chunks, int32_t *d_out, int *d_status,
+                      int sm_count, cudaStream_t stream)
+{
+    if (n_chunks <= 0) return BASIC_OK;
+    const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, nullptr);
+    const int smem = smem_for(tb);
+    static bool attr_done = false;
+    if (!attr_done) {
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        attr_done = true;
+    }
+    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem, stream>>>(P, d_seg, seg_cap, d_idx, d_out, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+// Adds the estimated size in bits of the segment to *d_bits (device float, zeroed by the caller).
+int launch_estimate_bits(const RansTables &tb, int bypass, int bypass_precision, const int32_t *d_sym, const int32_t *d_idx,
+                         int64_t n, float *d_bits, cudaStream_t stream)
+{
+    if (n <= 0) return BASIC_OK;
+    const LaneParams P = make_params(tb, bypass, bypass_precision, n, 128, 0, nullptr);
+    const long long max_samples = 1 << 16;
+    const long long stride = n > max_samples ? n / max_samples : 1;
+    const long long samples = (n + stride - 1) / stride;
+    int blocks = (int)((samples + 255) / 256);
+    if (blocks > 64) blocks = 64;
+    k_estimate_bits<<<blocks, 256, 0, stream>>>(P, d_sym, d_idx, stride, samples, d_bits);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+}  // namespace basic

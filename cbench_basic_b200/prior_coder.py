@@ -1,0 +1,304 @@
+"""Drop-in for the reference's y-node prior coder on the encode / decode / update_state path:
+
+    cbench.modules.prior_model.prior_coder.pgm_coder.GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder
+    cbench.nn.layers.masked_conv.TopoGroupDynamicMaskConv2dContextModel
+
+Same class names, constructor keywords (the ones that matter for coding), state_dict keys, and
+``encode(input, prior=, pgm=) -> bytes`` / ``decode(bytes, prior=, pgm=) -> Tensor`` / ``update_state()``
+semantics (pgm_coder.py:544-618, :912-981, torch_ans.py:237-251).  The hot loop -- per group: context model,
+scale index, quantisation, ANS coding, write-back -- runs entirely in the CUDA library
+(basic_ypath_encode / basic_ypath_decode, include/basic_b200.h); Python only builds the group map and
+frames the bytes.  ``forward()`` (the training likelihood) is not part of the hot path and is not provided.
+"""
+import ctypes as C
+import math
+import struct
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from . import ans, topo_groups
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):  # noqa: A002  (reference signature)
+    """compressai_coder.py:23-30."""
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+class TopoGroupDynamicMaskConv2dContextModel(nn.Module):
+    """Weight container with the reference's parameter names (masked_conv.py:231-305): a 5x5 context
+    convolution C -> 2C and the three 1x1 "param merger" convolutions 4C -> 10C/3 -> 8C/3 -> 2C, all with
+    nn.Conv2d's default initialisation, so a reference state_dict loads unchanged.  Inference happens in the
+    CUDA library; this module has no forward()."""
+
+    def __init__(self, in_channels=192, out_channels=384, kernel_size=5, use_param_merger=True,
+                 param_merger_in_channels=None, param_merger_mid_channels_list=None, param_merger_kernel_size=1, **kwargs):
+        super().__init__()
+        if param_merger_kernel_size != 1:
+            raise NotImplementedError("param_merger_kernel_size != 1")
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.use_param_merger = use_param_merger
+        self.context_prediction = nn.Conv2d(in_channels, out_channels, kernel_size, padding=kernel_size // 2)
+        if use_param_merger:
+            cin = out_channels * 2 if param_merger_in_channels is None else param_merger_in_channels
+            mids = [out_channels * 5 // 3, out_channels * 4 // 3] if param_merger_mid_channels_list is None \
+                else list(param_merger_mid_channels_list)
+            if cin != out_channels * 2 or len(mids) != 2:
+                raise NotImplementedError("only the default merger geometry (4C -> 10C/3 -> 8C/3 -> 2C) is accelerated")
+            self.param_merger_in = nn.Conv2d(cin, mids[0], 1)
+            self.param_merger_out = nn.Sequential(nn.LeakyReLU(inplace=True), nn.Conv2d(mids[0], mids[1], 1),
+                                                  nn.LeakyReLU(inplace=True), nn.Conv2d(mids[1], out_channels, 1))
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("inference runs in the CUDA library (prior_coder.encode / decode)")
+
+
+class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
+    """encode / decode / update_state of the reference coder of the same name (pgm_coder.py:983-2070).
+
+    Extra keywords: ``lanes`` (1 = reference bitstream byte for byte; 0 = multi-lane container within 0.5 % of it,
+    the default; N = ceil(N/32) chunks per group segment), ``ans_params_device`` (device of the float32 Gaussian
+    pmf evaluation in update_state; None = the module's device, like the reference; "cpu" reproduces a
+    CPU-run reference table bit for bit)."""
+
+    def __init__(self, *args, in_channels=256, channel_groups=1, default_topo_group_method="none",
+                 default_num_topo_groups=-1, topo_group_context_model=None, kernel_size=5, use_param_merger=True,
+                 use_joint_ar_model_impl=False, coder_type="rans64", freq_precision=16, use_bypass_coding=True,
+                 bypass_precision=4, data_precision=8, quantizer_type="uniform", quantizer_params=None,
+                 fixed_input_shape=None, force_input_prior_shape_aligned=True, use_autoregressive_encode=True,
+                 lower_bound_scale=0.11, scale_table=None, topo_group_predictor=None, lanes=0, ans_params_device=None,
+                 **kwargs):
+        super().__init__()
+        if use_joint_ar_model_impl:
+            raise NotImplementedError("use_joint_ar_model_impl (CompressAI-style serial coder) is SURVEY row f4")
+        if coder_type not in ("rans", "rans64"):
+            # torch_ans.py:241-243 builds Tans* with table_log = freq_precision = 16, which the reference decoder
+            # itself refuses (TANS_MAX_TABLELOG = 12); tANS is available through cbench_basic_b200.ans only.
+            raise NotImplementedError(f"Unknown coder type {coder_type}")
+        if quantizer_type != "uniform" or (quantizer_params is not None and list(quantizer_params) != [0.0, 128, 1.0]):
+            raise NotImplementedError("only the default uniform quantiser [0, 128, 1] is accelerated")
+        if not use_autoregressive_encode:
+            raise NotImplementedError("use_autoregressive_encode=False")
+        if topo_group_context_model is None and use_param_merger:
+            raise NotImplementedError("the internal param_merger variant (pgm_coder.py:1207-1239) is not accelerated; "
+                                      "pass topo_group_context_model=... or use_param_merger=False")
+        if default_topo_group_method not in topo_groups.METHODS:
+            raise NotImplementedError(f"Unknown default_topo_group_method {default_topo_group_method}")
+        self.in_channels = in_channels
+        self.channel_groups = channel_groups
+        if default_topo_group_method in ("channelwise-g10", "elic"):
+            self.channel_groups = in_channels // 16
+        self.default_topo_group_method = default_topo_group_method
+        self.kernel_size = kernel_size
+        self.use_param_merger = use_param_merger
+        self.coder_type, self.freq_precision = coder_type, freq_precision
+        self.use_bypass_coding, self.bypass_precision = use_bypass_coding, bypass_precision
+        self.fixed_input_shape = fixed_input_shape
+        self.force_input_prior_shape_aligned = force_input_prior_shape_aligned
+        self.lower_bound_scale = lower_bound_scale
+        self.lanes = lanes
+        self.ans_params_device = ans_params_device
+        self.scale_table = get_scale_table() if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
+        self.topo_group_predictor = topo_group_predictor
+        if topo_group_predictor is not None:
+            self.register_buffer("topo_group_predictor_cache", topo_group_predictor())   # pgm_coder.py:1097-1103
+        self.topo_group_context_model = topo_group_context_model
+        if topo_group_context_model is None:
+            self.context_prediction = nn.Conv2d(in_channels, 2 * in_channels, kernel_size, padding=kernel_size // 2)
+        self.register_buffer("_device_indicator", torch.zeros(1), persistent=False)
+        self.out_channels = 2 * in_channels
+        self.profile = {}          # wall-clock ms of the last calls, keyed like the reference's profiler scopes
+        self._ctx = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    @property
+    def device(self):
+        return self._device_indicator.device
+
+    def _dev_index(self):
+        if self.device.type != "cuda":
+            raise N.CudaError("cbench_basic_b200 coders run on CUDA devices only: move the module with .cuda() "
+                              "(there is no CPU fallback)")
+        return self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+    def _get_ans_params(self):
+        """torch_ans.py:284-310, the float32 torch calls verbatim (their rounding decides truncated counts)."""
+        device = self.device if self.ans_params_device is None else torch.device(self.ans_params_device)
+        freq_cnt = 1 << self.freq_precision
+        tail_mass = torch.tensor([0.5 / freq_cnt], device=device)
+        bound = torch.tensor([float(self.lower_bound_scale)], device=device)
+        cnts, nsym, offs = [], [], []
+        for s in self.scale_table.to(device=device):
+            scale = torch.max(s.reshape(1, 1), bound)
+            dist = torch.distributions.Normal(torch.zeros(1, 1, device=device), scale)
+            dmin = int(dist.icdf(tail_mass).floor().item())
+            dmax = int(dist.icdf(1 - tail_mass).ceil().item())
+            offs.append(dmin)
+            nsym.append(dmax - dmin + 1)
+            pts = torch.arange(dmin - 1, dmax + 1, device=device).type_as(dist.mean) + 0.5
+            logp = (dist.cdf(pts[1:]) - dist.cdf(pts[:-1])).log()[0]
+            cnt = (torch.softmax(logp, dim=-1) * freq_cnt).clamp_min(1)
+            cnts.append(cnt.detach().cpu().contiguous().numpy().astype(np.int32))
+        freqs = np.zeros((len(cnts), max(len(c) for c in cnts)), dtype=np.int32)
+        for i, c in enumerate(cnts):
+            freqs[i, :len(c)] = c
+        return freqs, np.array(nsym, dtype=np.int32), np.array(offs, dtype=np.int32)
+
+    def update_state(self, *args, **kwargs) -> None:
+        """torch_ans.py:237-251: builds the coder objects and their tables -- here on the GPU, plus the
+        context-model weights in the layout the kernels want."""
+        dev = self._dev_index()
+        kw = dict(freq_precision=self.freq_precision, bypass_coding=self.use_bypass_coding,
+                  bypass_precision=self.bypass_precision, lanes=self.lanes, device=dev)
+        encoder, decoder = ans.Rans64Encoder(**kw), ans.Rans64Decoder(**kw)
+        freqs, nfreqs, offsets = self._get_ans_params()
+        tab = np.ascontiguousarray(self.scale_table.detach().cpu().numpy(), dtype=np.float32)
+        for coder in (encoder, decoder):
+            coder.init_params(freqs, nfreqs, offsets)
+            N.check(N.lib().basic_coder_set_scale_table(coder.handle, tab.ctypes.data, tab.size))
+        self.ans_encoder, self.ans_decoder = encoder, decoder
+        self._upload_weights(dev)
+
+    def _upload_weights(self, dev):
+        if self._ctx is not None:
+            N.lib().basic_ctx_destroy(self._ctx)
+            self._ctx = None
+        h = C.c_void_p()
+        N.check(N.lib().basic_ctx_create(self.in_channels, self.channel_groups, self.kernel_size, dev, C.byref(h)))
+        self._ctx = h
+        keep = []
+
+        def ptr(t):
+            t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        cm = self.topo_group_context_model
+        if cm is not None:
+            ptrs = [ptr(cm.context_prediction.weight), ptr(cm.context_prediction.bias)]
+            if getattr(cm, "use_param_merger", True):
+                ptrs += [ptr(cm.param_merger_in.weight), ptr(cm.param_merger_in.bias),
+                         ptr(cm.param_merger_out[1].weight), ptr(cm.param_merger_out[1].bias),
+                         ptr(cm.param_merger_out[3].weight), ptr(cm.param_merger_out[3].bias)]
+            else:
+                ptrs += [None] * 6
+        else:
+            ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias)] + [None] * 6
+        torch.cuda.synchronize(self.device)
+        N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            try:
+                N.lib().basic_ctx_destroy(ctx)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------------------------------ group map
+    def _get_pgm(self, input_shape, pgm=None):
+        """pgm_coder.py:1498-1604 (eval branch): explicit map > cached predictor output > default method."""
+        H, W = int(input_shape[-2]), int(input_shape[-1])
+        if pgm is None and self.topo_group_predictor is not None:
+            pgm = self.topo_group_predictor_cache
+        if pgm is None:
+            return topo_groups.default_map(self.default_topo_group_method, self.channel_groups, H, W)
+        return topo_groups.tile_map(pgm, self.channel_groups, H, W)
+
+    def _set_map(self, tg):
+        tg32 = np.ascontiguousarray(tg[0].numpy(), dtype=np.int32)
+        N.check(N.lib().basic_ctx_set_map(self._ctx, tg32.ctypes.data, tg32.shape[1], tg32.shape[2]))
+
+    # ------------------------------------------------------------------------------------------ coding
+    def encode(self, input, *args, prior=None, pgm=None, quantizer_params=None, return_yhat=False, **kwargs) -> bytes:
+        assert hasattr(self, "ans_encoder"), "Not Initialized! Should call self.update_state() before coding!"
+        if prior is None:
+            raise ValueError("prior should not be None!")
+        t0 = time.perf_counter()
+        if self.force_input_prior_shape_aligned:
+            assert input.shape[2:] == prior.shape[2:], "Input and prior shape not aligned! Consider setting force_input_prior_shape_aligned = False, which may add a little overhead to the bitstream to save the input shape!"
+        else:
+            for dim, size in enumerate(input.shape[2:], 2):
+                prior = prior.narrow(dim, 0, size)
+        B, Cc, H, W = input.shape
+        assert Cc == self.in_channels and prior.shape[1] == 2 * Cc
+        y = input.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        p = prior.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self._set_map(self._get_pgm(input.shape, pgm))
+        h = self.ans_encoder.handle
+        cap = int(N.lib().basic_ypath_encode_bound(h, B, Cc, H, W, self.lanes))
+        out = np.empty(cap, dtype=np.uint8)
+        out_len = C.c_int64(0)
+        yhat = torch.empty_like(y) if return_yhat else None
+        N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, out.ctypes.data,
+                                           cap, C.byref(out_len), yhat.data_ptr() if return_yhat else None,
+                                           torch.cuda.current_stream(self.device).cuda_stream))
+        byte_string = out[:out_len.value].tobytes()
+        head = b""
+        if self.fixed_input_shape is not None:
+            assert B == self.fixed_input_shape[0] and tuple(input.shape[2:]) == tuple(self.fixed_input_shape[1:])
+        elif not (self.force_input_prior_shape_aligned and prior is not None):
+            head = struct.pack("B", 3) + struct.pack("<H", B) + struct.pack("<H", H) + struct.pack("<H", W)  # :581-597
+        self.profile["time_ans_encode"] = (time.perf_counter() - t0) * 1e3
+        return (head + byte_string, yhat) if return_yhat else head + byte_string
+
+    def decode(self, byte_string: bytes, *args, prior=None, pgm=None, quantizer_params=None, **kwargs) -> torch.Tensor:
+        assert hasattr(self, "ans_decoder"), "Not Initialized! Should call self.update_state() before coding!"
+        assert prior is not None
+        t0 = time.perf_counter()
+        if self.fixed_input_shape is not None:
+            ptr, B, spatial = 0, self.fixed_input_shape[0], tuple(self.fixed_input_shape[1:])
+        elif self.force_input_prior_shape_aligned:
+            ptr, B, spatial = 0, prior.shape[0], tuple(prior.shape[2:])
+        else:
+            nd = struct.unpack("B", byte_string[:1])[0]
+            flat = [struct.unpack("<H", byte_string[1 + 2 * i:3 + 2 * i])[0] for i in range(nd)]
+            ptr, B, spatial = 1 + 2 * nd, flat[0], tuple(flat[1:])
+            for dim, size in enumerate(spatial, 2):
+                prior = prior.narrow(dim, 0, size)
+        H, W = spatial
+        Cc = self.in_channels
+        p = prior.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self._set_map(self._get_pgm((B, Cc, H, W), pgm))
+        enc = np.frombuffer(byte_string, dtype=np.uint8, offset=ptr)
+        yhat = torch.empty(B, Cc, H, W, dtype=torch.float32, device=self.device)
+        N.check(N.lib().basic_ypath_decode(self.ans_decoder.handle, self._ctx, enc.ctypes.data if enc.size else None, enc.size,
+                                           p.data_ptr(), B, Cc, H, W, self.lanes, yhat.data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream))
+        self.profile["pgm_generate_coding"] = (time.perf_counter() - t0) * 1e3
+        return yhat
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training likelihood (pgm_coder.py:391-539) is outside the accelerated hot path; "
+                                  "use the reference module for training and load its state_dict here for coding")
+
+
+class CombinedNNTrainablePGMPriorCoder(nn.Module):
+    """BaSIC "dynamic entropy coder" dispatch (pgm_coder.py:632-715): picks one sub-coder by blend_weight.argmax()."""
+
+    def __init__(self, coders, *args, fix_weight=False, **kwargs):
+        super().__init__()
+        self.coders = nn.ModuleList(coders)
+        if fix_weight:
+            self.register_buffer("default_blend_weight", torch.zeros(len(coders)), persistent=False)
+        else:
+            self.default_blend_weight = nn.Parameter(torch.zeros(len(coders)))
+
+    def _pick(self, blend_weight):
+        if blend_weight is None:
+            blend_weight = torch.softmax(self.default_blend_weight, dim=0)
+        return self.coders[int(blend_weight.argmax().item())]
+
+    def encode(self, input, *args, prior=None, blend_weight=None, **kwargs) -> bytes:
+        return self._pick(blend_weight).encode(input, prior=prior, **kwargs)
+
+    def decode(self, byte_string, *args, prior=None, blend_weight=None, **kwargs):
+        return self._pick(blend_weight).decode(byte_string, prior=prior, **kwargs)
+
+    def update_state(self, *args, **kwargs) -> None:
+        for coder in self.coders:
+            coder.update_state(*args, **kwargs)

@@ -578,8 +578,8 @@ int orc_tans_decode(const orc_tans_tables *tb, const uint8_t *enc, int64_t len, 
  *    interleaved lanes sharing one word stream.  Within a chunk, local symbol j belongs to lane
  *    (j % 128) / 4 and is coded at step (j / 128) * 4 + (j % 4).
  *
- *    Segment layout (little endian): u32 n_chunks | u32 n_words[n_chunks] | u32 state[n_chunks][32] |
- *    u16 words of chunk 0, chunk 1, ... | zero pad to 4 bytes.
+ *    Segment layout (little endian): u32 n_chunks | u32 chunk_syms | u32 end_word[n_chunks] (cumulative word count up to and
+ *    including chunk k) | u32 state[n_chunks][32] | u16 words of chunk 0, chunk 1, ... | zero pad to 4 bytes.
  * ---------------------------------------------------------------------------------------------- */
 #define BLS_LANES 32
 #define BLS_L (1u << 16)
@@ -659,7 +659,7 @@ static int bls_encode_chunk(const orc_rans64_tables *tb, const int32_t *sym, con
 int64_t orc_bls_bound(int64_t n, int64_t chunk_syms)
 {
     int64_t nc = orc_bls_num_chunks(n, chunk_syms);
-    return 4 + nc * (4 + 128) + n * 24 + 64;
+    return 8 + nc * (4 + 128) + n * 24 + 64;
 }
 
 int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int64_t n,
@@ -667,12 +667,13 @@ int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_
 {
     if (chunk_syms <= 0 || chunk_syms % 128) return ORC_ERR_GENERIC;
     const int64_t nc = orc_bls_num_chunks(n, chunk_syms);
-    int64_t hdr = 4 + nc * 4 + nc * 128;
+    int64_t hdr = 8 + nc * 4 + nc * 128;
     if (cap < hdr) return ORC_ERR_CAPACITY;
     uint32_t *h32 = (uint32_t *)out;
     h32[0] = (uint32_t)nc;
-    uint32_t *nwords = h32 + 1, *states = h32 + 1 + nc;
-    int64_t pos = hdr;
+    h32[1] = (uint32_t)chunk_syms;
+    uint32_t *nwords = h32 + 2, *states = h32 + 2 + nc;
+    int64_t pos = hdr, cum_words = 0;
     const int64_t wcap = chunk_syms * 12 + 64;
     uint16_t *wbuf = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)wcap);
     int rc = ORC_OK;
@@ -683,7 +684,8 @@ int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_
         if (rc) break;
         const int64_t nw = wcap - first;
         if (pos + nw * 2 + 4 > cap) { rc = ORC_ERR_CAPACITY; break; }
-        nwords[k] = (uint32_t)nw;
+        cum_words += nw;
+        nwords[k] = (uint32_t)cum_words;
         memcpy(out + pos, wbuf + first, (size_t)nw * 2);
         pos += nw * 2;
     }
@@ -698,18 +700,20 @@ int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_
 int orc_bls_decode(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len, const int32_t *idx, int64_t n,
                    int64_t chunk_syms, int32_t *out, int64_t *consumed)
 {
-    if (len < 4) return ORC_ERR_SRC_SIZE;
+    if (len < 8) return ORC_ERR_SRC_SIZE;
     const uint32_t *h32 = (const uint32_t *)enc;
     const int64_t nc = h32[0];
-    if (nc != orc_bls_num_chunks(n, chunk_syms)) return ORC_ERR_SRC_SIZE;
-    const uint32_t *nwords = h32 + 1, *states = h32 + 1 + nc;
-    int64_t pos = 4 + nc * 4 + nc * 128;
+    if (chunk_syms <= 0) chunk_syms = h32[1];
+    if ((int64_t)h32[1] != chunk_syms || chunk_syms % 128 || nc != orc_bls_num_chunks(n, chunk_syms)) return ORC_ERR_SRC_SIZE;
+    const uint32_t *nwords = h32 + 2, *states = h32 + 2 + nc;
+    int64_t pos = 8 + nc * 4 + nc * 128;
     if (len < pos) return ORC_ERR_SRC_SIZE;
     const int prec = tb->precision, bp = tb->bypass_precision;
     const uint32_t maxb = (1u << bp) - 1, pmask = (1u << prec) - 1;
     for (int64_t k = 0; k < nc; ++k) {
         const int64_t b = k * chunk_syms, m = (n - b) < chunk_syms ? (n - b) : chunk_syms;
-        if (pos + (int64_t)nwords[k] * 2 > len) return ORC_ERR_SRC_SIZE;
+        const int64_t nw_k = (int64_t)nwords[k] - (k ? (int64_t)nwords[k - 1] : 0);
+        if (nw_k < 0 || pos + nw_k * 2 > len) return ORC_ERR_SRC_SIZE;
         const uint16_t *w = (const uint16_t *)(enc + pos);
         int64_t wp = 0;
         uint32_t x[BLS_LANES];
@@ -757,8 +761,8 @@ int orc_bls_decode(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len,
             for (int l = 0; l < BLS_LANES; ++l)
                 if (cc[l] >= 0) out[b + bls_local_index(t, l)] = value[l] + tb->offsets[cc[l]];
         }
-        if (wp != (int64_t)nwords[k]) return ORC_ERR_SRC_SIZE;
-        pos += (int64_t)nwords[k] * 2;
+        if (wp != nw_k) return ORC_ERR_SRC_SIZE;
+        pos += nw_k * 2;
     }
     while (pos & 3) pos++;
     *consumed = pos;

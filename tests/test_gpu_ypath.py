@@ -1,0 +1,242 @@
+"""-m gpu: Gaussian conditional, context model and the whole y path (CUDA, through the C ABI) against the CPU
+oracle and the golden vectors of the unmodified reference.
+
+Bars (BASELINE.json north_star): symbols, scale indexes, CDF tables and decoded latents bit-exact; means and
+scales within 1e-5 relative error before quantisation; lanes=1 streams byte-for-byte; multi-lane lossless and
+within 0.5 % of the lanes=1 size."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ypath_oracle as Y
+from tests.test_oracle_golden import YCASES, load_ycase
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5      # north_star: floating-point means / scales, relative error before quantisation
+
+
+@pytest.fixture(scope="module")
+def yv(golden_dir):
+    return np.load(os.path.join(golden_dir, "ypath_vectors.npz"))
+
+
+def make_coder(c, lanes, method="none"):
+    from cbench_basic_b200.prior_coder import (GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder,
+                                               TopoGroupDynamicMaskConv2dContextModel as Ctx)
+    w, C_, G = c["w"], c["C"], c["G"]
+    if "m1_w" in w:
+        cm = Ctx(in_channels=C_, out_channels=2 * C_)
+        sd = {"context_prediction.weight": w["ctx_w"], "context_prediction.bias": w["ctx_b"],
+              "param_merger_in.weight": w["m1_w"], "param_merger_in.bias": w["m1_b"],
+              "param_merger_out.1.weight": w["m2_w"], "param_merger_out.1.bias": w["m2_b"],
+              "param_merger_out.3.weight": w["m3_w"], "param_merger_out.3.bias": w["m3_b"]}
+        cm.load_state_dict(sd)
+        coder = Coder(in_channels=C_, channel_groups=G, default_topo_group_method=method, topo_group_context_model=cm,
+                      lanes=lanes, ans_params_device="cpu")
+    else:
+        coder = Coder(in_channels=C_, channel_groups=G, default_topo_group_method=method, use_param_merger=False,
+                      lanes=lanes, ans_params_device="cpu")
+        coder.load_state_dict({"context_prediction.weight": w["ctx_w"], "context_prediction.bias": w["ctx_b"]})
+    coder = coder.cuda().eval()
+    coder.update_state()
+    return coder
+
+
+def rel_err(a, b):
+    return float(((a - b).abs() / b.abs().clamp_min(1e-3)).max())
+
+
+# ------------------------------------------------------------------------------------- update_state
+def test_update_state_tables_match_reference(golden_dir):
+    from cbench_basic_b200.prior_coder import GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder
+    g = np.load(os.path.join(golden_dir, "gaussian_tables.npz"))
+    coder = Coder(in_channels=8, use_param_merger=False, ans_params_device="cpu").cuda()
+    assert np.array_equal(coder.scale_table.numpy(), g["scale_table"])
+    freqs, nsym, offs = coder._get_ans_params()
+    assert np.array_equal(freqs, g["freqs"]) and np.array_equal(nsym, g["nsym"]) and np.array_equal(offs, g["offsets"])
+    coder.update_state()
+    cd = coder.ans_encoder.get_cdfs()
+    flat = np.concatenate([cd[t, :nsym[t] + 2] for t in range(64)])
+    assert np.array_equal(flat, g["cdf_flat"])
+    # the same float32 evaluation on the GPU (what a GPU-resident reference would do) may differ from the CPU
+    # libm in the last ulp of a few truncated counts; alphabet sizes and offsets must not
+    coder2 = Coder(in_channels=8, use_param_merger=False).cuda()
+    f2, n2, o2 = coder2._get_ans_params()
+    assert np.array_equal(n2, nsym) and np.array_equal(o2, offs)
+    assert np.abs(f2.astype(np.int64) - freqs).max() <= 1
+
+
+# --------------------------------------------------------------------------- quantise + scale index
+def test_quantize_index_bit_exact():
+    from cbench_basic_b200 import _native as N, ans
+    torch.manual_seed(0)
+    B, C_, H, W = 3, 16, 9, 11
+    tab = Y.get_scale_table()
+    y = 3 * torch.randn(B, C_, H, W)
+    params = torch.randn(B, 2 * C_, H, W) * 2
+    sc = params[:, 1::2]
+    # stress the argmin: exact table entries, exact midpoints (ties -> lower index), negatives, huge, tiny
+    flat = sc.reshape(-1)
+    mids = ((tab[:-1].double() + tab[1:].double()) / 2).float()
+    flat[:64] = tab
+    flat[64:127] = mids
+    flat[127:190] = torch.nextafter(mids, torch.tensor(float("inf")))
+    flat[190:253] = torch.nextafter(mids, torch.tensor(0.0))
+    flat[253:258] = torch.tensor([-1.0, 0.0, 1e9, 0.1099999, 256.0])
+    ym = y - params[:, 0::2]
+    y.reshape(-1)[:400] = (params[:, 0::2].reshape(-1)[:400] + torch.arange(400).float() % 7 - 3 + 0.5)  # exact .5 ties
+    enc = ans.Rans64Encoder()
+    N.check(N.lib().basic_coder_set_scale_table(enc.handle, np.ascontiguousarray(tab.numpy()).ctypes.data, 64))
+    pos = torch.randperm(C_ * H * W)[:1000].sort().values.int()
+    dy, dp, dpos = y.cuda(), params.cuda(), pos.cuda()
+    n = B * pos.numel()
+    sym, idx = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    buf = torch.zeros_like(dy)
+    N.check(N.lib().basic_gauss_quantize_index(enc.handle, dy.data_ptr(), dp.data_ptr(), dpos.data_ptr(), pos.numel(), B, C_,
+                                               H * W, sym.data_ptr(), idx.data_ptr(), buf.data_ptr(), 0))
+    torch.cuda.synchronize()
+    mean, scale = Y.split_mean_scale(params)
+    p = pos.long()
+    mean_s, scale_s, y_s = (t.reshape(B, -1)[:, p] for t in (mean, scale, y))
+    ref_idx = Y.select_indexes(scale_s, tab)
+    ref_sym = torch.round(y_s - mean_s)
+    assert torch.equal(idx.cpu().reshape(B, -1).long(), ref_idx)
+    assert torch.equal(sym.cpu().reshape(B, -1).float(), ref_sym)
+    ref_buf = torch.zeros(B, C_ * H * W)
+    ref_buf[:, p] = ref_sym + mean_s
+    assert torch.equal(buf.cpu().reshape(B, -1), ref_buf)
+    # decoder side
+    out = torch.zeros_like(dy)
+    N.check(N.lib().basic_gauss_dequantize(enc.handle, sym.data_ptr(), dp.data_ptr(), dpos.data_ptr(), pos.numel(), B, C_, H * W,
+                                           out.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu().reshape(B, -1), ref_buf * 1.0 + 0.0)
+
+
+# ----------------------------------------------------------------------------------- context model
+@pytest.mark.parametrize("name", [n for n in YCASES])
+def test_context_model_params_within_tolerance(yv, name):
+    """Every stage's distribution parameters, computed cell by cell on the GPU, against the reference's
+    full-tensor evaluation on the final y_hat (golden `params_full`): groups < g are all a cell may see, so the
+    two agree wherever the cell is coded."""
+    from cbench_basic_b200 import _native as N
+    c = load_ycase(yv, name)
+    coder = make_coder(c, lanes=1)
+    coder._set_map(c["tg"])
+    B, C_, H, W = c["B"], c["C"], c["H"], c["W"]
+    buf, prior = c["yhat"].cuda().contiguous(), c["prior"].cuda().contiguous()
+    params = torch.full((B, 2 * C_, H, W), float("nan"), device="cuda")
+    S = N.lib().basic_ctx_num_stages(coder._ctx)
+    assert S == int(c["tg"].max()) + 1
+    for g in range(S):
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, buf.data_ptr(), prior.data_ptr(), B, params.data_ptr(), 0))
+    torch.cuda.synchronize()
+    got = params.cpu()
+    assert not torch.isnan(got).any()            # every cell belongs to exactly one stage
+    assert rel_err(got, c["params_full"]) <= REL_TOL, rel_err(got, c["params_full"])
+
+
+@pytest.mark.parametrize("name", YCASES)
+@pytest.mark.parametrize("lanes", [1, 0, 64])
+def test_ypath_golden(yv, name, lanes):
+    c = load_ycase(yv, name)
+    coder = make_coder(c, lanes=lanes)
+    kw = dict(prior=c["prior"].cuda(), pgm=c["tg"])
+    bs, yhat_enc = coder.encode(c["y"].cuda(), return_yhat=True, **kw)
+    yhat = coder.decode(bs, **kw)
+    assert torch.equal(yhat.cpu(), c["yhat"])                      # decoded latents bit-exact vs the reference
+    assert torch.equal(yhat_enc.cpu() * 1.0 + 0.0, c["yhat"])
+    if lanes == 1:
+        assert bs == c["bytes"]                                    # reference bitstream, byte for byte
+        assert torch.equal(coder.decode(c["bytes"], **kw).cpu(), c["yhat"])
+    else:
+        assert len(bs) <= len(c["bytes"]) + 140 * (int(c["tg"].max()) + 1) * (1 if lanes == 0 else 2) + 8
+
+
+@pytest.mark.parametrize("name,method", [("ckbd", "checkerboard"), ("cwckbd", "channelwise-checkerboard"),
+                                         ("scanline", "scanline"), ("raster", "raster2x2"), ("meanscale", "none")])
+def test_default_maps_through_constructor(yv, name, method):
+    c = load_ycase(yv, name)
+    coder = make_coder(c, lanes=1, method=method)
+    bs = coder.encode(c["y"].cuda(), prior=c["prior"].cuda())
+    assert bs == c["bytes"]
+    assert torch.equal(coder.decode(bs, prior=c["prior"].cuda()).cpu(), c["yhat"])
+
+
+# ------------------------------------------------------- larger, seeded: oracle parity + properties
+def _random_case(C_, G, B, H, W, seed, method="checkerboard", ctx=True):
+    torch.manual_seed(seed)
+    w = Y.random_weights(C_, seed) if ctx else None
+    y, prior = 3 * torch.randn(B, C_, H, W), torch.randn(B, 2 * C_, H, W)
+    tg = Y.default_pgm(method, G, H, W)
+    if w is None:
+        w = {"ctx_w": torch.zeros(2 * C_, C_, 5, 5), "ctx_b": torch.zeros(2 * C_)}
+    return dict(C=C_, G=G, B=B, H=H, W=W, w=w, y=y, prior=prior, tg=tg)
+
+
+def test_ypath_vs_oracle_c192_checkerboard():
+    """BASELINE configs[1] geometry (C = 192, checkerboard) on one Kodak-shape image, against the CPU oracle."""
+    c = _random_case(192, 1, 1, 32, 48, 7)
+    with torch.no_grad():
+        sym, idx, yhat_ref = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], Y.get_scale_table())
+    o = Y.YPathOracle(192, 1, c["w"])
+    o.update_state()
+    ref_bytes = o.enc.encode_with_indexes(sym, idx)
+    for lanes in (1, 0):
+        coder = make_coder(c, lanes=lanes, method="checkerboard")
+        bs, yhat_enc = coder.encode(c["y"].cuda(), prior=c["prior"].cuda(), return_yhat=True)
+        yhat = coder.decode(bs, prior=c["prior"].cuda())
+        assert torch.equal(yhat.cpu(), yhat_enc.cpu() * 1.0 + 0.0)          # lossless w.r.t. the encoder's own y_hat
+        mism = int((yhat.cpu() != yhat_ref).sum())
+        assert mism == 0, f"{mism} latents differ from the oracle"           # symbols / indexes agree everywhere
+        if lanes == 1:
+            assert bs == ref_bytes
+        else:
+            assert len(bs) <= len(ref_bytes) * 1.005 + 300
+
+
+def test_ypath_round_trip_properties_large():
+    """Size-independent properties at a bigger batch: lossless round trip, |y_hat - y| <= 0.5, stream size close to
+    the lanes=1 stream."""
+    c = _random_case(192, 1, 6, 32, 48, 21)
+    coder1, coder0 = make_coder(c, 1, "checkerboard"), make_coder(c, 0, "checkerboard")
+    y, p = c["y"].cuda(), c["prior"].cuda()
+    b1, yh1 = coder1.encode(y, prior=p, return_yhat=True)
+    b0, yh0 = coder0.encode(y, prior=p, return_yhat=True)
+    assert torch.equal(yh0, yh1)
+    d1, d0 = coder1.decode(b1, prior=p), coder0.decode(b0, prior=p)
+    assert torch.equal(d0, d1) and torch.equal(d0, yh0 * 1.0 + 0.0)
+    assert float((d0 - y).abs().max()) <= 0.5
+    assert len(b0) <= len(b1) * 1.005 + 300
+
+
+def test_mean_scale_4k_320ch_tiles():
+    """BASELINE configs[4] geometry: 135 x 240 x 320 latent, mean-scale coder (tiling is exact there), coded as
+    row-band tiles; every tile decodes on its own and the union equals the untiled result."""
+    from cbench_basic_b200 import sharding
+    c = _random_case(320, 1, 1, 135, 240, 5, method="none", ctx=False)
+    coder = make_coder(c, 0, "none")
+    y, p = c["y"].cuda(), c["prior"].cuda()
+    whole, yh = coder.encode(y, prior=p, return_yhat=True)
+    parts, total = [], 0
+    for band in sharding.row_band_tiles(135, 8):
+        ys, ps = y[:, :, band.start:band.stop].contiguous(), p[:, :, band.start:band.stop].contiguous()
+        bs = coder.encode(ys, prior=ps)
+        total += len(bs)
+        parts.append(coder.decode(bs, prior=ps))
+    assert torch.equal(torch.cat(parts, dim=2), yh * 1.0 + 0.0)
+    assert total <= len(whole) * 1.01
+
+
+def test_combined_coder_dispatch(yv):
+    from cbench_basic_b200.prior_coder import CombinedNNTrainablePGMPriorCoder
+    c = load_ycase(yv, "ckbd")
+    a, b = make_coder(c, 1, "checkerboard"), make_coder(c, 1, "none")
+    comb = CombinedNNTrainablePGMPriorCoder([a, b])
+    w = torch.tensor([0.1, 0.9])
+    bs = comb.encode(c["y"].cuda(), prior=c["prior"].cuda(), blend_weight=w)
+    assert bs == b.encode(c["y"].cuda(), prior=c["prior"].cuda())
+    assert torch.equal(comb.decode(bs, prior=c["prior"].cuda(), blend_weight=w), b.decode(bs, prior=c["prior"].cuda()))
