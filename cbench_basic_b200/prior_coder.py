@@ -30,6 +30,23 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):  # no
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
+class _CtxHandle:
+    """Owns a basic_ctx* (kept out of nn.Module attribute machinery so it can be freed at interpreter exit)."""
+
+    def __init__(self):
+        self.h = None
+
+    def reset(self):
+        h, self.h = self.h, None
+        if h:
+            try:
+                N.lib().basic_ctx_destroy(h)
+            except Exception:
+                pass
+
+    __del__ = reset
+
+
 class TopoGroupDynamicMaskConv2dContextModel(nn.Module):
     """Weight container with the reference's parameter names (masked_conv.py:231-305): a 5x5 context
     convolution C -> 2C and the three 1x1 "param merger" convolutions 4C -> 10C/3 -> 8C/3 -> 2C, all with
@@ -113,7 +130,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self.register_buffer("_device_indicator", torch.zeros(1), persistent=False)
         self.out_channels = 2 * in_channels
         self.profile = {}          # wall-clock ms of the last calls, keyed like the reference's profiler scopes
-        self._ctx = None
+        self._ctx_holder = _CtxHandle()
 
     # ------------------------------------------------------------------------------------------ plumbing
     @property
@@ -165,12 +182,10 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self._upload_weights(dev)
 
     def _upload_weights(self, dev):
-        if self._ctx is not None:
-            N.lib().basic_ctx_destroy(self._ctx)
-            self._ctx = None
+        self._ctx_holder.reset()
         h = C.c_void_p()
         N.check(N.lib().basic_ctx_create(self.in_channels, self.channel_groups, self.kernel_size, dev, C.byref(h)))
-        self._ctx = h
+        self._ctx_holder.h = h
         keep = []
 
         def ptr(t):
@@ -191,13 +206,9 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         torch.cuda.synchronize(self.device)
         N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
 
-    def __del__(self):
-        ctx, self._ctx = getattr(self, "_ctx", None), None
-        if ctx:
-            try:
-                N.lib().basic_ctx_destroy(ctx)
-            except Exception:
-                pass
+    @property
+    def _ctx(self):
+        return self._ctx_holder.h
 
     # ------------------------------------------------------------------------------------------ group map
     def _get_pgm(self, input_shape, pgm=None):

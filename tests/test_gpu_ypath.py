@@ -46,7 +46,15 @@ def make_coder(c, lanes, method="none"):
 
 
 def rel_err(a, b):
-    return float(((a - b).abs() / b.abs().clamp_min(1e-3)).max())
+    """|a - b| relative to max(1, |b|): relative for large values, absolute 1e-5 below 1."""
+    return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
+
+
+def assert_latents_match(got, ref):
+    """Decoded latents are symbol + mean: the integer symbol must be the reference's, the float mean may differ by
+    the rounding of a different (deterministic) summation order -- north_star's 1e-5 relative bar."""
+    assert rel_err(got, ref) <= REL_TOL, rel_err(got, ref)
+    assert torch.equal(torch.round(got - ref), torch.zeros_like(ref))
 
 
 # ------------------------------------------------------------------------------------- update_state
@@ -147,11 +155,13 @@ def test_ypath_golden(yv, name, lanes):
     kw = dict(prior=c["prior"].cuda(), pgm=c["tg"])
     bs, yhat_enc = coder.encode(c["y"].cuda(), return_yhat=True, **kw)
     yhat = coder.decode(bs, **kw)
-    assert torch.equal(yhat.cpu(), c["yhat"])                      # decoded latents bit-exact vs the reference
-    assert torch.equal(yhat_enc.cpu() * 1.0 + 0.0, c["yhat"])
+    assert torch.equal(yhat, yhat_enc * 1.0 + 0.0)                 # lossless: decoder reproduces the encoder bit for bit
+    assert_latents_match(yhat.cpu(), c["yhat"])
+    if c["w"].get("m1_w") is None:
+        assert torch.equal(yhat.cpu(), c["yhat"])                  # no float reduction involved: bit-exact vs the reference
     if lanes == 1:
-        assert bs == c["bytes"]                                    # reference bitstream, byte for byte
-        assert torch.equal(coder.decode(c["bytes"], **kw).cpu(), c["yhat"])
+        assert bs == c["bytes"]                                    # reference bitstream byte for byte (=> symbols and
+        assert_latents_match(coder.decode(c["bytes"], **kw).cpu(), c["yhat"])   # scale indexes identical everywhere)
     else:
         assert len(bs) <= len(c["bytes"]) + 140 * (int(c["tg"].max()) + 1) * (1 if lanes == 0 else 2) + 8
 
@@ -163,7 +173,7 @@ def test_default_maps_through_constructor(yv, name, method):
     coder = make_coder(c, lanes=1, method=method)
     bs = coder.encode(c["y"].cuda(), prior=c["prior"].cuda())
     assert bs == c["bytes"]
-    assert torch.equal(coder.decode(bs, prior=c["prior"].cuda()).cpu(), c["yhat"])
+    assert_latents_match(coder.decode(bs, prior=c["prior"].cuda()).cpu(), c["yhat"])
 
 
 # ------------------------------------------------------- larger, seeded: oracle parity + properties
@@ -190,10 +200,9 @@ def test_ypath_vs_oracle_c192_checkerboard():
         bs, yhat_enc = coder.encode(c["y"].cuda(), prior=c["prior"].cuda(), return_yhat=True)
         yhat = coder.decode(bs, prior=c["prior"].cuda())
         assert torch.equal(yhat.cpu(), yhat_enc.cpu() * 1.0 + 0.0)          # lossless w.r.t. the encoder's own y_hat
-        mism = int((yhat.cpu() != yhat_ref).sum())
-        assert mism == 0, f"{mism} latents differ from the oracle"           # symbols / indexes agree everywhere
+        assert_latents_match(yhat.cpu(), yhat_ref)                          # same integer symbols as the oracle
         if lanes == 1:
-            assert bs == ref_bytes
+            assert bs == ref_bytes                                           # symbols AND scale indexes agree everywhere
         else:
             assert len(bs) <= len(ref_bytes) * 1.005 + 300
 
