@@ -187,14 +187,59 @@ def _random_case(C_, G, B, H, W, seed, method="checkerboard", ctx=True):
     return dict(C=C_, G=G, B=B, H=H, W=W, w=w, y=y, prior=prior, tg=tg)
 
 
+def _stagewise_symbols(coder, c):
+    """Our symbols / scale indexes in stream order, through the C-ABI building blocks (the same calls
+    basic_ypath_encode makes): per stage, context model -> quantise + index -> write-back."""
+    from cbench_basic_b200 import _native as N
+    B, C_, H, W = c["B"], c["C"], c["H"], c["W"]
+    coder._set_map(c["tg"])
+    y, prior = c["y"].cuda().contiguous(), c["prior"].cuda().contiguous()
+    buf = torch.zeros_like(y)
+    params = torch.zeros(B, 2 * C_, H, W, device="cuda")
+    syms, idxs = [], []
+    h = coder.ans_encoder.handle
+    for g in range(N.lib().basic_ctx_num_stages(coder._ctx)):
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, buf.data_ptr(), prior.data_ptr(), B, params.data_ptr(), 0))
+        pos, n_pos = C.c_void_p(), C.c_int64()
+        N.check(N.lib().basic_ctx_stage_positions(coder._ctx, g, C.byref(pos), C.byref(n_pos)))
+        n = B * n_pos.value
+        sym, idx = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+        N.check(N.lib().basic_gauss_quantize_index(h, y.data_ptr(), params.data_ptr(), pos, n_pos.value, B, C_, H * W,
+                                                   sym.data_ptr(), idx.data_ptr(), buf.data_ptr(), 0))
+        syms.append(sym)
+        idxs.append(idx)
+    torch.cuda.synchronize()
+    return torch.cat(syms).cpu().numpy(), torch.cat(idxs).cpu().numpy(), params.cpu()
+
+
 def test_ypath_vs_oracle_c192_checkerboard():
-    """BASELINE configs[1] geometry (C = 192, checkerboard) on one Kodak-shape image, against the CPU oracle."""
+    """BASELINE configs[1] geometry (C = 192, checkerboard) on one Kodak-shape image, against the CPU oracle:
+    295k symbols through a 4800-deep FP32 reduction.  Symbols must agree everywhere.  A scale index may differ
+    only where the ORACLE's own scale sits within the float tolerance of the midpoint between two table entries
+    (a different, equally valid FP32 summation order decides such a tie) -- any other disagreement fails."""
     c = _random_case(192, 1, 1, 32, 48, 7)
+    tab = Y.get_scale_table()
     with torch.no_grad():
-        sym, idx, yhat_ref = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], Y.get_scale_table())
+        sym, idx, yhat_ref = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
+        params_ref = Y.params_for(yhat_ref, c["tg"], c["prior"], c["w"])
     o = Y.YPathOracle(192, 1, c["w"])
     o.update_state()
     ref_bytes = o.enc.encode_with_indexes(sym, idx)
+    coder = make_coder(c, lanes=1, method="checkerboard")
+    gsym, gidx, gparams = _stagewise_symbols(coder, c)
+    assert rel_err(gparams, params_ref) <= REL_TOL
+    assert np.array_equal(gsym, sym), f"{int((gsym != sym).sum())} symbols differ from the oracle"
+    bad = np.nonzero(gidx != idx)[0]
+    assert bad.size <= 4, f"{bad.size} scale indexes differ"
+    if bad.size:
+        # stream order -> element: stage-major, then (c, h, w) of the stage's mask
+        gmap = Y.group_of_elements(c["tg"], 1, 192).reshape(-1)
+        order = torch.cat([torch.nonzero(gmap == g).reshape(-1) for g in range(2)])
+        sc = Y.split_mean_scale(params_ref)[1].reshape(-1)[order][bad].double()
+        lo = np.minimum(gidx[bad], idx[bad])
+        assert np.all(np.abs(gidx[bad] - idx[bad]) == 1)
+        mid = (tab.double()[lo] + tab.double()[lo + 1]) / 2
+        assert float(((sc - mid).abs() / mid).max()) <= REL_TOL, "scale-index disagreement away from a tie"
     for lanes in (1, 0):
         coder = make_coder(c, lanes=lanes, method="checkerboard")
         bs, yhat_enc = coder.encode(c["y"].cuda(), prior=c["prior"].cuda(), return_yhat=True)
@@ -202,7 +247,9 @@ def test_ypath_vs_oracle_c192_checkerboard():
         assert torch.equal(yhat.cpu(), yhat_enc.cpu() * 1.0 + 0.0)          # lossless w.r.t. the encoder's own y_hat
         assert_latents_match(yhat.cpu(), yhat_ref)                          # same integer symbols as the oracle
         if lanes == 1:
-            assert bs == ref_bytes                                           # symbols AND scale indexes agree everywhere
+            assert bs == o.enc.encode_with_indexes(gsym, gidx)               # the reference coder on OUR symbols/indexes
+            if bad.size == 0:
+                assert bs == ref_bytes
         else:
             assert len(bs) <= len(ref_bytes) * 1.005 + 300
 
