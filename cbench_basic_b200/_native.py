@@ -10,6 +10,7 @@ OK, ERR_VALUE, ERR_CUDA, ERR_CAPACITY, ERR_STREAM = 0, -1, -2, -3, -4
 KIND_RANS64, KIND_TANS = 0, 1
 ROLE_BOTH, ROLE_ENCODER, ROLE_DECODER = 0, 1, 2
 LANES_REFERENCE, LANES_AUTO = 1, 0
+CTX_FP32, CTX_TF32X3 = 0, 1
 
 # every extern "C" symbol declared in include/basic_b200.h
 SYMBOLS = [
@@ -18,7 +19,7 @@ SYMBOLS = [
     "basic_coder_encode_bound", "basic_coder_encode", "basic_coder_flush", "basic_coder_decode", "basic_coder_set_stream",
     "basic_coder_decode_stream", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
     "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_map", "basic_ctx_num_stages",
-    "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
+    "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
     "basic_ypath_decode", "basic_launch_count",
 ]
 
@@ -71,6 +72,7 @@ def lib():
     L.basic_ctx_set_weights.argtypes = [vp] + [f32p] * 8
     L.basic_ctx_set_map.argtypes = [vp, i32p, C.c_int, C.c_int]
     L.basic_ctx_num_stages.argtypes = [vp]
+    L.basic_ctx_set_precision.argtypes = [vp, C.c_int, C.c_int]
     L.basic_ctx_stage_positions.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
     L.basic_ctx_stage_params.argtypes = [vp, C.c_int, f32p, f32p, C.c_int, f32p, vp]
     L.basic_ypath_encode_bound.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]

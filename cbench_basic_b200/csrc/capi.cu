@@ -33,6 +33,7 @@ int ctx_set_weights(CtxModel &, const float *, const float *, const float *, con
 int ctx_set_map(CtxModel &, const int32_t *, int, int);
 int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t);
 int ctx_num_stages(const CtxModel &);
+int ctx_set_precision(CtxModel &, int, int);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
 
@@ -615,6 +616,12 @@ int basic_ctx_set_map(basic_ctx *m, const int32_t *tg, int H, int W)
 }
 
 int basic_ctx_num_stages(basic_ctx *m) { return m ? ctx_num_stages(*m->m) : 0; }
+
+int basic_ctx_set_precision(basic_ctx *m, int precision, int nacc)
+{
+    if (!m) return value_error("null model");
+    return ctx_set_precision(*m->m, precision, nacc);
+}
 
 int basic_ctx_stage_positions(basic_ctx *m, int g, const int32_t **positions_dev, int64_t *n_pos)
 {

@@ -11,67 +11,14 @@
 // Deterministic (fixed K order, no atomics): the decoder recomputes bit-identical parameters.
 #include <algorithm>
 
-#include "common.cuh"
+#include "ctx.cuh"
 
 namespace basic {
-
-struct CtxModel {
-    int C = 0, G = 1, k = 5, device = 0, sm_count = 148;
-    bool has_conv = false, has_merger = false;
-    int c_ctx = 0, c_m1 = 0, c_m2 = 0;  // 2C, 10C/3, 8C/3
-    // weights, K-major ("transposed"): wt[kk][o]
-    DevBuf w_ctx, b_ctx;                // conv: kk = tap * C + c
-    DevBuf w_m1, b_m1, w_m2, b_m2, w_m3, b_m3;
-    // map
-    int H = 0, W = 0, S = 0;
-    std::vector<int32_t> h_tg;
-    struct Stage {
-        std::vector<int> cell_off;       // [G + 1] offsets into the stage's cell arrays
-        size_t cells_at = 0;             // offset of this stage inside d_cells (in cells)
-        size_t pos_at = 0;               // offset inside d_positions
-        int64_t n_pos = 0;
-        uint32_t tap_or = 0;             // OR of all tap masks of the stage (0 -> conv contributes bias only)
-    };
-    std::vector<Stage> stages;
-    DevBuf d_cell_hw;    // int32 [ncells]            cell -> h*W+w
-    DevBuf d_cell_tap;   // uint32 [ncells][G]        visible 5x5 taps per input channel group
-    DevBuf d_cell_grp;   // uint32 [ncells]           bit j: in-group j visible through "<="
-    DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
-    // activations (grow-only)
-    DevBuf a_ctx, a_m1, a_m2;
-    int act_B = 0;
-};
 
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 16, NT = 256;
 constexpr float kSlope = 0.01f;  // nn.LeakyReLU default negative_slope
-
-struct Source {          // one block of K coming from an NCHW activation tensor
-    const float *ptr;    // [B, channels, H, W]
-    int channels;        // channels of this tensor
-    int groups;          // channel groups subject to the visibility rule (0 = always visible)
-};
-
-struct LayerArgs {
-    // rows = B x cells(stage, out-group)
-    const int32_t *cell_hw;
-    const uint32_t *cell_tap;   // conv only
-    const uint32_t *cell_grp;   // dense only
-    int ncells, cell_base;      // cells of this (stage, out-group) start at cell_base
-    int B, HW, W_img, H_img, G;
-    // K
-    int is_conv, ksize, Cin;    // conv: Cin input channels of `src0`
-    Source src0, src1;          // dense: K = src0.channels + src1.channels
-    const float *wt;            // [K][Ntot] K-major
-    const float *bias;          // [Ntot]
-    int Ntot, n_begin, n_count; // this out-group's output channels [n_begin, n_begin + n_count)
-    // epilogue
-    float *out;                 // [B, Ntot, H, W]
-    const float *add;           // optional [B, Ntot, H, W] added in the epilogue (merger-less: + prior)
-    int lrelu;
-    uint32_t tap_or;            // stage-level OR of the tap masks (conv)
-};
 
 __global__ void __launch_bounds__(NT)
 k_layer(LayerArgs a)
@@ -290,6 +237,19 @@ int upload_transposed(DevBuf &dst, const float *src, int N, int Cin, int k2, cud
     return BASIC_OK;
 }
 
+// stages `src` (host or device, state_dict layout) on the device and packs it for the tensor-core path
+int pack_from(PackedW &dst, const float *src, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1, cudaStream_t s)
+{
+    const size_t count = is_conv ? (size_t)N * Cin * k2 : (size_t)N * (c_src0 + c_src1);
+    DevBuf tmp;
+    BASIC_TRY(tmp.reserve(count * sizeof(float)));
+    BASIC_CUDA(cudaMemcpyAsync(tmp.p, src, count * sizeof(float), cudaMemcpyDefault, s));
+    const int rc = pack_weights_tc(dst, tmp.as<float>(), N, G, is_conv, Cin, k2, c_src0, c_src1, s);
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    tmp.release();
+    return rc;
+}
+
 }  // namespace
 
 int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b,
@@ -306,10 +266,16 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
     if (m.has_merger && !m.has_conv) return value_error("param merger needs the context convolution weights");
     if (m.has_merger && (m.c_m1 % m.G || m.c_m2 % m.G)) return value_error("2C*5/3 and 2C*4/3 must be divisible by channel_groups");
     if (C % m.G) return value_error("in_channels must be divisible by channel_groups");
-    if (m.has_conv) BASIC_TRY(upload_transposed(m.w_ctx, ctx_w, m.c_ctx, C, m.k * m.k, s));
+    if (m.has_conv) {
+        BASIC_TRY(upload_transposed(m.w_ctx, ctx_w, m.c_ctx, C, m.k * m.k, s));
+        BASIC_TRY(pack_from(m.p_ctx, ctx_w, m.c_ctx, m.G, 1, C, m.k * m.k, 0, 0, s));
+    }
     if (ctx_b) BASIC_TRY(upload(m.b_ctx, ctx_b, m.c_ctx, s)); else m.b_ctx.release();
     if (m.has_merger) {
         BASIC_TRY(upload_transposed(m.w_m1, m1_w, m.c_m1, 2 * m.c_ctx, 1, s));
+        BASIC_TRY(pack_from(m.p_m1, m1_w, m.c_m1, m.G, 0, 0, 1, m.c_ctx, m.c_ctx, s));
+        BASIC_TRY(pack_from(m.p_m2, m2_w, m.c_m2, m.G, 0, 0, 1, m.c_m1, 0, s));
+        BASIC_TRY(pack_from(m.p_m3, m3_w, m.c_ctx, m.G, 0, 0, 1, m.c_m2, 0, s));
         BASIC_TRY(upload(m.b_m1, m1_b, m.c_m1, s));
         BASIC_TRY(upload_transposed(m.w_m2, m2_w, m.c_m2, m.c_m1, 1, s));
         BASIC_TRY(upload(m.b_m2, m2_b, m.c_m2, s));
@@ -336,6 +302,10 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     }
     m.H = H; m.W = W; m.S = S; m.h_tg = tg;
     m.stages.assign(S, CtxModel::Stage());
+    for (auto &st : m.stages) {
+        st.og_tap_or.assign((size_t)G * G, 0u);
+        st.og_grp_or.assign((size_t)G, 0u);
+    }
     // bucket cells by stage, ordered by (out-group, hw)
     std::vector<std::vector<int>> per_stage_count(S, std::vector<int>(G, 0));
     for (int g = 0; g < G; ++g)
@@ -372,8 +342,10 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
                 }
                 cell_tap[cell * G + j] = taps;
                 st.tap_or |= taps;
+                st.og_tap_or[(size_t)g * G + j] |= taps;
             }
             cell_grp[cell] = grp;
+            st.og_grp_or[g] |= grp;
         }
     // coded positions: stage-major, then (c, hw) row-major inside an image == boolean-mask order
     for (int s = 0; s < S; ++s) {
@@ -395,10 +367,21 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     return BASIC_OK;
 }
 
-static int launch_layer(const CtxModel &m, LayerArgs a, cudaStream_t stream)
+static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, cudaStream_t stream)
 {
+    for (int j = 0; j < 8; ++j) a.vis_or[j] = 0;
+    if (m.G <= 8) {
+        if (a.is_conv) for (int j = 0; j < m.G; ++j) a.vis_or[j] = st.og_tap_or[(size_t)og * m.G + j];
+        else a.vis_or[0] = st.og_grp_or[og];
+    }
     const int rows = a.B * a.ncells;
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
+    a.wpack = pw.buf.as<unsigned char>();
+    a.kb_total = pw.kb_total;
+    a.kb_src0 = pw.kb_src0;
+    a.ntile_base = og * pw.ntiles_per_group;
+    a.nacc = m.nacc;
+    if (tc_eligible(m, a)) return launch_layer_tc(m, a, stream);
     dim3 grid((rows + BM - 1) / BM, (a.n_count + BN - 1) / BN);
     k_layer<<<grid, NT, 0, stream>>>(a);
     BASIC_LAUNCHED();
@@ -447,7 +430,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         a.add = m.has_merger ? nullptr : prior;
         a.lrelu = 0;
         a.tap_or = st.tap_or;
-        BASIC_TRY(launch_layer(m, a, stream));
+        BASIC_TRY(launch_layer(m, a, m.p_ctx, og, st, stream));
     }
     if (!m.has_merger) return BASIC_OK;
     // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
@@ -480,7 +463,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             }
             a.n_begin = og * (a.Ntot / G);
             a.n_count = a.Ntot / G;
-            BASIC_TRY(launch_layer(m, a, stream));
+            BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3, og, st, stream));
         }
     }
     return BASIC_OK;
@@ -498,12 +481,22 @@ void ctx_delete(CtxModel *m)
 {
     if (!m) return;
     DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
-                      &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2};
+                      &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
+                      &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }
 
 int ctx_num_stages(const CtxModel &m) { return m.S; }
+
+int ctx_set_precision(CtxModel &m, int precision, int nacc)
+{
+    if (precision != BASIC_CTX_FP32 && precision != BASIC_CTX_TF32X3) return value_error("unknown context-model precision");
+    if (nacc < 1 || nacc > 64) return value_error("segment length must be 1..64 k-blocks");
+    m.precision = precision;
+    m.nacc = nacc;
+    return BASIC_OK;
+}
 
 int ctx_stage_positions(const CtxModel &m, int g, const int32_t **positions_dev, int64_t *n_pos)
 {

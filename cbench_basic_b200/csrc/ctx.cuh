@@ -1,0 +1,88 @@
+// Context-model state shared by the exact-FP32 path (ctx.cu) and the tcgen05 3xTF32 path (ctx_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace basic {
+
+// Packed weights of one layer for the tensor-core path: per (out-group, n-tile, k-block) one 32 KB image
+// [hi: 128 rows x 128 B, SWIZZLE_128B K-major | lo: same], ready for a single bulk copy into shared memory.
+struct PackedW {
+    DevBuf buf;
+    int kb_total = 0;         // k-blocks (32 k each) per n-tile
+    int ntiles_per_group = 0; // n-tiles (128 output channels each) per out-group
+    int kb_src0 = 0;          // dense: k-blocks of the first source; conv: k-blocks per tap
+};
+
+struct CtxModel {
+    int C = 0, G = 1, k = 5, device = 0, sm_count = 148;
+    bool has_conv = false, has_merger = false;
+    int c_ctx = 0, c_m1 = 0, c_m2 = 0;  // 2C, 10C/3, 8C/3
+    // weights, K-major ("transposed"): wt[kk][o]
+    DevBuf w_ctx, b_ctx;                // conv: kk = tap * C + c
+    DevBuf w_m1, b_m1, w_m2, b_m2, w_m3, b_m3;
+    // map
+    int H = 0, W = 0, S = 0;
+    std::vector<int32_t> h_tg;
+    struct Stage {
+        std::vector<int> cell_off;       // [G + 1] offsets into the stage's cell arrays
+        size_t cells_at = 0;             // offset of this stage inside d_cells (in cells)
+        size_t pos_at = 0;               // offset inside d_positions
+        int64_t n_pos = 0;
+        uint32_t tap_or = 0;             // OR of all tap masks of the stage (0 -> conv contributes bias only)
+        std::vector<uint32_t> og_tap_or; // [G out-groups][G in-groups] OR of the tap masks over the (stage, out-group) cells
+        std::vector<uint32_t> og_grp_or; // [G out-groups] OR of the group-visibility bits
+    };
+    std::vector<Stage> stages;
+    DevBuf d_cell_hw;    // int32 [ncells]            cell -> h*W+w
+    DevBuf d_cell_tap;   // uint32 [ncells][G]        visible 5x5 taps per input channel group
+    DevBuf d_cell_grp;   // uint32 [ncells]           bit j: in-group j visible through "<="
+    DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
+    // activations (grow-only)
+    DevBuf a_ctx, a_m1, a_m2;
+    int act_B = 0;
+    // tensor-core path
+    int precision = 0;   // BASIC_CTX_FP32 | BASIC_CTX_TF32X3
+    int nacc = 4;        // k-blocks (32 k each) accumulated in TMEM before a segment is drained into FP32 registers
+    PackedW p_ctx, p_m1, p_m2, p_m3;
+};
+
+
+struct Source {          // one block of K coming from an NCHW activation tensor
+    const float *ptr;    // [B, channels, H, W]
+    int channels;        // channels of this tensor
+    int groups;          // channel groups subject to the visibility rule (0 = always visible)
+};
+
+struct LayerArgs {
+    // rows = B x cells(stage, out-group)
+    const int32_t *cell_hw;
+    const uint32_t *cell_tap;   // conv only
+    const uint32_t *cell_grp;   // dense only
+    int ncells, cell_base;      // cells of this (stage, out-group) start at cell_base
+    int B, HW, W_img, H_img, G;
+    // K
+    int is_conv, ksize, Cin;    // conv: Cin input channels of `src0`
+    Source src0, src1;          // dense: K = src0.channels + src1.channels
+    const float *wt;            // [K][Ntot] K-major
+    const float *bias;          // [Ntot]
+    int Ntot, n_begin, n_count; // this out-group's output channels [n_begin, n_begin + n_count)
+    // epilogue
+    float *out;                 // [B, Ntot, H, W]
+    const float *add;           // optional [B, Ntot, H, W] added in the epilogue (merger-less: + prior)
+    int lrelu;
+    uint32_t tap_or;            // stage-level OR of the tap masks (conv)
+    // tensor-core path
+    const unsigned char *wpack; // PackedW image
+    int kb_total, kb_src0, ntile_base, nacc;
+    int debug;
+    uint32_t vis_or[8];         // conv: OR over the launch's rows of the tap mask per input group; dense: [0] = OR of group bits
+};
+
+
+// ctx_tc.cu
+bool tc_eligible(const CtxModel &m, const LayerArgs &a);
+int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream);
+int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
+                    int k2, int c_src0, int c_src1, cudaStream_t stream);
+
+}  // namespace basic

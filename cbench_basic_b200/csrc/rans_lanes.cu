@@ -46,7 +46,7 @@ struct LaneParams {
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
 // Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 1)
 k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
              uint32_t *__restrict__ states, int *status)
@@ -61,19 +61,19 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
     const uint32_t xmax_bits = 1u << (32 - bp);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
-    for (int k = blockIdx.x * kWarps + warp; k < n_chunks; k += gridDim.x * kWarps) {
+    // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
+    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
         const long long base = (long long)k * P.chunk_syms;
         const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
         uint16_t *wbuf = scratch + (size_t)k * cap_words;
         int pos = cap_words;  // warp-uniform
         uint32_t x = kRansL;
         const int nblocks = (m + 127) >> 7;
-        for (int blk = nblocks - 1; blk >= 0; --blk) {
+        auto load_ops = [&](int blk, int32_t(&sy)[4], int32_t(&ix)[4]) {
             const int j0 = blk * 128 + lane * 4;
-            int32_t sy[4], ix[4];
             if (vec_ok && j0 + 3 < m) {
-                const int4 a = *reinterpret_cast<const int4 *>(symbols + base + j0);
-                const int4 b = *reinterpret_cast<const int4 *>(indexes + base + j0);
+                const int4 a = __ldg(reinterpret_cast<const int4 *>(symbols + base + j0));
+                const int4 b = __ldg(reinterpret_cast<const int4 *>(indexes + base + j0));
                 sy[0] = a.x; sy[1] = a.y; sy[2] = a.z; sy[3] = a.w;
                 ix[0] = b.x; ix[1] = b.y; ix[2] = b.z; ix[3] = b.w;
             } else {
@@ -84,6 +84,14 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                     ix[q] = ok ? indexes[base + j0 + q] : 0;
                 }
             }
+        };
+        int32_t sy[4], ix[4], syn[4] = {0, 0, 0, 0}, ixn[4] = {0, 0, 0, 0};
+        if (nblocks > 0) load_ops(nblocks - 1, syn, ixn);
+        for (int blk = nblocks - 1; blk >= 0; --blk) {
+            const int j0 = blk * 128 + lane * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { sy[q] = syn[q]; ix[q] = ixn[q]; }
+            if (blk > 0) load_ops(blk - 1, syn, ixn);  // one block ahead: off the dependency chain
 #pragma unroll
             for (int q = 3; q >= 0; --q) {
                 const bool active = j0 + q < m;
@@ -109,9 +117,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                         ncnt = nd / (int)maxb + 1;
                         ntok = ncnt + nd;
                     }
-                    int maxtok = ntok;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) maxtok = max(maxtok, __shfl_xor_sync(kFull, maxtok, o));
+                    const int maxtok = (int)__reduce_max_sync(kFull, (unsigned)ntok);
                     for (int u = maxtok - 1; u >= 0; --u) {
                         const bool part = ntok > u;
                         const bool emit = part && x >= xmax_bits;
@@ -141,8 +147,19 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                     x >>= 16;
                 }
                 if (active) {
-                    const uint32_t qt = x / freq;
-                    x = (qt << prec) + (x - qt * freq) + start;
+                    // x < freq << 16 after the renormalisation above, so qt < 2^16 and a float estimate is within
+                    // one of it (exact general division when the invariant does not hold: prec < 16)
+                    uint32_t qt, rem;
+                    if (prec == 16) {
+                        qt = __float2uint_rz(__fdividef(__uint2float_rz(x), __uint2float_rz(freq)));
+                        rem = x - qt * freq;
+                        if ((int32_t)rem < 0) { --qt; rem += freq; }
+                        else if (rem >= freq) { ++qt; rem -= freq; }
+                    } else {
+                        qt = x / freq;
+                        rem = x - qt * freq;
+                    }
+                    x = (qt << prec) + rem + start;
                 }
             }
         }
@@ -208,12 +225,29 @@ k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, const uint16_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------------ decode
-__global__ void __launch_bounds__(kWarps * 32)
+// The renormalisation words of a chunk are consumed strictly in order (wp is warp-uniform), so each warp streams
+// them through a private shared-memory ring filled by cp.async two groups ahead: the state update chain never
+// waits on a global load.  Ring = kRingUnits u32 units (2 words each), filled in groups of kGroupUnits.
+constexpr int kRingUnits = 512, kGroupUnits = 128;
+
+__device__ inline void cp_async4(uint32_t smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kWarps * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
              int32_t *__restrict__ out, int *status)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem, smem);
+    // ring first (fixed size), tables behind it
+    uint32_t *ring32 = reinterpret_cast<uint32_t *>(smem) + (threadIdx.x >> 5) * kRingUnits;
+    const uint16_t *ring16 = reinterpret_cast<const uint16_t *>(ring32);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring32);
+    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem,
+                                      smem + kWarps * kRingUnits * 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks;
@@ -223,30 +257,62 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2;
     const uint32_t *states = end_word + n_chunks;
     const long long words_at = kSegHdr + 4ll * n_chunks + 128ll * n_chunks;
-    const uint16_t *words = reinterpret_cast<const uint16_t *>(seg + words_at);
+    const uint32_t *units = reinterpret_cast<const uint32_t *>(seg + words_at);  // 2 words per unit, 4-byte aligned
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
-    for (int k = blockIdx.x * kWarps + warp; k < n_chunks; k += gridDim.x * kWarps) {
+    // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
+    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
         const long long base = (long long)k * P.chunk_syms;
         const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
         uint32_t wend = end_word[k], wbeg = k ? end_word[k - 1] : 0;
         if (wend < wbeg || words_at + 2ll * wend > seg_cap) { st |= 4; wend = wbeg = 0; }  // corrupt directory
-        const uint16_t *w = words + wbeg;
-        const uint32_t nw = wend - wbeg;
-        uint32_t wp = 0;  // warp-uniform
+        const uint32_t u_lim = (wend + 1) >> 1;       // units holding words of this chunk end here
+        uint32_t wp = wbeg;                           // absolute word index, warp-uniform
+        uint32_t fill_u = wbeg >> 1, ready_u = fill_u;
+        auto issue_group = [&]() {
+#pragma unroll
+            for (int i = 0; i < kGroupUnits / 32; ++i) {
+                const uint32_t u = fill_u + i * 32 + lane;
+                if (u < u_lim) cp_async4(ring_s + (u & (kRingUnits - 1)) * 4, units + u);
+            }
+            cp_async_commit();
+            fill_u += kGroupUnits;
+        };
+        __syncwarp();  // the previous chunk's readers are done with the ring
+        issue_group();
+        issue_group();
+        cp_async_wait<1>();
+        __syncwarp();
+        ready_u = fill_u - kGroupUnits;
+        // before an event that may consume up to 32 words: make sure they have landed
+        auto ensure = [&]() {
+            if (((wp + 32) >> 1) + 1 > ready_u) {
+                cp_async_wait<0>();
+                __syncwarp();
+                ready_u = fill_u;
+                issue_group();
+            }
+        };
         uint32_t x = states[(size_t)k * 32 + lane];
         const int nblocks = (m + 127) >> 7;
+        auto load_ix = [&](int blk) -> int4 {
+            const int j0 = blk * 128 + lane * 4;
+            if (vec_ok && j0 + 3 < m) return __ldg(reinterpret_cast<const int4 *>(indexes + base + j0));
+            int4 b;
+            b.x = j0 + 0 < m ? indexes[base + j0 + 0] : 0;
+            b.y = j0 + 1 < m ? indexes[base + j0 + 1] : 0;
+            b.z = j0 + 2 < m ? indexes[base + j0 + 2] : 0;
+            b.w = j0 + 3 < m ? indexes[base + j0 + 3] : 0;
+            return b;
+        };
+        int4 ixn = make_int4(0, 0, 0, 0);
+        if (nblocks > 0) ixn = load_ix(0);
         for (int blk = 0; blk < nblocks; ++blk) {
             const int j0 = blk * 128 + lane * 4;
-            int32_t ix[4], res[4];
+            int32_t res[4];
             const bool full4 = vec_ok && j0 + 3 < m;
-            if (full4) {
-                const int4 b = *reinterpret_cast<const int4 *>(indexes + base + j0);
-                ix[0] = b.x; ix[1] = b.y; ix[2] = b.z; ix[3] = b.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ix[q] = j0 + q < m ? indexes[base + j0 + q] : 0;
-            }
+            const int32_t ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
+            if (blk + 1 < nblocks) ixn = load_ix(blk + 1);  // one block ahead: off the dependency chain
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const bool active = j0 + q < m;
@@ -260,13 +326,14 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                 while (s + 1 < nsyms && cd[s + 1] <= cum) ++s;
                 const uint32_t start = cd[s], freq = (uint16_t)(cd[s + 1] - start);
                 if (active) x = freq * (x >> prec) + cum - start;
+                ensure();
                 {
                     const bool need = active && x < kRansL;
                     const unsigned nm = __ballot_sync(kFull, need);
                     if (need) {
                         const uint32_t at = wp + __popc(nm & lt_mask);
                         uint32_t word = 0;
-                        if (at < nw) word = w[at]; else st |= 4;
+                        if (at < wend) word = ring16[at & (2 * kRingUnits - 1)]; else st |= 4;
                         x = (x << 16) | word;
                     }
                     wp += __popc(nm);
@@ -280,12 +347,13 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                     while (__any_sync(kFull, in)) {
                         uint32_t val = 0;
                         if (in) { val = x & maxb; x >>= bp; }
+                        ensure();
                         const bool need = in && x < kRansL;
                         const unsigned nm = __ballot_sync(kFull, need);
                         if (need) {
                             const uint32_t at = wp + __popc(nm & lt_mask);
                             uint32_t word = 0;
-                            if (at < nw) word = w[at]; else st |= 4;
+                            if (at < wend) word = ring16[at & (2 * kRingUnits - 1)]; else st |= 4;
                             x = (x << 16) | word;
                         }
                         wp += __popc(nm);
@@ -314,7 +382,8 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                 for (int q = 0; q < 4; ++q) if (j0 + q < m) out[base + j0 + q] = res[q];
             }
         }
-        if (wp != nw && lane == 0) st |= 4;
+        cp_async_wait<0>();
+        if (wp != wend && lane == 0) st |= 4;
     }
     if (st) atomicOr(status, st);
 }
@@ -363,6 +432,7 @@ k_estimate_bits(LaneParams P, const int32_t *__restrict__ symbols, const int32_t
 }  // namespace
 
 static int smem_for(const RansTables &tb) { return tb.blob_bytes <= (size_t)kMaxSmemTables ? (int)tb.blob_bytes : 0; }
+static constexpr int kRingBytes = kWarps * kRingUnits * 4;
 
 static LaneParams make_params(const RansTables &tb, int bypass, int bypass_precision, int64_t n, int chunk_syms, int n_chunks,
                               const int *n_chunks_dev)
@@ -386,8 +456,7 @@ static LaneParams make_params(const RansTables &tb, int bypass, int bypass_preci
 
 static int grid_for(int n_chunks, int sm_count)
 {
-    int g = (n_chunks + kWarps - 1) / kWarps;
-    if (g > sm_count) g = sm_count;
+    int g = n_chunks < sm_count ? n_chunks : sm_count;  // one resident CTA per SM (tables fill its shared memory)
     return g < 1 ? 1 : g;
 }
 
@@ -402,7 +471,7 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     static bool attr_done = false;
     if (!attr_done) {
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables + kRingBytes));
         attr_done = true;
     }
     if (n_chunks > 0) {
@@ -431,10 +500,10 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     static bool attr_done = false;
     if (!attr_done) {
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables + kRingBytes));
         attr_done = true;
     }
-    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem, stream>>>(P, d_seg, seg_cap, d_idx, d_out, d_status);
+    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem + kRingBytes, stream>>>(P, d_seg, seg_cap, d_idx, d_out, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

@@ -81,7 +81,10 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
     Extra keywords: ``lanes`` (1 = reference bitstream byte for byte; 0 = multi-lane container within 0.5 % of it,
     the default; N = ceil(N/32) chunks per group segment), ``ans_params_device`` (device of the float32 Gaussian
     pmf evaluation in update_state; None = the module's device, like the reference; "cpu" reproduces a
-    CPU-run reference table bit for bit)."""
+    CPU-run reference table bit for bit), ``ctx_precision`` ("fp32" = exact FP32 FMA kernel, "tf32x3" = tcgen05 tensor
+    cores with error-compensated TF32 products, "auto" = fp32 in the lanes=1 compatibility mode and tf32x3 otherwise;
+    encoder and decoder must agree) and ``ctx_accumulators`` (k-blocks of 32 accumulated in tensor memory before a
+    partial sum is drained into the FP32 register accumulator)."""
 
     def __init__(self, *args, in_channels=256, channel_groups=1, default_topo_group_method="none",
                  default_num_topo_groups=-1, topo_group_context_model=None, kernel_size=5, use_param_merger=True,
@@ -89,7 +92,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                  bypass_precision=4, data_precision=8, quantizer_type="uniform", quantizer_params=None,
                  fixed_input_shape=None, force_input_prior_shape_aligned=True, use_autoregressive_encode=True,
                  lower_bound_scale=0.11, scale_table=None, topo_group_predictor=None, lanes=0, ans_params_device=None,
-                 **kwargs):
+                 ctx_precision="auto", ctx_accumulators=4, **kwargs):
         super().__init__()
         if use_joint_ar_model_impl:
             raise NotImplementedError("use_joint_ar_model_impl (CompressAI-style serial coder) is SURVEY row f4")
@@ -120,6 +123,9 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self.lower_bound_scale = lower_bound_scale
         self.lanes = lanes
         self.ans_params_device = ans_params_device
+        if ctx_precision not in ("auto", "fp32", "tf32x3"):
+            raise ValueError(f"Unknown ctx_precision {ctx_precision}")
+        self.ctx_precision, self.ctx_accumulators = ctx_precision, ctx_accumulators
         self.scale_table = get_scale_table() if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
         self.topo_group_predictor = topo_group_predictor
         if topo_group_predictor is not None:
@@ -205,6 +211,11 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias)] + [None] * 6
         torch.cuda.synchronize(self.device)
         N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
+        prec = self.ctx_precision
+        if prec == "auto":
+            prec = "fp32" if self.lanes == 1 else "tf32x3"
+        N.check(N.lib().basic_ctx_set_precision(self._ctx, N.CTX_TF32X3 if prec == "tf32x3" else N.CTX_FP32,
+                                                int(self.ctx_accumulators)))
 
     @property
     def _ctx(self):

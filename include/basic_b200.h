@@ -112,6 +112,14 @@ int basic_ctx_set_weights(basic_ctx *m, const float *ctx_w, const float *ctx_b, 
  * (pgm_coder.py:1299-1414).  Builds the per-stage cell and position lists on the device. */
 int basic_ctx_set_map(basic_ctx *m, const int32_t *tg, int H, int W);
 int basic_ctx_num_stages(basic_ctx *m);
+/* Arithmetic of the context model.  BASIC_CTX_FP32: exact FP32 FMA kernel (the parity mode, default).
+ * BASIC_CTX_TF32X3: tcgen05 tensor cores, every product split hi*hi + hi*lo + lo*hi (error-compensated TF32,
+ * ~1e-6 relative; means / scales stay inside north_star's 1e-5); `nacc` = k-blocks (32 k each) accumulated in
+ * tensor memory before the partial sum is drained into an FP32 register accumulator (shorter = more accurate).  Encoder and decoder must use the same setting (the parameters must be bit-identical on both
+ * sides); layers the tensor path cannot take (tiny stages, channel groups not a multiple of 4) use FP32. */
+#define BASIC_CTX_FP32 0
+#define BASIC_CTX_TF32X3 1
+int basic_ctx_set_precision(basic_ctx *m, int precision, int nacc);
 /* positions of stage g (device pointer, int32 offsets into [C,H,W]) and their count */
 int basic_ctx_stage_positions(basic_ctx *m, int g, const int32_t **positions_dev, int64_t *n_pos);
 /* One autoregressive step: distribution parameters of every cell of stage g, written into `params`
