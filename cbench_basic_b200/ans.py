@@ -145,22 +145,17 @@ class _EncoderMixin:
         if sym.size != idx.size:
             raise ValueError("symbols and indexes must have the same number of elements")
         n = sym.size
-        cap = int(N.lib().basic_coder_encode_bound(self._h, n, self.lanes)) if not cache else 0
-        out = np.empty(max(cap, 1), dtype=np.uint8)
         out_len = C.c_int64(0)
-        N.check(N.lib().basic_coder_encode(self._h, sym.ptr, idx.ptr, n, self.lanes, int(bool(cache)), out.ctypes.data,
-                                           cap, C.byref(out_len), _stream(sym, idx)))
+        N.check(N.lib().basic_coder_encode(self._h, sym.ptr, idx.ptr, n, self.lanes, int(bool(cache)), None, 0,
+                                           C.byref(out_len), _stream(sym, idx)))
         self._cached = getattr(self, "_cached", 0) + (n if cache else 0)
-        return out[:out_len.value].tobytes()
+        return N.last_output(self._h) if not cache else b""
 
     def flush(self):
-        n = getattr(self, "_cached", 0)
-        cap = int(N.lib().basic_coder_encode_bound(self._h, n, self.lanes)) + 64
-        out = np.empty(cap, dtype=np.uint8)
         out_len = C.c_int64(0)
-        N.check(N.lib().basic_coder_flush(self._h, self.lanes, out.ctypes.data, cap, C.byref(out_len), 0))
+        N.check(N.lib().basic_coder_flush(self._h, self.lanes, None, 0, C.byref(out_len), 0))
         self._cached = 0
-        return out[:out_len.value].tobytes()
+        return N.last_output(self._h)
 
 
 class _DecoderMixin:

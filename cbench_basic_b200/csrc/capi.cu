@@ -16,10 +16,10 @@ int launch_rans64_encode(const RansTables &, const int32_t *, const int32_t *, i
                          long long *, int *, cudaStream_t);
 int launch_rans64_decode(const RansTables &, const uint32_t *, int64_t, void *, int, const int32_t *, int64_t, int, int,
                          int32_t *, int *, cudaStream_t);
-int launch_bls_encode(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, int, int, uint16_t *, int,
+int launch_bls_encode(const RansTables &, int, int, const int32_t *, const int32_t *, int, const void *, int, uint16_t *, int,
                       uint32_t *, uint32_t *, unsigned char *, long long *, int *, int, cudaStream_t);
-int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64_t, const int32_t *, int64_t, int, int,
-                      int32_t *, int *, int, cudaStream_t);
+int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64_t, const int32_t *, int64_t, int, int, int, int,
+                      uint32_t *, uint32_t *, int32_t *, int *, int, cudaStream_t);
 int launch_estimate_bits(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, float *, cudaStream_t);
 int launch_quantize_index(const float *, const float *, const int32_t *, int64_t, int, int, int, const float *, int, int32_t *,
                           int32_t *, float *, int, cudaStream_t);
@@ -54,6 +54,11 @@ int64_t g_launches = 0;
 static constexpr double kAutoBudget = 0.004;  // target container overhead in auto mode (bar: 0.5 %)
 static constexpr int kChunkOverhead = 132;    // 32 states + directory entry
 
+struct SliceDesc {  // mirrors rans_lanes.cu
+    long long off, n;
+    int cs, pad;
+};
+
 }  // namespace basic
 
 using namespace basic;
@@ -70,14 +75,19 @@ struct basic_coder {
     DevBuf d_scale;
     // scratch
     DevBuf in_a, in_b, out_i32, words, first, states, segs, small, stream_dev, y_dev, prior_dev, buf, params, sym_all, idx_all,
-        yhat_stage;
+        yhat_stage, slices_dev, carry_x, carry_wp;
     void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
+    // pinned host staging (grow-only): encoded output kept for basic_coder_last_output, and the stream being decoded
+    uint8_t *host_out = nullptr, *host_in = nullptr;
+    size_t host_out_cap = 0, host_in_cap = 0;
+    int64_t last_len = 0;
+    cudaEvent_t in_event = nullptr;  // completion of the last upload out of host_in
     // cache for cache=1 / flush()
     std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
     std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
     // streaming decode state
     int stream_lanes = 1;
-    std::vector<uint8_t> h_stream;
+    int64_t stream_len = 0;  // bytes of the stream in host_in / stream_dev
     int64_t stream_pos = 0;
     bool stream_set = false;
 };
@@ -128,16 +138,6 @@ int need_init(basic_coder *c)
     return BASIC_OK;
 }
 
-void chunking(int64_t n, int64_t want_chunks, int *chunk_syms, int *n_chunks)
-{
-    if (want_chunks < 1) want_chunks = 1;
-    int64_t cs = (n + want_chunks - 1) / want_chunks;
-    cs = ((cs + 127) / 128) * 128;
-    if (cs < 128) cs = 128;
-    *chunk_syms = (int)cs;
-    *n_chunks = (int)((n + cs - 1) / cs);
-}
-
 // lanes = 1: reference stream of (d_sym, d_idx) into c->segs; returns byte length via *len (host, synchronised).
 int encode_compat(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, int64_t n, cudaStream_t s, const uint8_t **d_bytes,
                   int64_t *len)
@@ -162,12 +162,16 @@ int encode_compat(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, in
     return BASIC_ERR_CUDA;
 }
 
-// One multi-lane segment into c->segs at byte offset `at` (must be 4-aligned); *seg_len host value (synchronised).
-int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, int64_t n, int lanes, size_t at, cudaStream_t s,
-                   int64_t *seg_len)
+// One multi-lane segment of `n_slices` slices (slice g = slice_n[g] symbols, laid out one after the other in
+// d_sym / d_idx) into c->segs at byte offset `at` (4-aligned); *seg_len host value (synchronised).
+// Chunk count: lanes / 32, or in auto mode as many as keep the flush overhead (132 B per chunk) inside the budget.
+int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, int n_slices, const int64_t *slice_n, int lanes,
+                   size_t at, cudaStream_t s, int64_t *seg_len)
 {
     Small *ds = c->small.as<Small>();
     Small *hs = reinterpret_cast<Small *>(c->pinned);
+    int64_t n = 0, n_max = 0;
+    for (int g = 0; g < n_slices; ++g) { n += slice_n[g]; n_max = std::max(n_max, slice_n[g]); }
     int64_t want_chunks;
     if (lanes == BASIC_LANES_AUTO) {
         BASIC_CUDA(cudaMemsetAsync(&ds->bits, 0, sizeof(float), s));
@@ -179,12 +183,27 @@ int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, i
     } else {
         want_chunks = (lanes + kLanes - 1) / kLanes;
     }
-    int chunk_syms, n_chunks;
-    chunking(n, want_chunks, &chunk_syms, &n_chunks);
+    if (want_chunks < 1) want_chunks = 1;
+    // chunk_syms[g] = ceil(n_g / want) rounded up to whole 128-symbol blocks; chunks that own nothing are dropped
+    std::vector<SliceDesc> sl((size_t)n_slices);
+    int64_t off = 0, n_chunks = 0, cs_sum = 0;
+    for (int g = 0; g < n_slices; ++g) {
+        int64_t cs = (slice_n[g] + want_chunks - 1) / want_chunks;
+        cs = std::max<int64_t>(128, ((cs + 127) / 128) * 128);
+        sl[g].off = off; sl[g].n = slice_n[g]; sl[g].cs = (int)cs; sl[g].pad = 0;
+        off += slice_n[g];
+        n_chunks = std::max(n_chunks, (slice_n[g] + cs - 1) / cs);
+        cs_sum += cs;
+    }
+    BASIC_TRY(c->slices_dev.reserve(sizeof(SliceDesc) * (size_t)std::max(n_slices, 1)));
+    if (n_slices) BASIC_CUDA(cudaMemcpyAsync(c->slices_dev.p, sl.data(), sizeof(SliceDesc) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
+    const size_t hdr = 8 + 4 * (size_t)n_slices + (size_t)n_chunks * 132;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int cap_words = attempt == 0 ? chunk_syms + chunk_syms / 4 + 64 : 12 * chunk_syms + 64;
-        cap_words = (cap_words + 7) & ~7;
-        const size_t seg_bound = 8 + (size_t)n_chunks * 132 + (size_t)n_chunks * cap_words * 2 + 8;
+        int64_t cap_words64 = attempt == 0 ? cs_sum + cs_sum / 4 + 64 : 12 * cs_sum + 64;
+        cap_words64 = (cap_words64 + 7) & ~(int64_t)7;
+        if (cap_words64 > 0x7fffffff) return value_error("chunk too large: use more lanes");
+        const int cap_words = (int)cap_words64;
+        const size_t seg_bound = hdr + (size_t)n_chunks * cap_words * 2 + 8;
         BASIC_TRY(c->words.reserve((size_t)n_chunks * cap_words * 2 + 16));
         BASIC_TRY(c->first.reserve((size_t)n_chunks * 4 + 16));
         BASIC_TRY(c->states.reserve((size_t)n_chunks * 128 + 16));
@@ -197,7 +216,7 @@ int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, i
             c->segs = bigger;
         }
         BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
-        BASIC_TRY(launch_bls_encode(c->rt, c->bypass, (int)c->bypass_precision, d_sym, d_idx, n, chunk_syms, n_chunks,
+        BASIC_TRY(launch_bls_encode(c->rt, c->bypass, (int)c->bypass_precision, d_sym, d_idx, n_slices, c->slices_dev.p, (int)n_chunks,
                                     c->words.as<uint16_t>(), cap_words, c->first.as<uint32_t>(), c->states.as<uint32_t>(),
                                     c->segs.as<unsigned char>() + at, &ds->len[0], &ds->status, c->sm_count, s));
         BASIC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, s));
@@ -210,32 +229,69 @@ int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, i
     return BASIC_ERR_CUDA;
 }
 
-int copy_out(const void *d_src, int64_t len, uint8_t *out, int64_t cap, cudaStream_t s)
+int reserve_pinned(uint8_t **buf, size_t *cap, size_t bytes)
 {
-    if (len > cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    if (bytes <= *cap) return BASIC_OK;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    BASIC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(buf), want, cudaHostAllocDefault));
+    *cap = want;
+    return BASIC_OK;
+}
+
+// Delivers `len` encoded bytes that live on the device: into the caller's buffer, or (out == NULL) into the
+// coder's pinned staging buffer, from where basic_coder_last_output hands them out without another device trip.
+int copy_out(basic_coder *c, const void *d_src, int64_t len, uint8_t *out, int64_t cap, cudaStream_t s)
+{
+    if (!out) {
+        BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)len));
+        out = c->host_out;
+        c->last_len = len;
+    } else if (len > cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
     if (len > 0) BASIC_CUDA(cudaMemcpyAsync(out, d_src, (size_t)len, cudaMemcpyDefault, s));
     BASIC_CUDA(cudaStreamSynchronize(s));
     return BASIC_OK;
 }
 
-// Parses a segment header that lives in host memory.
-int parse_segment(const uint8_t *p, int64_t avail, int64_t n, int *chunk_syms, int *n_chunks, int64_t *seg_len)
+// Parses a segment header that lives in host memory: n_slices slices of slice_n[g] symbols are expected.
+struct SegInfo {
+    int n_chunks = 0, n_slices = 0;
+    std::vector<int> cs;  // chunk_syms per slice
+    int64_t len = 0;      // bytes of the segment
+};
+
+int parse_segment(const uint8_t *p, int64_t avail, int n_slices, const int64_t *slice_n, SegInfo *out)
 {
     if (avail < 8) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
-    uint32_t nc, cs;
+    uint32_t nc, ns;
     memcpy(&nc, p, 4);
-    memcpy(&cs, p + 4, 4);
-    if (cs == 0 || cs % 128 || (int64_t)nc != (n + cs - 1) / cs) { set_error("multi-lane segment does not match the number of indexes"); return BASIC_ERR_STREAM; }
-    const int64_t hdr = 8 + (int64_t)nc * 132;
-    if (avail < hdr) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
+    memcpy(&ns, p + 4, 4);
+    if ((int64_t)ns != n_slices || avail < 8 + 4 * (int64_t)ns) { set_error("multi-lane segment does not match the coding groups"); return BASIC_ERR_STREAM; }
+    out->cs.resize(ns);
+    int64_t nc_need = 0;  // the encoder drops chunks that own nothing: n_chunks = max over slices of ceil(n_g / cs_g)
+    for (uint32_t g = 0; g < ns; ++g) {
+        uint32_t cs;
+        memcpy(&cs, p + 8 + 4 * (int64_t)g, 4);
+        if (cs == 0 || cs % 128 || cs > 0x7fffff80u || (slice_n[g] + cs - 1) / cs > (int64_t)nc) {
+            set_error("multi-lane segment does not match the number of indexes");
+            return BASIC_ERR_STREAM;
+        }
+        out->cs[g] = (int)cs;
+        nc_need = std::max(nc_need, (slice_n[g] + cs - 1) / cs);
+    }
+    if (nc_need != (int64_t)nc) { set_error("multi-lane segment does not match the number of indexes"); return BASIC_ERR_STREAM; }
+    const int64_t hdr = 8 + 4 * (int64_t)ns + (int64_t)nc * 132;
+    if (nc > 0x3fffffffu || avail < hdr) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
     uint32_t total_words = 0;
-    if (nc) memcpy(&total_words, p + 8 + 4 * (int64_t)(nc - 1), 4);
+    if (nc) memcpy(&total_words, p + 8 + 4 * (int64_t)ns + 4 * (int64_t)(nc - 1), 4);
     int64_t len = hdr + 2 * (int64_t)total_words;
     len = (len + 3) & ~(int64_t)3;
     if (len > avail) { set_error("truncated multi-lane stream"); return BASIC_ERR_STREAM; }
-    *chunk_syms = (int)cs;
-    *n_chunks = (int)nc;
-    *seg_len = len;
+    out->n_chunks = (int)nc;
+    out->n_slices = (int)ns;
+    out->len = len;
     return BASIC_OK;
 }
 
@@ -295,9 +351,12 @@ void basic_coder_destroy(basic_coder *c)
     DeviceGuard guard(c->device);
     DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
                       &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
-                      &c->idx_all, &c->yhat_stage};
+                      &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp};
     for (DevBuf *b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->host_out) cudaFreeHost(c->host_out);
+    if (c->host_in) cudaFreeHost(c->host_in);
+    if (c->in_event) cudaEventDestroy(c->in_event);
     if (c->tt) tans_delete(c->tt);
     delete c;
 }
@@ -354,7 +413,7 @@ int64_t basic_coder_encode_bound(basic_coder *c, int64_t n, int lanes)
 {
     if (c && c->kind == BASIC_KIND_TANS) return n * (int64_t)c->precision / 8 + 16;
     if (lanes == BASIC_LANES_REFERENCE) return (12 * n + 64) * 4;
-    return 16 + ((n + 127) / 128) * 132 + 24 * n + 64;
+    return 20 + ((n + 127) / 128) * 132 + 24 * n + 64;
 }
 
 int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, int lanes, int cache,
@@ -388,7 +447,7 @@ int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *in
         BASIC_CUDA(cudaStreamSynchronize(s));
         if (hs->status & 8) return value_error("Destination buffer is too small");
         BASIC_TRY(status_error(hs->status));
-        BASIC_TRY(copy_out(c->segs.p, hs->len[0], out, out_cap, s));
+        BASIC_TRY(copy_out(c, c->segs.p, hs->len[0], out, out_cap, s));
         if (out_len) *out_len = hs->len[0];
         return BASIC_OK;
     }
@@ -396,14 +455,14 @@ int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *in
         const uint8_t *d_bytes;
         int64_t len;
         BASIC_TRY(encode_compat(c, d_sym, d_idx, n, s, &d_bytes, &len));
-        BASIC_TRY(copy_out(d_bytes, len, out, out_cap, s));
+        BASIC_TRY(copy_out(c, d_bytes, len, out, out_cap, s));
         if (out_len) *out_len = len;
         return BASIC_OK;
     }
     // multi-lane container: magic | segment
     BASIC_TRY(c->segs.reserve(64));
     int64_t seg_len = 0;
-    BASIC_TRY(encode_segment(c, d_sym, d_idx, n, lanes, 4, s, &seg_len));
+    BASIC_TRY(encode_segment(c, d_sym, d_idx, 1, &n, lanes, 4, s, &seg_len));
     if (cache) {
         std::vector<uint8_t> seg((size_t)seg_len);
         BASIC_CUDA(cudaMemcpyAsync(seg.data(), c->segs.as<unsigned char>() + 4, (size_t)seg_len, cudaMemcpyDeviceToHost, s));
@@ -412,8 +471,16 @@ int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *in
         return BASIC_OK;
     }
     BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
-    BASIC_TRY(copy_out(c->segs.p, 4 + seg_len, out, out_cap, s));
+    BASIC_TRY(copy_out(c, c->segs.p, 4 + seg_len, out, out_cap, s));
     if (out_len) *out_len = 4 + seg_len;
+    return BASIC_OK;
+}
+
+int basic_coder_last_output(basic_coder *c, const uint8_t **ptr, int64_t *len)
+{
+    if (!c || !ptr || !len) return value_error("null argument");
+    *ptr = c->host_out;
+    *len = c->last_len;
     return BASIC_OK;
 }
 
@@ -431,7 +498,11 @@ int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, 
     }
     int64_t total = 4;
     for (auto &sg : c->cache_segments) total += (int64_t)sg.size();
-    if (total > out_cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    if (!out) {
+        BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)total));
+        out = c->host_out;
+        c->last_len = total;
+    } else if (total > out_cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
     std::vector<uint8_t> all((size_t)total);
     memcpy(all.data(), &kMagic, 4);
     size_t at = 4;
@@ -449,19 +520,31 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
     DeviceGuard guard(c->device);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (len < 0) return value_error("negative length");
-    c->h_stream.resize((size_t)len);
-    if (len) BASIC_CUDA(cudaMemcpyAsync(c->h_stream.data(), encoded, (size_t)len, cudaMemcpyDefault, s));
+    // host copy in pinned memory (segment directories are parsed on the host; the upload runs asynchronously)
+    if (c->in_event && (size_t)len + 64 > c->host_in_cap) BASIC_CUDA(cudaEventSynchronize(c->in_event));
+    BASIC_TRY(reserve_pinned(&c->host_in, &c->host_in_cap, (size_t)len + 64));
+    if ((size_t)len + 64 > c->stream_dev.cap) BASIC_CUDA(cudaStreamSynchronize(s));
     BASIC_TRY(c->stream_dev.reserve((size_t)len + 64));
-    BASIC_CUDA(cudaMemsetAsync(c->stream_dev.p, 0, (size_t)len + 64, s));
-    if (len) BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyDefault, s));
-    BASIC_CUDA(cudaStreamSynchronize(s));
+    if (len && is_device_ptr(encoded)) {
+        BASIC_CUDA(cudaMemcpyAsync(c->host_in, encoded, (size_t)len, cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyDeviceToDevice, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+    } else if (len) {
+        if (!c->in_event) BASIC_CUDA(cudaEventCreateWithFlags(&c->in_event, cudaEventDisableTiming));
+        BASIC_CUDA(cudaEventSynchronize(c->in_event));  // an earlier upload out of host_in may still be in flight
+        memcpy(c->host_in, encoded, (size_t)len);       // the GPU keeps working on what is already queued on `s`
+        BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, c->host_in, (size_t)len, cudaMemcpyHostToDevice, s));
+        BASIC_CUDA(cudaEventRecord(c->in_event, s));
+    }
+    BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, s));
+    c->stream_len = len;
     c->stream_lanes = lanes;
     c->stream_set = true;
     if (lanes == BASIC_LANES_REFERENCE) {
         c->stream_pos = -1;  // state is initialised by the first decode_stream launch
     } else {
         uint32_t magic = 0;
-        if (len >= 4) memcpy(&magic, c->h_stream.data(), 4);
+        if (len >= 4) memcpy(&magic, c->host_in, 4);
         if (magic != kMagic) { c->stream_set = false; set_error("not a multi-lane (BLS1) container"); return BASIC_ERR_STREAM; }
         c->stream_pos = 4;
     }
@@ -485,18 +568,17 @@ int basic_coder_decode_stream(basic_coder *c, const int32_t *indexes, int64_t n,
     BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
     if (c->stream_lanes == BASIC_LANES_REFERENCE) {
         const int init = c->stream_pos < 0;
-        BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), (int64_t)c->h_stream.size() / 4, &ds->len[2], init, d_idx,
+        BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), c->stream_len / 4, &ds->len[2], init, d_idx,
                                        n, c->bypass, (int)c->bypass_precision, d_out, &ds->status, s));
         c->stream_pos = 0;
     } else {
-        int chunk_syms = 128, n_chunks = 0;
-        int64_t seg_len = 0;
-        if (n > 0 || c->stream_pos < (int64_t)c->h_stream.size()) {
-            BASIC_TRY(parse_segment(c->h_stream.data() + c->stream_pos, (int64_t)c->h_stream.size() - c->stream_pos, n, &chunk_syms,
-                                    &n_chunks, &seg_len));
+        if (n > 0 || c->stream_pos < c->stream_len) {
+            SegInfo si;
+            BASIC_TRY(parse_segment(c->host_in + c->stream_pos, c->stream_len - c->stream_pos, 1, &n, &si));
             BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
-                                        seg_len, d_idx, n, chunk_syms, n_chunks, d_out, &ds->status, c->sm_count, s));
-            c->stream_pos += seg_len;
+                                        si.len, d_idx, n, si.cs[0], si.n_chunks, 1, 0, nullptr, nullptr, d_out, &ds->status,
+                                        c->sm_count, s));
+            c->stream_pos += si.len;
         }
     }
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -641,7 +723,7 @@ int basic_ctx_stage_params(basic_ctx *m, int g, const float *buf, const float *p
 int64_t basic_ypath_encode_bound(basic_coder *c, int B, int C, int H, int W, int lanes)
 {
     const int64_t n = (int64_t)B * C * H * W;
-    return basic_coder_encode_bound(c, n, lanes) + 64 + 16 * (int64_t)H * W * 33;  // + per-stage headers (scanline worst case)
+    return basic_coder_encode_bound(c, n, lanes) + 64 + 4 * (int64_t)C * H * W;  // + one chunk_syms word per coding group
 }
 
 static int ypath_setup(basic_coder *c, basic_ctx *model, int B, int C, int H, int W, int *S)
@@ -683,9 +765,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
     const float *params_src = params;
-    std::vector<int64_t> seg_at, seg_len;
-    size_t at = 4, done = 0;
-    if (lanes != BASIC_LANES_REFERENCE) BASIC_TRY(c->segs.reserve(64));
+    // the encoder knows y: all groups' symbols and indexes first (group g's context = the reconstructions of groups
+    // < g, written back by the quantiser), then ONE coding pass over all of them
+    std::vector<int64_t> slice_n;
+    size_t done = 0;
     for (int g = 0; g < S; ++g) {
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
@@ -696,14 +779,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             params_src = d_prior;
         }
         const int64_t cnt = (int64_t)B * n_pos;
+        slice_n.push_back(cnt);
         if (cnt == 0) continue;
         BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                         sym + done, idx + done, buf, c->sm_count, s));
-        if (lanes != BASIC_LANES_REFERENCE) {
-            int64_t len = 0;
-            BASIC_TRY(encode_segment(c, sym + done, idx + done, cnt, lanes, at, s, &len));
-            at += (size_t)len;
-        }
         done += (size_t)cnt;
     }
     if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
@@ -711,13 +790,17 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         const uint8_t *d_bytes;
         int64_t len;
         BASIC_TRY(encode_compat(c, sym, idx, (int64_t)done, s, &d_bytes, &len));
-        BASIC_TRY(copy_out(d_bytes, len, out, out_cap, s));
+        BASIC_TRY(copy_out(c, d_bytes, len, out, out_cap, s));
         if (out_len) *out_len = len;
         return BASIC_OK;
     }
+    // multi-lane container: magic | one segment with one slice per coding group (lane states carried across groups)
+    BASIC_TRY(c->segs.reserve(64));
+    int64_t seg_len = 0;
+    BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));
     BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
-    BASIC_TRY(copy_out(c->segs.p, (int64_t)at, out, out_cap, s));
-    if (out_len) *out_len = (int64_t)at;
+    BASIC_TRY(copy_out(c, c->segs.p, 4 + seg_len, out, out_cap, s));
+    if (out_len) *out_len = 4 + seg_len;
     return BASIC_OK;
 }
 
@@ -732,42 +815,58 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const size_t n = (size_t)B * C * HW;
     const float *d_prior;
     BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
-    BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     float *buf = c->buf.as<float>(), *params = c->params.as<float>();
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
     const float *params_src = params;
     Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
     BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
+    // memory and upload it while the GPU is busy
+    if (model) BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s));
+    BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
+    // per-group symbol counts = the slices of the segment
+    std::vector<int64_t> slice_n((size_t)S);
+    for (int g = 0; g < S; ++g) {
+        const int32_t *pos = nullptr;
+        int64_t n_pos = (int64_t)C * HW;
+        if (model) BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
+        slice_n[g] = (int64_t)B * n_pos;
+    }
+    SegInfo si;
+    if (lanes != BASIC_LANES_REFERENCE) {
+        BASIC_TRY(parse_segment(c->host_in + c->stream_pos, c->stream_len - c->stream_pos, S, slice_n.data(), &si));
+        BASIC_TRY(c->carry_x.reserve((size_t)si.n_chunks * 128 + 16));
+        BASIC_TRY(c->carry_wp.reserve((size_t)si.n_chunks * 4 + 16));
+    }
     for (int g = 0; g < S; ++g) {
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
-            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
+            if (g > 0) BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
             params_src = d_prior;
         }
-        const int64_t cnt = (int64_t)B * n_pos;
-        if (cnt == 0) continue;
-        BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                        nullptr, idx, nullptr, c->sm_count, s));
+        const int64_t cnt = slice_n[g];
+        if (cnt > 0)
+            BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
+                                            nullptr, idx, nullptr, c->sm_count, s));
         if (lanes == BASIC_LANES_REFERENCE) {
+            if (cnt == 0) continue;
             const int init = c->stream_pos < 0;
-            BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), (int64_t)c->h_stream.size() / 4, &ds->len[2], init, idx,
+            BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), c->stream_len / 4, &ds->len[2], init, idx,
                                            cnt, c->bypass, (int)c->bypass_precision, sym, &ds->status, s));
             c->stream_pos = 0;
         } else {
-            int chunk_syms, n_chunks;
-            int64_t seg_len;
-            BASIC_TRY(parse_segment(c->h_stream.data() + c->stream_pos, (int64_t)c->h_stream.size() - c->stream_pos, cnt, &chunk_syms,
-                                    &n_chunks, &seg_len));
+            // every slice is launched, empty ones too: the lane states must travel from slice to slice
             BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
-                                        seg_len, idx, cnt, chunk_syms, n_chunks, sym, &ds->status, c->sm_count, s));
-            c->stream_pos += seg_len;
+                                        si.len, idx, cnt, si.cs[g], si.n_chunks, S, g, c->carry_x.as<uint32_t>(),
+                                        c->carry_wp.as<uint32_t>(), sym, &ds->status, c->sm_count, s));
         }
-        BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
+        if (cnt > 0) BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
     }
+    if (lanes != BASIC_LANES_REFERENCE) c->stream_pos += si.len;
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
     BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     BASIC_CUDA(cudaStreamSynchronize(s));

@@ -7,8 +7,12 @@
 //   every lane moves its operands with one 128-bit load / store per 128-symbol block.  Within one event
 //   (a coding step, or one escape sub-step) the lanes that renormalise take consecutive words in lane
 //   order: a warp ballot + popc prefix gives each lane its word, no atomics, no divergence.
-//   Segment bytes: u32 n_chunks | u32 chunk_syms | u32 end_word[n_chunks] (cumulative) | u32 state[n_chunks][32] |
-//   u16 words | zero pad to 4 bytes.
+//   A segment may consist of several SLICES (the y path: one per coding group): chunk k owns symbols
+//   [k * chunk_syms[g], (k + 1) * chunk_syms[g]) of every slice g and codes them slice after slice with the lane states
+//   carried over -- one state flush per lane for the whole segment, and the decoder can stop after any slice, compute
+//   the next group's parameters, and continue (states parked in HBM between launches).
+//   Segment bytes: u32 n_chunks | u32 n_slices | u32 chunk_syms[n_slices] | u32 end_word[n_chunks] (cumulative) |
+//   u32 state[n_chunks][32] | u16 words | zero pad to 4 bytes.
 //
 // Tables (u16 CDFs + bucket LUTs, tables.cu) are staged once per CTA into shared memory.
 #include "common.cuh"
@@ -19,7 +23,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSegHdr = 8;  // u32 n_chunks | u32 chunk_syms
+constexpr int kSegHdr = 8;  // u32 n_chunks | u32 n_slices, followed by u32 chunk_syms[n_slices]
 
 __device__ inline const TableView stage_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
                                                 bool to_smem, unsigned char *smem)
@@ -32,15 +36,22 @@ __device__ inline const TableView stage_tables(const void *blob, size_t blob_byt
     return make_view(smem, meta_bytes, cdf16_bytes);
 }
 
+struct SliceDesc {  // one slice of a segment: `n` symbols starting at `off` in the operand arrays
+    long long off, n;
+    int cs, pad;
+};
+
 struct LaneParams {
     const void *blob;
     size_t blob_bytes, meta_bytes, cdf16_bytes;
     int tables_in_smem;
     int T, precision, bypass, bypass_precision;
-    long long n;            // symbols in the segment
-    int chunk_syms;         // multiple of 128
+    long long n;            // symbols in the slice being coded (decoder) / unused (encoder)
+    int chunk_syms;         // chunk_syms of that slice, multiple of 128
     const int *n_chunks_dev;  // device scalar (the auto mode decides it on the device); nullptr -> n_chunks
     int n_chunks;
+    int n_slices;           // encoder: slices of the segment, walked last to first
+    const SliceDesc *slices;
 };
 
 // ------------------------------------------------------------------------------------------------ encode
@@ -59,15 +70,20 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
     const int prec = P.precision;
     const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
     const uint32_t xmax_bits = 1u << (32 - bp);
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
     for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
-        const long long base = (long long)k * P.chunk_syms;
-        const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
         uint16_t *wbuf = scratch + (size_t)k * cap_words;
         int pos = cap_words;  // warp-uniform
         uint32_t x = kRansL;
+        for (int g = P.n_slices - 1; g >= 0; --g) {  // the encoder walks the chunk's symbols backwards
+        const SliceDesc sd = P.slices[g];
+        const long long rem = sd.n - (long long)k * sd.cs;
+        if (rem <= 0) continue;
+        const long long base = sd.off + (long long)k * sd.cs;
+        const int m = (int)(rem < sd.cs ? rem : sd.cs);
+        const bool vec_ok = ptr_ok && (sd.off & 3) == 0;
         const int nblocks = (m + 127) >> 7;
         auto load_ops = [&](int blk, int32_t(&sy)[4], int32_t(&ix)[4]) {
             const int j0 = blk * 128 + lane * 4;
@@ -163,6 +179,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                 }
             }
         }
+        }
         states[(size_t)k * 32 + lane] = x;
         if (lane == 0) first_word[k] = (uint32_t)(pos < 0 ? 0 : pos);
     }
@@ -171,8 +188,9 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
 
 // One CTA: cumulative word counts -> directory, plus the total segment size in bytes.
 __global__ void __launch_bounds__(1024)
-k_bls_scan(const int *n_chunks_dev, int n_chunks_arg, int chunk_syms, const uint32_t *__restrict__ first_word, int cap_words,
-           uint32_t *__restrict__ seg /* segment header in the output buffer */, long long *seg_bytes)
+k_bls_scan(const int *n_chunks_dev, int n_chunks_arg, int n_slices, const SliceDesc *__restrict__ slices,
+           const uint32_t *__restrict__ first_word, int cap_words, uint32_t *__restrict__ seg /* segment header in the output buffer */,
+           long long *seg_bytes)
 {
     __shared__ uint32_t part[1024];
     const int n_chunks = n_chunks_dev ? *n_chunks_dev : n_chunks_arg;
@@ -189,8 +207,9 @@ k_bls_scan(const int *n_chunks_dev, int n_chunks_arg, int chunk_syms, const uint
         uint32_t run = 0;
         for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
         seg[0] = (uint32_t)n_chunks;
-        seg[1] = (uint32_t)chunk_syms;
-        const long long words_at = kSegHdr + 4ll * n_chunks + 128ll * n_chunks;
+        seg[1] = (uint32_t)n_slices;
+        for (int g = 0; g < n_slices; ++g) seg[2 + g] = (uint32_t)slices[g].cs;
+        const long long words_at = kSegHdr + 4ll * n_slices + 4ll * n_chunks + 128ll * n_chunks;
         long long total = words_at + 2ll * run;
         total = (total + 3) & ~3ll;
         *seg_bytes = total;
@@ -201,20 +220,20 @@ k_bls_scan(const int *n_chunks_dev, int n_chunks_arg, int chunk_syms, const uint
         const int k = tid * per + i;
         if (k < n_chunks) {
             run += (uint32_t)cap_words - first_word[k];
-            seg[2 + k] = run;  // cumulative END of chunk k, in words
+            seg[2 + n_slices + k] = run;  // cumulative END of chunk k, in words
         }
     }
 }
 
 // Gather: states + words of every chunk into the contiguous segment.
 __global__ void __launch_bounds__(256)
-k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, const uint16_t *__restrict__ scratch, int cap_words,
+k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, int n_slices, const uint16_t *__restrict__ scratch, int cap_words,
              const uint32_t *__restrict__ first_word, const uint32_t *__restrict__ states, unsigned char *__restrict__ seg)
 {
     const int n_chunks = n_chunks_dev ? *n_chunks_dev : n_chunks_arg;
-    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2;
-    uint32_t *out_states = reinterpret_cast<uint32_t *>(seg) + 2 + n_chunks;
-    uint16_t *out_words = reinterpret_cast<uint16_t *>(seg + kSegHdr + 4ll * n_chunks + 128ll * n_chunks);
+    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2 + n_slices;
+    uint32_t *out_states = reinterpret_cast<uint32_t *>(seg) + 2 + n_slices + n_chunks;
+    uint16_t *out_words = reinterpret_cast<uint16_t *>(seg + kSegHdr + 4ll * n_slices + 4ll * n_chunks + 128ll * n_chunks);
     for (int k = blockIdx.x; k < n_chunks; k += gridDim.x) {
         if (threadIdx.x < 32) out_states[(size_t)k * 32 + threadIdx.x] = states[(size_t)k * 32 + threadIdx.x];
         const uint32_t end = end_word[k], beg = k ? end_word[k - 1] : 0;
@@ -239,7 +258,8 @@ template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async
 
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
-             int32_t *__restrict__ out, int *status)
+             int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
+             uint32_t *__restrict__ carry_wp, int *status)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     // ring first (fixed size), tables behind it
@@ -254,21 +274,24 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     const int prec = P.precision;
     const uint32_t pmask = (1u << prec) - 1;
     const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
-    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2;
+    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2 + seg_slices;
     const uint32_t *states = end_word + n_chunks;
-    const long long words_at = kSegHdr + 4ll * n_chunks + 128ll * n_chunks;
+    const long long words_at = kSegHdr + 4ll * seg_slices + 4ll * n_chunks + 128ll * n_chunks;
     const uint32_t *units = reinterpret_cast<const uint32_t *>(seg + words_at);  // 2 words per unit, 4-byte aligned
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
     for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
         const long long base = (long long)k * P.chunk_syms;
-        const int m = (int)(P.n - base < P.chunk_syms ? P.n - base : P.chunk_syms);
+        const long long rem = P.n - base;
+        const int m = (int)(rem <= 0 ? 0 : rem < P.chunk_syms ? rem : P.chunk_syms);
         uint32_t wend = end_word[k], wbeg = k ? end_word[k - 1] : 0;
         if (wend < wbeg || words_at + 2ll * wend > seg_cap) { st |= 4; wend = wbeg = 0; }  // corrupt directory
         const uint32_t u_lim = (wend + 1) >> 1;       // units holding words of this chunk end here
-        uint32_t wp = wbeg;                           // absolute word index, warp-uniform
-        uint32_t fill_u = wbeg >> 1, ready_u = fill_u;
+        // absolute word index, warp-uniform; a later slice continues where the previous launch stopped
+        uint32_t wp = first_slice ? wbeg : carry_wp[k];
+        if (wp < wbeg || wp > wend) { st |= 4; wp = wend; }
+        uint32_t fill_u = wp >> 1, ready_u = fill_u;
         auto issue_group = [&]() {
 #pragma unroll
             for (int i = 0; i < kGroupUnits / 32; ++i) {
@@ -293,7 +316,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                 issue_group();
             }
         };
-        uint32_t x = states[(size_t)k * 32 + lane];
+        uint32_t x = first_slice ? states[(size_t)k * 32 + lane] : carry_x[(size_t)k * 32 + lane];
         const int nblocks = (m + 127) >> 7;
         auto load_ix = [&](int blk) -> int4 {
             const int j0 = blk * 128 + lane * 4;
@@ -383,7 +406,12 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
             }
         }
         cp_async_wait<0>();
-        if (wp != wend && lane == 0) st |= 4;
+        if (last_slice) {
+            if (wp != wend && lane == 0) st |= 4;
+        } else {
+            carry_x[(size_t)k * 32 + lane] = x;
+            if (lane == 0) carry_wp[k] = wp;
+        }
     }
     if (st) atomicOr(status, st);
 }
@@ -435,7 +463,7 @@ static int smem_for(const RansTables &tb) { return tb.blob_bytes <= (size_t)kMax
 static constexpr int kRingBytes = kWarps * kRingUnits * 4;
 
 static LaneParams make_params(const RansTables &tb, int bypass, int bypass_precision, int64_t n, int chunk_syms, int n_chunks,
-                              const int *n_chunks_dev)
+                              int n_slices, const SliceDesc *slices)
 {
     LaneParams P;
     P.blob = tb.blob.p;
@@ -450,7 +478,9 @@ static LaneParams make_params(const RansTables &tb, int bypass, int bypass_preci
     P.n = n;
     P.chunk_syms = chunk_syms;
     P.n_chunks = n_chunks;
-    P.n_chunks_dev = n_chunks_dev;
+    P.n_chunks_dev = nullptr;
+    P.n_slices = n_slices;
+    P.slices = slices;
     return P;
 }
 
@@ -460,50 +490,56 @@ static int grid_for(int n_chunks, int sm_count)
     return g < 1 ? 1 : g;
 }
 
-// Encodes one segment into `seg_out` (device).  *d_seg_bytes (device) receives its size.
-int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, const int32_t *d_sym, const int32_t *d_idx,
-                      int64_t n, int chunk_syms, int n_chunks, uint16_t *d_scratch, int cap_words, uint32_t *d_first,
-                      uint32_t *d_states, unsigned char *d_seg_out, long long *d_seg_bytes, int *d_status, int sm_count,
-                      cudaStream_t stream)
+static int set_attrs()
 {
-    const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, nullptr);
-    const int smem = smem_for(tb);
     static bool attr_done = false;
     if (!attr_done) {
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables + kRingBytes));
         attr_done = true;
     }
+    return BASIC_OK;
+}
+
+// Encodes one segment of `n_slices` slices (device array `d_slices`: offsets into d_sym / d_idx, symbol counts and
+// chunk_syms) into `seg_out` (device).  *d_seg_bytes (device) receives its size.
+int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, const int32_t *d_sym, const int32_t *d_idx,
+                      int n_slices, const void *d_slices, int n_chunks, uint16_t *d_scratch, int cap_words, uint32_t *d_first,
+                      uint32_t *d_states, unsigned char *d_seg_out, long long *d_seg_bytes, int *d_status, int sm_count,
+                      cudaStream_t stream)
+{
+    const SliceDesc *sl = reinterpret_cast<const SliceDesc *>(d_slices);
+    const LaneParams P = make_params(tb, bypass, bypass_precision, 0, 128, n_chunks, n_slices, sl);
+    const int smem = smem_for(tb);
+    BASIC_TRY(set_attrs());
     if (n_chunks > 0) {
         k_bls_encode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words,
                                                                                  d_first, d_states, d_status);
         BASIC_LAUNCHED();
     }
-    k_bls_scan<<<1, 1024, 0, stream>>>(nullptr, n_chunks, chunk_syms, d_first, cap_words, reinterpret_cast<uint32_t *>(d_seg_out),
+    k_bls_scan<<<1, 1024, 0, stream>>>(nullptr, n_chunks, n_slices, sl, d_first, cap_words, reinterpret_cast<uint32_t *>(d_seg_out),
                                        d_seg_bytes);
     BASIC_LAUNCHED();
     if (n_chunks > 0) {
         int g = n_chunks < 4 * sm_count ? n_chunks : 4 * sm_count;
-        k_bls_gather<<<g, 256, 0, stream>>>(nullptr, n_chunks, d_scratch, cap_words, d_first, d_states, d_seg_out);
+        k_bls_gather<<<g, 256, 0, stream>>>(nullptr, n_chunks, n_slices, d_scratch, cap_words, d_first, d_states, d_seg_out);
         BASIC_LAUNCHED();
     }
     return BASIC_OK;
 }
 
+// Decodes slice `slice` (n symbols, chunk_syms) of a segment with seg_slices slices; lane states and word positions
+// are parked in d_carry_x [n_chunks * 32] / d_carry_wp [n_chunks] between the slices of one segment.
 int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, const unsigned char *d_seg, int64_t seg_cap,
-                      const int32_t *d_idx, int64_t n, int chunk_syms, int n_chunks, int32_t *d_out, int *d_status,
-                      int sm_count, cudaStream_t stream)
+                      const int32_t *d_idx, int64_t n, int chunk_syms, int n_chunks, int seg_slices, int slice, uint32_t *d_carry_x,
+                      uint32_t *d_carry_wp, int32_t *d_out, int *d_status, int sm_count, cudaStream_t stream)
 {
     if (n_chunks <= 0) return BASIC_OK;
-    const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, nullptr);
+    const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, 0, nullptr);
     const int smem = smem_for(tb);
-    static bool attr_done = false;
-    if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables + kRingBytes));
-        attr_done = true;
-    }
-    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem + kRingBytes, stream>>>(P, d_seg, seg_cap, d_idx, d_out, d_status);
+    BASIC_TRY(set_attrs());
+    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem + kRingBytes, stream>>>(
+        P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
@@ -513,7 +549,7 @@ int launch_estimate_bits(const RansTables &tb, int bypass, int bypass_precision,
                          int64_t n, float *d_bits, cudaStream_t stream)
 {
     if (n <= 0) return BASIC_OK;
-    const LaneParams P = make_params(tb, bypass, bypass_precision, n, 128, 0, nullptr);
+    const LaneParams P = make_params(tb, bypass, bypass_precision, n, 128, 0, 0, nullptr);
     const long long max_samples = 1 << 16;
     const long long stride = n > max_samples ? n / max_samples : 1;
     const long long samples = (n + stride - 1) / stride;

@@ -252,14 +252,13 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         p = prior.detach().to(device=self.device, dtype=torch.float32).contiguous()
         self._set_map(self._get_pgm(input.shape, pgm))
         h = self.ans_encoder.handle
-        cap = int(N.lib().basic_ypath_encode_bound(h, B, Cc, H, W, self.lanes))
-        out = np.empty(cap, dtype=np.uint8)
         out_len = C.c_int64(0)
         yhat = torch.empty_like(y) if return_yhat else None
-        N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, out.ctypes.data,
-                                           cap, C.byref(out_len), yhat.data_ptr() if return_yhat else None,
+        # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object
+        N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
+                                           C.byref(out_len), yhat.data_ptr() if return_yhat else None,
                                            torch.cuda.current_stream(self.device).cuda_stream))
-        byte_string = out[:out_len.value].tobytes()
+        byte_string = N.last_output(h)
         head = b""
         if self.fixed_input_shape is not None:
             assert B == self.fixed_input_shape[0] and tuple(input.shape[2:]) == tuple(self.fixed_input_shape[1:])

@@ -75,6 +75,10 @@ int64_t basic_coder_encode_bound(basic_coder *c, int64_t n, int lanes);
 int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, int lanes,
                        int cache, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream);
 int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream);
+/* Every encoding call (basic_coder_encode / _flush / basic_ypath_encode) accepts out == NULL: the stream then stays
+ * in the coder's own pinned host buffer and this call returns its address and length (valid until the next
+ * encoding call on the same coder).  Saves sizing and page-faulting a worst-case caller buffer. */
+int basic_coder_last_output(basic_coder *c, const uint8_t **ptr, int64_t *len);
 
 /* ---- decode_with_indexes / set_stream / decode_stream (rans64.cpp:389-598, rans64.hpp:104-124) ------- */
 int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, const int32_t *indexes, int64_t n,

@@ -578,8 +578,9 @@ int orc_tans_decode(const orc_tans_tables *tb, const uint8_t *enc, int64_t len, 
  *    interleaved lanes sharing one word stream.  Within a chunk, local symbol j belongs to lane
  *    (j % 128) / 4 and is coded at step (j / 128) * 4 + (j % 4).
  *
- *    Segment layout (little endian): u32 n_chunks | u32 chunk_syms | u32 end_word[n_chunks] (cumulative word count up to and
- *    including chunk k) | u32 state[n_chunks][32] | u16 words of chunk 0, chunk 1, ... | zero pad to 4 bytes.
+ *    Segment layout (little endian): u32 n_chunks | u32 n_slices | u32 chunk_syms[n_slices] | u32 end_word[n_chunks]
+ *    (cumulative word count up to and including chunk k) | u32 state[n_chunks][32] | u16 words of chunk 0, chunk 1, ...
+ *    | zero pad to 4 bytes.  Slices: see orc_bls_encode_slices.
  * ---------------------------------------------------------------------------------------------- */
 #define BLS_LANES 32
 #define BLS_L (1u << 16)
@@ -590,16 +591,15 @@ static inline int64_t bls_local_index(int64_t step, int lane) { return (step >> 
 
 int64_t orc_bls_num_chunks(int64_t n, int64_t chunk_syms) { return n <= 0 ? 0 : (n + chunk_syms - 1) / chunk_syms; }
 
-/* Encode one chunk; words are written back-to-front into wbuf[cap]; returns first word index. */
-static int bls_encode_chunk(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int64_t m,
-                            uint16_t *wbuf, int64_t cap, int64_t *first, uint32_t *states)
+/* Encode the m symbols of one slice of one chunk on top of the running lane states x[] ; words are written
+ * back-to-front into wbuf, *p is the index of the first word written so far. */
+static int bls_encode_slice(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int64_t m,
+                            uint16_t *wbuf, int64_t *pp, uint32_t *x)
 {
-    uint32_t x[BLS_LANES];
     bls_esc *esc = (bls_esc *)malloc(sizeof(bls_esc) * BLS_LANES);
     uint32_t start[BLS_LANES], freq[BLS_LANES];
     int active[BLS_LANES];
-    for (int l = 0; l < BLS_LANES; ++l) x[l] = BLS_L;
-    int64_t p = cap;
+    int64_t p = *pp;
     const int prec = tb->precision, bp = tb->bypass_precision;
     const int64_t nsteps = ((m + 127) / 128) * 4;
     int rc = ORC_OK;
@@ -649,39 +649,56 @@ static int bls_encode_chunk(const orc_rans64_tables *tb, const int32_t *sym, con
         }
     }
     free(esc);
-    if (rc) return rc;
-    memcpy(states, x, sizeof(x));
-    *first = p;
-    return ORC_OK;
+    *pp = p;
+    return rc;
 }
 
 /* Encode a whole segment.  out must hold orc_bls_bound(n, chunk_syms) bytes. */
 int64_t orc_bls_bound(int64_t n, int64_t chunk_syms)
 {
     int64_t nc = orc_bls_num_chunks(n, chunk_syms);
-    return 8 + nc * (4 + 128) + n * 24 + 64;
+    return 12 + nc * (4 + 128) + n * 24 + 64;
 }
 
-int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int64_t n,
-                   int64_t chunk_syms, uint8_t *out, int64_t cap, int64_t *out_len)
+/* General form: the segment's symbols are n_slices consecutive runs (slice g has slice_n[g] symbols and follows
+ * slice g - 1 in sym / idx).  Chunk k owns symbols [k * slice_cs[g], min(slice_n[g], (k + 1) * slice_cs[g])) of EVERY
+ * slice (possibly none); its 32 lanes code slice 0 first, then slice 1, ... with the lane states carried over, so a
+ * decoder can stop after any slice, learn more (the next group's parameters) and continue.  Each slice starts on
+ * a fresh 128-symbol block (the tail of its last block is idle).  One state flush per lane for the whole segment. */
+int orc_bls_encode_slices(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int n_slices,
+                          const int64_t *slice_n, const int64_t *slice_cs, int64_t nc, uint8_t *out, int64_t cap, int64_t *out_len)
 {
-    if (chunk_syms <= 0 || chunk_syms % 128) return ORC_ERR_GENERIC;
-    const int64_t nc = orc_bls_num_chunks(n, chunk_syms);
-    int64_t hdr = 8 + nc * 4 + nc * 128;
+    int64_t wcap = 64, total = 0;
+    for (int g = 0; g < n_slices; ++g) {
+        if (slice_cs[g] <= 0 || slice_cs[g] % 128 || orc_bls_num_chunks(slice_n[g], slice_cs[g]) > nc) return ORC_ERR_GENERIC;
+        /* callers pass nc = max over slices of ceil(n_g / cs_g): chunks that own nothing are not stored */
+        wcap += slice_cs[g] * 12;
+        total += slice_n[g];
+    }
+    int64_t hdr = 8 + 4 * (int64_t)n_slices + nc * 4 + nc * 128;
     if (cap < hdr) return ORC_ERR_CAPACITY;
     uint32_t *h32 = (uint32_t *)out;
     h32[0] = (uint32_t)nc;
-    h32[1] = (uint32_t)chunk_syms;
-    uint32_t *nwords = h32 + 2, *states = h32 + 2 + nc;
+    h32[1] = (uint32_t)n_slices;
+    for (int g = 0; g < n_slices; ++g) h32[2 + g] = (uint32_t)slice_cs[g];
+    uint32_t *nwords = h32 + 2 + n_slices, *states = nwords + nc;
     int64_t pos = hdr, cum_words = 0;
-    const int64_t wcap = chunk_syms * 12 + 64;
     uint16_t *wbuf = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)wcap);
     int rc = ORC_OK;
     for (int64_t k = 0; k < nc && !rc; ++k) {
-        const int64_t b = k * chunk_syms, m = (n - b) < chunk_syms ? (n - b) : chunk_syms;
-        int64_t first;
-        rc = bls_encode_chunk(tb, sym + b, idx + b, m, wbuf, wcap, &first, states + k * 32);
+        uint32_t x[BLS_LANES];
+        for (int l = 0; l < BLS_LANES; ++l) x[l] = BLS_L;
+        int64_t first = wcap, off = total;
+        for (int g = n_slices - 1; g >= 0 && !rc; --g) {   /* the encoder walks the chunk's symbols backwards */
+            off -= slice_n[g];
+            const int64_t b = k * slice_cs[g];
+            int64_t m = slice_n[g] - b;
+            if (m > slice_cs[g]) m = slice_cs[g];
+            if (m <= 0) continue;
+            rc = bls_encode_slice(tb, sym + off + b, idx + off + b, m, wbuf, &first, x);
+        }
         if (rc) break;
+        memcpy(states + k * 32, x, sizeof(x));
         const int64_t nw = wcap - first;
         if (pos + nw * 2 + 4 > cap) { rc = ORC_ERR_CAPACITY; break; }
         cum_words += nw;
@@ -696,70 +713,102 @@ int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_
     return ORC_OK;
 }
 
-/* Decode a segment; *consumed = bytes of `enc` belonging to it. */
-int orc_bls_decode(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len, const int32_t *idx, int64_t n,
-                   int64_t chunk_syms, int32_t *out, int64_t *consumed)
+int orc_bls_encode(const orc_rans64_tables *tb, const int32_t *sym, const int32_t *idx, int64_t n,
+                   int64_t chunk_syms, uint8_t *out, int64_t cap, int64_t *out_len)
+{
+    if (chunk_syms <= 0 || chunk_syms % 128) return ORC_ERR_GENERIC;
+    return orc_bls_encode_slices(tb, sym, idx, 1, &n, &chunk_syms, orc_bls_num_chunks(n, chunk_syms), out, cap, out_len);
+}
+
+/* Decode the m symbols of one slice of one chunk, continuing from lane states x[] and word position *wpp. */
+static int bls_decode_slice(const orc_rans64_tables *tb, const uint16_t *w, int64_t *wpp, uint32_t *x, const int32_t *idx,
+                            int64_t m, int32_t *out)
+{
+    const int prec = tb->precision, bp = tb->bypass_precision;
+    const uint32_t maxb = (1u << bp) - 1, pmask = (1u << prec) - 1;
+    int64_t wp = *wpp;
+    const int64_t nsteps = ((m + 127) / 128) * 4;
+    for (int64_t t = 0; t < nsteps; ++t) {
+        int32_t value[BLS_LANES], maxv[BLS_LANES], cc[BLS_LANES];
+        int escl[BLS_LANES], phase[BLS_LANES]; uint32_t nb[BLS_LANES], raw[BLS_LANES], jj[BLS_LANES];
+        int any = 0;
+        /* main event: decode + advance for all active lanes, then renormalise in lane order */
+        for (int l = 0; l < BLS_LANES; ++l) {
+            const int64_t j = bls_local_index(t, l);
+            escl[l] = 0; cc[l] = -1;
+            if (j >= m) continue;
+            const int32_t c = idx[j];
+            if (c < 0 || c >= tb->T) return ORC_ERR_RANGE;
+            cc[l] = c;
+            const int32_t *cdf = tb->cdfs + (size_t)c * tb->stride;
+            const int32_t size = tb->sizes[c];
+            maxv[l] = size - 2;
+            const uint32_t cum = x[l] & pmask;
+            int s = 0;
+            while (s < size && (uint32_t)cdf[s] <= cum) ++s;
+            s -= 1;
+            x[l] = (uint32_t)(cdf[s + 1] - cdf[s]) * (x[l] >> prec) + cum - (uint32_t)cdf[s];
+            value[l] = s;
+            if (tb->bypass && s == maxv[l]) { escl[l] = 1; phase[l] = 0; nb[l] = 0; raw[l] = 0; jj[l] = 0; any = 1; }
+        }
+        for (int l = 0; l < BLS_LANES; ++l)
+            if (cc[l] >= 0 && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
+        /* escape sub-steps */
+        while (any) {
+            uint32_t val[BLS_LANES];
+            for (int l = 0; l < BLS_LANES; ++l) if (escl[l]) { val[l] = x[l] & maxb; x[l] >>= bp; }
+            for (int l = 0; l < BLS_LANES; ++l) if (escl[l] && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
+            any = 0;
+            for (int l = 0; l < BLS_LANES; ++l) {
+                if (!escl[l]) continue;
+                if (phase[l] == 0) { nb[l] += val[l]; if (val[l] != maxb) { phase[l] = 1; if (nb[l] == 0) escl[l] = 0; } }
+                else { raw[l] |= val[l] << (jj[l] * bp); if (++jj[l] == nb[l]) escl[l] = 0; }
+                if (escl[l]) any = 1;
+                else { int32_t v = (int32_t)(raw[l] >> 1); value[l] = (raw[l] & 1) ? -v - 1 : v + maxv[l]; }
+            }
+        }
+        for (int l = 0; l < BLS_LANES; ++l)
+            if (cc[l] >= 0) out[bls_local_index(t, l)] = value[l] + tb->offsets[cc[l]];
+    }
+    *wpp = wp;
+    return ORC_OK;
+}
+
+/* Decode a segment of n_slices slices (indexes / out laid out slice after slice); *consumed = its bytes. */
+int orc_bls_decode_slices(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len, const int32_t *idx, int n_slices,
+                          const int64_t *slice_n, int32_t *out, int64_t *consumed)
 {
     if (len < 8) return ORC_ERR_SRC_SIZE;
     const uint32_t *h32 = (const uint32_t *)enc;
     const int64_t nc = h32[0];
-    if (chunk_syms <= 0) chunk_syms = h32[1];
-    if ((int64_t)h32[1] != chunk_syms || chunk_syms % 128 || nc != orc_bls_num_chunks(n, chunk_syms)) return ORC_ERR_SRC_SIZE;
-    const uint32_t *nwords = h32 + 2, *states = h32 + 2 + nc;
-    int64_t pos = 8 + nc * 4 + nc * 128;
+    if ((int64_t)h32[1] != n_slices || len < 8 + 4 * (int64_t)n_slices) return ORC_ERR_SRC_SIZE;
+    const uint32_t *cs = h32 + 2;
+    int64_t nc_need = 0;
+    for (int g = 0; g < n_slices; ++g) {
+        if (cs[g] == 0 || cs[g] % 128) return ORC_ERR_SRC_SIZE;
+        const int64_t need = orc_bls_num_chunks(slice_n[g], cs[g]);
+        if (need > nc_need) nc_need = need;
+    }
+    if (nc_need != nc) return ORC_ERR_SRC_SIZE;
+    const uint32_t *nwords = h32 + 2 + n_slices, *states = nwords + nc;
+    int64_t pos = 8 + 4 * (int64_t)n_slices + nc * 4 + nc * 128;
     if (len < pos) return ORC_ERR_SRC_SIZE;
-    const int prec = tb->precision, bp = tb->bypass_precision;
-    const uint32_t maxb = (1u << bp) - 1, pmask = (1u << prec) - 1;
     for (int64_t k = 0; k < nc; ++k) {
-        const int64_t b = k * chunk_syms, m = (n - b) < chunk_syms ? (n - b) : chunk_syms;
         const int64_t nw_k = (int64_t)nwords[k] - (k ? (int64_t)nwords[k - 1] : 0);
         if (nw_k < 0 || pos + nw_k * 2 > len) return ORC_ERR_SRC_SIZE;
         const uint16_t *w = (const uint16_t *)(enc + pos);
-        int64_t wp = 0;
+        int64_t wp = 0, off = 0;
         uint32_t x[BLS_LANES];
         memcpy(x, states + k * 32, sizeof(x));
-        const int64_t nsteps = ((m + 127) / 128) * 4;
-        for (int64_t t = 0; t < nsteps; ++t) {
-            int32_t value[BLS_LANES], maxv[BLS_LANES], cc[BLS_LANES];
-            int escl[BLS_LANES], phase[BLS_LANES]; uint32_t nb[BLS_LANES], raw[BLS_LANES], jj[BLS_LANES];
-            int any = 0;
-            /* main event: decode + advance for all active lanes, then renormalise in lane order */
-            for (int l = 0; l < BLS_LANES; ++l) {
-                const int64_t j = bls_local_index(t, l);
-                escl[l] = 0; cc[l] = -1;
-                if (j >= m) continue;
-                const int32_t c = idx[b + j];
-                if (c < 0 || c >= tb->T) return ORC_ERR_RANGE;
-                cc[l] = c;
-                const int32_t *cdf = tb->cdfs + (size_t)c * tb->stride;
-                const int32_t size = tb->sizes[c];
-                maxv[l] = size - 2;
-                const uint32_t cum = x[l] & pmask;
-                int s = 0;
-                while (s < size && (uint32_t)cdf[s] <= cum) ++s;
-                s -= 1;
-                x[l] = (uint32_t)(cdf[s + 1] - cdf[s]) * (x[l] >> prec) + cum - (uint32_t)cdf[s];
-                value[l] = s;
-                if (tb->bypass && s == maxv[l]) { escl[l] = 1; phase[l] = 0; nb[l] = 0; raw[l] = 0; jj[l] = 0; any = 1; }
+        for (int g = 0; g < n_slices; ++g) {
+            const int64_t b = k * (int64_t)cs[g];
+            int64_t m = slice_n[g] - b;
+            if (m > (int64_t)cs[g]) m = cs[g];
+            if (m > 0) {
+                const int rc = bls_decode_slice(tb, w, &wp, x, idx + off + b, m, out + off + b);
+                if (rc) return rc;
             }
-            for (int l = 0; l < BLS_LANES; ++l)
-                if (cc[l] >= 0 && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
-            /* escape sub-steps */
-            while (any) {
-                uint32_t val[BLS_LANES];
-                for (int l = 0; l < BLS_LANES; ++l) if (escl[l]) { val[l] = x[l] & maxb; x[l] >>= bp; }
-                for (int l = 0; l < BLS_LANES; ++l) if (escl[l] && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
-                any = 0;
-                for (int l = 0; l < BLS_LANES; ++l) {
-                    if (!escl[l]) continue;
-                    if (phase[l] == 0) { nb[l] += val[l]; if (val[l] != maxb) { phase[l] = 1; if (nb[l] == 0) escl[l] = 0; } }
-                    else { raw[l] |= val[l] << (jj[l] * bp); if (++jj[l] == nb[l]) escl[l] = 0; }
-                    if (escl[l]) any = 1;
-                    else { int32_t v = (int32_t)(raw[l] >> 1); value[l] = (raw[l] & 1) ? -v - 1 : v + maxv[l]; }
-                }
-            }
-            for (int l = 0; l < BLS_LANES; ++l)
-                if (cc[l] >= 0) out[b + bls_local_index(t, l)] = value[l] + tb->offsets[cc[l]];
+            off += slice_n[g];
         }
         if (wp != nw_k) return ORC_ERR_SRC_SIZE;
         pos += nw_k * 2;
@@ -768,3 +817,14 @@ int orc_bls_decode(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len,
     *consumed = pos;
     return ORC_OK;
 }
+
+int orc_bls_decode(const orc_rans64_tables *tb, const uint8_t *enc, int64_t len, const int32_t *idx, int64_t n,
+                   int64_t chunk_syms, int32_t *out, int64_t *consumed)
+{
+    if (len < 12) return ORC_ERR_SRC_SIZE;
+    const uint32_t *h32 = (const uint32_t *)enc;
+    if (chunk_syms > 0 && (int64_t)h32[2] != chunk_syms) return ORC_ERR_SRC_SIZE;
+    if ((int64_t)h32[0] != orc_bls_num_chunks(n, h32[2] ? h32[2] : 1)) return ORC_ERR_SRC_SIZE;
+    return orc_bls_decode_slices(tb, enc, len, idx, 1, &n, out, consumed);
+}
+

@@ -144,6 +144,22 @@ class Rans64Encoder(_Rans64Base):
                                     _p(out, C.c_uint8), C.c_int64(cap), C.byref(out_len)))
         return out[:out_len.value].tobytes()
 
+    def encode_lanes_slices(self, symbols, indexes, slice_n, n_chunks):
+        """Multi-slice segment (the y path: one slice per coding group, lane states carried across groups):
+        chunk_syms[g] = ceil(slice_n[g] / n_chunks) rounded up to 128."""
+        self._need_init()
+        sym, idx = _i32(symbols).reshape(-1), _i32(indexes).reshape(-1)
+        sn = np.ascontiguousarray(slice_n, dtype=np.int64)
+        cs = np.maximum(128, ((-(-sn // n_chunks) + 127) // 128) * 128).astype(np.int64)
+        n_chunks = int(max(1 if sn.size == 0 else 0, (-(-sn // cs)).max() if sn.size else 0))  # drop chunks that own nothing
+        cap = 64 + 4 * sn.size + n_chunks * 132 + int(sn.sum()) * 24 + 64
+        out = np.empty(cap, dtype=np.uint8)
+        out_len = C.c_int64(0)
+        _check(lib().orc_bls_encode_slices(C.byref(self._tb), _p(sym), _p(idx), C.c_int(sn.size), _p(sn, C.c_int64),
+                                           _p(cs, C.c_int64), C.c_int64(n_chunks), _p(out, C.c_uint8), C.c_int64(cap),
+                                           C.byref(out_len)))
+        return out[:out_len.value].tobytes()
+
 
 class _DState(C.Structure):
     _fields_ = [("x", C.c_uint64), ("pos", C.c_int64)]
@@ -176,6 +192,17 @@ class Rans64Decoder(_Rans64Base):
         consumed = C.c_int64(0)
         _check(lib().orc_bls_decode(C.byref(self._tb), _p(enc, C.c_uint8), C.c_int64(enc.size), _p(idx),
                                     C.c_int64(idx.size), C.c_int64(chunk_syms), _p(out), C.byref(consumed)))
+        return out, consumed.value
+
+    def decode_lanes_slices(self, encoded, indexes, slice_n):
+        self._need_init()
+        idx = _i32(indexes).reshape(-1)
+        sn = np.ascontiguousarray(slice_n, dtype=np.int64)
+        enc = np.frombuffer(bytes(encoded), dtype=np.uint8)
+        out = np.empty(idx.shape, dtype=np.int32)
+        consumed = C.c_int64(0)
+        _check(lib().orc_bls_decode_slices(C.byref(self._tb), _p(enc, C.c_uint8), C.c_int64(enc.size), _p(idx),
+                                           C.c_int(sn.size), _p(sn, C.c_int64), _p(out), C.byref(consumed)))
         return out, consumed.value
 
 

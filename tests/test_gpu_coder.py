@@ -163,8 +163,8 @@ def test_multilane_matches_cpu_spec_and_is_lossless(A, cv, lanes):
         oenc = O.Rans64Encoder(bypass_coding=True)
         oenc.init_params(cv["a_freqs"], cv["a_nsym"], cv[off])
         bs = enc.encode_with_indexes(data, idx)
-        magic, n_chunks, chunk = struct.unpack_from("<III", bs, 0)
-        assert magic == 0x31534C42 and chunk % 128 == 0 and n_chunks == -(-data.size // chunk)
+        magic, n_chunks, n_slices, chunk = struct.unpack_from("<IIII", bs, 0)
+        assert magic == 0x31534C42 and n_slices == 1 and chunk % 128 == 0 and n_chunks == -(-data.size // chunk)
         assert n_chunks <= -(-lanes // 32)
         assert bs[4:] == oenc.encode_lanes(data, idx, chunk)       # byte-identical to the CPU specification
         assert np.array_equal(dec.decode_with_indexes(bs, idx), data)

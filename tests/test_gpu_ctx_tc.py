@@ -59,9 +59,9 @@ def test_tc_matches_fp32(C_, G, method, B, H, W, merger, nacc):
     assert err <= (REL_TOL if nacc <= 4 else 3 * REL_TOL), err   # long TMEM chains (16 k-blocks) drift: why the default is 4
 
 
-def test_tc_round_trip_and_oracle_symbols():
-    """Whole y path with the tensor-core context model: decoder reproduces the encoder bit for bit, and the symbols
-    agree with the CPU oracle wherever the oracle's own rounding margin exceeds the float tolerance."""
+def test_tc_round_trip():
+    """Whole y path with the tensor-core context model: the decoder reproduces the encoder's y_hat bit for bit (both
+    sides run the same deterministic kernels) and the reconstruction is within half a quantisation step."""
     C_, B, H, W = 96, 2, 8, 12
     coder = build(C_, 1, "checkerboard", "tf32x3", 4)
     torch.manual_seed(3)
@@ -70,14 +70,57 @@ def test_tc_round_trip_and_oracle_symbols():
     yhat = coder.decode(bs, prior=prior.cuda())
     assert torch.equal(yhat, yhat_enc * 1.0 + 0.0)
     assert float((yhat.cpu() - y).abs().max()) <= 0.5 + 1e-4
-    w = Y.weights_from_state_dict(coder.topo_group_context_model.state_dict(), prefix="")
-    w = {k: v.cpu() for k, v in w.items()}
-    oracle = Y.YPathOracle(C_, 1, w)
-    oracle.update_state()
-    tg = Y.default_pgm("checkerboard", 1, H, W)
+
+
+def test_tc_vs_oracle_c192_teacher_forced():
+    """BASELINE configs[1] geometry (C = 192, checkerboard, one Kodak-shape image) in the tensor-core mode against
+    the CPU oracle, stage by stage with the ORACLE's y_hat as context (so one rounding tie cannot cascade):
+    parameters within 1e-5; a symbol / scale index may differ only where the oracle's own value sits within the
+    float tolerance of the decision boundary (a .5 rounding tie / a scale-table midpoint)."""
+    import ctypes as C
+    from cbench_basic_b200 import _native as N
+    from tests.test_gpu_ypath import _random_case, make_coder
+    c = _random_case(192, 1, 1, 32, 48, 7)
+    tab = Y.get_scale_table()
     with torch.no_grad():
-        ref = oracle.decode(oracle.encode(y, prior, tg), prior, tg)
-    d = (yhat.cpu() - ref).abs()
-    flips = int((d > 0.5).sum())
-    assert flips <= 2, flips                      # a .5 rounding tie moved by the 1e-6 float difference
-    assert float((d[d <= 0.5] / ref.abs().clamp_min(1.0)[d <= 0.5]).max()) <= REL_TOL
+        sym, idx, yhat_ref = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
+        params_ref = Y.params_for(yhat_ref, c["tg"], c["prior"], c["w"])
+    coder = make_coder(c, lanes=0, method="checkerboard", ctx_precision="tf32x3")
+    B, C_, H, W = 1, 192, 32, 48
+    coder._set_map(c["tg"])
+    y, prior, buf = c["y"].cuda().contiguous(), c["prior"].cuda().contiguous(), yhat_ref.cuda().contiguous()
+    params = torch.zeros(B, 2 * C_, H, W, device="cuda")
+    scratch = torch.zeros_like(y)
+    h = coder.ans_encoder.handle
+    gs, gi = [], []
+    for g in range(N.lib().basic_ctx_num_stages(coder._ctx)):
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, buf.data_ptr(), prior.data_ptr(), B, params.data_ptr(), 0))
+        pos, n_pos = C.c_void_p(), C.c_int64()
+        N.check(N.lib().basic_ctx_stage_positions(coder._ctx, g, C.byref(pos), C.byref(n_pos)))
+        n = B * n_pos.value
+        s_, i_ = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+        N.check(N.lib().basic_gauss_quantize_index(h, y.data_ptr(), params.data_ptr(), pos, n_pos.value, B, C_, H * W,
+                                                   s_.data_ptr(), i_.data_ptr(), scratch.data_ptr(), 0))
+        gs.append(s_)
+        gi.append(i_)
+    torch.cuda.synchronize()
+    gsym, gidx, gparams = torch.cat(gs).cpu().numpy(), torch.cat(gi).cpu().numpy(), params.cpu()
+    err = float(((gparams - params_ref).abs() / params_ref.abs().clamp_min(1.0)).max())
+    print(f"c192 tf32x3 vs oracle: params max rel err {err:.3e}; symbol diffs {int((gsym != sym).sum())}, index diffs {int((gidx != idx).sum())}")
+    assert err <= REL_TOL
+    gmap = Y.group_of_elements(c["tg"], 1, 192).reshape(-1)
+    order = torch.cat([torch.nonzero(gmap == g).reshape(-1) for g in range(2)])
+    mean_ref, scale_ref = (t.reshape(-1)[order].double() for t in Y.split_mean_scale(params_ref))
+    bad_s = np.nonzero(gsym != sym)[0]
+    assert bad_s.size <= 8
+    if bad_s.size:
+        d = (c["y"].reshape(-1)[order][bad_s].double() - mean_ref[bad_s])
+        assert np.all(np.abs(gsym[bad_s] - sym[bad_s]) == 1)
+        assert float(((d - d.floor()) - 0.5).abs().max()) <= 2 * REL_TOL, "symbol disagreement away from a .5 tie"
+    bad_i = np.nonzero(gidx != idx)[0]
+    assert bad_i.size <= 8
+    if bad_i.size:
+        lo = np.minimum(gidx[bad_i], idx[bad_i])
+        assert np.all(np.abs(gidx[bad_i] - idx[bad_i]) == 1)
+        mid = (tab.double()[lo] + tab.double()[lo + 1]) / 2
+        assert float(((scale_ref[bad_i] - mid).abs() / mid).max()) <= 2 * REL_TOL, "scale-index disagreement away from a tie"

@@ -23,7 +23,9 @@ def yv(golden_dir):
     return np.load(os.path.join(golden_dir, "ypath_vectors.npz"))
 
 
-def make_coder(c, lanes, method="none"):
+def make_coder(c, lanes, method="none", ctx_precision="fp32"):
+    """ctx_precision="fp32": the parity mode (exact FP32 context model) -- what the oracle comparisons below pin; the
+    tensor-core mode has its own tests (tests/test_gpu_ctx_tc.py)."""
     from cbench_basic_b200.prior_coder import (GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder,
                                                TopoGroupDynamicMaskConv2dContextModel as Ctx)
     w, C_, G = c["w"], c["C"], c["G"]
@@ -35,10 +37,10 @@ def make_coder(c, lanes, method="none"):
               "param_merger_out.3.weight": w["m3_w"], "param_merger_out.3.bias": w["m3_b"]}
         cm.load_state_dict(sd)
         coder = Coder(in_channels=C_, channel_groups=G, default_topo_group_method=method, topo_group_context_model=cm,
-                      lanes=lanes, ans_params_device="cpu")
+                      lanes=lanes, ans_params_device="cpu", ctx_precision=ctx_precision)
     else:
         coder = Coder(in_channels=C_, channel_groups=G, default_topo_group_method=method, use_param_merger=False,
-                      lanes=lanes, ans_params_device="cpu")
+                      lanes=lanes, ans_params_device="cpu", ctx_precision=ctx_precision)
         coder.load_state_dict({"context_prediction.weight": w["ctx_w"], "context_prediction.bias": w["ctx_b"]})
     coder = coder.cuda().eval()
     coder.update_state()
@@ -252,6 +254,28 @@ def test_ypath_vs_oracle_c192_checkerboard():
                 assert bs == ref_bytes
         else:
             assert len(bs) <= len(ref_bytes) * 1.005 + 300
+
+
+def test_ypath_multilane_container_matches_cpu_spec():
+    """The y path's multi-lane container = magic + ONE segment with one slice per coding group (lane states carried
+    across groups, one flush per lane): byte-identical to the CPU specification run on our symbols / indexes."""
+    import struct
+    from oracle import ans_oracle as O
+    c = _random_case(24, 4, 3, 9, 14, 5, method="channelwise-checkerboard")
+    coder = make_coder(c, lanes=96, method="channelwise-checkerboard")
+    gsym, gidx, _ = _stagewise_symbols(coder, c)
+    bs = coder.encode(c["y"].cuda(), prior=c["prior"].cuda())
+    magic, n_chunks, n_slices = struct.unpack_from("<III", bs, 0)
+    gmap = Y.group_of_elements(c["tg"], c["B"], c["C"]).reshape(-1)
+    slice_n = [int((gmap == g).sum()) for g in range(n_slices)]
+    assert magic == 0x31534C42 and n_slices == int(c["tg"].max()) + 1 and sum(slice_n) == gsym.size
+    o = Y.YPathOracle(24, 4, c["w"])
+    o.update_state()
+    assert bs[4:] == o.enc.encode_lanes_slices(gsym, gidx, slice_n, 3)
+    out, used = o.dec.decode_lanes_slices(bs[4:], gidx, slice_n)
+    assert used == len(bs) - 4 and np.array_equal(out, gsym)
+    yhat = coder.decode(bs, prior=c["prior"].cuda())
+    assert float((yhat.cpu() - c["y"]).abs().max()) <= 0.5
 
 
 def test_ypath_round_trip_properties_large():
