@@ -31,7 +31,10 @@ void ctx_delete(CtxModel *);
 int ctx_set_weights(CtxModel &, const float *, const float *, const float *, const float *, const float *, const float *,
                     const float *, const float *);
 int ctx_set_map(CtxModel &, const int32_t *, int, int);
-int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t);
+int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t, const float *buf_cl = nullptr,
+                     const float *prior_cl = nullptr);
+bool ctx_uses_tc(const CtxModel &, int B);
+int launch_nchw_to_cl(const float *, float *, int, int, int, cudaStream_t);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
@@ -75,7 +78,7 @@ struct basic_coder {
     DevBuf d_scale;
     // scratch
     DevBuf in_a, in_b, out_i32, words, first, states, segs, small, stream_dev, y_dev, prior_dev, buf, params, sym_all, idx_all,
-        yhat_stage, slices_dev, carry_x, carry_wp;
+        yhat_stage, slices_dev, carry_x, carry_wp, buf_cl, prior_cl;
     void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
     // pinned host staging (grow-only): encoded output kept for basic_coder_last_output, and the stream being decoded
     uint8_t *host_out = nullptr, *host_in = nullptr;
@@ -351,7 +354,7 @@ void basic_coder_destroy(basic_coder *c)
     DeviceGuard guard(c->device);
     DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
                       &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
-                      &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp};
+                      &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp, &c->buf_cl, &c->prior_cl};
     for (DevBuf *b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->host_out) cudaFreeHost(c->host_out);
@@ -765,6 +768,18 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
     const float *params_src = params;
+    // tensor-core context model: it reads channels-last copies of the prior (made once) and of the y_hat buffer
+    // (refreshed after every group's write-back)
+    const bool tc = model && ctx_uses_tc(*model->m, B);
+    float *buf_cl = nullptr, *prior_cl = nullptr;
+    if (tc) {
+        BASIC_TRY(c->buf_cl.reserve(n * 4));
+        BASIC_TRY(c->prior_cl.reserve(2 * n * 4));
+        buf_cl = c->buf_cl.as<float>();
+        prior_cl = c->prior_cl.as<float>();
+        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, n * 4, s));
+        BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
+    }
     // the encoder knows y: all groups' symbols and indexes first (group g's context = the reconstructions of groups
     // < g, written back by the quantiser), then ONE coding pass over all of them
     std::vector<int64_t> slice_n;
@@ -773,7 +788,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
-            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
+            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
             params_src = d_prior;
@@ -783,6 +798,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         if (cnt == 0) continue;
         BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                         sym + done, idx + done, buf, c->sm_count, s));
+        if (tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
         done += (size_t)cnt;
     }
     if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
@@ -821,9 +837,19 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const float *params_src = params;
     Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
     BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    const bool tc = model && ctx_uses_tc(*model->m, B);
+    float *buf_cl = nullptr, *prior_cl = nullptr;
+    if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
+        BASIC_TRY(c->buf_cl.reserve(n * 4));
+        BASIC_TRY(c->prior_cl.reserve(2 * n * 4));
+        buf_cl = c->buf_cl.as<float>();
+        prior_cl = c->prior_cl.as<float>();
+        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, n * 4, s));
+        BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
+    }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
     // memory and upload it while the GPU is busy
-    if (model) BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s));
+    if (model) BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl));
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     // per-group symbol counts = the slices of the segment
     std::vector<int64_t> slice_n((size_t)S);
@@ -843,7 +869,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
-            if (g > 0) BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s));
+            if (g > 0) BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
             params_src = d_prior;
@@ -865,6 +891,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
                                         c->carry_wp.as<uint32_t>(), sym, &ds->status, c->sm_count, s));
         }
         if (cnt > 0) BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
+        if (cnt > 0 && tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
     }
     if (lanes != BASIC_LANES_REFERENCE) c->stream_pos += si.len;
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));

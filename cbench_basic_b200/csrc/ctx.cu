@@ -367,7 +367,8 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     return BASIC_OK;
 }
 
-static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, cudaStream_t stream)
+static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, bool tc,
+                        cudaStream_t stream)
 {
     for (int j = 0; j < 8; ++j) a.vis_or[j] = 0;
     if (m.G <= 8) {
@@ -381,15 +382,20 @@ static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int o
     a.kb_src0 = pw.kb_src0;
     a.ntile_base = og * pw.ntiles_per_group;
     a.nacc = m.nacc;
-    if (tc_eligible(m, a)) return launch_layer_tc(m, a, stream);
+    if (tc) return launch_layer_tc(m, a, stream);
     dim3 grid((rows + BM - 1) / BM, (a.n_count + BN - 1) / BN);
     k_layer<<<grid, NT, 0, stream>>>(a);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
 
-// One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).
-int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, int B, float *params, cudaStream_t stream)
+bool ctx_uses_tc(const CtxModel &m, int B) { return tc_model_eligible(m, B); }
+
+// One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).  buf / prior are NCHW; the tensor path
+// reads channels-last copies: the caller's (buf_cl / prior_cl, kept up to date by the y-path driver) or, when they
+// are NULL (the public stage API), copies made here.
+int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, int B, float *params, cudaStream_t stream,
+                     const float *buf_cl, const float *prior_cl)
 {
     if (g < 0 || g >= m.S) return value_error("stage out of range");
     const int HW = m.H * m.W, G = m.G;
@@ -403,17 +409,31 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         }
         return BASIC_OK;
     }
-    if (m.act_B < B || !m.a_ctx.p) {
-        BASIC_TRY(m.a_ctx.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
+    const bool tc = tc_model_eligible(m, B);
+    if (m.act_B < B || !(tc ? m.cl_ctx.p : m.a_ctx.p)) {
+        DevBuf &x0 = tc ? m.cl_ctx : m.a_ctx, &x1 = tc ? m.cl_m1 : m.a_m1, &x2 = tc ? m.cl_m2 : m.a_m2;
+        BASIC_TRY(x0.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
         if (m.has_merger) {
-            BASIC_TRY(m.a_m1.reserve((size_t)B * m.c_m1 * HW * sizeof(float)));
-            BASIC_TRY(m.a_m2.reserve((size_t)B * m.c_m2 * HW * sizeof(float)));
+            BASIC_TRY(x1.reserve((size_t)B * m.c_m1 * HW * sizeof(float)));
+            BASIC_TRY(x2.reserve((size_t)B * m.c_m2 * HW * sizeof(float)));
         }
         m.act_B = B;
     }
-    for (int og = 0; og < G; ++og) {
-        const int ncells = st.cell_off[og + 1] - st.cell_off[og];
-        if (ncells == 0) continue;
+    if (tc && !buf_cl) {
+        BASIC_TRY(m.cl_buf.reserve((size_t)B * m.C * HW * sizeof(float)));
+        BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, stream));
+        buf_cl = m.cl_buf.as<float>();
+    }
+    if (tc && !prior_cl && (m.has_merger || true)) {
+        BASIC_TRY(m.cl_prior.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
+        BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream));
+        prior_cl = m.cl_prior.as<float>();
+    }
+    float *act0 = tc ? m.cl_ctx.as<float>() : m.a_ctx.as<float>();
+    float *act1 = tc ? m.cl_m1.as<float>() : m.a_m1.as<float>();
+    float *act2 = tc ? m.cl_m2.as<float>() : m.a_m2.as<float>();
+    const int cl = tc ? 1 : 0;
+    auto base_args = [&](int og, int ncells) {
         LayerArgs a = {};
         a.cell_hw = m.d_cell_hw.as<int32_t>();
         a.cell_tap = m.d_cell_tap.as<uint32_t>();
@@ -421,16 +441,25 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         a.ncells = ncells;
         a.cell_base = (int)(st.cells_at + st.cell_off[og]);
         a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = G;
+        return a;
+    };
+    for (int og = 0; og < G; ++og) {
+        const int ncells = st.cell_off[og + 1] - st.cell_off[og];
+        if (ncells == 0) continue;
+        LayerArgs a = base_args(og, ncells);
         a.is_conv = 1; a.ksize = m.k; a.Cin = m.C;
-        a.src0 = Source{buf, m.C, G};
-        a.src1 = Source{nullptr, 0, 0};
+        a.src0 = Source{tc ? buf_cl : buf, m.C, G, cl};
+        a.src1 = Source{nullptr, 0, 0, 0};
         a.wt = m.w_ctx.as<float>(); a.bias = m.b_ctx.as<float>();
         a.Ntot = m.c_ctx; a.n_begin = og * (m.c_ctx / G); a.n_count = m.c_ctx / G;
-        a.out = m.has_merger ? m.a_ctx.as<float>() : params;
-        a.add = m.has_merger ? nullptr : prior;
+        if (m.has_merger) {
+            a.out = act0; a.out_cl = cl; a.add = nullptr;
+        } else {  // params = ctx + prior: written straight to the NCHW parameter tensor
+            a.out = params; a.out_cl = 0; a.add = prior;
+        }
         a.lrelu = 0;
         a.tap_or = st.tap_or;
-        BASIC_TRY(launch_layer(m, a, m.p_ctx, og, st, stream));
+        BASIC_TRY(launch_layer(m, a, m.p_ctx, og, st, tc, stream));
     }
     if (!m.has_merger) return BASIC_OK;
     // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
@@ -439,31 +468,25 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         for (int og = 0; og < G; ++og) {
             const int ncells = st.cell_off[og + 1] - st.cell_off[og];
             if (ncells == 0) continue;
-            LayerArgs a = {};
-            a.cell_hw = m.d_cell_hw.as<int32_t>();
-            a.cell_tap = m.d_cell_tap.as<uint32_t>();
-            a.cell_grp = m.d_cell_grp.as<uint32_t>();
-            a.ncells = ncells;
-            a.cell_base = (int)(st.cells_at + st.cell_off[og]);
-            a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = G;
+            LayerArgs a = base_args(og, ncells);
             a.is_conv = 0;
             if (layer == 1) {
-                a.src0 = Source{m.a_ctx.as<float>(), m.c_ctx, G};
-                a.src1 = Source{prior, m.c_ctx, 0};
+                a.src0 = Source{act0, m.c_ctx, G, cl};
+                a.src1 = Source{tc ? prior_cl : prior, m.c_ctx, 0, cl};
                 a.wt = m.w_m1.as<float>(); a.bias = m.b_m1.as<float>();
-                a.Ntot = m.c_m1; a.out = m.a_m1.as<float>(); a.lrelu = 1;
+                a.Ntot = m.c_m1; a.out = act1; a.out_cl = cl; a.lrelu = 1;
             } else if (layer == 2) {
-                a.src0 = Source{m.a_m1.as<float>(), m.c_m1, G};
+                a.src0 = Source{act1, m.c_m1, G, cl};
                 a.wt = m.w_m2.as<float>(); a.bias = m.b_m2.as<float>();
-                a.Ntot = m.c_m2; a.out = m.a_m2.as<float>(); a.lrelu = 1;
+                a.Ntot = m.c_m2; a.out = act2; a.out_cl = cl; a.lrelu = 1;
             } else {
-                a.src0 = Source{m.a_m2.as<float>(), m.c_m2, G};
+                a.src0 = Source{act2, m.c_m2, G, cl};
                 a.wt = m.w_m3.as<float>(); a.bias = m.b_m3.as<float>();
-                a.Ntot = m.c_ctx; a.out = params; a.lrelu = 0;
+                a.Ntot = m.c_ctx; a.out = params; a.out_cl = 0; a.lrelu = 0;
             }
             a.n_begin = og * (a.Ntot / G);
             a.n_count = a.Ntot / G;
-            BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3, og, st, stream));
+            BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3, og, st, tc, stream));
         }
     }
     return BASIC_OK;
@@ -482,7 +505,8 @@ void ctx_delete(CtxModel *m)
     if (!m) return;
     DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
-                      &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf};
+                      &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
+                      &m->cl_prior};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }
@@ -493,6 +517,7 @@ int ctx_set_precision(CtxModel &m, int precision, int nacc)
 {
     if (precision != BASIC_CTX_FP32 && precision != BASIC_CTX_TF32X3) return value_error("unknown context-model precision");
     if (nacc < 1 || nacc > 64) return value_error("segment length must be 1..64 k-blocks");
+    if (m.precision != precision) m.act_B = 0;  // the two paths keep their activations in different layouts
     m.precision = precision;
     m.nacc = nacc;
     return BASIC_OK;

@@ -44,6 +44,8 @@ struct CtxModel {
     int precision = 0;   // BASIC_CTX_FP32 | BASIC_CTX_TF32X3
     int nacc = 4;        // k-blocks (32 k each) accumulated in TMEM before a segment is drained into FP32 registers
     PackedW p_ctx, p_m1, p_m2, p_m3;
+    DevBuf cl_ctx, cl_m1, cl_m2;      // channels-last activations of the tensor path
+    DevBuf cl_buf, cl_prior;          // channels-last copies made when the caller only has NCHW (public stage API)
 };
 
 
@@ -51,6 +53,7 @@ struct Source {          // one block of K coming from an NCHW activation tensor
     const float *ptr;    // [B, channels, H, W]
     int channels;        // channels of this tensor
     int groups;          // channel groups subject to the visibility rule (0 = always visible)
+    int cl;              // 1: channels-last [B, H*W, channels] (tensor-core path), 0: NCHW
 };
 
 struct LayerArgs {
@@ -70,6 +73,7 @@ struct LayerArgs {
     float *out;                 // [B, Ntot, H, W]
     const float *add;           // optional [B, Ntot, H, W] added in the epilogue (merger-less: + prior)
     int lrelu;
+    int out_cl;                 // tensor path: `out` (and `add`) are channels-last [B, H*W, Ntot]
     uint32_t tap_or;            // stage-level OR of the tap masks (conv)
     // tensor-core path
     const unsigned char *wpack; // PackedW image
@@ -80,7 +84,8 @@ struct LayerArgs {
 
 
 // ctx_tc.cu
-bool tc_eligible(const CtxModel &m, const LayerArgs &a);
+bool tc_model_eligible(const CtxModel &m, int B);
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream);
 int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream);
 int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
                     int k2, int c_src0, int c_src1, cudaStream_t stream);

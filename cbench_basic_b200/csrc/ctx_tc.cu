@@ -220,8 +220,10 @@ k_layer_tc(LayerArgs a)
                         vis |= a.is_conv ? ((a.vis_or[g] >> tap) & 1u) : ((a.vis_or[0] >> g) & 1u);
                     }
                 }
-                e = make_uint4((uint32_t)i, (uint32_t)(c0 * HW + shift), (uint32_t)src | ((uint32_t)tap << 1) | ((uint32_t)nvalid << 8) |
-                               (groups ? 1u << 16 : 0u), gids);
+                const bool src_cl = a.is_conv ? a.src0.cl : (src ? a.src1.cl : a.src0.cl);
+                const int rel = src_cl ? shift * nch + c0 : c0 * HW + shift;   // from the row's base pointer, in elements
+                e = make_uint4((uint32_t)i, (uint32_t)rel, (uint32_t)src | ((uint32_t)tap << 1) | ((uint32_t)nvalid << 8) |
+                               (groups ? 1u << 16 : 0u) | (src_cl ? 1u << 17 : 0u), gids);
             }
             const unsigned m = __ballot_sync(0xffffffffu, vis);
             if (vis) s_list[count + __popc(m & ((1u << lane) - 1))] = e;
@@ -311,8 +313,12 @@ k_layer_tc(LayerArgs a)
                 }
             }
             // per-row base pointers (an invalid row never loads: its visibility mask is forced to 0)
-            const float *row0p = a.src0.ptr + ((long long)(rb < 0 ? 0 : rb) * (a.is_conv ? a.Cin : a.src0.channels)) * HW + rhw;
-            const float *row1p = a.src1.ptr ? a.src1.ptr + ((long long)(rb < 0 ? 0 : rb) * a.src1.channels) * HW + rhw : nullptr;
+            const long long rbz = rb < 0 ? 0 : rb;
+            const int nch0 = a.is_conv ? a.Cin : a.src0.channels;
+            const float *row0p = a.src0.cl ? a.src0.ptr + (rbz * HW + rhw) * nch0 : a.src0.ptr + rbz * nch0 * HW + rhw;
+            const float *row1p = !a.src1.ptr ? nullptr
+                                 : a.src1.cl ? a.src1.ptr + (rbz * HW + rhw) * a.src1.channels
+                                             : a.src1.ptr + rbz * a.src1.channels * HW + rhw;
             // gathers the 32 k of k-block i for this thread's row into registers (masked elements = 0)
             auto gather = [&](int i, float(&v)[BK]) {
                 const uint4 e = s_list[i];
@@ -333,13 +339,22 @@ k_layer_tc(LayerArgs a)
                 vis &= (1u << nvalid) - 1u;
                 if (rb < 0 || (a.debug & 1)) vis = 0;
                 int idx = (int)e.y;
+                if ((e.z >> 17) & 1u) {  // channels-last source: the 32 channels of the block are contiguous
+                    const float4 *p4 = reinterpret_cast<const float4 *>(p + idx);
 #pragma unroll
-                for (int j = 0; j < BK / 4; ++j) {
-                    const bool ok = (vis >> j) & 1u;
+                    for (int j = 0; j < BK / 4; ++j) {
+                        const float4 t = ((vis >> j) & 1u) ? __ldg(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                    }
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        v[4 * j + q] = ok ? __ldg(p + idx) : 0.f;
-                        idx += HW;
+                    for (int j = 0; j < BK / 4; ++j) {
+                        const bool ok = (vis >> j) & 1u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            v[4 * j + q] = ok ? __ldg(p + idx) : 0.f;
+                            idx += HW;
+                        }
                     }
                 }
             };
@@ -405,7 +420,29 @@ k_layer_tc(LayerArgs a)
                 tc_fence_before();
                 mbar_arrive(bar_slot_empty(slot));
             }
-            if (rb >= 0) {
+            if (rb >= 0 && a.out_cl) {
+                // channels-last: this row's 128 channels are contiguous -> 128-bit stores, full sectors
+                const long long o0 = ((long long)rb * HW + rhw) * a.Ntot + a.n_begin + nt * BN;
+#pragma unroll
+                for (int q = 0; q < BN; q += 4) {
+                    if (nt * BN + q < a.n_count) {  // n_count % 4 == 0 on this path
+                        float4 val = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
+                        if (a.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + a.n_begin + nt * BN + q));
+                            val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
+                        }
+                        if (a.add) {
+                            const float4 av = __ldg(reinterpret_cast<const float4 *>(a.add + o0 + q));
+                            val.x += av.x; val.y += av.y; val.z += av.z; val.w += av.w;
+                        }
+                        if (a.lrelu) {
+                            val.x = val.x > 0.f ? val.x : val.x * kSlope; val.y = val.y > 0.f ? val.y : val.y * kSlope;
+                            val.z = val.z > 0.f ? val.z : val.z * kSlope; val.w = val.w > 0.f ? val.w : val.w * kSlope;
+                        }
+                        *reinterpret_cast<float4 *>(a.out + o0 + q) = val;
+                    }
+                }
+            } else if (rb >= 0) {
                 const long long obase = (long long)rb * ohw + rhw;
 #pragma unroll
                 for (int q = 0; q < BN; ++q) {
@@ -495,21 +532,48 @@ int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv,
     return BASIC_OK;
 }
 
-// The tensor path needs 4-channel chunks that never straddle a visibility group, at most MAX_G groups and a
-// k-block list that fits; everything else (and tiny row counts, where a 128-row MMA tile is mostly padding)
-// stays on the exact-FP32 kernel.
-bool tc_eligible(const CtxModel &m, const LayerArgs &a)
+// The tensor path takes every layer of every stage of a model or none (its activations are channels-last).  It
+// needs 4-channel chunks that never straddle a visibility group, at most MAX_G groups, a k-block list that fits,
+// and stages big enough for 128-row MMA tiles to make sense (scanline-like maps stay on the exact-FP32 kernel).
+bool tc_model_eligible(const CtxModel &m, int B)
 {
-    if (m.precision != BASIC_CTX_TF32X3 || !a.wpack) return false;
-    if (a.G > MAX_G || a.kb_total > MAX_KB) return false;
-    if ((long long)a.B * a.ncells < 64) return false;
-    auto chunk_ok = [](const Source &s) {
-        if (!s.ptr || s.channels == 0) return true;
-        if (s.channels % 4) return false;
-        return s.groups == 0 || (s.channels % s.groups == 0 && (s.channels / s.groups) % 4 == 0);
-    };
-    if (a.is_conv) return a.Cin % 4 == 0 && (a.Cin / a.G) % 4 == 0;
-    return chunk_ok(a.src0) && chunk_ok(a.src1);
+    if (m.precision != BASIC_CTX_TF32X3 || !m.has_conv || m.S < 1) return false;
+    if (m.G > MAX_G || m.k * m.k * ((m.C + BK - 1) / BK) > MAX_KB || m.k * m.k > 31) return false;
+    auto ok4 = [&](int channels) { return channels % m.G == 0 && (channels / m.G) % 4 == 0; };
+    if (!ok4(m.C) || !ok4(m.c_ctx)) return false;
+    if (m.has_merger && (!ok4(m.c_m1) || !ok4(m.c_m2))) return false;
+    return (long long)B * m.G * m.H * m.W / m.S >= 64;
+}
+
+// [B, channels, HW] -> [B, HW, channels], 32 x 32 tiles through shared memory (both sides coalesced)
+__global__ void __launch_bounds__(256)
+k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *s = src + (size_t)b * channels * HW;
+    float *d = dst + (size_t)b * channels * HW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, hw = hw0 + tx;
+        tile[ty + 8 * i][tx] = (c < channels && hw < HW) ? s[(size_t)c * HW + hw] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int hw = hw0 + ty + 8 * i, c = c0 + tx;
+        if (c < channels && hw < HW) d[(size_t)hw * channels + c] = tile[tx][ty + 8 * i];
+    }
+}
+
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream)
+{
+    if (B == 0) return BASIC_OK;
+    dim3 grid((HW + 31) / 32, (channels + 31) / 32, B);
+    k_nchw_to_cl<<<grid, 256, 0, stream>>>(src, dst, channels, HW);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
 }
 
 int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream)
