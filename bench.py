@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 rANS states / int32 symbols, f32 context model (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "sample": f"{n_img} image per step"},
-            "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": r["kind"],
+            "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port",
                              "sample": f"{n_img} of {B} images per step, encode+decode, torch CPU context model + reference coder "
                                        f"({r['kind']}); coder alone single-thread: enc {r['n_symbols'] / r['coder_enc'] / 1e6:.1f} "
                                        f"Msym/s, dec {r['n_symbols'] / r['coder_dec'] / 1e6:.1f} Msym/s"},
@@ -258,57 +258,52 @@ def run_ours(args, rank, world, local_rank):
     n_sym = B * C_ * H * W
     hbm_peak, tf_peak, peak_src = peaks()
 
-    # --- dominant kernel: live CUDA-event timing of the context-model launches of one pass
-    roofline, coder_roof = None, None
+    # --- per-phase device time, live: CUDA events recorded by the library on the launching stream around the phases
+    # of the same step that was timed above (basic_profile_enable / basic_profile_read, include/basic_b200.h)
+    roofline, coder_roof, phases = None, None, None
     try:
-        import ctypes as C
+        prof_steps = 5
+        N.profile(True)
+        N.profile_read()
+        N.launch_count(reset=True)
+        for _ in range(prof_steps):
+            flush_l2(scratch)
+            step_resident()
+        torch.cuda.synchronize(dev)
+        n_launch = N.launch_count() // prof_steps
+        ph = N.profile_read()
+        N.profile(False)
+        phases = {k: {"ms_per_step": v[0] / prof_steps, "spans_per_step": v[1] / prof_steps} for k, v in ph.items()}
+        cbytes = stream_bytes / n_sym
+        dec_ms, enc_ms = phases["coder_decode"]["ms_per_step"], phases["coder_encode"]["ms_per_step"]
+        if dec_ms > 0:
+            ach = (8 + cbytes) * n_sym / (dec_ms * 1e-3) / 1e9  # 4 B index + 4 B symbol + c stream bytes per symbol
+            coder_roof = {"kernel": "k_bls_decode (multi-lane rANS decode, one launch per coding group)", "bound": "hbm",
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                          "decode_ms_per_step": dec_ms, "launches_per_step": phases["coder_decode"]["spans_per_step"],
+                          "encode_phase_ms_per_step": enc_ms, "bytes_per_symbol": 8 + cbytes,
+                          "decode_msym_s": n_sym / dec_ms / 1e3, "encode_msym_s": n_sym / enc_ms / 1e3 if enc_ms > 0 else None,
+                          "peak_source": peak_src,
+                          "note": "lane count is capped by the 0.5 % bpp bar (one 132 B flush per 32 lanes): "
+                                  "latency-bound, not bandwidth-bound, at this stream size (DESIGN.md section 6)"}
         if ctx:
-            params = torch.empty(B, 2 * C_, H, W, device=dev)
-            S = N.lib().basic_ctx_num_stages(coder._ctx)
-
-            def ctx_pass():
-                for g in range(S):
-                    N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, out.data_ptr(), pd.data_ptr(), B, params.data_ptr(),
-                                                           stream.cuda_stream))
-            N.launch_count(reset=True)
-            ctx_pass()
-            n_ctx_launch = N.launch_count()
-            ctx_ms = timed(ctx_pass, 5, 2)
-            flops = 2 * 77.56 * C_ * C_ * B * H * W          # dense-equivalent, each position once
+            ctx_ms = phases["context_model"]["ms_per_step"]            # both passes (encoder + decoder side)
+            flops = 2 * 2 * 77.56 * C_ * C_ * B * H * W                # dense-equivalent, each position once, x 2 passes
             ach = flops / (ctx_ms * 1e-3) / 1e12
             tc = coder.ctx_precision == "tf32x3" or (coder.ctx_precision == "auto" and coder.lanes != 1)
             roofline = {"kernel": "k_layer_tc (context conv + 1x1 merger; tcgen05 kind::tf32, 3 MMAs per product = error-compensated TF32)"
                         if tc else "k_layer (context conv + 1x1 merger, FP32 SIMT exact path)", "bound": "tensor", "achieved": ach,
                         "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
-                        "ms_per_pass": ctx_ms, "launches_per_pass": n_ctx_launch, "share_of_step": 2 * ctx_ms / ms,
-                        "peak_source": peak_src,
-                        "note": "algorithmic FLOPs = 2*77.56*C^2 per latent position (dense-equivalent, each position once; masked "
-                                "taps are skipped, so executed FLOPs are lower). The 1e-5 parity bar forces 3 TF32 MMAs per product: "
-                                "ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)"}
-        # --- coder kernels alone (HBM-bound integer work): standalone API on device-resident int32 operands
-        from cbench_basic_b200 import ans
-        tab = coder.scale_table.numpy()
-        rng = np.random.default_rng(0)
-        idx = rng.integers(0, 64, n_sym).astype(np.int32)
-        sym = np.rint(rng.standard_normal(n_sym) * tab[idx]).astype(np.int32)
-        freqs, nsym, offs = coder._get_ans_params()
-        enc, dec = ans.Rans64Encoder(lanes=args.lanes, device=local_rank), ans.Rans64Decoder(lanes=args.lanes, device=local_rank)
-        for c in (enc, dec):
-            c.init_params(freqs, nsym, offs)
-        ts, ti = torch.from_numpy(sym).to(dev), torch.from_numpy(idx).to(dev)
-        cb = enc.encode_with_indexes(ts, ti)
-        enc_ms = timed(lambda: enc.encode_with_indexes(ts, ti), 5, 2)
-        dec_ms = timed(lambda: dec.decode_with_indexes(cb, ti), 5, 2)
-        cbytes = len(cb) / n_sym
-        ach = (8 + cbytes) * n_sym / (dec_ms * 1e-3) / 1e9
-        coder_roof = {"kernel": "k_bls_decode (+ H2D of the stream, launch and sync of the call)", "bound": "hbm", "achieved": ach,
-                      "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                      "decode_ms": dec_ms, "encode_ms": enc_ms, "bytes_per_symbol": 8 + cbytes,
-                      "decode_msym_s": n_sym / dec_ms / 1e3, "encode_msym_s": n_sym / enc_ms / 1e3, "peak_source": peak_src}
-        if roofline is None:
+                        "ms_per_step": ctx_ms, "launches_per_step": phases["context_model"]["spans_per_step"] * 4,
+                        "share_of_step": ctx_ms / ms, "peak_source": peak_src,
+                        "note": "algorithmic FLOPs = 2*77.56*C^2 per latent position and pass (dense-equivalent, each position once; "
+                                "masked taps are skipped, so executed FLOPs are lower). The 1e-5 parity bar forces 3 TF32 MMAs per "
+                                "product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)"}
+        else:
             roofline = coder_roof
     except Exception as e:  # never lose the headline line to a side measurement
         roofline = roofline or {"error": repr(e)}
+        n_launch = None
 
     # --- Delta bpp against the lanes=1 reference stream on the same symbols
     dbpp = None
@@ -327,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             r = cpu_reference_step(args.workload, y, prior, w, 1)
             v = 256 * H * W / (r["t_enc"] + r["t_dec"]) / 1e6
-            cpu = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": r["kind"] if False else "port",
+            cpu = {"value": v, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"1 of {B} images, encode+decode; torch-CPU restatement of the y path (oracle/ypath_oracle.py) with the "
                              f"{r['kind']} rANS coder; coder alone, 1 thread: enc {r['n_symbols'] / r['coder_enc'] / 1e6:.1f} Msym/s, "
                              f"dec {r['n_symbols'] / r['coder_dec'] / 1e6:.1f} Msym/s "
@@ -344,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "256 MB buffer rewritten between timed iterations", "step": "encode + decode"},
             "e2e": {"value": pix_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_coder": coder_roof,
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_coder": coder_roof, "phases": phases,
             "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes]}
     print(json.dumps(line), flush=True)
 

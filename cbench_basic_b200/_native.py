@@ -20,7 +20,7 @@ SYMBOLS = [
     "basic_coder_decode_stream", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
     "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_map", "basic_ctx_num_stages",
     "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
-    "basic_ypath_decode", "basic_launch_count",
+    "basic_ypath_decode", "basic_profile_enable", "basic_profile_read", "basic_launch_count",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
     L.basic_ypath_encode.argtypes = [vp, vp, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, i64,
                                      C.POINTER(i64), f32p, vp]
     L.basic_ypath_decode.argtypes = [vp, vp, u8p, i64, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]
+    L.basic_profile_enable.argtypes = [C.c_int]
+    L.basic_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     L.basic_launch_count.argtypes = [C.c_int]
     L.basic_launch_count.restype = i64
     _lib = L
@@ -119,6 +121,20 @@ def last_output(handle):
     ptr, n = C.c_void_p(), C.c_int64(0)
     check(lib().basic_coder_last_output(handle, C.byref(ptr), C.byref(n)))
     return C.string_at(ptr.value, n.value) if n.value else b""
+
+
+PHASES = ("context_model", "quantise", "coder_encode", "coder_decode")
+
+
+def profile(on):
+    check(lib().basic_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{phase: (total ms, spans)} accumulated since the last read (CUDA events on the launching stream)."""
+    ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+    check(lib().basic_profile_read(ms, n))
+    return {name: (ms[i], n[i]) for i, name in enumerate(PHASES)}
 
 
 def launch_count(reset=False):

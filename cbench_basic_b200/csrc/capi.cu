@@ -50,6 +50,37 @@ int tans_encode(TansTables &, const int32_t *d_sym, const int32_t *d_idx, int64_
 int tans_decode(TansTables &, const uint8_t *d_enc, int64_t len, const int32_t *d_idx, int64_t n, int32_t *d_out, int *d_status,
                 cudaStream_t);
 
+// ---- optional in-library profiling: CUDA events on the launching stream around the phases of the y path
+enum { PROF_CTX = 0, PROF_GAUSS = 1, PROF_ENCODE = 2, PROF_DECODE = 3, PROF_N = 8 };
+struct ProfSpan { int cat; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof_spans;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    cudaStream_t s;
+    ProfSpan sp{};
+    bool on;
+    ProfScope(int cat, cudaStream_t stream) : s(stream), on(g_prof_on)
+    {
+        if (!on) return;
+        sp.cat = cat; sp.e0 = prof_event(); sp.e1 = prof_event();
+        cudaEventRecord(sp.e0, s);
+    }
+    ~ProfScope()
+    {
+        if (!on) return;
+        cudaEventRecord(sp.e1, s);
+        g_prof_spans.push_back(sp);
+    }
+};
+
 static thread_local std::string t_error;
 void set_error(const std::string &msg) { t_error = msg; }
 int64_t g_launches = 0;
@@ -310,6 +341,29 @@ int basic_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int basic_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    return BASIC_OK;
+}
+
+int basic_profile_read(double *ms, int64_t *spans)
+{
+    for (int i = 0; i < PROF_N; ++i) { ms[i] = 0.0; spans[i] = 0; }
+    for (auto &sp : g_prof_spans) {
+        float t = 0.f;
+        if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) {
+            ms[sp.cat] += t;
+            spans[sp.cat] += 1;
+        }
+        g_prof_pool.push_back(sp.e0);
+        g_prof_pool.push_back(sp.e1);
+    }
+    g_prof_spans.clear();
+    cudaGetLastError();
+    return BASIC_OK;
 }
 
 int64_t basic_launch_count(int reset)
@@ -788,6 +842,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
+            ProfScope ps(PROF_CTX, s);
             BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
@@ -796,6 +851,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         const int64_t cnt = (int64_t)B * n_pos;
         slice_n.push_back(cnt);
         if (cnt == 0) continue;
+        ProfScope ps(PROF_GAUSS, s);
         BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                         sym + done, idx + done, buf, c->sm_count, s));
         if (tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
@@ -813,7 +869,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     // multi-lane container: magic | one segment with one slice per coding group (lane states carried across groups)
     BASIC_TRY(c->segs.reserve(64));
     int64_t seg_len = 0;
-    BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));
+    {
+        ProfScope ps(PROF_ENCODE, s);
+        BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));
+    }
     BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
     BASIC_TRY(copy_out(c, c->segs.p, 4 + seg_len, out, out_cap, s));
     if (out_len) *out_len = 4 + seg_len;
@@ -849,7 +908,10 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
     // memory and upload it while the GPU is busy
-    if (model) BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl));
+    if (model) {
+        ProfScope ps(PROF_CTX, s);
+        BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl));
+    }
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     // per-group symbol counts = the slices of the segment
     std::vector<int64_t> slice_n((size_t)S);
@@ -869,15 +931,20 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
-            if (g > 0) BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
+            if (g > 0) {
+                ProfScope ps(PROF_CTX, s);
+                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
+            }
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
             params_src = d_prior;
         }
         const int64_t cnt = slice_n[g];
-        if (cnt > 0)
+        if (cnt > 0) {
+            ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                             nullptr, idx, nullptr, c->sm_count, s));
+        }
         if (lanes == BASIC_LANES_REFERENCE) {
             if (cnt == 0) continue;
             const int init = c->stream_pos < 0;
@@ -886,12 +953,16 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
             c->stream_pos = 0;
         } else {
             // every slice is launched, empty ones too: the lane states must travel from slice to slice
+            ProfScope ps(PROF_DECODE, s);
             BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
                                         si.len, idx, cnt, si.cs[g], si.n_chunks, S, g, c->carry_x.as<uint32_t>(),
                                         c->carry_wp.as<uint32_t>(), sym, &ds->status, c->sm_count, s));
         }
-        if (cnt > 0) BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
-        if (cnt > 0 && tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
+        if (cnt > 0) {
+            ProfScope ps(PROF_GAUSS, s);
+            BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
+            if (tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
+        }
     }
     if (lanes != BASIC_LANES_REFERENCE) c->stream_pos += si.len;
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));

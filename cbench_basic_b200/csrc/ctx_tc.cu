@@ -32,17 +32,29 @@ namespace basic {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3, NTHREADS = 320, SLOTS = 4;
+constexpr int BM = 128, BN = 128, BK = 32, NTHREADS = 320;
 constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB: one of A_hi, A_lo, B_hi, B_lo
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // 64 KB
+// Operand staging.  TS = true: the A operand (hi and lo images of the gathered rows) is written by the producers
+// straight into tensor memory (tcgen05.st, thread = row = TMEM lane) and tcgen05.mma reads it from there; shared
+// memory only holds the weights.  That halves the shared-memory traffic per MMA, which is what bounds 3xTF32 with
+// both operands in shared memory (24 KB of operand reads per 128x128x8 k-step against 128 B/cycle).
+// TS = false: both operands in shared memory (SWIZZLE_128B K-major), kept as the reference variant.
+template <bool TS> struct Cfg {
+    static constexpr int STAGES = TS ? 4 : 3;
+    static constexpr int SLOTS = TS ? 2 : 4;                          // TMEM accumulator slots of BN columns
+    static constexpr int STAGE_BYTES = (TS ? 2 : 4) * TILE_BYTES;     // [A_hi | A_lo |] B_hi | B_lo
+    static constexpr int B_OFF = TS ? 0 : 2 * TILE_BYTES;
+    static constexpr int A_COL0 = SLOTS * BN;                         // TS: stage s keeps A_hi at A_COL0 + 64 s, A_lo 32 further
+};
+constexpr int MAX_STAGES = 4, MAX_SLOTS = 4;
 constexpr int MAX_KB = 512;                  // k-blocks a CTA may walk (conv: 25 taps x ceil(C / 32))
 constexpr int MAX_G = 8;
 constexpr float kSlope = 0.01f;              // nn.LeakyReLU default negative_slope
 
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int OFF_STAGES = 0;
-constexpr int OFF_BARS = STAGES * STAGE_BYTES;          // full[STAGES], empty[STAGES], slot_full[SLOTS], slot_empty[SLOTS]
-constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * STAGES + 2 * SLOTS);
+constexpr int OFF_BARS = 3 * 4 * TILE_BYTES;            // stages: 192 KB (SS) / 128 KB (TS); then full[], empty[], slot_full[], slot_empty[]
+constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * MAX_STAGES + 2 * MAX_SLOTS);
 constexpr int OFF_NKB = OFF_TMEM + 4;
 constexpr int OFF_LIST = ((OFF_NKB + 4 + 15) / 16) * 16;         // uint4 [MAX_KB]
 constexpr int OFF_MASK = OFF_LIST + 16 * MAX_KB;        // uint32 [MAX_G][BM]
@@ -105,6 +117,28 @@ __device__ inline void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ inline void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ inline void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ inline void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -145,9 +179,11 @@ __device__ inline uint32_t tf32_hi(float v)
 __device__ __host__ inline int swz(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
 // ------------------------------------------------------------------------------------------------- the kernel
+template <bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_layer_tc(LayerArgs a)
 {
+    constexpr int STAGES = Cfg<TS>::STAGES, SLOTS = Cfg<TS>::SLOTS, STAGE_BYTES = Cfg<TS>::STAGE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
@@ -159,15 +195,15 @@ k_layer_tc(LayerArgs a)
     uint4 *s_list = reinterpret_cast<uint4 *>(smem + OFF_LIST);
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + OFF_MASK);  // [MAX_G][BM]: a producer thread's private row masks
     auto bar_full = [&](int s) { return s_base + OFF_BARS + 8 * s; };
-    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (STAGES + s); };
-    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + q); };
-    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + SLOTS + q); };
+    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (MAX_STAGES + s); };
+    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + q); };
+    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + MAX_SLOTS + q); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows = a.B * a.ncells;
     const int G = a.G, HW = a.HW;
     const int seg_kb = a.nacc;                         // k-blocks per TMEM accumulation segment
-    constexpr uint32_t tmem_cols = SLOTS * BN;         // 512: all of this SM's tensor memory (1 CTA / SM)
+    constexpr uint32_t tmem_cols = 512;                // all of this SM's tensor memory (1 CTA / SM)
     // persistent: tiles are dealt round-robin, n-tile fastest, so the CTAs gathering the same rows run together (L2)
     const int n_ntiles = (a.n_count + BN - 1) / BN;
     const int n_tiles = n_ntiles * ((rows + BM - 1) / BM);
@@ -249,7 +285,7 @@ k_layer_tc(LayerArgs a)
                     mbar_wait(bar_empty(s), (round & 1) ^ 1);
                     if (a.debug & 2) { mbar_arrive(bar_full(s)); continue; }
                     mbar_arrive_expect_tx(bar_full(s), 2 * TILE_BYTES);
-                    bulk_g2s(s_base + OFF_STAGES + s * STAGE_BYTES + 2 * TILE_BYTES, wsrc + (size_t)s_list[i].x * (2 * TILE_BYTES),
+                    bulk_g2s(s_base + OFF_STAGES + s * STAGE_BYTES + Cfg<TS>::B_OFF, wsrc + (size_t)s_list[i].x * (2 * TILE_BYTES),
                              2 * TILE_BYTES, bar_full(s));
                 }
             }
@@ -272,12 +308,20 @@ k_layer_tc(LayerArgs a)
                     const uint32_t st = s_base + OFF_STAGES + s * STAGE_BYTES;
                     const uint32_t d = tmem_base + (uint32_t)(slot * BN);
 #pragma unroll
-                    for (int ks = 0; ks < ((a.debug & 4) ? 1 : BK / 8); ++ks) {
-                        const uint64_t ah = smem_desc(st + ks * 32), al = smem_desc(st + TILE_BYTES + ks * 32);
-                        const uint64_t bh = smem_desc(st + 2 * TILE_BYTES + ks * 32), bl = smem_desc(st + 3 * TILE_BYTES + ks * 32);
-                        umma_tf32(d, ah, bh, kIdesc, (seg_first && ks == 0) ? 0u : 1u);
-                        umma_tf32(d, ah, bl, kIdesc, 1u);
-                        umma_tf32(d, al, bh, kIdesc, 1u);
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t bh = smem_desc(st + Cfg<TS>::B_OFF + ks * 32), bl = smem_desc(st + Cfg<TS>::B_OFF + TILE_BYTES + ks * 32);
+                        const uint32_t acc0 = (seg_first && ks == 0) ? 0u : 1u;
+                        if constexpr (TS) {
+                            const uint32_t ah = tmem_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64 + ks * 8), al = ah + 32;
+                            umma_tf32_ts(d, ah, bh, kIdesc, acc0);
+                            umma_tf32_ts(d, ah, bl, kIdesc, 1u);
+                            umma_tf32_ts(d, al, bh, kIdesc, 1u);
+                        } else {
+                            const uint64_t ah = smem_desc(st + ks * 32), al = smem_desc(st + TILE_BYTES + ks * 32);
+                            umma_tf32(d, ah, bh, kIdesc, acc0);
+                            umma_tf32(d, ah, bl, kIdesc, 1u);
+                            umma_tf32(d, al, bh, kIdesc, 1u);
+                        }
                     }
                     umma_commit(bar_empty(s));  // frees the stage once the MMAs above have read it
                     if (seg_last) {
@@ -289,7 +333,9 @@ k_layer_tc(LayerArgs a)
         }
     } else if (warp < 6) {
         // ================================================================================== A producers
-        const int r = tid - 64;  // this thread's row of the tile
+        // this thread's row of the tile; with A in tensor memory a warp can only write TMEM lanes 32 * (warp % 4) .. + 31
+        const int r = TS ? (warp & 3) * 32 + lane : tid - 64;
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // shared-space addresses of this row's eight 16-byte chunks inside a SWIZZLE_128B tile
         uint32_t chunk_off[BK / 4];
 #pragma unroll
@@ -363,6 +409,20 @@ k_layer_tc(LayerArgs a)
                 const int s = it % STAGES, round = it / STAGES;
                 ++it;
                 mbar_wait(bar_empty(s), (round & 1) ^ 1);
+                if constexpr (TS) {
+                    tc_fence_after();  // the MMAs that read this stage's TMEM columns have completed (tcgen05.commit)
+                    uint32_t h[BK];
+#pragma unroll
+                    for (int q = 0; q < BK; ++q) h[q] = tf32_hi(v[q]);
+                    tmem_st32(lane_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64), h);
+#pragma unroll
+                    for (int q = 0; q < BK; ++q) h[q] = __float_as_uint(v[q] - __uint_as_float(h[q]));
+                    tmem_st32(lane_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64 + 32), h);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_full(s));
+                    return;
+                }
                 const uint32_t st = s_base + OFF_STAGES + s * STAGE_BYTES;
 #pragma unroll
                 for (int j = 0; j < BK / 4; ++j) {
@@ -581,8 +641,10 @@ int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream)
     const int rows = a.B * a.ncells;
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
     static bool attr_done = false;
+    static const bool ts = !(getenv("BASIC_TC_SS") && atoi(getenv("BASIC_TC_SS")));
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
     const long long tiles = (long long)((a.n_count + BN - 1) / BN) * ((rows + BM - 1) / BM);
@@ -590,7 +652,8 @@ int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream)
     LayerArgs b = a;
     static const int dbg = getenv("BASIC_TC_DEBUG") ? atoi(getenv("BASIC_TC_DEBUG")) : 0;
     b.debug = dbg;
-    k_layer_tc<<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    if (ts) k_layer_tc<true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    else k_layer_tc<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

@@ -142,6 +142,13 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
 int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded, int64_t len, const float *prior, int B,
                        int C, int H, int W, int lanes, float *yhat_out, void *stream);
 
+/* Phase timing for bench.py: with profiling enabled the y-path calls bracket their phases with CUDA events on the
+ * launching stream; basic_profile_read returns (and clears) the accumulated milliseconds and span counts per
+ * phase: [0] context model, [1] quantise / dequantise (+ layout copies), [2] multi-lane encode, [3] multi-lane
+ * decode; arrays of 8. */
+int basic_profile_enable(int on);
+int basic_profile_read(double *ms, int64_t *spans);
+
 /* Counters for bench.py ("gpu_launches"): kernels launched by this library since the last reset. */
 int64_t basic_launch_count(int reset);
 
