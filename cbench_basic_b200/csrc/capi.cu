@@ -35,6 +35,7 @@ int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *
                      const float *prior_cl = nullptr);
 bool ctx_uses_tc(const CtxModel &, int B);
 int launch_nchw_to_cl(const float *, float *, int, int, int, cudaStream_t);
+size_t ctx_cl_elems(int B, int channels, int HW);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
@@ -827,11 +828,11 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     const bool tc = model && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {
-        BASIC_TRY(c->buf_cl.reserve(n * 4));
-        BASIC_TRY(c->prior_cl.reserve(2 * n * 4));
+        BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
+        BASIC_TRY(c->prior_cl.reserve(ctx_cl_elems(B, 2 * C, HW) * 4));
         buf_cl = c->buf_cl.as<float>();
         prior_cl = c->prior_cl.as<float>();
-        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, n * 4, s));
+        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
         BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
     }
     // the encoder knows y: all groups' symbols and indexes first (group g's context = the reconstructions of groups
@@ -899,11 +900,11 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const bool tc = model && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
-        BASIC_TRY(c->buf_cl.reserve(n * 4));
-        BASIC_TRY(c->prior_cl.reserve(2 * n * 4));
+        BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
+        BASIC_TRY(c->prior_cl.reserve(ctx_cl_elems(B, 2 * C, HW) * 4));
         buf_cl = c->buf_cl.as<float>();
         prior_cl = c->prior_cl.as<float>();
-        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, n * 4, s));
+        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
         BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
     }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned

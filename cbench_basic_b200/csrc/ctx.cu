@@ -257,6 +257,7 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
 {
     cudaStream_t s = 0;
     const int C = m.C;
+    m.kb_count.clear();
     m.c_ctx = 2 * C;
     m.c_m1 = m.c_ctx * 5 / 3;
     m.c_m2 = m.c_ctx * 4 / 3;
@@ -301,6 +302,7 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
         S = std::max(S, v + 1);
     }
     m.H = H; m.W = W; m.S = S; m.h_tg = tg;
+    m.kb_count.clear();  // the k-block lists of the tensor path depend on the map
     m.stages.assign(S, CtxModel::Stage());
     for (auto &st : m.stages) {
         st.og_tap_or.assign((size_t)G * G, 0u);
@@ -367,7 +369,7 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     return BASIC_OK;
 }
 
-static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, bool tc,
+static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, bool tc,
                         cudaStream_t stream)
 {
     for (int j = 0; j < 8; ++j) a.vis_or[j] = 0;
@@ -390,6 +392,7 @@ static int launch_layer(const CtxModel &m, LayerArgs a, const PackedW &pw, int o
 }
 
 bool ctx_uses_tc(const CtxModel &m, int B) { return tc_model_eligible(m, B); }
+size_t ctx_cl_elems(int B, int channels, int HW) { return cl_elems(B, channels, HW); }
 
 // One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).  buf / prior are NCHW; the tensor path
 // reads channels-last copies: the caller's (buf_cl / prior_cl, kept up to date by the y-path driver) or, when they
@@ -412,20 +415,20 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
     const bool tc = tc_model_eligible(m, B);
     if (m.act_B < B || !(tc ? m.cl_ctx.p : m.a_ctx.p)) {
         DevBuf &x0 = tc ? m.cl_ctx : m.a_ctx, &x1 = tc ? m.cl_m1 : m.a_m1, &x2 = tc ? m.cl_m2 : m.a_m2;
-        BASIC_TRY(x0.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
+        BASIC_TRY(x0.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));  // (the padded size also covers NCHW)
         if (m.has_merger) {
-            BASIC_TRY(x1.reserve((size_t)B * m.c_m1 * HW * sizeof(float)));
-            BASIC_TRY(x2.reserve((size_t)B * m.c_m2 * HW * sizeof(float)));
+            BASIC_TRY(x1.reserve(cl_elems(B, m.c_m1, HW) * sizeof(float)));
+            BASIC_TRY(x2.reserve(cl_elems(B, m.c_m2, HW) * sizeof(float)));
         }
         m.act_B = B;
     }
     if (tc && !buf_cl) {
-        BASIC_TRY(m.cl_buf.reserve((size_t)B * m.C * HW * sizeof(float)));
+        BASIC_TRY(m.cl_buf.reserve(cl_elems(B, m.C, HW) * sizeof(float)));
         BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, stream));
         buf_cl = m.cl_buf.as<float>();
     }
     if (tc && !prior_cl && (m.has_merger || true)) {
-        BASIC_TRY(m.cl_prior.reserve((size_t)B * m.c_ctx * HW * sizeof(float)));
+        BASIC_TRY(m.cl_prior.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));
         BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream));
         prior_cl = m.cl_prior.as<float>();
     }
@@ -459,6 +462,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         }
         a.lrelu = 0;
         a.tap_or = st.tap_or;
+        a.list_key = (g * G + og) * 4;
         BASIC_TRY(launch_layer(m, a, m.p_ctx, og, st, tc, stream));
     }
     if (!m.has_merger) return BASIC_OK;
@@ -486,6 +490,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             }
             a.n_begin = og * (a.Ntot / G);
             a.n_count = a.Ntot / G;
+            a.list_key = (g * G + og) * 4 + layer;
             BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3, og, st, tc, stream));
         }
     }

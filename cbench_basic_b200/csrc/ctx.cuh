@@ -44,6 +44,8 @@ struct CtxModel {
     int precision = 0;   // BASIC_CTX_FP32 | BASIC_CTX_TF32X3
     int nacc = 4;        // k-blocks (32 k each) accumulated in TMEM before a segment is drained into FP32 registers
     PackedW p_ctx, p_m1, p_m2, p_m3;
+    DevBuf kb_pool;                   // k-block lists of the tensor path, one slot of 512 entries per (stage, out-group, layer)
+    std::vector<int> kb_count;        // entries per slot, -1 = not built yet (reset by set_map / set_weights)
     DevBuf cl_ctx, cl_m1, cl_m2;      // channels-last activations of the tensor path
     DevBuf cl_buf, cl_prior;          // channels-last copies made when the caller only has NCHW (public stage API)
 };
@@ -78,15 +80,24 @@ struct LayerArgs {
     // tensor-core path
     const unsigned char *wpack; // PackedW image
     int kb_total, kb_src0, ntile_base, nacc;
+    int list_key;               // (stage * G + out-group) * 4 + layer: slot of this launch's k-block list
+    const uint4 *kb_list;       // k-block list (built on the host once per key) and its length
+    int n_kb;
     int debug;
+    long long *timeline;        // optional [grid][16 tiles][8] clock64 stamps (BASIC_TC_TIMELINE), else NULL
     uint32_t vis_or[8];         // conv: OR over the launch's rows of the tap mask per input group; dense: [0] = OR of group bits
 };
 
 
 // ctx_tc.cu
+// Activation layout of the tensor-core path ("blocked channels-last"): element (b, hw, c) of a [B, channels, HW] tensor
+// lives at (((b * NB + hw / 32) * (channels / 4) + c / 4) * 32 + hw % 32) * 4 + c % 4, NB = ceil(HW / 32): the 4-channel
+// chunks of 32 neighbouring positions are 512 contiguous bytes, so a warp whose lanes are neighbouring positions reads
+// or writes whole lines per 128-bit access (plain channels-last costs one line per lane).
+inline size_t cl_elems(int B, int channels, int HW) { return (size_t)B * ((HW + 31) / 32) * 32 * channels; }
 bool tc_model_eligible(const CtxModel &m, int B);
 int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream);
-int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream);
+int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream);
 int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
                     int k2, int c_src0, int c_src1, cudaStream_t stream);
 

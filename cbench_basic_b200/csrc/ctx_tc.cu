@@ -11,20 +11,25 @@
 // cut into segments of `seg_kb` k-blocks, each accumulated in its own TMEM slot (4 slots, round-robin) and drained
 // by dedicated warps into an FP32 register accumulator (round-to-nearest adds) while the next segment runs.
 //
-// Structure (persistent: one CTA per SM walks 128 x 128 output tiles, n-tile fastest; 320 threads):
-//   warp 0 lane 0 : weight producer -- one cp.async.bulk (UBLKCP) of a pre-packed, pre-swizzled 32 KB [hi|lo]
-//                   tile per k-block, completing on the stage's mbarrier
-//   warp 1        : allocates TMEM; lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8),
-//                   tcgen05.commit releases the stage / publishes the accumulators
-//   warps 2..5    : A producers -- thread = row; gather 32 k per k-block from the NCHW activations (coalesced
-//                   across the warp for a fixed channel), mask, split hi/lo, st.shared.v4 into the SWIZZLE_128B
-//                   K-major image
-//   warps 6..9    : drain + epilogue -- thread = row (a warp reads its own TMEM lane quarter): tcgen05.ld of every
-//                   finished segment into registers, at the end bias / + prior / LeakyReLU -> NCHW store
+// Structure (persistent: one CTA per SM walks 128 x 128 output tiles, n-tile fastest; 512 threads = 4 warpgroups,
+// registers moved between them with setmaxnreg):
+//   WG0 warp 0 lane 0 : weight producer -- one cp.async.bulk (UBLKCP) of a pre-packed, pre-swizzled 32 KB [hi|lo]
+//                       tile per k-block, completing on the stage's mbarrier
+//       warp 1        : allocates TMEM; lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8, A from
+//                       TMEM), tcgen05.commit releases the stage / publishes the accumulators
+//   WG1, WG2          : A producers, alternating k-blocks -- thread = row = TMEM lane; gather 32 k per k-block from
+//                       the channels-last activations (128 contiguous bytes), mask, split hi/lo, tcgen05.st.  One
+//                       k-block costs a producer ~1500 cycles of dependent latency (barrier, split, TMEM store round
+//                       trip, next gather) against 768 cycles of MMA, hence two groups
+//   WG3               : drain + epilogue -- thread = row (a warp reads its own TMEM lane quarter): tcgen05.ld of every
+//                       finished segment into registers; at the end bias / LeakyReLU -> padded shared-memory row ->
+//                       one cp.async.bulk store per row (channels-last), or strided stores (+ prior) for NCHW
 // K-blocks no row of the launch can see (masked taps, invisible channel groups) are skipped by every role.  The
 // roles only meet through mbarriers, so tile t's epilogue overlaps tile t + 1's main loop.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "ctx.cuh"
 
@@ -32,33 +37,34 @@ namespace basic {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, NTHREADS = 320;
-constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB: one of A_hi, A_lo, B_hi, B_lo
-// Operand staging.  TS = true: the A operand (hi and lo images of the gathered rows) is written by the producers
-// straight into tensor memory (tcgen05.st, thread = row = TMEM lane) and tcgen05.mma reads it from there; shared
-// memory only holds the weights.  That halves the shared-memory traffic per MMA, which is what bounds 3xTF32 with
-// both operands in shared memory (24 KB of operand reads per 128x128x8 k-step against 128 B/cycle).
-// TS = false: both operands in shared memory (SWIZZLE_128B K-major), kept as the reference variant.
-template <bool TS> struct Cfg {
-    static constexpr int STAGES = TS ? 4 : 3;
-    static constexpr int SLOTS = TS ? 2 : 4;                          // TMEM accumulator slots of BN columns
-    static constexpr int STAGE_BYTES = (TS ? 2 : 4) * TILE_BYTES;     // [A_hi | A_lo |] B_hi | B_lo
-    static constexpr int B_OFF = TS ? 0 : 2 * TILE_BYTES;
-    static constexpr int A_COL0 = SLOTS * BN;                         // TS: stage s keeps A_hi at A_COL0 + 64 s, A_lo 32 further
-};
-constexpr int MAX_STAGES = 4, MAX_SLOTS = 4;
+constexpr int BM = 128, BN = 128, BK = 32, NTHREADS = 512;
+constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB: one of B_hi, B_lo
+// Operand staging: the A operand (hi and lo images of the gathered rows) is written by the producers straight into
+// tensor memory (tcgen05.st, thread = row = TMEM lane) and tcgen05.mma reads it from there; shared memory only
+// holds the weights.  With both operands in shared memory 3xTF32 is shared-memory bound (24 KB of operand reads
+// per 128x128x8 k-step against 128 B/cycle = 2x the MMA time).
+constexpr int STAGES = 4;                    // operand ring: B in shared memory, A in TMEM columns
+constexpr int SLOTS = 2;                     // TMEM accumulator slots of BN columns
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // B_hi | B_lo
+constexpr int A_COL0 = SLOTS * BN;           // stage s keeps A_hi at TMEM column A_COL0 + 64 s, A_lo 32 further
+constexpr int NGROUPS = 2;                   // A-producer warpgroups, alternating k-blocks
 constexpr int MAX_KB = 512;                  // k-blocks a CTA may walk (conv: 25 taps x ceil(C / 32))
 constexpr int MAX_G = 8;
 constexpr float kSlope = 0.01f;              // nn.LeakyReLU default negative_slope
+constexpr int OUT_ROW = BN * 4 + 16;         // bytes between rows of the epilogue staging tile (16 B pad: conflict-free v4 stores)
 
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int OFF_STAGES = 0;
-constexpr int OFF_BARS = 3 * 4 * TILE_BYTES;            // stages: 192 KB (SS) / 128 KB (TS); then full[], empty[], slot_full[], slot_empty[]
-constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * MAX_STAGES + 2 * MAX_SLOTS);
+constexpr int OFF_OUT = STAGES * STAGE_BYTES;            // epilogue staging: BM rows of OUT_ROW bytes
+constexpr int OFF_BARS = OFF_OUT + BM * OUT_ROW;         // full[STAGES], empty[STAGES], slot_full[SLOTS], slot_empty[SLOTS]
+constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * STAGES + 2 * SLOTS);
 constexpr int OFF_NKB = OFF_TMEM + 4;
 constexpr int OFF_LIST = ((OFF_NKB + 4 + 15) / 16) * 16;         // uint4 [MAX_KB]
-constexpr int OFF_MASK = OFF_LIST + 16 * MAX_KB;        // uint32 [MAX_G][BM]
-constexpr int SMEM_BYTES = OFF_MASK + 4 * MAX_G * BM + 1024 /* alignment slack */;
+constexpr int OFF_MASK = OFF_LIST + 16 * MAX_KB;        // uint32 [NGROUPS][MAX_G][BM]: a producer thread's private row masks
+constexpr int MAX_BIAS = 2048;                          // output channels of one launch (n_count) the bias cache holds
+constexpr int OFF_BIAS = OFF_MASK + 4 * NGROUPS * MAX_G * BM;     // float [MAX_BIAS]: bias[n_begin ..] (zeros without a bias)
+constexpr int SMEM_BYTES = OFF_BIAS + 4 * MAX_BIAS + 1024 /* alignment slack */;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ inline uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,15 +114,6 @@ __device__ inline void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ inline void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ inline void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -138,6 +135,15 @@ __device__ inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
         "r"(r[31])
         : "memory");
 }
+__device__ inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ inline void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ inline void umma_commit(uint32_t bar)
 {
@@ -156,6 +162,20 @@ __device__ inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+__device__ inline bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int R> __device__ inline void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ inline void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ inline void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ inline void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ inline void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ inline void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused
@@ -179,27 +199,24 @@ __device__ inline uint32_t tf32_hi(float v)
 __device__ __host__ inline int swz(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
 
 // ------------------------------------------------------------------------------------------------- the kernel
-template <bool TS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_layer_tc(LayerArgs a)
 {
-    constexpr int STAGES = Cfg<TS>::STAGES, SLOTS = Cfg<TS>::SLOTS, STAGE_BYTES = Cfg<TS>::STAGE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
-    int *s_nkb = reinterpret_cast<int *>(smem + OFF_NKB);
     // k-block list entry: x = weight k-block index; y = element offset of the block's first channel from the row's
     // base pointer (c0 * HW + tap shift); z = source (bit 0) | tap << 1 | valid 4-channel chunks << 8 | grouped << 16;
     // w = visibility group of each of the 8 chunks, 4 bits each
     uint4 *s_list = reinterpret_cast<uint4 *>(smem + OFF_LIST);
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + OFF_MASK);  // [MAX_G][BM]: a producer thread's private row masks
+    float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
     auto bar_full = [&](int s) { return s_base + OFF_BARS + 8 * s; };
-    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (MAX_STAGES + s); };
-    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + q); };
-    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + MAX_SLOTS + q); };
+    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (STAGES + s); };
+    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + q); };
+    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + SLOTS + q); };
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
     const int rows = a.B * a.ncells;
     const int G = a.G, HW = a.HW;
     const int seg_kb = a.nacc;                         // k-blocks per TMEM accumulation segment
@@ -210,7 +227,7 @@ k_layer_tc(LayerArgs a)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full(s), 128 + 1);  // 128 A-producer threads + the weight producer's expect_tx arrive
+            mbar_init(bar_full(s), 128 + 1);  // the 128 threads of one A-producer group + the weight producer's expect_tx arrive
             mbar_init(bar_empty(s), 1);       // one tcgen05.commit
         }
         for (int q = 0; q < SLOTS; ++q) {
@@ -220,241 +237,212 @@ k_layer_tc(LayerArgs a)
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), tmem_cols);
-    // ---- warp 0: the k-block list every role walks, from the launch-level visibility (a.vis_or): k-blocks no row
-    // of this (stage, out-group) can see -- masked taps, invisible channel groups -- are skipped by everybody
-    if (warp == 0) {
-        int count = 0;
-        const int total = a.is_conv ? a.ksize * a.ksize * a.kb_src0 : a.kb_total;
-        for (int i0 = 0; i0 < total; i0 += 32) {
-            const int i = i0 + lane;
-            bool vis = false;
-            uint4 e = make_uint4(0, 0, 0, 0);
-            if (i < total) {
-                int src = 0, tap = 0, c0, nch, groups, shift = 0;
-                if (a.is_conv) {
-                    const int kbt = a.kb_src0 /* k-blocks per tap */, pad = a.ksize / 2;
-                    tap = i / kbt;
-                    c0 = (i - tap * kbt) * BK;
-                    nch = a.Cin;
-                    groups = G;
-                    shift = (tap / a.ksize - pad) * a.W_img + (tap % a.ksize - pad);
-                } else {
-                    src = i >= a.kb_src0;
-                    c0 = (src ? i - a.kb_src0 : i) * BK;
-                    const Source sc = src ? a.src1 : a.src0;
-                    nch = sc.channels;
-                    groups = sc.groups;
-                }
-                const int nvalid = min(BK / 4, (nch - c0) / 4);
-                uint32_t gids = 0;
-                if (groups == 0) vis = true;
-                else {
-                    const int cpg = nch / groups;
-                    for (int j = 0; j < nvalid; ++j) {
-                        const int g = (c0 + 4 * j) / cpg;
-                        gids |= (uint32_t)g << (4 * j);
-                        vis |= a.is_conv ? ((a.vis_or[g] >> tap) & 1u) : ((a.vis_or[0] >> g) & 1u);
-                    }
-                }
-                const bool src_cl = a.is_conv ? a.src0.cl : (src ? a.src1.cl : a.src0.cl);
-                const int rel = src_cl ? shift * nch + c0 : c0 * HW + shift;   // from the row's base pointer, in elements
-                e = make_uint4((uint32_t)i, (uint32_t)rel, (uint32_t)src | ((uint32_t)tap << 1) | ((uint32_t)nvalid << 8) |
-                               (groups ? 1u << 16 : 0u) | (src_cl ? 1u << 17 : 0u), gids);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, vis);
-            if (vis) s_list[count + __popc(m & ((1u << lane) - 1))] = e;
-            count += __popc(m);
-        }
-        if (lane == 0) *s_nkb = count;
-    }
+    // the epilogue reads its bias from shared memory (a dependent global load per stored vector serialised it)
+    if (wg == 3)
+        for (int i = tid - 384; i < ((a.n_count + 3) & ~3); i += 128) s_bias[i] = (a.bias && i < a.n_count) ? __ldg(a.bias + a.n_begin + i) : 0.f;
+    // ---- the k-block list every role walks (built on the host, launch_layer_tc): k-blocks no row of this
+    // (stage, out-group) can see -- masked taps, invisible channel groups -- are not in it
+    for (int i = tid; i < a.n_kb; i += NTHREADS) s_list[i] = a.kb_list[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const int n_kb = *s_nkb;
+    const int n_kb = a.n_kb;
     const uint32_t tmem_base = *s_tmem;
+    // debug timeline: slot j of local tile lt of this CTA
+    auto stamp_v = [&](int lt, int j, long long v) {
+        if (a.timeline && lt < 16) a.timeline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = v;
+    };
+    auto stamp = [&](int lt, int j) {
+        if (a.timeline && lt < 16) a.timeline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = clock64();
+    };
 
-    if (warp == 0) {
-        // ================================================================================ weight producer
-        if (lane == 0) {
-            int it = 0;
+    if (wg == 0) {
+        reg_dec<32>();
+        // both loops run warp-wide with one elected lane issuing, so that addresses and descriptors stay in uniform
+        // registers (a lane-0 branch makes the compiler wrap every tcgen05.mma in a divergence loop of register moves)
+        if (warp == 0) {
+            // ============================================================================ weight producer
+            int s = 0, par = 1;  // stage and the parity that means "this round's buffer is free"
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int nt = t % n_ntiles;
                 const unsigned char *wsrc = a.wpack + (size_t)(a.ntile_base + nt) * a.kb_total * (2 * TILE_BYTES);
-                for (int i = 0; i < n_kb; ++i, ++it) {
-                    const int s = it % STAGES, round = it / STAGES;
-                    mbar_wait(bar_empty(s), (round & 1) ^ 1);
-                    if (a.debug & 2) { mbar_arrive(bar_full(s)); continue; }
-                    mbar_arrive_expect_tx(bar_full(s), 2 * TILE_BYTES);
-                    bulk_g2s(s_base + OFF_STAGES + s * STAGE_BYTES + Cfg<TS>::B_OFF, wsrc + (size_t)s_list[i].x * (2 * TILE_BYTES),
-                             2 * TILE_BYTES, bar_full(s));
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ==================================================================================== MMA issuer
-        if (lane == 0) {
-            int it = 0, segg = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                for (int i = 0; i < n_kb; ++i, ++it) {
-                    const int s = it % STAGES, round = it / STAGES;
-                    const int slot = segg % SLOTS;
-                    const bool seg_first = i % seg_kb == 0, seg_last = (i % seg_kb == seg_kb - 1) || i == n_kb - 1;
-                    if (seg_first) {  // the slot must have been drained (fresh barrier: passes)
-                        mbar_wait(bar_slot_empty(slot), ((segg / SLOTS) & 1) ^ 1);
-                        tc_fence_after();
-                    }
-                    mbar_wait(bar_full(s), round & 1);
-                    tc_fence_after();
-                    const uint32_t st = s_base + OFF_STAGES + s * STAGE_BYTES;
-                    const uint32_t d = tmem_base + (uint32_t)(slot * BN);
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t bh = smem_desc(st + Cfg<TS>::B_OFF + ks * 32), bl = smem_desc(st + Cfg<TS>::B_OFF + TILE_BYTES + ks * 32);
-                        const uint32_t acc0 = (seg_first && ks == 0) ? 0u : 1u;
-                        if constexpr (TS) {
-                            const uint32_t ah = tmem_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64 + ks * 8), al = ah + 32;
-                            umma_tf32_ts(d, ah, bh, kIdesc, acc0);
-                            umma_tf32_ts(d, ah, bl, kIdesc, 1u);
-                            umma_tf32_ts(d, al, bh, kIdesc, 1u);
-                        } else {
-                            const uint64_t ah = smem_desc(st + ks * 32), al = smem_desc(st + TILE_BYTES + ks * 32);
-                            umma_tf32(d, ah, bh, kIdesc, acc0);
-                            umma_tf32(d, ah, bl, kIdesc, 1u);
-                            umma_tf32(d, al, bh, kIdesc, 1u);
+                for (int i = 0; i < n_kb; ++i) {
+                    mbar_wait(bar_empty(s), par);
+                    const unsigned char *src = wsrc + (size_t)s_list[i].x * (2 * TILE_BYTES);
+                    if (elect_one()) {
+                        if (a.debug & 2) mbar_arrive(bar_full(s));
+                        else {
+                            mbar_arrive_expect_tx(bar_full(s), 2 * TILE_BYTES);
+                            bulk_g2s(s_base + OFF_STAGES + s * STAGE_BYTES, src, 2 * TILE_BYTES, bar_full(s));
                         }
                     }
-                    umma_commit(bar_empty(s));  // frees the stage once the MMAs above have read it
-                    if (seg_last) {
-                        umma_commit(bar_slot_full(slot));  // segment complete -> drain warps
-                        ++segg;
-                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; par ^= 1; }
                 }
             }
-        }
-    } else if (warp < 6) {
-        // ================================================================================== A producers
-        // this thread's row of the tile; with A in tensor memory a warp can only write TMEM lanes 32 * (warp % 4) .. + 31
-        const int r = TS ? (warp & 3) * 32 + lane : tid - 64;
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // shared-space addresses of this row's eight 16-byte chunks inside a SWIZZLE_128B tile
-        uint32_t chunk_off[BK / 4];
+        } else if (warp == 1) {
+            // ================================================================================ MMA issuer
+            const uint64_t desc0 = smem_desc(s_base + OFF_STAGES);  // stage 0, k-step 0, hi image; addresses advance the low field
+            int s = 0, par = 0, slot = 0, slot_par = 1, in_seg = 0, lt = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+                if (lane == 0) stamp(lt, 0);
+                long long w_full = 0, w_slot = 0, w_issue = 0;
+                for (int i = 0; i < n_kb; ++i) {
+                    const bool seg_first = in_seg == 0, seg_last = in_seg == seg_kb - 1 || i == n_kb - 1;
+                    const long long c0 = a.timeline ? clock64() : 0;
+                    if (seg_first) {  // the slot must have been drained (fresh barrier: passes)
+                        mbar_wait(bar_slot_empty(slot), slot_par);
+                    }
+                    const long long c1 = a.timeline ? clock64() : 0;
+                    mbar_wait(bar_full(s), par);
+                    tc_fence_after();
+                    const long long c2 = a.timeline ? clock64() : 0;
+                    if (elect_one()) {
+                        const uint64_t bh0 = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
+                        const uint32_t d = tmem_base + (uint32_t)(slot * BN), a0 = tmem_base + (uint32_t)(A_COL0 + s * 64);
+                        if (!(a.debug & 4)) {
 #pragma unroll
-        for (int j = 0; j < BK / 4; ++j) chunk_off[j] = (uint32_t)swz(r, j);
-        int it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                            for (int ks = 0; ks < BK / 8; ++ks) {
+                                const uint64_t bh = bh0 + (uint64_t)(ks * 2), bl = bh + (uint64_t)(TILE_BYTES >> 4);
+                                const uint32_t ah = a0 + ks * 8, al = ah + 32;
+                                umma_tf32_ts(d, ah, bh, kIdesc, (seg_first && ks == 0) ? 0u : 1u);
+                                umma_tf32_ts(d, ah, bl, kIdesc, 1u);
+                                umma_tf32_ts(d, al, bh, kIdesc, 1u);
+                            }
+                        }
+                        umma_commit(bar_empty(s));                       // frees the stage once the MMAs above have read it
+                        if (seg_last) umma_commit(bar_slot_full(slot));  // segment complete -> drain warps
+                    }
+                    __syncwarp();
+                    if (a.timeline) { w_slot += c1 - c0; w_full += c2 - c1; w_issue += clock64() - c2; }
+                    if (i == 0 && lane == 0) stamp(lt, 1);
+                    if (++s == STAGES) { s = 0; par ^= 1; }
+                    if (seg_last) {
+                        in_seg = 0;
+                        if (++slot == SLOTS) { slot = 0; slot_par ^= 1; }
+                    } else ++in_seg;
+                }
+                if (lane == 0) { stamp(lt, 2); stamp_v(lt, 8, w_full); stamp_v(lt, 9, w_slot); stamp_v(lt, 15, w_issue); }
+            }
+        }
+    } else if (wg <= NGROUPS) {
+        // ================================================================================== A producers
+        // group `grp` takes the k-blocks whose running number is = grp (mod NGROUPS)
+        reg_inc<144>();
+        const int grp = wg - 1;
+        const int r = (warp & 3) * 32 + lane;  // this thread's row of the tile = TMEM lane (a warp reaches lanes 32 * (warp % 4) ..)
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int it0 = 0, lt = 0;  // running k-block number of the tile's first k-block
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt, it0 += n_kb) {
             if (n_kb == 0) break;
+            if (tid == 128) stamp(lt, 3);
             // ---- per-row facts of this tile
             const int row = (t / n_ntiles) * BM + r;
             int rb = -1, rhw = 0;
-            uint32_t rgrp = 0, row_tap0 = 0;
+            uint32_t rgrp = 0;
+            uint32_t *my_mask = reinterpret_cast<uint32_t *>(smem + OFF_MASK) + grp * (MAX_G * BM) + r;  // [g * BM]: private to this thread
             if (row < rows) {
                 rb = row / a.ncells;
                 const int cell = a.cell_base + (row - rb * a.ncells);
                 rhw = a.cell_hw[cell];
-                if (a.is_conv) {
-                    if (G == 1) row_tap0 = a.cell_tap[cell];
-                    else for (int j = 0; j < G; ++j) s_mask[j * BM + r] = a.cell_tap[(size_t)cell * G + j];  // private to this thread
-                } else {
-                    rgrp = a.cell_grp[cell];
-                }
+                if (a.is_conv) for (int j = 0; j < G; ++j) my_mask[j * BM] = a.cell_tap[(size_t)cell * G + j];
+                else rgrp = a.cell_grp[cell];
             }
-            // per-row base pointers (an invalid row never loads: its visibility mask is forced to 0)
+            // sources are blocked channels-last (ctx.cuh): chunk c4 of position hw of image b starts at
+            // ((b * NB + hw / 32) * (channels / 4) + c4) * 128 + (hw % 32) * 4
             const long long rbz = rb < 0 ? 0 : rb;
-            const int nch0 = a.is_conv ? a.Cin : a.src0.channels;
-            const float *row0p = a.src0.cl ? a.src0.ptr + (rbz * HW + rhw) * nch0 : a.src0.ptr + rbz * nch0 * HW + rhw;
-            const float *row1p = !a.src1.ptr ? nullptr
-                                 : a.src1.cl ? a.src1.ptr + (rbz * HW + rhw) * a.src1.channels
-                                             : a.src1.ptr + rbz * a.src1.channels * HW + rhw;
+            const int NB = (HW + 31) >> 5;
+            const int nq0 = (a.is_conv ? a.Cin : a.src0.channels) >> 2, nq1 = a.src1.channels >> 2;
             // gathers the 32 k of k-block i for this thread's row into registers (masked elements = 0)
             auto gather = [&](int i, float(&v)[BK]) {
                 const uint4 e = s_list[i];
-                const float *p = (e.z & 1u) ? row1p : row0p;
+                const int hw2 = rhw + (int)(short)(e.y & 0xffffu);  // the tap's position (inside the image whenever the tap is visible)
+                const bool s1 = e.z & 1u;
                 const int tap = (int)((e.z >> 1) & 31u), nvalid = (int)((e.z >> 8) & 15u);
-                uint32_t vis;  // bit j: chunk j (channels c0 + 4j .. + 3) is loaded
-                if (!((e.z >> 16) & 1u)) vis = 0xffu;                                  // ungrouped source: always visible
-                else if (G == 1) vis = a.is_conv ? (((row_tap0 >> tap) & 1u) ? 0xffu : 0u) : ((rgrp & 1u) ? 0xffu : 0u);
+                const float *p = (s1 ? a.src1.ptr : a.src0.ptr) +
+                                 ((rbz * NB + (hw2 >> 5)) * (s1 ? nq1 : nq0) + (int)(e.y >> 16)) * 128 + (hw2 & 31) * 4;
+                uint32_t vis = 0;  // bit j: chunk j (channels c0 + 4j .. + 3) is loaded
+                if (!((e.z >> 16) & 1u)) vis = 0xffu;  // ungrouped source: always visible
                 else {
-                    vis = 0;
 #pragma unroll
                     for (int j = 0; j < BK / 4; ++j) {
                         const uint32_t g = (e.w >> (4 * j)) & 15u;
-                        const uint32_t bit = a.is_conv ? ((s_mask[g * BM + r] >> tap) & 1u) : ((rgrp >> g) & 1u);
+                        const uint32_t bit = a.is_conv ? ((my_mask[g * BM] >> tap) & 1u) : ((rgrp >> g) & 1u);
                         vis |= bit << j;
                     }
                 }
                 vis &= (1u << nvalid) - 1u;
                 if (rb < 0 || (a.debug & 1)) vis = 0;
-                int idx = (int)e.y;
-                if ((e.z >> 17) & 1u) {  // channels-last source: the 32 channels of the block are contiguous
-                    const float4 *p4 = reinterpret_cast<const float4 *>(p + idx);
-#pragma unroll
-                    for (int j = 0; j < BK / 4; ++j) {
-                        const float4 t = ((vis >> j) & 1u) ? __ldg(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < BK / 4; ++j) {
-                        const bool ok = (vis >> j) & 1u;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            v[4 * j + q] = ok ? __ldg(p + idx) : 0.f;
-                            idx += HW;
-                        }
-                    }
-                }
-            };
-            // splits into hi = tf32(v), lo = v - hi and stores both SWIZZLE_128B images of the stage
-            auto publish = [&](const float(&v)[BK]) {
-                const int s = it % STAGES, round = it / STAGES;
-                ++it;
-                mbar_wait(bar_empty(s), (round & 1) ^ 1);
-                if constexpr (TS) {
-                    tc_fence_after();  // the MMAs that read this stage's TMEM columns have completed (tcgen05.commit)
-                    uint32_t h[BK];
-#pragma unroll
-                    for (int q = 0; q < BK; ++q) h[q] = tf32_hi(v[q]);
-                    tmem_st32(lane_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64), h);
-#pragma unroll
-                    for (int q = 0; q < BK; ++q) h[q] = __float_as_uint(v[q] - __uint_as_float(h[q]));
-                    tmem_st32(lane_base + (uint32_t)(Cfg<TS>::A_COL0 + s * 64 + 32), h);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(bar_full(s));
-                    return;
-                }
-                const uint32_t st = s_base + OFF_STAGES + s * STAGE_BYTES;
+                // eight 4-channel chunks, 512 bytes apart; the warp's lanes are neighbouring positions of one or two blocks
 #pragma unroll
                 for (int j = 0; j < BK / 4; ++j) {
-                    const uint32_t h0 = tf32_hi(v[4 * j + 0]), h1 = tf32_hi(v[4 * j + 1]), h2 = tf32_hi(v[4 * j + 2]), h3 = tf32_hi(v[4 * j + 3]);
-                    const float l0 = v[4 * j + 0] - __uint_as_float(h0), l1 = v[4 * j + 1] - __uint_as_float(h1);
-                    const float l2 = v[4 * j + 2] - __uint_as_float(h2), l3 = v[4 * j + 3] - __uint_as_float(h3);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + chunk_off[j]), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + TILE_BYTES + chunk_off[j]), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+                    const float4 t4 = ((vis >> j) & 1u) ? __ldg(reinterpret_cast<const float4 *>(p + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * j + 0] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
                 }
-                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-                mbar_arrive(bar_full(s));
             };
-            // software pipeline: the loads of k-block i + 1 are in flight while k-block i is split and stored
-            float va[BK], vb[BK];
-            gather(0, va);
-            for (int i = 0; i < n_kb; i += 2) {
-                if (i + 1 < n_kb) gather(i + 1, vb);
-                publish(va);
-                if (i + 1 < n_kb) {
-                    if (i + 2 < n_kb) gather(i + 2, va);
-                    publish(vb);
+            // splits k-block i into hi = tf32(v), lo = v - hi and stores both into the stage's TMEM columns
+            long long w_empty = 0, w_st = 0, w_g = 0;
+            auto publish = [&](int i, const float(&v)[BK]) {
+                const int it = it0 + i, s = it % STAGES, round = it / STAGES;
+                const long long c0 = a.timeline ? clock64() : 0;
+                mbar_wait(bar_empty(s), (round & 1) ^ 1);
+                const long long c1 = a.timeline ? clock64() : 0;
+                w_empty += c1 - c0;
+                if (a.debug & 16) { mbar_arrive(bar_full(s)); return; }
+                tc_fence_after();  // the MMAs that read this stage's TMEM columns have completed (tcgen05.commit)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {  // 16 columns at a time keeps the temporaries small
+                    uint32_t h[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) h[q] = tf32_hi(v[half * 16 + q]);
+                    tmem_st16(lane_base + (uint32_t)(A_COL0 + s * 64 + half * 16), h);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) h[q] = __float_as_uint(v[half * 16 + q] - __uint_as_float(h[q]));
+                    tmem_st16(lane_base + (uint32_t)(A_COL0 + s * 64 + 32 + half * 16), h);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_full(s));
+                if (a.timeline) w_st += clock64() - c1;
+            };
+            // this group's k-blocks of the tile: i = i_first, i_first + NGROUPS, ...; the loads of the next one are in
+            // flight while the current one is split and stored
+            const int i_first = ((grp - it0) % NGROUPS + NGROUPS) % NGROUPS;
+            float v0[BK], v1[BK], v2[BK];
+            auto gather_t = [&](int i, float(&v)[BK]) {
+                const long long c0 = a.timeline ? clock64() : 0;
+                gather(i, v);
+                if (a.timeline) w_g += clock64() - c0;
+            };
+            // three register buffers: the loads of this group's next two k-blocks are in flight while one is published
+            constexpr int NG = NGROUPS;
+            if (i_first < n_kb) gather_t(i_first, v0);
+            if (i_first + NG < n_kb) gather_t(i_first + NG, v1);
+            for (int i = i_first; i < n_kb; i += 3 * NG) {
+                if (i + 2 * NG < n_kb) gather_t(i + 2 * NG, v2);
+                publish(i, v0);
+                if (i + NG < n_kb) {
+                    if (i + 3 * NG < n_kb) gather_t(i + 3 * NG, v0);
+                    publish(i + NG, v1);
+                }
+                if (i + 2 * NG < n_kb) {
+                    if (i + 4 * NG < n_kb) gather_t(i + 4 * NG, v1);
+                    publish(i + 2 * NG, v2);
                 }
             }
+            if (tid == 128) { stamp(lt, 4); stamp_v(lt, 10, w_empty); stamp_v(lt, 11, w_st); stamp_v(lt, 12, w_g); }
         }
     } else {
         // ============================================================================= drain + epilogue
+        reg_inc<192>();
         const int r = (warp & 3) * 32 + lane;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int n_seg = (n_kb + seg_kb - 1) / seg_kb;
         const long long ohw = (long long)a.Ntot * HW;
-        int segg = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t out_row = s_base + OFF_OUT + (uint32_t)r * OUT_ROW;  // this thread's private staging row
+        int segg = 0, lt = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+            if (tid == 384) stamp(lt, 5);
             const int nt = t % n_ntiles;
             const int row = (t / n_ntiles) * BM + r;
             int rb = -1, rhw = 0;
@@ -465,12 +453,16 @@ k_layer_tc(LayerArgs a)
             float acc[BN];
 #pragma unroll
             for (int q = 0; q < BN; ++q) acc[q] = 0.f;
+            long long w_sf = 0;
             for (int seg = 0; seg < n_seg; ++seg, ++segg) {
                 const int slot = segg % SLOTS;
+                const long long c0 = a.timeline ? clock64() : 0;
                 mbar_wait(bar_slot_full(slot), (segg / SLOTS) & 1);
+                if (a.timeline) w_sf += clock64() - c0;
                 tc_fence_after();
 #pragma unroll
                 for (int cc = 0; cc < BN / 32; ++cc) {
+                    if (a.debug & 8) break;
                     uint32_t tt[32];
                     tmem_ld32(lane_base + (uint32_t)(slot * BN + cc * 32), tt);
                     tmem_ld_wait();
@@ -480,43 +472,49 @@ k_layer_tc(LayerArgs a)
                 tc_fence_before();
                 mbar_arrive(bar_slot_empty(slot));
             }
-            if (rb >= 0 && a.out_cl) {
-                // channels-last: this row's 128 channels are contiguous -> 128-bit stores, full sectors
-                const long long o0 = ((long long)rb * HW + rhw) * a.Ntot + a.n_begin + nt * BN;
+            if (tid == 384) { stamp(lt, 6); stamp_v(lt, 14, w_sf); }
+            // phase 1 (unrolled: the accumulators are registers): raw sums -> this thread's padded staging row
 #pragma unroll
-                for (int q = 0; q < BN; q += 4) {
-                    if (nt * BN + q < a.n_count) {  // n_count % 4 == 0 on this path
-                        float4 val = make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
-                        if (a.bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(a.bias + a.n_begin + nt * BN + q));
-                            val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
-                        }
-                        if (a.add) {
-                            const float4 av = __ldg(reinterpret_cast<const float4 *>(a.add + o0 + q));
-                            val.x += av.x; val.y += av.y; val.z += av.z; val.w += av.w;
-                        }
+            for (int q = 0; q < BN; q += 4)
+                if (!(a.debug & 128))
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + q * 4), "f"(acc[q]), "f"(acc[q + 1]), "f"(acc[q + 2]), "f"(acc[q + 3]) : "memory");
+            __syncwarp();
+            const int n_left = min(BN, a.n_count - nt * BN);
+            // phase 2 (compact loops: the instruction cache has to hold every role's code)
+            if (a.out_cl) {
+                // blocked channels-last: chunk by chunk, the warp's rows (neighbouring positions) fill 16-byte slots of
+                // one or two 512-byte blocks (n_count % 4 == 0 on this path)
+                if (rb >= 0) {
+                    const int NB = (HW + 31) >> 5;
+                    float *op = a.out + (((long long)rb * NB + (rhw >> 5)) * (a.Ntot >> 2) + ((a.n_begin + nt * BN) >> 2)) * 128 + (rhw & 31) * 4;
+                    const float *bp = s_bias + nt * BN;
+#pragma unroll 4
+                    for (int q = 0; q < n_left; q += 4) {
+                        float4 val;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(out_row + q * 4));
+                        const float4 bv = *reinterpret_cast<const float4 *>(bp + q);
+                        val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
                         if (a.lrelu) {
                             val.x = val.x > 0.f ? val.x : val.x * kSlope; val.y = val.y > 0.f ? val.y : val.y * kSlope;
                             val.z = val.z > 0.f ? val.z : val.z * kSlope; val.w = val.w > 0.f ? val.w : val.w * kSlope;
                         }
-                        *reinterpret_cast<float4 *>(a.out + o0 + q) = val;
+                        if (!(a.debug & 64)) *reinterpret_cast<float4 *>(op + q * 32) = val;
                     }
                 }
             } else if (rb >= 0) {
-                const long long obase = (long long)rb * ohw + rhw;
-#pragma unroll
-                for (int q = 0; q < BN; ++q) {
-                    const int n = nt * BN + q;
-                    if (n < a.n_count) {
-                        const int ch = a.n_begin + n;
-                        const long long o = obase + (long long)ch * HW;
-                        float val = acc[q] + (a.bias ? __ldg(a.bias + ch) : 0.f);
-                        if (a.add) val += __ldg(a.add + o);
-                        if (a.lrelu) val = val > 0.f ? val : val * kSlope;
-                        a.out[o] = val;
-                    }
+                // NCHW (+ prior): for a fixed channel the warp's rows are neighbouring cells -> a strided sector run per store
+                const float *srow = reinterpret_cast<const float *>(smem + OFF_OUT + r * OUT_ROW);
+                float *op = a.out + (long long)rb * ohw + rhw + (long long)(a.n_begin + nt * BN) * HW;
+                const float *ap = a.add ? a.add + (long long)rb * ohw + rhw + (long long)(a.n_begin + nt * BN) * HW : nullptr;
+#pragma unroll 2
+                for (int q = 0; q < n_left; ++q) {
+                    float val = srow[q] + s_bias[nt * BN + q];
+                    if (ap) val += __ldg(ap + (long long)q * HW);
+                    if (a.lrelu) val = val > 0.f ? val : val * kSlope;
+                    op[(long long)q * HW] = val;
                 }
             }
+            if (tid == 384) stamp(lt, 7);
         }
     }
     tc_fence_before();
@@ -599,31 +597,34 @@ bool tc_model_eligible(const CtxModel &m, int B)
 {
     if (m.precision != BASIC_CTX_TF32X3 || !m.has_conv || m.S < 1) return false;
     if (m.G > MAX_G || m.k * m.k * ((m.C + BK - 1) / BK) > MAX_KB || m.k * m.k > 31) return false;
+    if (std::max(m.c_ctx, std::max(m.c_m1, m.c_m2)) / m.G > MAX_BIAS) return false;
     auto ok4 = [&](int channels) { return channels % m.G == 0 && (channels / m.G) % 4 == 0; };
     if (!ok4(m.C) || !ok4(m.c_ctx)) return false;
     if (m.has_merger && (!ok4(m.c_m1) || !ok4(m.c_m2))) return false;
     return (long long)B * m.G * m.H * m.W / m.S >= 64;
 }
 
-// [B, channels, HW] -> [B, HW, channels], 32 x 32 tiles through shared memory (both sides coalesced)
+// [B, channels, HW] -> blocked channels-last (ctx.cuh), 32 positions x 32 channels per CTA through shared memory
+// (both sides coalesced); positions past HW in the last block are written as zeros
 __global__ void __launch_bounds__(256)
 k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
 {
     __shared__ float tile[32][33];
-    const int b = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int b = blockIdx.z, blk = blockIdx.x, hw0 = blk * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float *s = src + (size_t)b * channels * HW;
-    float *d = dst + (size_t)b * channels * HW;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + ty + 8 * i, hw = hw0 + tx;
         tile[ty + 8 * i][tx] = (c < channels && hw < HW) ? s[(size_t)c * HW + hw] : 0.f;
     }
     __syncthreads();
+    float *d = dst + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2)) * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int hw = hw0 + ty + 8 * i, c = c0 + tx;
-        if (c < channels && hw < HW) d[(size_t)hw * channels + c] = tile[tx][ty + 8 * i];
+        const int o = threadIdx.x + 256 * i;  // chunk (8 per CTA) * 128 + position * 4 + channel % 4
+        const int chunk = o >> 7, hwl = (o >> 2) & 31, cl = o & 3;
+        if (c0 + chunk * 4 < channels) d[o] = tile[chunk * 4 + cl][hwl];
     }
 }
 
@@ -636,25 +637,107 @@ int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW,
     return BASIC_OK;
 }
 
-int launch_layer_tc(const CtxModel &m, const LayerArgs &a, cudaStream_t stream)
+// The k-block list of one (stage, out-group, layer): every 32-k block at least one row of the launch can see, in
+// weight order.  Entry: x = weight k-block index; y = position shift of the tap (int16) | first 4-channel chunk << 16; z = source (bit 0) | tap << 1 | valid 4-channel chunks << 8 |
+// grouped << 16; w = visibility group of each of the 8 chunks, 4 bits each.
+static void build_kb_list(const LayerArgs &a, std::vector<uint4> &out)
+{
+    out.clear();
+    const int total = a.is_conv ? a.ksize * a.ksize * a.kb_src0 : a.kb_total;
+    for (int i = 0; i < total; ++i) {
+        int src = 0, tap = 0, c0, nch, groups, shift = 0;
+        if (a.is_conv) {
+            const int kbt = a.kb_src0 /* k-blocks per tap */, pad = a.ksize / 2;
+            tap = i / kbt;
+            c0 = (i - tap * kbt) * BK;
+            nch = a.Cin;
+            groups = a.G;
+            shift = (tap / a.ksize - pad) * a.W_img + (tap % a.ksize - pad);
+        } else {
+            src = i >= a.kb_src0;
+            c0 = (src ? i - a.kb_src0 : i) * BK;
+            const Source sc = src ? a.src1 : a.src0;
+            nch = sc.channels;
+            groups = sc.groups;
+        }
+        const int nvalid = std::min(BK / 4, (nch - c0) / 4);
+        uint32_t gids = 0;
+        bool vis = groups == 0;
+        if (groups) {
+            const int cpg = nch / groups;
+            for (int j = 0; j < nvalid; ++j) {
+                const int g = (c0 + 4 * j) / cpg;
+                gids |= (uint32_t)g << (4 * j);
+                vis |= a.is_conv ? ((a.vis_or[g] >> tap) & 1u) : ((a.vis_or[0] >> g) & 1u);
+            }
+        }
+        if (!vis) continue;
+        out.push_back(make_uint4((uint32_t)i, ((uint32_t)shift & 0xffffu) | ((uint32_t)(c0 / 4) << 16),
+                                 (uint32_t)src | ((uint32_t)tap << 1) | ((uint32_t)nvalid << 8) | (groups ? 1u << 16 : 0u), gids));
+    }
+}
+
+int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
 {
     const int rows = a.B * a.ncells;
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
     static bool attr_done = false;
-    static const bool ts = !(getenv("BASIC_TC_SS") && atoi(getenv("BASIC_TC_SS")));
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
     const long long tiles = (long long)((a.n_count + BN - 1) / BN) * ((rows + BM - 1) / BM);
     dim3 grid((unsigned)(tiles < m.sm_count ? tiles : m.sm_count));  // persistent: one CTA per SM
     LayerArgs b = a;
+    // k-block list of this (stage, out-group, layer): built once per map, kept in device memory
+    const int n_keys = m.S * m.G * 4;
+    if ((int)m.kb_count.size() != n_keys) {
+        BASIC_CUDA(cudaStreamSynchronize(stream));  // launches in flight may still read the old pool
+        m.kb_count.assign((size_t)n_keys, -1);
+        BASIC_TRY(m.kb_pool.reserve((size_t)n_keys * MAX_KB * sizeof(uint4)));
+    }
+    if (a.list_key < 0 || a.list_key >= n_keys) return value_error("k-block list key out of range");
+    uint4 *slot = m.kb_pool.as<uint4>() + (size_t)a.list_key * MAX_KB;
+    if (m.kb_count[a.list_key] < 0) {
+        std::vector<uint4> list;
+        build_kb_list(a, list);
+        if ((int)list.size() > MAX_KB) return value_error("k-block list too long for the tensor-core context kernel");
+        if (!list.empty()) BASIC_CUDA(cudaMemcpy(slot, list.data(), list.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+        m.kb_count[a.list_key] = (int)list.size();
+    }
+    b.kb_list = slot;
+    b.n_kb = m.kb_count[a.list_key];
     static const int dbg = getenv("BASIC_TC_DEBUG") ? atoi(getenv("BASIC_TC_DEBUG")) : 0;
     b.debug = dbg;
-    if (ts) k_layer_tc<true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-    else k_layer_tc<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    static const int nacc_env = getenv("BASIC_TC_NACC") ? atoi(getenv("BASIC_TC_NACC")) : 0;
+    if (nacc_env > 0) b.nacc = nacc_env;
+    // BASIC_TC_TIMELINE=<launch index>: clock64 stamps of the roles of that launch, printed for a few CTAs
+    static const int tl_at = getenv("BASIC_TC_TIMELINE") ? atoi(getenv("BASIC_TC_TIMELINE")) : -1;
+    static int tl_count = 0;
+    static long long *tl_buf = nullptr;
+    const bool tl = tl_at >= 0 && tl_count++ == tl_at;
+    if (tl) {
+        cudaMalloc(&tl_buf, (size_t)grid.x * 16 * 16 * sizeof(long long));
+        cudaMemset(tl_buf, 0, (size_t)grid.x * 16 * 16 * sizeof(long long));
+        b.timeline = tl_buf;
+    }
+    k_layer_tc<<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
     BASIC_LAUNCHED();
+    if (tl) {
+        std::vector<long long> h((size_t)grid.x * 16 * 16);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), tl_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "timeline: launch %d rows %d n_count %d conv %d tiles %lld (cycles from the CTA's first stamp)\n", tl_at, rows, a.n_count, a.is_conv, tiles);
+        for (unsigned cta : {0u, grid.x / 2, grid.x - 1}) {
+            long long t0 = h[(size_t)cta * 256 + 0];
+            for (int lt = 0; lt < 16; ++lt) {
+                const long long *e = &h[((size_t)cta * 16 + lt) * 16];
+                if (!e[0]) break;
+                fprintf(stderr, "  cta %3u tile %d | mma: start %7lld first-issue %7lld last-commit %7lld | producer: start %7lld done %7lld | drain: start %7lld drained %7lld stored %7lld || waits: mma full %lld slot %lld | prodA empty %lld st %lld gather %lld (%lld) | drain slot_full %lld | mma issue %lld\n",
+                        cta, lt, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0, e[6] - t0, e[7] - t0, e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15]);
+            }
+        }
+    }
     return BASIC_OK;
 }
 
