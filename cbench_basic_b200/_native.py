@@ -16,7 +16,7 @@ CTX_FP32, CTX_TF32X3 = 0, 1
 SYMBOLS = [
     "basic_last_error", "basic_device_count", "basic_coder_create", "basic_coder_destroy", "basic_coder_init_params",
     "basic_coder_init_cdf_params", "basic_coder_cdfs_shape", "basic_coder_get_cdfs", "basic_pmf_to_quantized_cdf",
-    "basic_coder_encode_bound", "basic_coder_encode", "basic_coder_flush", "basic_coder_last_output", "basic_coder_decode", "basic_coder_set_stream",
+    "basic_coder_encode_bound", "basic_coder_encode", "basic_coder_flush", "basic_coder_last_output", "basic_coder_output_size", "basic_coder_take_output", "basic_coder_decode", "basic_coder_set_stream",
     "basic_coder_decode_stream", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
     "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_map", "basic_ctx_num_stages",
     "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
@@ -61,6 +61,9 @@ def lib():
     L.basic_coder_encode.argtypes = [vp, i32p, i32p, i64, C.c_int, C.c_int, u8p, i64, C.POINTER(i64), vp]
     L.basic_coder_flush.argtypes = [vp, C.c_int, u8p, i64, C.POINTER(i64), vp]
     L.basic_coder_last_output.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.basic_coder_output_size.argtypes = [vp]
+    L.basic_coder_output_size.restype = i64
+    L.basic_coder_take_output.argtypes = [vp, vp, i64]
     L.basic_coder_decode.argtypes = [vp, u8p, i64, i32p, i64, C.c_int, i32p, vp]
     L.basic_coder_set_stream.argtypes = [vp, u8p, i64, C.c_int, vp]
     L.basic_coder_decode_stream.argtypes = [vp, i32p, i64, i32p, vp]
@@ -116,11 +119,23 @@ def require_gpu():
         raise CudaError("cbench_basic_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
 
 
+_new_bytes = C.pythonapi.PyBytes_FromStringAndSize   # (NULL, n): an uninitialised bytes object to be filled in place
+_new_bytes.restype = C.py_object
+_new_bytes.argtypes = [C.c_void_p, C.c_ssize_t]
+_bytes_ptr = C.pythonapi.PyBytes_AsString
+_bytes_ptr.restype = C.c_void_p
+_bytes_ptr.argtypes = [C.py_object]
+
+
 def last_output(handle):
-    """bytes of the stream the last encoding call (made with out == NULL) left in the coder's pinned host buffer."""
-    ptr, n = C.c_void_p(), C.c_int64(0)
-    check(lib().basic_coder_last_output(handle, C.byref(ptr), C.byref(n)))
-    return C.string_at(ptr.value, n.value) if n.value else b""
+    """The stream of the last encoding call made with out == NULL, as a bytes object.  The object is allocated at
+    its final size and the library copies into it directly (chunk by chunk while the rest is still in flight)."""
+    n = int(lib().basic_coder_output_size(handle))
+    if n == 0:
+        return b""
+    out = _new_bytes(None, n)
+    check(lib().basic_coder_take_output(handle, _bytes_ptr(out), n))
+    return out
 
 
 PHASES = ("context_model", "quantise", "coder_encode", "coder_decode")

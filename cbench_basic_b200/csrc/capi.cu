@@ -2,6 +2,10 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -116,6 +120,8 @@ struct basic_coder {
     uint8_t *host_out = nullptr, *host_in = nullptr;
     size_t host_out_cap = 0, host_in_cap = 0;
     int64_t last_len = 0;
+    std::vector<cudaEvent_t> out_events;  // one per chunk of the last device-to-host delivery into host_out
+    int out_chunks = 0;                   // chunks of that delivery still to be awaited (0 = host_out is complete)
     cudaEvent_t in_event = nullptr;  // completion of the last upload out of host_in
     // cache for cache=1 / flush()
     std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
@@ -278,15 +284,94 @@ int reserve_pinned(uint8_t **buf, size_t *cap, size_t bytes)
 
 // Delivers `len` encoded bytes that live on the device: into the caller's buffer, or (out == NULL) into the
 // coder's pinned staging buffer, from where basic_coder_last_output hands them out without another device trip.
+int finish_out(basic_coder *c);
+constexpr int64_t kHostChunk = 1 << 20;  // granularity of the pipelined host copies
+constexpr int kHostThreads = 4;
+
+// A few persistent host threads for the staging copies (a 16 MB memcpy on one core costs more than its bus transfer).
+// run(nt, fn) executes fn(t) for t = 0 .. nt - 1 (t = 0 on the caller) and returns when all are done; one job at a time.
+class HostPool {
+public:
+    static HostPool &get() { static HostPool *p = new HostPool(); return *p; }  // leaked on purpose: no join at exit
+    void run(int nt, const std::function<void(int)> &fn)
+    {
+        std::lock_guard<std::mutex> job(job_mu_);
+        if (nt > kHostThreads) nt = kHostThreads;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            fn_ = &fn; want_ = nt - 1; done_ = 0; ++gen_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> l(mu_);
+        cv_done_.wait(l, [&] { return done_ == want_; });
+        fn_ = nullptr;
+    }
+private:
+    HostPool()
+    {
+        for (int t = 1; t < kHostThreads; ++t) std::thread([this, t] { loop(t); }).detach();
+    }
+    void loop(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn = nullptr;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (t <= want_) fn = fn_;
+            }
+            if (!fn) continue;
+            (*fn)(t);
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                ++done_;
+            }
+            cv_done_.notify_one();
+        }
+    }
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int want_ = 0, done_ = 0;
+    unsigned long long gen_ = 0;
+};
+
 int copy_out(basic_coder *c, const void *d_src, int64_t len, uint8_t *out, int64_t cap, cudaStream_t s)
 {
-    if (!out) {
-        BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)len));
-        out = c->host_out;
-        c->last_len = len;
-    } else if (len > cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
-    if (len > 0) BASIC_CUDA(cudaMemcpyAsync(out, d_src, (size_t)len, cudaMemcpyDefault, s));
-    BASIC_CUDA(cudaStreamSynchronize(s));
+    if (out) {
+        if (len > cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+        if (len > 0) BASIC_CUDA(cudaMemcpyAsync(out, d_src, (size_t)len, cudaMemcpyDefault, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        return BASIC_OK;
+    }
+    // into the pinned staging buffer, chunk by chunk with an event each: basic_coder_take_output copies chunk k to
+    // the caller while chunk k + 1 is still on the bus (the call returns without waiting for the copies)
+    BASIC_TRY(finish_out(c));  // (an unread earlier delivery; the buffer may move)
+    BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)len));
+    c->last_len = len;
+    const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
+    while ((int)c->out_events.size() < chunks) {
+        cudaEvent_t e;
+        BASIC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->out_events.push_back(e);
+    }
+    for (int k = 0; k < chunks; ++k) {
+        const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
+        BASIC_CUDA(cudaMemcpyAsync(c->host_out + at, static_cast<const uint8_t *>(d_src) + at, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaEventRecord(c->out_events[k], s));
+    }
+    c->out_chunks = chunks;
+    return BASIC_OK;
+}
+
+// Waits for the pending chunks of host_out (all of them) -- for the pointer-returning accessor.
+int finish_out(basic_coder *c)
+{
+    for (int k = 0; k < c->out_chunks; ++k) BASIC_CUDA(cudaEventSynchronize(c->out_events[k]));
+    c->out_chunks = 0;
     return BASIC_OK;
 }
 
@@ -415,6 +500,7 @@ void basic_coder_destroy(basic_coder *c)
     if (c->host_out) cudaFreeHost(c->host_out);
     if (c->host_in) cudaFreeHost(c->host_in);
     if (c->in_event) cudaEventDestroy(c->in_event);
+    for (cudaEvent_t e : c->out_events) cudaEventDestroy(e);
     if (c->tt) tans_delete(c->tt);
     delete c;
 }
@@ -537,9 +623,36 @@ int basic_coder_encode(basic_coder *c, const int32_t *symbols, const int32_t *in
 int basic_coder_last_output(basic_coder *c, const uint8_t **ptr, int64_t *len)
 {
     if (!c || !ptr || !len) return value_error("null argument");
+    DeviceGuard guard(c->device);
+    BASIC_TRY(finish_out(c));
     *ptr = c->host_out;
     *len = c->last_len;
     return BASIC_OK;
+}
+
+int64_t basic_coder_output_size(basic_coder *c) { return c ? c->last_len : 0; }
+
+int basic_coder_take_output(basic_coder *c, uint8_t *dst, int64_t cap)
+{
+    if (!c || (!dst && c->last_len)) return value_error("null argument");
+    if (cap < c->last_len) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    DeviceGuard guard(c->device);
+    const int64_t len = c->last_len;
+    const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
+    const int pending = c->out_chunks;  // chunks [0, pending) still have an event to wait for
+    const int nt = std::max(1, std::min(kHostThreads, chunks));
+    const std::function<void(int)> work = [&](int t) {
+        if (t > 0) cudaSetDevice(c->device);
+        for (int k = t; k < chunks; k += nt) {
+            if (k < pending) cudaEventSynchronize(c->out_events[k]);
+            const int64_t at = (int64_t)k * kHostChunk;
+            memcpy(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
+        }
+    };
+    if (nt <= 1) work(0);
+    else HostPool::get().run(nt, work);
+    c->out_chunks = 0;
+    return cudaGetLastError() == cudaSuccess ? BASIC_OK : value_error("device-to-host delivery failed");
 }
 
 int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream)
@@ -557,6 +670,7 @@ int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, 
     int64_t total = 4;
     for (auto &sg : c->cache_segments) total += (int64_t)sg.size();
     if (!out) {
+        BASIC_TRY(finish_out(c));
         BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)total));
         out = c->host_out;
         c->last_len = total;
@@ -590,8 +704,21 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
     } else if (len) {
         if (!c->in_event) BASIC_CUDA(cudaEventCreateWithFlags(&c->in_event, cudaEventDisableTiming));
         BASIC_CUDA(cudaEventSynchronize(c->in_event));  // an earlier upload out of host_in may still be in flight
-        memcpy(c->host_in, encoded, (size_t)len);       // the GPU keeps working on what is already queued on `s`
-        BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, c->host_in, (size_t)len, cudaMemcpyHostToDevice, s));
+        // staged through pinned memory chunk by chunk: every chunk goes on the bus as soon as it is copied, the host
+        // copies run on a few threads (the GPU keeps working on what is already queued on `s`)
+        const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
+        const int nt = std::min(kHostThreads, chunks);
+        const std::function<void(int)> work = [&](int t) {
+            if (t > 0) cudaSetDevice(c->device);
+            for (int k = t; k < chunks; k += nt) {
+                const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
+                memcpy(c->host_in + at, encoded + at, (size_t)nb);
+                cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + at, c->host_in + at, (size_t)nb, cudaMemcpyHostToDevice, s);
+            }
+        };
+        if (nt <= 1) work(0);
+        else HostPool::get().run(nt, work);
+        BASIC_CUDA(cudaGetLastError());
         BASIC_CUDA(cudaEventRecord(c->in_event, s));
     }
     BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, s));

@@ -79,6 +79,12 @@ int basic_coder_flush(basic_coder *c, int lanes, uint8_t *out, int64_t out_cap, 
  * in the coder's own pinned host buffer and this call returns its address and length (valid until the next
  * encoding call on the same coder).  Saves sizing and page-faulting a worst-case caller buffer. */
 int basic_coder_last_output(basic_coder *c, const uint8_t **ptr, int64_t *len);
+/* Same delivery, copied into the caller's buffer (a freshly allocated `bytes` object in the Python binding): with
+ * out == NULL the encoding call returns while the device-to-host copy is still running in chunks, and this call
+ * moves every chunk to `dst` as it lands (a few host threads), so the bus transfer and the host copy overlap.
+ * basic_coder_output_size = length of the pending delivery. */
+int64_t basic_coder_output_size(basic_coder *c);
+int basic_coder_take_output(basic_coder *c, uint8_t *dst, int64_t cap);
 
 /* ---- decode_with_indexes / set_stream / decode_stream (rans64.cpp:389-598, rans64.hpp:104-124) ------- */
 int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, const int32_t *indexes, int64_t n,
