@@ -108,7 +108,8 @@ def build_coder(workload, w, lanes, device):
                             "param_merger_in.weight": w["m1_w"], "param_merger_in.bias": w["m1_b"],
                             "param_merger_out.1.weight": w["m2_w"], "param_merger_out.1.bias": w["m2_b"],
                             "param_merger_out.3.weight": w["m3_w"], "param_merger_out.3.bias": w["m3_b"]})
-        coder = Coder(in_channels=C_, default_topo_group_method=method, topo_group_context_model=cm, lanes=lanes)
+        coder = Coder(in_channels=C_, default_topo_group_method=method, topo_group_context_model=cm, lanes=lanes,
+                      ctx_precision=os.environ.get("BASIC_CTX_PRECISION", "auto"))
     else:
         coder = Coder(in_channels=C_, default_topo_group_method=method, use_param_merger=False, lanes=lanes)
         with torch.no_grad():

@@ -10,7 +10,7 @@ OK, ERR_VALUE, ERR_CUDA, ERR_CAPACITY, ERR_STREAM = 0, -1, -2, -3, -4
 KIND_RANS64, KIND_TANS = 0, 1
 ROLE_BOTH, ROLE_ENCODER, ROLE_DECODER = 0, 1, 2
 LANES_REFERENCE, LANES_AUTO = 1, 0
-CTX_FP32, CTX_TF32X3 = 0, 1
+CTX_FP32, CTX_TF32X3, CTX_FP16X3 = 0, 1, 2
 
 # every extern "C" symbol declared in include/basic_b200.h
 SYMBOLS = [

@@ -38,10 +38,14 @@ int ctx_set_map(CtxModel &, const int32_t *, int, int);
 int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t, const float *buf_cl = nullptr,
                      const float *prior_cl = nullptr);
 bool ctx_uses_tc(const CtxModel &, int B);
-int launch_nchw_to_cl(const float *, float *, int, int, int, cudaStream_t);
+int ctx_to_cl(CtxModel &, const float *src, float *dst, int B, int channels, cudaStream_t);
 size_t ctx_cl_elems(int B, int channels, int HW);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
+int ctx_precision(const CtxModel &);
+void ctx_set_run_precision(CtxModel &, int);
+int ctx_range_flag_clear(CtxModel &, cudaStream_t);
+int ctx_range_flag_read(CtxModel &, cudaStream_t, int *);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
 
@@ -128,6 +132,7 @@ struct basic_coder {
     std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
     // streaming decode state
     int stream_lanes = 1;
+    bool stream_fp16 = false;  // the container was written with the context model in 3xFP16 ("BLS2")
     int64_t stream_len = 0;  // bytes of the stream in host_in / stream_dev
     int64_t stream_pos = 0;
     bool stream_set = false;
@@ -730,7 +735,8 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
     } else {
         uint32_t magic = 0;
         if (len >= 4) memcpy(&magic, c->host_in, 4);
-        if (magic != kMagic) { c->stream_set = false; set_error("not a multi-lane (BLS1) container"); return BASIC_ERR_STREAM; }
+        if (magic != kMagic && magic != kMagic2) { c->stream_set = false; set_error("not a multi-lane (BLS1) container"); return BASIC_ERR_STREAM; }
+        c->stream_fp16 = magic == kMagic2;
         c->stream_pos = 4;
     }
     return BASIC_OK;
@@ -901,7 +907,20 @@ int basic_ctx_stage_params(basic_ctx *m, int g, const float *buf, const float *p
     if (!m) return value_error("null model");
     DeviceGuard guard(m->device);
     if (!is_device_ptr(buf) || !is_device_ptr(prior) || !is_device_ptr(params)) return value_error("basic_ctx_stage_params works on device memory");
-    return ctx_stage_params(*m->m, g, buf, prior, B, params, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int prec = ctx_precision(*m->m);
+    ctx_set_run_precision(*m->m, prec);
+    if (prec != BASIC_CTX_FP16X3) return ctx_stage_params(*m->m, g, buf, prior, B, params, s);
+    // 3xFP16 needs |activation| < 4000: the kernels raise a flag otherwise and the stage is repeated in 3xTF32
+    BASIC_TRY(ctx_range_flag_clear(*m->m, s));
+    BASIC_TRY(ctx_stage_params(*m->m, g, buf, prior, B, params, s));
+    int flag = 0;
+    BASIC_TRY(ctx_range_flag_read(*m->m, s, &flag));
+    if (!flag) return BASIC_OK;
+    ctx_set_run_precision(*m->m, BASIC_CTX_TF32X3);
+    const int rc = ctx_stage_params(*m->m, g, buf, prior, B, params, s);
+    ctx_set_run_precision(*m->m, prec);
+    return rc;
 }
 
 // -------------------------------------------------------------------------------------- whole y path
@@ -948,10 +967,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
     float *buf = c->buf.as<float>(), *params = c->params.as<float>();
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
-    BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
     const float *params_src = params;
     // tensor-core context model: it reads channels-last copies of the prior (made once) and of the y_hat buffer
     // (refreshed after every group's write-back)
+    if (model) ctx_set_run_precision(*model->m, ctx_precision(*model->m));
     const bool tc = model && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {
@@ -959,31 +978,58 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         BASIC_TRY(c->prior_cl.reserve(ctx_cl_elems(B, 2 * C, HW) * 4));
         buf_cl = c->buf_cl.as<float>();
         prior_cl = c->prior_cl.as<float>();
-        BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
-        BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
     }
     // the encoder knows y: all groups' symbols and indexes first (group g's context = the reconstructions of groups
     // < g, written back by the quantiser), then ONE coding pass over all of them
     std::vector<int64_t> slice_n;
     size_t done = 0;
-    for (int g = 0; g < S; ++g) {
-        const int32_t *pos = nullptr;
-        int64_t n_pos = (int64_t)C * HW;
-        if (model) {
-            ProfScope ps(PROF_CTX, s);
-            BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
-            BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
-        } else {
-            params_src = d_prior;
+    auto run_groups = [&]() -> int {
+        slice_n.clear();
+        done = 0;
+        BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
+        if (tc) {  // (in the operand format of the current mode: redone by the 3xTF32 fallback)
+            BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
+            BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
         }
-        const int64_t cnt = (int64_t)B * n_pos;
-        slice_n.push_back(cnt);
-        if (cnt == 0) continue;
-        ProfScope ps(PROF_GAUSS, s);
-        BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                        sym + done, idx + done, buf, c->sm_count, s));
-        if (tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
-        done += (size_t)cnt;
+        for (int g = 0; g < S; ++g) {
+            const int32_t *pos = nullptr;
+            int64_t n_pos = (int64_t)C * HW;
+            if (model) {
+                ProfScope ps(PROF_CTX, s);
+                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
+                BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
+            } else {
+                params_src = d_prior;
+            }
+            const int64_t cnt = (int64_t)B * n_pos;
+            slice_n.push_back(cnt);
+            if (cnt == 0) continue;
+            ProfScope ps(PROF_GAUSS, s);
+            BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
+                                            sym + done, idx + done, buf, c->sm_count, s));
+            if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
+            done += (size_t)cnt;
+        }
+        return BASIC_OK;
+    };
+    // 3xFP16 context model: valid while every activation stays below 4000 in magnitude; the kernels raise a flag
+    // otherwise and the pass is repeated in 3xTF32.  The container's magic tells the decoder which mode was used.
+    bool fp16 = tc && ctx_precision(*model->m) == BASIC_CTX_FP16X3;
+    if (fp16) BASIC_TRY(ctx_range_flag_clear(*model->m, s));
+    BASIC_TRY(run_groups());
+    if (fp16) {
+        int flag = 0;
+        BASIC_TRY(ctx_range_flag_read(*model->m, s, &flag));
+        if (flag) {
+            if (lanes == BASIC_LANES_REFERENCE)
+                return value_error("context-model activation outside the 3xFP16 range and a lanes=1 stream cannot record the "
+                                   "fallback: use ctx_precision tf32x3 or fp32");
+            fp16 = false;
+            ctx_set_run_precision(*model->m, BASIC_CTX_TF32X3);
+            const int rc = run_groups();
+            ctx_set_run_precision(*model->m, ctx_precision(*model->m));
+            BASIC_TRY(rc);
+        }
     }
     if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     if (lanes == BASIC_LANES_REFERENCE) {
@@ -1001,7 +1047,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         ProfScope ps(PROF_ENCODE, s);
         BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));
     }
-    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, &kMagic, 4, cudaMemcpyHostToDevice, s));
+    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, fp16 ? &kMagic2 : &kMagic, 4, cudaMemcpyHostToDevice, s));
     BASIC_TRY(copy_out(c, c->segs.p, 4 + seg_len, out, out_cap, s));
     if (out_len) *out_len = 4 + seg_len;
     return BASIC_OK;
@@ -1024,6 +1070,21 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const float *params_src = params;
     Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
     BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    // the context model runs in the mode the stream was written with: "BLS2" = 3xFP16, otherwise the configured mode
+    // (a 3xFP16 configuration reads "BLS1" -- the encoder's range fallback -- in 3xTF32)
+    if (model) {
+        int prec = ctx_precision(*model->m);
+        if (lanes != BASIC_LANES_REFERENCE) {
+            uint32_t magic = 0;
+            if (len >= 4) {
+                if (is_device_ptr(encoded)) BASIC_CUDA(cudaMemcpy(&magic, encoded, 4, cudaMemcpyDeviceToHost));
+                else memcpy(&magic, encoded, 4);
+            }
+            if (magic == kMagic2) prec = BASIC_CTX_FP16X3;
+            else if (prec == BASIC_CTX_FP16X3) prec = BASIC_CTX_TF32X3;
+        }
+        ctx_set_run_precision(*model->m, prec);
+    }
     const bool tc = model && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
@@ -1032,7 +1093,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         buf_cl = c->buf_cl.as<float>();
         prior_cl = c->prior_cl.as<float>();
         BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
-        BASIC_TRY(launch_nchw_to_cl(d_prior, prior_cl, B, 2 * C, HW, s));
+        BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
     }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
     // memory and upload it while the GPU is busy
@@ -1089,13 +1150,14 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (cnt > 0) {
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
-            if (tc && g + 1 < S) BASIC_TRY(launch_nchw_to_cl(buf, buf_cl, B, C, HW, s));
+            if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
         }
     }
     if (lanes != BASIC_LANES_REFERENCE) c->stream_pos += si.len;
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
     BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     BASIC_CUDA(cudaStreamSynchronize(s));
+    if (model) ctx_set_run_precision(*model->m, ctx_precision(*model->m));
     return status_error(hs->status);
 }
 

@@ -238,13 +238,15 @@ int upload_transposed(DevBuf &dst, const float *src, int N, int Cin, int k2, cud
 }
 
 // stages `src` (host or device, state_dict layout) on the device and packs it for the tensor-core path
-int pack_from(PackedW &dst, const float *src, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1, cudaStream_t s)
+int pack_from(PackedW &dst, PackedW &dst16, const float *src, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1,
+              cudaStream_t s)
 {
     const size_t count = is_conv ? (size_t)N * Cin * k2 : (size_t)N * (c_src0 + c_src1);
     DevBuf tmp;
     BASIC_TRY(tmp.reserve(count * sizeof(float)));
     BASIC_CUDA(cudaMemcpyAsync(tmp.p, src, count * sizeof(float), cudaMemcpyDefault, s));
-    const int rc = pack_weights_tc(dst, tmp.as<float>(), N, G, is_conv, Cin, k2, c_src0, c_src1, s);
+    int rc = pack_weights_tc(dst, tmp.as<float>(), N, G, is_conv, Cin, k2, c_src0, c_src1, 0, s);
+    if (rc == BASIC_OK) rc = pack_weights_tc(dst16, tmp.as<float>(), N, G, is_conv, Cin, k2, c_src0, c_src1, 1, s);
     BASIC_CUDA(cudaStreamSynchronize(s));
     tmp.release();
     return rc;
@@ -269,14 +271,14 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
     if (C % m.G) return value_error("in_channels must be divisible by channel_groups");
     if (m.has_conv) {
         BASIC_TRY(upload_transposed(m.w_ctx, ctx_w, m.c_ctx, C, m.k * m.k, s));
-        BASIC_TRY(pack_from(m.p_ctx, ctx_w, m.c_ctx, m.G, 1, C, m.k * m.k, 0, 0, s));
+        BASIC_TRY(pack_from(m.p_ctx, m.q_ctx, ctx_w, m.c_ctx, m.G, 1, C, m.k * m.k, 0, 0, s));
     }
     if (ctx_b) BASIC_TRY(upload(m.b_ctx, ctx_b, m.c_ctx, s)); else m.b_ctx.release();
     if (m.has_merger) {
         BASIC_TRY(upload_transposed(m.w_m1, m1_w, m.c_m1, 2 * m.c_ctx, 1, s));
-        BASIC_TRY(pack_from(m.p_m1, m1_w, m.c_m1, m.G, 0, 0, 1, m.c_ctx, m.c_ctx, s));
-        BASIC_TRY(pack_from(m.p_m2, m2_w, m.c_m2, m.G, 0, 0, 1, m.c_m1, 0, s));
-        BASIC_TRY(pack_from(m.p_m3, m3_w, m.c_ctx, m.G, 0, 0, 1, m.c_m2, 0, s));
+        BASIC_TRY(pack_from(m.p_m1, m.q_m1, m1_w, m.c_m1, m.G, 0, 0, 1, m.c_ctx, m.c_ctx, s));
+        BASIC_TRY(pack_from(m.p_m2, m.q_m2, m2_w, m.c_m2, m.G, 0, 0, 1, m.c_m1, 0, s));
+        BASIC_TRY(pack_from(m.p_m3, m.q_m3, m3_w, m.c_ctx, m.G, 0, 0, 1, m.c_m2, 0, s));
         BASIC_TRY(upload(m.b_m1, m1_b, m.c_m1, s));
         BASIC_TRY(upload_transposed(m.w_m2, m2_w, m.c_m2, m.c_m1, 1, s));
         BASIC_TRY(upload(m.b_m2, m2_b, m.c_m2, s));
@@ -369,7 +371,7 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     return BASIC_OK;
 }
 
-static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, int og, const CtxModel::Stage &st, bool tc,
+static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, const PackedW &pw16, int og, const CtxModel::Stage &st, bool tc,
                         cudaStream_t stream)
 {
     for (int j = 0; j < 8; ++j) a.vis_or[j] = 0;
@@ -379,11 +381,16 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, int og, con
     }
     const int rows = a.B * a.ncells;
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
-    a.wpack = pw.buf.as<unsigned char>();
-    a.kb_total = pw.kb_total;
-    a.kb_src0 = pw.kb_src0;
-    a.ntile_base = og * pw.ntiles_per_group;
+    const bool f16 = tc && m.run_precision == BASIC_CTX_FP16X3;
+    const PackedW &pk = f16 ? pw16 : pw;
+    a.wpack = pk.buf.as<unsigned char>();
+    a.kb_total = pk.kb_total;
+    a.kb_src0 = pk.kb_src0;
+    a.ntile_base = og * pk.ntiles_per_group;
     a.nacc = m.nacc;
+    a.mode = f16 ? 1 : 0;
+    a.out_scale = f16 ? 1.f / (16.f * pk.scale) : 1.f;  // powers of two: exact
+    a.range_flag = f16 ? m.range_flag.as<int>() : nullptr;
     if (tc) return launch_layer_tc(m, a, stream);
     dim3 grid((rows + BM - 1) / BM, (a.n_count + BN - 1) / BN);
     k_layer<<<grid, NT, 0, stream>>>(a);
@@ -392,6 +399,34 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, int og, con
 }
 
 bool ctx_uses_tc(const CtxModel &m, int B) { return tc_model_eligible(m, B); }
+int ctx_precision(const CtxModel &m) { return m.precision; }
+// blocked channels-last copy in the operand format of the mode the next stage calls run in (floats, or split16)
+int ctx_to_cl(CtxModel &m, const float *src, float *dst, int B, int channels, cudaStream_t s)
+{
+    const bool f16 = m.run_precision == BASIC_CTX_FP16X3;
+    if (f16) BASIC_TRY(m.range_flag.reserve(16));
+    return launch_nchw_to_cl(src, dst, B, channels, m.H * m.W, s, f16 ? 1 : 0, f16 ? m.range_flag.as<int>() : nullptr);
+}
+void ctx_set_run_precision(CtxModel &m, int p)
+{
+    if (m.run_precision != p) m.act_B = 0;  // (FP32 and the tensor modes keep their activations in different layouts)
+    m.run_precision = p;
+}
+// FP16X3 range flag: cleared before a pass, read (with a stream sync) after it
+int ctx_range_flag_clear(CtxModel &m, cudaStream_t s)
+{
+    BASIC_TRY(m.range_flag.reserve(16));
+    BASIC_CUDA(cudaMemsetAsync(m.range_flag.p, 0, 16, s));
+    return BASIC_OK;
+}
+int ctx_range_flag_read(CtxModel &m, cudaStream_t s, int *flag)
+{
+    *flag = 0;
+    if (!m.range_flag.p) return BASIC_OK;
+    BASIC_CUDA(cudaMemcpyAsync(flag, m.range_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return BASIC_OK;
+}
 size_t ctx_cl_elems(int B, int channels, int HW) { return cl_elems(B, channels, HW); }
 
 // One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).  buf / prior are NCHW; the tensor path
@@ -413,6 +448,10 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         return BASIC_OK;
     }
     const bool tc = tc_model_eligible(m, B);
+    if (tc && !m.range_flag.p) {
+        BASIC_TRY(m.range_flag.reserve(16));
+        BASIC_CUDA(cudaMemsetAsync(m.range_flag.p, 0, 16, stream));
+    }
     if (m.act_B < B || !(tc ? m.cl_ctx.p : m.a_ctx.p)) {
         DevBuf &x0 = tc ? m.cl_ctx : m.a_ctx, &x1 = tc ? m.cl_m1 : m.a_m1, &x2 = tc ? m.cl_m2 : m.a_m2;
         BASIC_TRY(x0.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));  // (the padded size also covers NCHW)
@@ -422,14 +461,15 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         }
         m.act_B = B;
     }
+    const int f16 = tc && m.run_precision == BASIC_CTX_FP16X3;
     if (tc && !buf_cl) {
         BASIC_TRY(m.cl_buf.reserve(cl_elems(B, m.C, HW) * sizeof(float)));
-        BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, stream));
+        BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, stream, f16, m.range_flag.as<int>()));
         buf_cl = m.cl_buf.as<float>();
     }
     if (tc && !prior_cl && (m.has_merger || true)) {
         BASIC_TRY(m.cl_prior.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));
-        BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream));
+        BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream, f16, m.range_flag.as<int>()));
         prior_cl = m.cl_prior.as<float>();
     }
     float *act0 = tc ? m.cl_ctx.as<float>() : m.a_ctx.as<float>();
@@ -463,7 +503,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         a.lrelu = 0;
         a.tap_or = st.tap_or;
         a.list_key = (g * G + og) * 4;
-        BASIC_TRY(launch_layer(m, a, m.p_ctx, og, st, tc, stream));
+        BASIC_TRY(launch_layer(m, a, m.p_ctx, m.q_ctx, og, st, tc, stream));
     }
     if (!m.has_merger) return BASIC_OK;
     // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
@@ -491,7 +531,8 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             a.n_begin = og * (a.Ntot / G);
             a.n_count = a.Ntot / G;
             a.list_key = (g * G + og) * 4 + layer;
-            BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3, og, st, tc, stream));
+            BASIC_TRY(launch_layer(m, a, layer == 1 ? m.p_m1 : layer == 2 ? m.p_m2 : m.p_m3,
+                                   layer == 1 ? m.q_m1 : layer == 2 ? m.q_m2 : m.q_m3, og, st, tc, stream));
         }
     }
     return BASIC_OK;
@@ -511,7 +552,7 @@ void ctx_delete(CtxModel *m)
     DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
-                      &m->cl_prior};
+                      &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }
@@ -520,10 +561,12 @@ int ctx_num_stages(const CtxModel &m) { return m.S; }
 
 int ctx_set_precision(CtxModel &m, int precision, int nacc)
 {
-    if (precision != BASIC_CTX_FP32 && precision != BASIC_CTX_TF32X3) return value_error("unknown context-model precision");
+    if (precision != BASIC_CTX_FP32 && precision != BASIC_CTX_TF32X3 && precision != BASIC_CTX_FP16X3)
+        return value_error("unknown context-model precision");
     if (nacc < 1 || nacc > 64) return value_error("segment length must be 1..64 k-blocks");
     if (m.precision != precision) m.act_B = 0;  // the two paths keep their activations in different layouts
     m.precision = precision;
+    m.run_precision = precision;
     m.nacc = nacc;
     return BASIC_OK;
 }

@@ -11,6 +11,7 @@ struct PackedW {
     int kb_total = 0;         // k-blocks (32 k each) per n-tile
     int ntiles_per_group = 0; // n-tiles (128 output channels each) per out-group
     int kb_src0 = 0;          // dense: k-blocks of the first source; conv: k-blocks per tap
+    float scale = 1.f;        // fp16 images: power of two the weights were multiplied by
 };
 
 struct CtxModel {
@@ -41,7 +42,11 @@ struct CtxModel {
     DevBuf a_ctx, a_m1, a_m2;
     int act_B = 0;
     // tensor-core path
-    int precision = 0;   // BASIC_CTX_FP32 | BASIC_CTX_TF32X3
+    int precision = 0;   // configured: BASIC_CTX_FP32 | BASIC_CTX_TF32X3 | BASIC_CTX_FP16X3
+    int run_precision = 0;  // what the next stage calls use (the y-path driver falls back from FP16X3 to TF32X3 when an
+                            // activation leaves the fp16 range, and follows the mode recorded in a stream when decoding)
+    PackedW q_ctx, q_m1, q_m2, q_m3;  // fp16 images of the weights (FP16X3)
+    DevBuf range_flag;   // int: set by the FP16X3 kernels when |activation| >= 4000
     int nacc = 4;        // k-blocks (32 k each) accumulated in TMEM before a segment is drained into FP32 registers
     PackedW p_ctx, p_m1, p_m2, p_m3;
     DevBuf kb_pool;                   // k-block lists of the tensor path, one slot of 512 entries per (stage, out-group, layer)
@@ -80,6 +85,9 @@ struct LayerArgs {
     // tensor-core path
     const unsigned char *wpack; // PackedW image
     int kb_total, kb_src0, ntile_base, nacc;
+    int mode;                   // tensor path: 0 = 3xTF32, 1 = 3xFP16
+    float out_scale;            // 3xFP16: 1 / (activation scale * weight scale), applied to the accumulators
+    int *range_flag;            // 3xFP16: raised when an activation magnitude reaches 4000
     int list_key;               // (stage * G + out-group) * 4 + layer: slot of this launch's k-block list
     const uint4 *kb_list;       // k-block list (built on the host once per key) and its length
     int n_kb;
@@ -96,9 +104,10 @@ struct LayerArgs {
 // or writes whole lines per 128-bit access (plain channels-last costs one line per lane).
 inline size_t cl_elems(int B, int channels, int HW) { return (size_t)B * ((HW + 31) / 32) * 32 * channels; }
 bool tc_model_eligible(const CtxModel &m, int B);
-int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream);
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split = 0,
+                      int *range_flag = nullptr);
 int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream);
 int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
-                    int k2, int c_src0, int c_src1, cudaStream_t stream);
+                    int k2, int c_src0, int c_src1, int mode, cudaStream_t stream);
 
 }  // namespace basic

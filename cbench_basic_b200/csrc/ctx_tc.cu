@@ -26,6 +26,8 @@
 //                       one cp.async.bulk store per row (channels-last), or strided stores (+ prior) for NCHW
 // K-blocks no row of the launch can see (masked taps, invisible channel groups) are skipped by every role.  The
 // roles only meet through mbarriers, so tile t's epilogue overlaps tile t + 1's main loop.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -38,15 +40,36 @@ namespace basic {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32, NTHREADS = 512;
-constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB: one of B_hi, B_lo
 // Operand staging: the A operand (hi and lo images of the gathered rows) is written by the producers straight into
 // tensor memory (tcgen05.st, thread = row = TMEM lane) and tcgen05.mma reads it from there; shared memory only
 // holds the weights.  With both operands in shared memory 3xTF32 is shared-memory bound (24 KB of operand reads
 // per 128x128x8 k-step against 128 B/cycle = 2x the MMA time).
-constexpr int STAGES = 4;                    // operand ring: B in shared memory, A in TMEM columns
-constexpr int SLOTS = 2;                     // TMEM accumulator slots of BN columns
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // B_hi | B_lo
-constexpr int A_COL0 = SLOTS * BN;           // stage s keeps A_hi at TMEM column A_COL0 + 64 s, A_lo 32 further
+//
+// Two arithmetic modes, same structure (every product = hi*hi + hi*lo + lo*hi, ~22 significant bits):
+//   MODE 0  3xTF32: hi = tf32(x), lo = x - hi; kind::tf32, K = 8 per MMA, 4-byte operands.
+//   MODE 1  3xFP16: operands scaled by powers of two (activations x 16, weights so that max |w| lands in [2^12, 2^13)),
+//           hi = fp16(X), lo = fp16(X - hi); kind::f16, K = 16 per MMA, 2-byte operands: half the MMA instructions,
+//           half the operand bytes, twice the stages.  |activation| >= 4000 would leave the fp16 range: the producers
+//           raise a flag and the y-path driver repeats the call in MODE 0 (the container records the mode).
+template <int MODE> struct Cfg {
+    static constexpr int ESIZE = MODE ? 2 : 4;                 // operand bytes
+    static constexpr int TILE_BYTES = BM * BK * ESIZE;         // one of B_hi, B_lo: 16 KB / 8 KB
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES;         // B_hi | B_lo
+    static constexpr int STAGES = 4;                           // operand ring: B in shared memory, A in TMEM columns
+    static constexpr int SLOTS = MODE ? 3 : 2;                 // TMEM accumulator slots of BN columns (512 columns in all)
+    static constexpr int A_COL0 = SLOTS * BN;                  // stage s keeps A_hi at column A_COL0 + 2 A_COLS s, A_lo A_COLS further
+    static constexpr int A_COLS = BK * ESIZE / 4;              // TMEM columns of one A image (hi or lo) of a k-block
+    static constexpr int KSTEPS = MODE ? BK / 16 : BK / 8;     // MMAs (x 3) per k-block
+    // cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2) / F16 (0) at bits 7-9, 10-12, K-major both,
+    // N >> 3 at bit 17, M >> 4 at bit 24
+    static constexpr uint32_t IDESC = (1u << 4) | ((MODE ? 0u : 2u) << 7) | ((MODE ? 0u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                      ((uint32_t)(BM >> 4) << 24);
+};
+constexpr int MAX_STAGES = 8;
+constexpr int STAGE_REGION = 128 * 1024;     // >= STAGES * STAGE_BYTES of either mode
+constexpr int MAX_SLOTS = 3;
+constexpr float kActScale = 16.f;            // MODE 1: activations are multiplied by this before the fp16 split
+constexpr float kActLimit = 4000.f;          // ... and must stay below this in magnitude
 constexpr int NGROUPS = 2;                   // A-producer warpgroups, alternating k-blocks
 constexpr int MAX_KB = 512;                  // k-blocks a CTA may walk (conv: 25 taps x ceil(C / 32))
 constexpr int MAX_G = 8;
@@ -55,9 +78,9 @@ constexpr int OUT_ROW = BN * 4 + 16;         // bytes between rows of the epilog
 
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int OFF_STAGES = 0;
-constexpr int OFF_OUT = STAGES * STAGE_BYTES;            // epilogue staging: BM rows of OUT_ROW bytes
-constexpr int OFF_BARS = OFF_OUT + BM * OUT_ROW;         // full[STAGES], empty[STAGES], slot_full[SLOTS], slot_empty[SLOTS]
-constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * STAGES + 2 * SLOTS);
+constexpr int OFF_OUT = STAGE_REGION;                    // epilogue staging: BM rows of OUT_ROW bytes
+constexpr int OFF_BARS = OFF_OUT + BM * OUT_ROW;         // full[MAX_STAGES], empty[MAX_STAGES], slot_full[SLOTS], slot_empty[SLOTS]
+constexpr int OFF_TMEM = OFF_BARS + 8 * (2 * MAX_STAGES + 2 * MAX_SLOTS);
 constexpr int OFF_NKB = OFF_TMEM + 4;
 constexpr int OFF_LIST = ((OFF_NKB + 4 + 15) / 16) * 16;         // uint4 [MAX_KB]
 constexpr int OFF_MASK = OFF_LIST + 16 * MAX_KB;        // uint32 [NGROUPS][MAX_G][BM]: a producer thread's private row masks
@@ -114,14 +137,23 @@ __device__ inline void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ inline void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+template <int MODE>
+__device__ inline void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if constexpr (MODE == 0)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 __device__ inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
 {
@@ -178,15 +210,14 @@ __device__ inline void bulk_commit() { asm volatile("cp.async.bulk.commit_group;
 __device__ inline void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ inline void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused
-// for swizzled K-major, 1) | SBO = 1024 B between 8-row groups | version 1 | layout type 2 (SWIZZLE_128B).
-__device__ inline uint64_t smem_desc(uint32_t addr)
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused for swizzled
+// K-major, 1) | SBO = bytes between 8-row groups >> 4 | version 1 | layout type.  MODE 0: 128-byte rows, SWIZZLE_128B
+// (type 2), SBO 1024; MODE 1: 64-byte rows, SWIZZLE_64B (type 4), SBO 512.
+template <int MODE> __device__ inline uint64_t smem_desc(uint32_t addr)
 {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t sbo = MODE ? 512 : 1024, type = MODE ? 4 : 2;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (type << 61);
 }
-// cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both,
-// N >> 3 at bit 17, M >> 4 at bit 24.
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ inline uint32_t tf32_hi(float v)
 {
@@ -195,13 +226,42 @@ __device__ inline uint32_t tf32_hi(float v)
     return r;
 }
 
-// byte offset of 16-byte chunk j (k = 4j .. 4j+3) of row r inside a [128 rows x 128 B] SWIZZLE_128B tile
+// byte offset of 16-byte chunk j of row r inside a [128 rows x 128 B] SWIZZLE_128B / [128 rows x 64 B] SWIZZLE_64B tile
 __device__ __host__ inline int swz(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+__device__ __host__ inline int swz64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+// two floats -> packed fp16 pair (lo in the low half), and back
+__device__ inline uint32_t pack_h2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// Four consecutive channels -> the 16-byte chunk of the 3xFP16 activation format: X = 16 x, hi = fp16(X), lo = fp16(X - hi);
+// words {hi(c0, c1), hi(c2, c3), lo(c0, c1), lo(c2, c3)} are the TMEM columns the MMA reads, so a producer moves them
+// from global memory to tensor memory without touching them.  Returns max |x| for the range flag.
+__device__ inline float h_lo(uint32_t p);
+__device__ inline float h_hi(uint32_t p);
+__device__ inline uint4 split16(float4 x, float &amax)
+{
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    const float a = x.x * kActScale, b = x.y * kActScale, c = x.z * kActScale, d = x.w * kActScale;
+    uint4 r;
+    r.x = pack_h2(a, b);
+    r.y = pack_h2(c, d);
+    r.z = pack_h2(a - h_lo(r.x), b - h_hi(r.x));
+    r.w = pack_h2(c - h_lo(r.y), d - h_hi(r.y));
+    return r;
+}
+__device__ inline float h_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xffffu))); }
+__device__ inline float h_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
 
 // ------------------------------------------------------------------------------------------------- the kernel
+template <int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_layer_tc(LayerArgs a)
 {
+    constexpr int STAGES = Cfg<MODE>::STAGES, STAGE_BYTES = Cfg<MODE>::STAGE_BYTES, TILE_BYTES = Cfg<MODE>::TILE_BYTES;
+    constexpr int A_COLS = Cfg<MODE>::A_COLS, SLOTS = Cfg<MODE>::SLOTS, A_COL0 = Cfg<MODE>::A_COL0;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
@@ -212,9 +272,9 @@ k_layer_tc(LayerArgs a)
     uint4 *s_list = reinterpret_cast<uint4 *>(smem + OFF_LIST);
     float *s_bias = reinterpret_cast<float *>(smem + OFF_BIAS);
     auto bar_full = [&](int s) { return s_base + OFF_BARS + 8 * s; };
-    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (STAGES + s); };
-    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + q); };
-    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * STAGES + SLOTS + q); };
+    auto bar_empty = [&](int s) { return s_base + OFF_BARS + 8 * (MAX_STAGES + s); };
+    auto bar_slot_full = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + q); };
+    auto bar_slot_empty = [&](int q) { return s_base + OFF_BARS + 8 * (2 * MAX_STAGES + MAX_SLOTS + q); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
     const int rows = a.B * a.ncells;
@@ -282,7 +342,7 @@ k_layer_tc(LayerArgs a)
             }
         } else if (warp == 1) {
             // ================================================================================ MMA issuer
-            const uint64_t desc0 = smem_desc(s_base + OFF_STAGES);  // stage 0, k-step 0, hi image; addresses advance the low field
+            const uint64_t desc0 = smem_desc<MODE>(s_base + OFF_STAGES);  // stage 0, k-step 0, hi image; addresses advance the low field
             int s = 0, par = 0, slot = 0, slot_par = 1, in_seg = 0, lt = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
                 if (lane == 0) stamp(lt, 0);
@@ -299,15 +359,15 @@ k_layer_tc(LayerArgs a)
                     const long long c2 = a.timeline ? clock64() : 0;
                     if (elect_one()) {
                         const uint64_t bh0 = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
-                        const uint32_t d = tmem_base + (uint32_t)(slot * BN), a0 = tmem_base + (uint32_t)(A_COL0 + s * 64);
+                        const uint32_t d = tmem_base + (uint32_t)(slot * BN), a0 = tmem_base + (uint32_t)(A_COL0 + s * 2 * A_COLS);
                         if (!(a.debug & 4)) {
 #pragma unroll
-                            for (int ks = 0; ks < BK / 8; ++ks) {
+                            for (int ks = 0; ks < Cfg<MODE>::KSTEPS; ++ks) {  // one k-step = 32 bytes of K in either mode
                                 const uint64_t bh = bh0 + (uint64_t)(ks * 2), bl = bh + (uint64_t)(TILE_BYTES >> 4);
-                                const uint32_t ah = a0 + ks * 8, al = ah + 32;
-                                umma_tf32_ts(d, ah, bh, kIdesc, (seg_first && ks == 0) ? 0u : 1u);
-                                umma_tf32_ts(d, ah, bl, kIdesc, 1u);
-                                umma_tf32_ts(d, al, bh, kIdesc, 1u);
+                                const uint32_t ah = a0 + ks * 8, al = ah + A_COLS;
+                                umma_ts<MODE>(d, ah, bh, Cfg<MODE>::IDESC, (seg_first && ks == 0) ? 0u : 1u);
+                                umma_ts<MODE>(d, ah, bl, Cfg<MODE>::IDESC, 1u);
+                                umma_ts<MODE>(d, al, bh, Cfg<MODE>::IDESC, 1u);
                             }
                         }
                         umma_commit(bar_empty(s));                       // frees the stage once the MMAs above have read it
@@ -390,15 +450,28 @@ k_layer_tc(LayerArgs a)
                 w_empty += c1 - c0;
                 if (a.debug & 16) { mbar_arrive(bar_full(s)); return; }
                 tc_fence_after();  // the MMAs that read this stage's TMEM columns have completed (tcgen05.commit)
+                const uint32_t col = lane_base + (uint32_t)(A_COL0 + s * 2 * A_COLS);
+                if constexpr (MODE == 0) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {  // 16 columns at a time keeps the temporaries small
-                    uint32_t h[16];
+                    for (int half = 0; half < 2; ++half) {  // 16 columns at a time keeps the temporaries small
+                        uint32_t h[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) h[q] = tf32_hi(v[half * 16 + q]);
-                    tmem_st16(lane_base + (uint32_t)(A_COL0 + s * 64 + half * 16), h);
+                        for (int q = 0; q < 16; ++q) h[q] = tf32_hi(v[half * 16 + q]);
+                        tmem_st16(col + half * 16, h);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) h[q] = __float_as_uint(v[half * 16 + q] - __uint_as_float(h[q]));
-                    tmem_st16(lane_base + (uint32_t)(A_COL0 + s * 64 + 32 + half * 16), h);
+                        for (int q = 0; q < 16; ++q) h[q] = __float_as_uint(v[half * 16 + q] - __uint_as_float(h[q]));
+                        tmem_st16(col + A_COLS + half * 16, h);
+                    }
+                } else {
+                    // the activations arrive already split (split16): chunk j = {hi cols 2j, 2j + 1, lo cols 2j, 2j + 1}
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < BK / 4; ++j) {
+                        h[2 * j] = __float_as_uint(v[4 * j]); h[2 * j + 1] = __float_as_uint(v[4 * j + 1]);
+                        l[2 * j] = __float_as_uint(v[4 * j + 2]); l[2 * j + 1] = __float_as_uint(v[4 * j + 3]);
+                    }
+                    tmem_st16(col, h);
+                    tmem_st16(col + A_COLS, l);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -438,9 +511,11 @@ k_layer_tc(LayerArgs a)
         const int r = (warp & 3) * 32 + lane;  // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const int n_seg = (n_kb + seg_kb - 1) / seg_kb;
+        const float osc = MODE ? a.out_scale : 1.f;  // MODE 1: undoes the power-of-two operand scales (exact)
         const long long ohw = (long long)a.Ntot * HW;
         const uint32_t out_row = s_base + OFF_OUT + (uint32_t)r * OUT_ROW;  // this thread's private staging row
         int segg = 0, lt = 0;
+        float amax = 0.f;  // MODE 1: largest activation magnitude written (range flag)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
             if (tid == 384) stamp(lt, 5);
             const int nt = t % n_ntiles;
@@ -476,8 +551,7 @@ k_layer_tc(LayerArgs a)
             // phase 1 (unrolled: the accumulators are registers): raw sums -> this thread's padded staging row
 #pragma unroll
             for (int q = 0; q < BN; q += 4)
-                if (!(a.debug & 128))
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + q * 4), "f"(acc[q]), "f"(acc[q + 1]), "f"(acc[q + 2]), "f"(acc[q + 3]) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + q * 4), "f"(acc[q] * osc), "f"(acc[q + 1] * osc), "f"(acc[q + 2] * osc), "f"(acc[q + 3] * osc) : "memory");
             __syncwarp();
             const int n_left = min(BN, a.n_count - nt * BN);
             // phase 2 (compact loops: the instruction cache has to hold every role's code)
@@ -488,17 +562,18 @@ k_layer_tc(LayerArgs a)
                     const int NB = (HW + 31) >> 5;
                     float *op = a.out + (((long long)rb * NB + (rhw >> 5)) * (a.Ntot >> 2) + ((a.n_begin + nt * BN) >> 2)) * 128 + (rhw & 31) * 4;
                     const float *bp = s_bias + nt * BN;
-#pragma unroll 4
+                    const float *srow_c = reinterpret_cast<const float *>(smem + OFF_OUT + r * OUT_ROW);
+#pragma unroll 8
                     for (int q = 0; q < n_left; q += 4) {
-                        float4 val;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(out_row + q * 4));
+                        float4 val = *reinterpret_cast<const float4 *>(srow_c + q);
                         const float4 bv = *reinterpret_cast<const float4 *>(bp + q);
                         val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
                         if (a.lrelu) {
                             val.x = val.x > 0.f ? val.x : val.x * kSlope; val.y = val.y > 0.f ? val.y : val.y * kSlope;
                             val.z = val.z > 0.f ? val.z : val.z * kSlope; val.w = val.w > 0.f ? val.w : val.w * kSlope;
                         }
-                        if (!(a.debug & 64)) *reinterpret_cast<float4 *>(op + q * 32) = val;
+                        if constexpr (MODE == 1) *reinterpret_cast<uint4 *>(op + q * 32) = split16(val, amax);  // the next layer's operand format
+                        else *reinterpret_cast<float4 *>(op + q * 32) = val;
                     }
                 }
             } else if (rb >= 0) {
@@ -516,6 +591,7 @@ k_layer_tc(LayerArgs a)
             }
             if (tid == 384) stamp(lt, 7);
         }
+        if (MODE == 1 && !(amax < kActLimit) && a.range_flag) atomicOr(a.range_flag, 1);  // (NaN / inf raise it too)
     }
     tc_fence_before();
     __syncthreads();
@@ -525,13 +601,16 @@ k_layer_tc(LayerArgs a)
     }
 }
 
-// Packs weights into per-(out-group, n-tile, k-block) [hi | lo] SWIZZLE_128B images.
+// Packs weights into per-(out-group, n-tile, k-block) [hi | lo] K-major swizzled images (MODE 0: tf32 pairs in
+// SWIZZLE_128B rows of 32 floats; MODE 1: fp16 pairs of w * scale in SWIZZLE_64B rows of 32 halves).
 //   conv : w [N][Cin][k2]            K' = tap * Cpad + c            (Cpad = Cin rounded up to 32)
 //   dense: w [N][c_src0 + c_src1]    K' = [src0 padded to 32 | src1 padded to 32]
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_pack_w_tc(const float *__restrict__ w, unsigned char *__restrict__ out, int N, int G, int ntiles, int kb_total, int is_conv,
-            int Cin, int k2, int c_src0, int c_src1, int kb_src0)
+            int Cin, int k2, int c_src0, int c_src1, int kb_src0, float scale)
 {
+    constexpr int TILE_BYTES = Cfg<MODE>::TILE_BYTES;
     const int n_count = N / G;
     const long long total = (long long)G * ntiles * kb_total * BN * BK;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -559,18 +638,36 @@ k_pack_w_tc(const float *__restrict__ w, unsigned char *__restrict__ out, int N,
                 }
             }
         }
-        const uint32_t hi = tf32_hi(v);
-        const float lo = v - __uint_as_float(hi);
         unsigned char *t = out + (size_t)tkb * (2 * TILE_BYTES);
-        const int o = swz(nl, kk >> 2) + (kk & 3) * 4;
-        *reinterpret_cast<uint32_t *>(t + o) = hi;
-        *reinterpret_cast<float *>(t + TILE_BYTES + o) = lo;
+        if constexpr (MODE == 0) {
+            const uint32_t hi = tf32_hi(v);
+            const float lo = v - __uint_as_float(hi);
+            const int o = swz(nl, kk >> 2) + (kk & 3) * 4;
+            *reinterpret_cast<uint32_t *>(t + o) = hi;
+            *reinterpret_cast<float *>(t + TILE_BYTES + o) = lo;
+        } else {
+            const float x = v * scale;
+            const __half hi = __float2half_rn(x);
+            const __half lo = __float2half_rn(x - __half2float(hi));
+            const int o = swz64(nl, kk >> 3) + (kk & 7) * 2;
+            *reinterpret_cast<__half *>(t + o) = hi;
+            *reinterpret_cast<__half *>(t + TILE_BYTES + o) = lo;
+        }
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_absmax(const float *__restrict__ w, long long n, unsigned int *out)
+{
+    float m = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
 }
 
 }  // namespace
 
-int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1,
+int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1, int mode,
                     cudaStream_t stream)
 {
     const int n_count = N / G;
@@ -582,10 +679,31 @@ int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv,
         dst.kb_src0 = (c_src0 + BK - 1) / BK;
         dst.kb_total = dst.kb_src0 + (c_src1 + BK - 1) / BK;
     }
-    const size_t bytes = (size_t)G * dst.ntiles_per_group * dst.kb_total * (2 * TILE_BYTES);
-    BASIC_TRY(dst.buf.reserve(bytes));
-    k_pack_w_tc<<<1024, 256, 0, stream>>>(w_dev, dst.buf.as<unsigned char>(), N, G, dst.ntiles_per_group, dst.kb_total, is_conv,
-                                          Cin, k2, c_src0, c_src1, dst.kb_src0);
+    const int tile_bytes = mode ? Cfg<1>::TILE_BYTES : Cfg<0>::TILE_BYTES;
+    const size_t bytes = (size_t)G * dst.ntiles_per_group * dst.kb_total * (2 * tile_bytes);
+    BASIC_TRY(dst.buf.reserve(bytes + 16));
+    dst.scale = 1.f;
+    if (mode) {
+        // power-of-two scale that puts the largest weight magnitude into [2^12, 2^13): fp16 keeps 11 bits of it and the
+        // residual (2^-11 of the value) stays a normal fp16 number for every weight down to 2^-15 of the largest
+        unsigned int *d_max = reinterpret_cast<unsigned int *>(dst.buf.as<unsigned char>() + bytes);
+        BASIC_CUDA(cudaMemsetAsync(d_max, 0, 4, stream));
+        const long long nw = (long long)N * (is_conv ? (long long)Cin * k2 : (long long)(c_src0 + c_src1));
+        k_absmax<<<256, 256, 0, stream>>>(w_dev, nw, d_max);
+        BASIC_LAUNCHED();
+        float wmax = 0.f;
+        BASIC_CUDA(cudaMemcpyAsync(&wmax, d_max, 4, cudaMemcpyDeviceToHost, stream));
+        BASIC_CUDA(cudaStreamSynchronize(stream));
+        if (!(wmax < 3.0e38f)) return value_error("context-model weights are not finite");
+        int e = 0;
+        if (wmax > 0.f) frexpf(wmax, &e);  // wmax = f * 2^e, f in [0.5, 1)
+        dst.scale = ldexpf(1.f, 13 - e);
+        k_pack_w_tc<1><<<1024, 256, 0, stream>>>(w_dev, dst.buf.as<unsigned char>(), N, G, dst.ntiles_per_group, dst.kb_total, is_conv,
+                                                 Cin, k2, c_src0, c_src1, dst.kb_src0, dst.scale);
+    } else {
+        k_pack_w_tc<0><<<1024, 256, 0, stream>>>(w_dev, dst.buf.as<unsigned char>(), N, G, dst.ntiles_per_group, dst.kb_total, is_conv,
+                                                 Cin, k2, c_src0, c_src1, dst.kb_src0, 1.f);
+    }
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
@@ -595,7 +713,7 @@ int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv,
 // and stages big enough for 128-row MMA tiles to make sense (scanline-like maps stay on the exact-FP32 kernel).
 bool tc_model_eligible(const CtxModel &m, int B)
 {
-    if (m.precision != BASIC_CTX_TF32X3 || !m.has_conv || m.S < 1) return false;
+    if ((m.run_precision != BASIC_CTX_TF32X3 && m.run_precision != BASIC_CTX_FP16X3) || !m.has_conv || m.S < 1) return false;
     if (m.G > MAX_G || m.k * m.k * ((m.C + BK - 1) / BK) > MAX_KB || m.k * m.k > 31) return false;
     if (std::max(m.c_ctx, std::max(m.c_m1, m.c_m2)) / m.G > MAX_BIAS) return false;
     auto ok4 = [&](int channels) { return channels % m.G == 0 && (channels / m.G) % 4 == 0; };
@@ -605,9 +723,10 @@ bool tc_model_eligible(const CtxModel &m, int B)
 }
 
 // [B, channels, HW] -> blocked channels-last (ctx.cuh), 32 positions x 32 channels per CTA through shared memory
-// (both sides coalesced); positions past HW in the last block are written as zeros
+// (both sides coalesced); positions past HW in the last block are written as zeros.  split = 1: 3xFP16 operand
+// format (split16) instead of the floats themselves.
 __global__ void __launch_bounds__(256)
-k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
+k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW, int split, int *range_flag)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, blk = blockIdx.x, hw0 = blk * 32, c0 = blockIdx.y * 32;
@@ -619,20 +738,25 @@ k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channel
         tile[ty + 8 * i][tx] = (c < channels && hw < HW) ? s[(size_t)c * HW + hw] : 0.f;
     }
     __syncthreads();
-    float *d = dst + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2)) * 128;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int o = threadIdx.x + 256 * i;  // chunk (8 per CTA) * 128 + position * 4 + channel % 4
-        const int chunk = o >> 7, hwl = (o >> 2) & 31, cl = o & 3;
-        if (c0 + chunk * 4 < channels) d[o] = tile[chunk * 4 + cl][hwl];
+    // thread = (chunk ty of 4 channels, position tx): one 16-byte chunk each, a warp writes 512 contiguous bytes
+    if (c0 + ty * 4 < channels) {
+        float *d = dst + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2) + ty) * 128 + tx * 4;
+        const float4 x = make_float4(tile[ty * 4 + 0][tx], tile[ty * 4 + 1][tx], tile[ty * 4 + 2][tx], tile[ty * 4 + 3][tx]);
+        if (split) {
+            float amax = 0.f;
+            *reinterpret_cast<uint4 *>(d) = split16(x, amax);
+            if (!(amax < kActLimit) && range_flag) atomicOr(range_flag, 1);
+        } else {
+            *reinterpret_cast<float4 *>(d) = x;
+        }
     }
 }
 
-int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream)
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split, int *range_flag)
 {
     if (B == 0) return BASIC_OK;
     dim3 grid((HW + 31) / 32, (channels + 31) / 32, B);
-    k_nchw_to_cl<<<grid, 256, 0, stream>>>(src, dst, channels, HW);
+    k_nchw_to_cl<<<grid, 256, 0, stream>>>(src, dst, channels, HW, split, range_flag);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
@@ -683,7 +807,8 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
     static bool attr_done = false;
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
     const long long tiles = (long long)((a.n_count + BN - 1) / BN) * ((rows + BM - 1) / BM);
@@ -721,7 +846,8 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
         cudaMemset(tl_buf, 0, (size_t)grid.x * 16 * 16 * sizeof(long long));
         b.timeline = tl_buf;
     }
-    k_layer_tc<<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    if (b.mode) k_layer_tc<1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    else k_layer_tc<0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
     BASIC_LAUNCHED();
     if (tl) {
         std::vector<long long> h((size_t)grid.x * 16 * 16);

@@ -123,7 +123,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self.lower_bound_scale = lower_bound_scale
         self.lanes = lanes
         self.ans_params_device = ans_params_device
-        if ctx_precision not in ("auto", "fp32", "tf32x3"):
+        if ctx_precision not in ("auto", "fp32", "tf32x3", "fp16x3"):
             raise ValueError(f"Unknown ctx_precision {ctx_precision}")
         self.ctx_precision, self.ctx_accumulators = ctx_precision, ctx_accumulators
         self.scale_table = get_scale_table() if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
@@ -213,8 +213,8 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
         prec = self.ctx_precision
         if prec == "auto":
-            prec = "fp32" if self.lanes == 1 else "tf32x3"
-        N.check(N.lib().basic_ctx_set_precision(self._ctx, N.CTX_TF32X3 if prec == "tf32x3" else N.CTX_FP32,
+            prec = "fp32" if self.lanes == 1 else "fp16x3"
+        N.check(N.lib().basic_ctx_set_precision(self._ctx, {"fp32": N.CTX_FP32, "tf32x3": N.CTX_TF32X3, "fp16x3": N.CTX_FP16X3}[prec],
                                                 int(self.ctx_accumulators)))
 
     @property

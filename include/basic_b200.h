@@ -129,6 +129,7 @@ int basic_ctx_num_stages(basic_ctx *m);
  * sides); layers the tensor path cannot take (tiny stages, channel groups not a multiple of 4) use FP32. */
 #define BASIC_CTX_FP32 0
 #define BASIC_CTX_TF32X3 1
+#define BASIC_CTX_FP16X3 2
 int basic_ctx_set_precision(basic_ctx *m, int precision, int nacc);
 /* positions of stage g (device pointer, int32 offsets into [C,H,W]) and their count */
 int basic_ctx_stage_positions(basic_ctx *m, int g, const int32_t **positions_dev, int64_t *n_pos);

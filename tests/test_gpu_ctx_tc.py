@@ -1,5 +1,6 @@
-"""-m gpu: the tcgen05 3xTF32 context-model kernel (ctx_tc.cu) against the exact-FP32 kernel (ctx.cu), which the
-other tests pin to the oracle / the reference.  Bar: north_star's 1e-5 relative error on means and scales."""
+"""-m gpu: the tcgen05 context-model kernel (ctx_tc.cu), in both of its arithmetic modes (3xTF32 and 3xFP16), against
+the exact-FP32 kernel (ctx.cu), which the other tests pin to the oracle / the reference.  Bar: north_star's 1e-5
+relative error on means and scales."""
 import numpy as np
 import pytest
 import torch
@@ -45,7 +46,8 @@ CASES = [
 
 @pytest.mark.parametrize("C_,G,method,B,H,W,merger", CASES)
 @pytest.mark.parametrize("nacc", [2, 4, 16])
-def test_tc_matches_fp32(C_, G, method, B, H, W, merger, nacc):
+@pytest.mark.parametrize("mode", ["tf32x3", "fp16x3"])
+def test_tc_matches_fp32(C_, G, method, B, H, W, merger, nacc, mode):
     from cbench_basic_b200 import topo_groups
     if method not in topo_groups.METHODS:
         pytest.skip(f"{method} not a default method")
@@ -53,26 +55,53 @@ def test_tc_matches_fp32(C_, G, method, B, H, W, merger, nacc):
     buf = (3 * torch.randn(B, C_, H, W)).round().cuda() + torch.randn(B, C_, H, W).cuda()
     prior = torch.randn(B, 2 * C_, H, W).cuda()
     ref, S = stage_params(build(C_, G, method, "fp32", 1, merger=merger), buf, prior)
-    got, _ = stage_params(build(C_, G, method, "tf32x3", nacc, merger=merger), buf, prior)
+    got, _ = stage_params(build(C_, G, method, mode, nacc, merger=merger), buf, prior)
     err = float(((got - ref).abs() / ref.abs().clamp_min(1.0)).max())
-    print(f"C={C_} G={G} {method} S={S} nacc={nacc}: max rel err {err:.3e}")
+    print(f"C={C_} G={G} {method} S={S} nacc={nacc} {mode}: max rel err {err:.3e}")
     assert err <= (REL_TOL if nacc <= 4 else 3 * REL_TOL), err   # long TMEM chains (16 k-blocks) drift: why the default is 4
 
 
-def test_tc_round_trip():
+@pytest.mark.parametrize("mode", ["tf32x3", "fp16x3"])
+def test_tc_round_trip(mode):
     """Whole y path with the tensor-core context model: the decoder reproduces the encoder's y_hat bit for bit (both
     sides run the same deterministic kernels) and the reconstruction is within half a quantisation step."""
     C_, B, H, W = 96, 2, 8, 12
-    coder = build(C_, 1, "checkerboard", "tf32x3", 4)
+    coder = build(C_, 1, "checkerboard", mode, 4)
     torch.manual_seed(3)
     y, prior = 3 * torch.randn(B, C_, H, W), torch.randn(B, 2 * C_, H, W)
     bs, yhat_enc = coder.encode(y.cuda(), prior=prior.cuda(), return_yhat=True)
+    assert bs[:4] == (b"BLS2" if mode == "fp16x3" else b"BLS1")
     yhat = coder.decode(bs, prior=prior.cuda())
     assert torch.equal(yhat, yhat_enc * 1.0 + 0.0)
     assert float((yhat.cpu() - y).abs().max()) <= 0.5 + 1e-4
 
 
-def test_tc_vs_oracle_c192_teacher_forced():
+def test_fp16x3_range_fallback():
+    """An activation of magnitude >= 4000 does not fit the 3xFP16 operand scaling: the encoder notices (device flag),
+    repeats the pass in 3xTF32 and says so in the container ("BLS1"); a 3xFP16-configured decoder follows the stream.
+    The stage API falls back per stage: the stage that sees the large value is computed in 3xTF32, so everything stays
+    finite and within the bar."""
+    C_, B, H, W = 96, 2, 8, 12
+    coder = build(C_, 1, "checkerboard", "fp16x3", 4)
+    ref = build(C_, 1, "checkerboard", "tf32x3", 4)
+    torch.manual_seed(5)
+    y, prior = 3 * torch.randn(B, C_, H, W), torch.randn(B, 2 * C_, H, W)
+    y[0, 3, 0, 0] = 5000.0     # a group-0 position of the checkerboard: context of the second group
+    bs, yhat_enc = coder.encode(y.cuda(), prior=prior.cuda(), return_yhat=True)
+    assert bs[:4] == b"BLS1"
+    assert bs == ref.encode(y.cuda(), prior=prior.cuda())
+    yhat = coder.decode(bs, prior=prior.cuda())
+    assert torch.equal(yhat, yhat_enc * 1.0 + 0.0)
+    assert float((yhat.cpu() - y).abs().max()) <= 0.5 + 1e-3
+    buf = y.cuda().round()
+    p16, _ = stage_params(coder, buf, prior.cuda())
+    p32, _ = stage_params(ref, buf, prior.cuda())
+    assert bool(torch.isfinite(p16).all())
+    assert float(((p16 - p32).abs() / p32.abs().clamp_min(1.0)).max()) <= REL_TOL
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "fp16x3"])
+def test_tc_vs_oracle_c192_teacher_forced(mode):
     """BASELINE configs[1] geometry (C = 192, checkerboard, one Kodak-shape image) in the tensor-core mode against
     the CPU oracle, stage by stage with the ORACLE's y_hat as context (so one rounding tie cannot cascade):
     parameters within 1e-5; a symbol / scale index may differ only where the oracle's own value sits within the
@@ -85,7 +114,7 @@ def test_tc_vs_oracle_c192_teacher_forced():
     with torch.no_grad():
         sym, idx, yhat_ref = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
         params_ref = Y.params_for(yhat_ref, c["tg"], c["prior"], c["w"])
-    coder = make_coder(c, lanes=0, method="checkerboard", ctx_precision="tf32x3")
+    coder = make_coder(c, lanes=0, method="checkerboard", ctx_precision=mode)
     B, C_, H, W = 1, 192, 32, 48
     coder._set_map(c["tg"])
     y, prior, buf = c["y"].cuda().contiguous(), c["prior"].cuda().contiguous(), yhat_ref.cuda().contiguous()
@@ -106,7 +135,7 @@ def test_tc_vs_oracle_c192_teacher_forced():
     torch.cuda.synchronize()
     gsym, gidx, gparams = torch.cat(gs).cpu().numpy(), torch.cat(gi).cpu().numpy(), params.cpu()
     err = float(((gparams - params_ref).abs() / params_ref.abs().clamp_min(1.0)).max())
-    print(f"c192 tf32x3 vs oracle: params max rel err {err:.3e}; symbol diffs {int((gsym != sym).sum())}, index diffs {int((gidx != idx).sum())}")
+    print(f"c192 {mode} vs oracle: params max rel err {err:.3e}; symbol diffs {int((gsym != sym).sum())}, index diffs {int((gidx != idx).sum())}")
     assert err <= REL_TOL
     gmap = Y.group_of_elements(c["tg"], 1, 192).reshape(-1)
     order = torch.cat([torch.nonzero(gmap == g).reshape(-1) for g in range(2)])
