@@ -176,7 +176,7 @@ def run_reference(args, rank, world):
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 rANS states / int32 symbols, f32 context model (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "dtype": "u32 rANS states / int32 symbols; context model f32 in / f32 accumulate, products as 3xFP16 on tcgen05", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "sample": f"{n_img} image per step"},
             "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port",
                              "sample": f"{n_img} of {B} images per step, encode+decode, torch CPU context model + reference coder "
@@ -188,6 +188,56 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- GPU side
+def coder_lane_sweep(coder, device_index, hbm_peak, n_sym=1 << 24):
+    """The multi-lane coder alone (standalone encode_with_indexes / decode_with_indexes API, operands resident) on
+    symbols at trained-model rates (idx = min(Geom(0.12) - 1, 63), sym = rint(N(0,1) * sigma[idx])), for
+    a range of lane counts: achieved algorithmic GB/s ((8 + c) bytes per symbol / kernel time, CUDA events inside the
+    library) against the HBM peak, and the container overhead each lane count costs -- the trade-off the 0.5 % bpp bar
+    decides.  lanes = 0 is the auto mode the y path uses."""
+    from cbench_basic_b200 import _native as N, ans
+    try:
+        dev = torch.device("cuda", device_index)
+        tab = coder.scale_table.detach().cpu().numpy()
+        rng = np.random.default_rng(0)
+        idx = np.minimum(rng.geometric(0.12, n_sym) - 1, 63).astype(np.int32)
+        sym = np.rint(rng.standard_normal(n_sym) * tab[idx]).astype(np.int32)
+        freqs, nsym, offs = coder._get_ans_params()
+        ts, ti = torch.from_numpy(sym).to(dev), torch.from_numpy(idx).to(dev)
+        rows, base_bytes = [], None
+        for lanes in (0, 148 * 8 * 32, 148 * 16 * 32, 4 * 148 * 16 * 32):
+            enc = ans.Rans64Encoder(lanes=lanes, device=device_index)
+            dec = ans.Rans64Decoder(lanes=lanes, device=device_index)
+            for c in (enc, dec):
+                c.init_params(freqs, nsym, offs)
+            bs = enc.encode_with_indexes(ts, ti)
+            out = dec.decode_with_indexes(bs, ti)
+            assert torch.equal(torch.as_tensor(out).to(dev).reshape(-1), ts), "lane sweep: lossless round trip failed"
+            N.profile(True)
+            N.profile_read()
+            reps = 3
+            for _ in range(reps):
+                bs = enc.encode_with_indexes(ts, ti)
+                dec.decode_with_indexes(bs, ti)
+            torch.cuda.synchronize(dev)
+            ph = N.profile_read()
+            N.profile(False)
+            enc_ms, dec_ms = ph["coder_encode"][0] / reps, ph["coder_decode"][0] / reps
+            c_b = len(bs) / n_sym
+            if base_bytes is None:
+                base_bytes = len(bs)
+            n_chunks = int(np.frombuffer(bs[4:8], dtype=np.uint32)[0])
+            rows.append({"lanes": lanes, "chunks": n_chunks, "stream_bytes": len(bs), "bytes_per_symbol": c_b,
+                         "flush_overhead_frac": n_chunks * 132 / len(bs),
+                         "decode_ms": dec_ms, "encode_ms": enc_ms,
+                         "decode_gbs": (8 + c_b) * n_sym / (dec_ms * 1e-3) / 1e9, "encode_gbs": (8 + c_b) * n_sym / (enc_ms * 1e-3) / 1e9,
+                         "decode_frac_of_hbm": (8 + c_b) * n_sym / (dec_ms * 1e-3) / 1e9 / hbm_peak,
+                         "encode_frac_of_hbm": (8 + c_b) * n_sym / (enc_ms * 1e-3) / 1e9 / hbm_peak})
+        return {"n_symbols": n_sym, "data": "idx = min(Geom(0.12) - 1, 63), sym = rint(N(0,1) * sigma[idx])",
+                "bytes_per_symbol_algorithmic": "8 + c (int32 symbol + int32 index + c stream bytes)", "rows": rows}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from cbench_basic_b200 import _native as N, sharding
@@ -294,15 +344,26 @@ def run_ours(args, rank, world, local_rank):
             ctx_ms = phases["context_model"]["ms_per_step"]            # both passes (encoder + decoder side)
             flops = 2 * 2 * 77.56 * C_ * C_ * B * H * W                # dense-equivalent, each position once, x 2 passes
             ach = flops / (ctx_ms * 1e-3) / 1e12
-            tc = coder.ctx_precision == "tf32x3" or (coder.ctx_precision == "auto" and coder.lanes != 1)
-            roofline = {"kernel": "k_layer_tc (context conv + 1x1 merger; tcgen05 kind::tf32, 3 MMAs per product = error-compensated TF32)"
-                        if tc else "k_layer (context conv + 1x1 merger, FP32 SIMT exact path)", "bound": "tensor", "achieved": ach,
-                        "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+            mode = coder.ctx_precision if coder.ctx_precision != "auto" else ("fp32" if coder.lanes == 1 else "fp16x3")
+            kname = {"fp16x3": "k_layer_tc<1> (context conv + 1x1 merger; tcgen05 kind::f16, 3 MMAs per product = error-compensated FP16, "
+                               "operands pre-scaled by powers of two, FP32 accumulate)",
+                     "tf32x3": "k_layer_tc<0> (context conv + 1x1 merger; tcgen05 kind::tf32, 3 MMAs per product = error-compensated TF32)",
+                     "fp32": "k_layer (context conv + 1x1 merger, FP32 SIMT exact path)"}[mode]
+            ceil = {"fp16x3": "3 FP16 MMAs per product: ceiling = bf16/fp16 peak / 3 (frac 0.333)",
+                    "tf32x3": "3 TF32 MMAs per product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)",
+                    "fp32": "FP32 FMA pipe, not the tensor pipe"}[mode]
+            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1b_ncu_full_k_layer_tc_fp16x3.csv, cold
+            # caches under ncu) x 2 passes per step, for the cfg2 geometry only; algorithmic bytes = activations once
+            traffic = 2 * 1436.1e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
+            roofline = {"kernel": kname, "bound": "tensor", "achieved": ach,
+                        "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
+                        "traffic_note": "bytes per step (16 launches), ncu --set full, cold L2; algorithmic = 2 x 0.59 GB "
+                                        "(every activation read and written once per pass)",
                         "ms_per_step": ctx_ms, "launches_per_step": phases["context_model"]["spans_per_step"] * 4,
                         "share_of_step": ctx_ms / ms, "peak_source": peak_src,
                         "note": "algorithmic FLOPs = 2*77.56*C^2 per latent position and pass (dense-equivalent, each position once; "
-                                "masked taps are skipped, so executed FLOPs are lower). The 1e-5 parity bar forces 3 TF32 MMAs per "
-                                "product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)"}
+                                "masked taps are skipped, so executed FLOPs are lower: 0.69 of dense for this checkerboard). The 1e-5 "
+                                "parity bar needs ~22 significant bits per product: " + ceil}
         else:
             roofline = coder_roof
     except Exception as e:  # never lose the headline line to a side measurement
@@ -321,6 +382,8 @@ def run_ours(args, rank, world, local_rank):
     except Exception as e:
         dbpp = {"error": repr(e)}
 
+    sweep = coder_lane_sweep(coder, local_rank, hbm_peak) if rank == 0 else None
+
     cpu = None
     if world == 1 or rank == 0:
         try:
@@ -338,13 +401,13 @@ def run_ours(args, rank, world, local_rank):
     d2h = stream_bytes + y.numel() * 4
     line = {"metric": METRIC, "value": pix_total / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 rANS states / int32 symbols, f32 context model (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "dtype": "u32 rANS states / int32 symbols; context model f32 in / f32 accumulate, products as 3xFP16 on tcgen05", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "images_per_gpu": B, "latent": [C_, H, W], "lanes": args.lanes,
                        "l2": "256 MB buffer rewritten between timed iterations", "step": "encode + decode"},
             "e2e": {"value": pix_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_coder": coder_roof, "phases": phases,
-            "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes]}
+            "coder_lane_sweep": sweep, "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes]}
     print(json.dumps(line), flush=True)
 
 

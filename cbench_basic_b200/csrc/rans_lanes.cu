@@ -21,7 +21,8 @@ namespace basic {
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 8;      // warps per CTA when the chunks fit 8 per SM
+constexpr int kMaxWarps = 16;  // ... and when there are more (throughput mode: 16 x 148 chunks resident)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSegHdr = 8;  // u32 n_chunks | u32 n_slices, followed by u32 chunk_syms[n_slices]
 
@@ -57,7 +58,7 @@ struct LaneParams {
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
 // Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
-__global__ void __launch_bounds__(kWarps * 32, 1)
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
              uint32_t *__restrict__ states, int *status)
@@ -73,7 +74,8 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
-    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
+    const int nwarps = blockDim.x >> 5;
+    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * nwarps) {
         uint16_t *wbuf = scratch + (size_t)k * cap_words;
         int pos = cap_words;  // warp-uniform
         uint32_t x = kRansL;
@@ -256,7 +258,7 @@ __device__ inline void cp_async4(uint32_t smem_dst, const void *gsrc)
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kWarps * 32, 1)
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
              int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
              uint32_t *__restrict__ carry_wp, int *status)
@@ -267,7 +269,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     const uint16_t *ring16 = reinterpret_cast<const uint16_t *>(ring32);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring32);
     const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem,
-                                      smem + kWarps * kRingUnits * 4);
+                                      smem + (blockDim.x >> 5) * kRingUnits * 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks;
@@ -281,7 +283,8 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
-    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * kWarps) {
+    const int nwarps = blockDim.x >> 5;
+    for (int k = blockIdx.x + warp * gridDim.x; k < n_chunks; k += gridDim.x * nwarps) {
         const long long base = (long long)k * P.chunk_syms;
         const long long rem = P.n - base;
         const int m = (int)(rem <= 0 ? 0 : rem < P.chunk_syms ? rem : P.chunk_syms);
@@ -460,7 +463,14 @@ k_estimate_bits(LaneParams P, const int32_t *__restrict__ symbols, const int32_t
 }  // namespace
 
 static int smem_for(const RansTables &tb) { return tb.blob_bytes <= (size_t)kMaxSmemTables ? (int)tb.blob_bytes : 0; }
-static constexpr int kRingBytes = kWarps * kRingUnits * 4;
+static constexpr int kRingBytes = kMaxWarps * kRingUnits * 4;
+// warps per CTA: 8 while every chunk gets its own resident warp, 16 beyond that (more lanes in flight per SM)
+static constexpr int kSmemLimit = 232448;  // opt-in dynamic shared memory of one CTA on sm_100
+static int warps_for(int n_chunks, int sm_count, int table_smem)
+{
+    if (n_chunks <= kWarps * sm_count) return kWarps;
+    return table_smem + kMaxWarps * kRingUnits * 4 <= kSmemLimit ? kMaxWarps : kWarps;
+}
 
 static LaneParams make_params(const RansTables &tb, int bypass, int bypass_precision, int64_t n, int chunk_syms, int n_chunks,
                               int n_slices, const SliceDesc *slices)
@@ -495,7 +505,8 @@ static int set_attrs()
     static bool attr_done = false;
     if (!attr_done) {
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables + kRingBytes));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit));
         attr_done = true;
     }
     return BASIC_OK;
@@ -513,7 +524,7 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
     if (n_chunks > 0) {
-        k_bls_encode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words,
+        k_bls_encode<<<grid_for(n_chunks, sm_count), warps_for(n_chunks, sm_count, smem) * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words,
                                                                                  d_first, d_states, d_status);
         BASIC_LAUNCHED();
     }
@@ -538,7 +549,8 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, 0, nullptr);
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
-    k_bls_decode<<<grid_for(n_chunks, sm_count), kWarps * 32, smem + kRingBytes, stream>>>(
+    const int nw = warps_for(n_chunks, sm_count, smem);
+    k_bls_decode<<<grid_for(n_chunks, sm_count), nw * 32, smem + nw * kRingUnits * 4, stream>>>(
         P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
