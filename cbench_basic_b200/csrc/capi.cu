@@ -26,8 +26,9 @@ int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64
                       uint32_t *, uint32_t *, int32_t *, int *, int, cudaStream_t);
 int launch_estimate_bits(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, float *, cudaStream_t);
 int launch_quantize_index(const float *, const float *, const int32_t *, int64_t, int, int, int, const float *, int, int32_t *,
-                          int32_t *, float *, int, cudaStream_t);
-int launch_dequantize(const int32_t *, const float *, const int32_t *, int64_t, int, int, int, float *, int, cudaStream_t);
+                          int32_t *, float *, int, cudaStream_t, int params_cl = 0);
+int launch_dequantize(const int32_t *, const float *, const int32_t *, int64_t, int, int, int, float *, int, cudaStream_t,
+                      int params_cl = 0);
 
 struct CtxModel;
 CtxModel *ctx_new(int C, int G, int k, int device, int sm_count);
@@ -36,7 +37,7 @@ int ctx_set_weights(CtxModel &, const float *, const float *, const float *, con
                     const float *, const float *);
 int ctx_set_map(CtxModel &, const int32_t *, int, int);
 int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t, const float *buf_cl = nullptr,
-                     const float *prior_cl = nullptr);
+                     const float *prior_cl = nullptr, bool params_cl = false);
 bool ctx_uses_tc(const CtxModel &, int B);
 int ctx_to_cl(CtxModel &, const float *src, float *dst, int B, int channels, cudaStream_t);
 size_t ctx_cl_elems(int B, int channels, int HW);
@@ -94,7 +95,7 @@ static thread_local std::string t_error;
 void set_error(const std::string &msg) { t_error = msg; }
 int64_t g_launches = 0;
 
-static constexpr double kAutoBudget = 0.0046;  // target container overhead in auto mode (bar: 0.5 %; measured total = budget - 0.01 %)
+static constexpr double kAutoBudget = 0.0043;  // target container overhead in auto mode (bar: 0.5 %; measured total = budget + 0.00 .. 0.03 %)
 static constexpr int kChunkOverhead = 132;    // 32 states + directory entry
 
 struct SliceDesc {  // mirrors rans_lanes.cu
@@ -951,7 +952,7 @@ static int ypath_setup(basic_coder *c, basic_ctx *model, int B, int C, int H, in
     }
     const size_t n = (size_t)B * C * H * W;
     BASIC_TRY(c->buf.reserve(n * 4));
-    BASIC_TRY(c->params.reserve(n * 8));
+    BASIC_TRY(c->params.reserve(std::max(n * 8, ctx_cl_elems(B, 2 * C, H * W) * 4)));
     BASIC_TRY(c->sym_all.reserve(n * 4 + 16));
     BASIC_TRY(c->idx_all.reserve(n * 4 + 16));
     return BASIC_OK;
@@ -1000,7 +1001,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             int64_t n_pos = (int64_t)C * HW;
             if (model) {
                 ProfScope ps(PROF_CTX, s);
-                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
+                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
                 BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
             } else {
                 params_src = d_prior;
@@ -1010,7 +1011,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             if (cnt == 0) continue;
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                            sym + done, idx + done, buf, c->sm_count, s));
+                                            sym + done, idx + done, buf, c->sm_count, s, tc ? 1 : 0));
             if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
             done += (size_t)cnt;
         }
@@ -1103,7 +1104,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     // memory and upload it while the GPU is busy
     if (model) {
         ProfScope ps(PROF_CTX, s);
-        BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl));
+        BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
     }
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     // per-group symbol counts = the slices of the segment
@@ -1126,7 +1127,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (model) {
             if (g > 0) {
                 ProfScope ps(PROF_CTX, s);
-                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl));
+                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
             }
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
@@ -1136,7 +1137,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (cnt > 0) {
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                            nullptr, idx, nullptr, c->sm_count, s));
+                                            nullptr, idx, nullptr, c->sm_count, s, tc ? 1 : 0));
         }
         if (lanes == BASIC_LANES_REFERENCE) {
             if (cnt == 0) continue;
@@ -1153,7 +1154,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         }
         if (cnt > 0) {
             ProfScope ps(PROF_GAUSS, s);
-            BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s));
+            BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s, tc ? 1 : 0));
             if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
         }
     }

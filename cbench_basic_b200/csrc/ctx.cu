@@ -433,12 +433,14 @@ size_t ctx_cl_elems(int B, int channels, int HW) { return cl_elems(B, channels, 
 // reads channels-last copies: the caller's (buf_cl / prior_cl, kept up to date by the y-path driver) or, when they
 // are NULL (the public stage API), copies made here.
 int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, int B, float *params, cudaStream_t stream,
-                     const float *buf_cl, const float *prior_cl)
+                     const float *buf_cl, const float *prior_cl, bool params_cl)
 {
     if (g < 0 || g >= m.S) return value_error("stage out of range");
     const int HW = m.H * m.W, G = m.G;
     const auto &st = m.stages[g];
-    if (!m.has_conv) {  // params = prior (+ bias): elementwise over the whole tensor, only needed once (stage 0)
+    // no context weights, or a merger-less model whose single stage sees no neighbour (map "none": conv = bias):
+    // params = prior + bias, elementwise over the whole tensor, only needed once (stage 0)
+    if (!m.has_conv || (!m.has_merger && m.S == 1 && st.tap_or == 0)) {
         if (g == 0) {
             const long long total = (long long)B * m.c_ctx * HW;
             k_bias_prior<<<m.sm_count * 8, 256, 0, stream>>>(prior, m.b_ctx.p ? m.b_ctx.as<float>() : nullptr, total, HW,
@@ -472,6 +474,17 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream, f16, m.range_flag.as<int>()));
         prior_cl = m.cl_prior.as<float>();
     }
+    // tensor path: the parameters leave the last layer in blocked channels-last floats (full-line stores); the y-path
+    // driver reads them like that (params_cl), the public stage API gets an NCHW copy
+    float *params_out = params;
+    if (tc && !params_cl) {
+        const size_t need = cl_elems(B, m.c_ctx, HW) * sizeof(float);
+        if (m.cl_params.cap < need) {
+            BASIC_TRY(m.cl_params.reserve(need));
+            BASIC_CUDA(cudaMemsetAsync(m.cl_params.p, 0, need, stream));
+        }
+        params_out = m.cl_params.as<float>();
+    }
     float *act0 = tc ? m.cl_ctx.as<float>() : m.a_ctx.as<float>();
     float *act1 = tc ? m.cl_m1.as<float>() : m.a_m1.as<float>();
     float *act2 = tc ? m.cl_m2.as<float>() : m.a_m2.as<float>();
@@ -498,14 +511,18 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         if (m.has_merger) {
             a.out = act0; a.out_cl = cl; a.add = nullptr;
         } else {  // params = ctx + prior: written straight to the NCHW parameter tensor
-            a.out = params; a.out_cl = 0; a.add = prior;
+            a.out = params_out; a.out_cl = cl; a.out_f32 = 1; a.add = prior;
         }
         a.lrelu = 0;
         a.tap_or = st.tap_or;
         a.list_key = (g * G + og) * 4;
         BASIC_TRY(launch_layer(m, a, m.p_ctx, m.q_ctx, og, st, tc, stream));
     }
-    if (!m.has_merger) return BASIC_OK;
+    auto finish = [&]() -> int {  // public stage API on the tensor path: NCHW copy of the parameters
+        if (tc && !params_cl) return launch_cl_to_nchw(m.cl_params.as<float>(), params, B, m.c_ctx, HW, stream);
+        return BASIC_OK;
+    };
+    if (!m.has_merger) return finish();
     // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
     // same stage at the same position, hence one launch wave per layer
     for (int layer = 1; layer <= 3; ++layer) {
@@ -526,7 +543,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             } else {
                 a.src0 = Source{act2, m.c_m2, G, cl};
                 a.wt = m.w_m3.as<float>(); a.bias = m.b_m3.as<float>();
-                a.Ntot = m.c_ctx; a.out = params; a.out_cl = 0; a.lrelu = 0;
+                a.Ntot = m.c_ctx; a.out = params_out; a.out_cl = cl; a.out_f32 = 1; a.lrelu = 0;
             }
             a.n_begin = og * (a.Ntot / G);
             a.n_count = a.Ntot / G;
@@ -535,7 +552,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
                                    layer == 1 ? m.q_m1 : layer == 2 ? m.q_m2 : m.q_m3, og, st, tc, stream));
         }
     }
-    return BASIC_OK;
+    return finish();
 }
 
 CtxModel *ctx_new(int C, int G, int k, int device, int sm_count)

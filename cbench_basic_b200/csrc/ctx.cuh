@@ -53,6 +53,7 @@ struct CtxModel {
     std::vector<int> kb_count;        // entries per slot, -1 = not built yet (reset by set_map / set_weights)
     DevBuf cl_ctx, cl_m1, cl_m2;      // channels-last activations of the tensor path
     DevBuf cl_buf, cl_prior;          // channels-last copies made when the caller only has NCHW (public stage API)
+    DevBuf cl_params;                 // ... and the blocked channels-last parameters behind its NCHW result
 };
 
 
@@ -80,7 +81,8 @@ struct LayerArgs {
     float *out;                 // [B, Ntot, H, W]
     const float *add;           // optional [B, Ntot, H, W] added in the epilogue (merger-less: + prior)
     int lrelu;
-    int out_cl;                 // tensor path: `out` (and `add`) are channels-last [B, H*W, Ntot]
+    int out_cl;                 // tensor path: `out` is blocked channels-last (`add` stays NCHW)
+    int out_f32;                // tensor path, 3xFP16: write plain floats (the parameter tensor), not the split16 operand format
     uint32_t tap_or;            // stage-level OR of the tap masks (conv)
     // tensor-core path
     const unsigned char *wpack; // PackedW image
@@ -107,6 +109,7 @@ bool tc_model_eligible(const CtxModel &m, int B);
 int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split = 0,
                       int *range_flag = nullptr);
 int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream);
+int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream);
 int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
                     int k2, int c_src0, int c_src1, int mode, cudaStream_t stream);
 

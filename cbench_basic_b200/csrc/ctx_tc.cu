@@ -563,16 +563,21 @@ k_layer_tc(LayerArgs a)
                     float *op = a.out + (((long long)rb * NB + (rhw >> 5)) * (a.Ntot >> 2) + ((a.n_begin + nt * BN) >> 2)) * 128 + (rhw & 31) * 4;
                     const float *bp = s_bias + nt * BN;
                     const float *srow_c = reinterpret_cast<const float *>(smem + OFF_OUT + r * OUT_ROW);
+                    const float *ap = a.add ? a.add + (long long)rb * ohw + rhw + (long long)(a.n_begin + nt * BN) * HW : nullptr;
 #pragma unroll 8
                     for (int q = 0; q < n_left; q += 4) {
                         float4 val = *reinterpret_cast<const float4 *>(srow_c + q);
                         const float4 bv = *reinterpret_cast<const float4 *>(bp + q);
                         val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
+                        if (ap) {  // merger-less: + prior (NCHW)
+                            val.x += __ldg(ap + (long long)(q + 0) * HW); val.y += __ldg(ap + (long long)(q + 1) * HW);
+                            val.z += __ldg(ap + (long long)(q + 2) * HW); val.w += __ldg(ap + (long long)(q + 3) * HW);
+                        }
                         if (a.lrelu) {
                             val.x = val.x > 0.f ? val.x : val.x * kSlope; val.y = val.y > 0.f ? val.y : val.y * kSlope;
                             val.z = val.z > 0.f ? val.z : val.z * kSlope; val.w = val.w > 0.f ? val.w : val.w * kSlope;
                         }
-                        if constexpr (MODE == 1) *reinterpret_cast<uint4 *>(op + q * 32) = split16(val, amax);  // the next layer's operand format
+                        if (MODE == 1 && !a.out_f32) *reinterpret_cast<uint4 *>(op + q * 32) = split16(val, amax);  // the next layer's operand format
                         else *reinterpret_cast<float4 *>(op + q * 32) = val;
                     }
                 }
@@ -714,6 +719,7 @@ int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv,
 bool tc_model_eligible(const CtxModel &m, int B)
 {
     if ((m.run_precision != BASIC_CTX_TF32X3 && m.run_precision != BASIC_CTX_FP16X3) || !m.has_conv || m.S < 1) return false;
+    if (!m.has_merger && m.S == 1 && m.stages[0].tap_or == 0) return false;  // nothing to multiply: params = prior + bias
     if (m.G > MAX_G || m.k * m.k * ((m.C + BK - 1) / BK) > MAX_KB || m.k * m.k > 31) return false;
     if (std::max(m.c_ctx, std::max(m.c_m1, m.c_m2)) / m.G > MAX_BIAS) return false;
     auto ok4 = [&](int channels) { return channels % m.G == 0 && (channels / m.G) % 4 == 0; };
@@ -750,6 +756,35 @@ k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channel
             *reinterpret_cast<float4 *>(d) = x;
         }
     }
+}
+
+// blocked channels-last (floats) -> [B, channels, HW]: the inverse of k_nchw_to_cl, for the public stage API
+__global__ void __launch_bounds__(256)
+k_cl_to_nchw(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, blk = blockIdx.x, hw0 = blk * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (c0 + ty * 4 < channels) {
+        const float4 x = *reinterpret_cast<const float4 *>(src + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2) + ty) * 128 + tx * 4);
+        tile[ty * 4 + 0][tx] = x.x; tile[ty * 4 + 1][tx] = x.y; tile[ty * 4 + 2][tx] = x.z; tile[ty * 4 + 3][tx] = x.w;
+    }
+    __syncthreads();
+    float *d = dst + (size_t)b * channels * HW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, hw = hw0 + tx;
+        if (c < channels && hw < HW) d[(size_t)c * HW + hw] = tile[ty + 8 * i][tx];
+    }
+}
+
+int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream)
+{
+    if (B == 0) return BASIC_OK;
+    dim3 grid((HW + 31) / 32, (channels + 31) / 32, B);
+    k_cl_to_nchw<<<grid, 256, 0, stream>>>(src, dst, channels, HW);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
 }
 
 int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split, int *range_flag)

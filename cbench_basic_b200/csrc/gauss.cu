@@ -25,7 +25,7 @@ __device__ inline int scale_index(float sigma, const float *__restrict__ tab, in
 __global__ void __launch_bounds__(256)
 k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, const int32_t *__restrict__ positions,
                  long long n_pos, int B, int C, int HW, const float *__restrict__ scale_table, int n_scales,
-                 int32_t *__restrict__ symbols, int32_t *__restrict__ indexes, float *__restrict__ yhat)
+                 int32_t *__restrict__ symbols, int32_t *__restrict__ indexes, float *__restrict__ yhat, int params_cl)
 {
     __shared__ float tab[256];
     for (int i = threadIdx.x; i < n_scales; i += blockDim.x) tab[i] = scale_table[i];
@@ -37,8 +37,18 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
         const long long k = e - b * n_pos;
         const int p = positions ? positions[k] : (int)k;
         const int c = p / HW;
-        const long long po = b * 2 * chw + p + (long long)c * HW;  // channel 2c (mean); scale is HW further
-        const float mean = params[po], sigma = params[po + HW];
+        float mean, sigma;
+        if (params_cl) {  // blocked channels-last parameters of the tensor path (ctx.cuh): (mean, scale) are neighbours
+            const int hw = p - c * HW;
+            const float2 ms = *reinterpret_cast<const float2 *>(
+                params + ((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2);
+            mean = ms.x;
+            sigma = ms.y;
+        } else {
+            const long long po = b * 2 * chw + p + (long long)c * HW;  // channel 2c (mean); scale is HW further
+            mean = params[po];
+            sigma = params[po + HW];
+        }
         indexes[e] = scale_index(sigma, tab, n_scales);
         if (y) {
             const float s = rintf(__fsub_rn(y[b * chw + p], mean));  // torch.round: half to even
@@ -50,7 +60,7 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
 
 __global__ void __launch_bounds__(256)
 k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ params, const int32_t *__restrict__ positions,
-             long long n_pos, int B, int C, int HW, float *__restrict__ yhat)
+             long long n_pos, int B, int C, int HW, float *__restrict__ yhat, int params_cl)
 {
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
@@ -59,7 +69,9 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
         const long long k = e - b * n_pos;
         const int p = positions ? positions[k] : (int)k;
         const int c = p / HW;
-        const float mean = params[b * 2 * chw + p + (long long)c * HW];
+        const int hw = p - c * HW;
+        const float mean = params_cl ? params[((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2]
+                                     : params[b * 2 * chw + p + (long long)c * HW];
         // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
         yhat[b * chw + p] = __fadd_rn(__fadd_rn((float)symbols[e], mean), 0.0f);
     }
@@ -69,26 +81,26 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
 
 int launch_quantize_index(const float *y, const float *params, const int32_t *positions, int64_t n_pos, int B, int C, int HW,
                           const float *d_scale_table, int n_scales, int32_t *symbols, int32_t *indexes, float *yhat,
-                          int sm_count, cudaStream_t stream)
+                          int sm_count, cudaStream_t stream, int params_cl)
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
     k_quantize_index<<<(int)blocks, 256, 0, stream>>>(y, params, positions, n_pos, B, C, HW, d_scale_table, n_scales, symbols,
-                                                      indexes, yhat);
+                                                      indexes, yhat, params_cl);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
 
 int launch_dequantize(const int32_t *symbols, const float *params, const int32_t *positions, int64_t n_pos, int B, int C,
-                      int HW, float *yhat, int sm_count, cudaStream_t stream)
+                      int HW, float *yhat, int sm_count, cudaStream_t stream, int params_cl)
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat);
+    k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat, params_cl);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
