@@ -81,9 +81,10 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
     Extra keywords: ``lanes`` (1 = reference bitstream byte for byte; 0 = multi-lane container within 0.5 % of it,
     the default; N = ceil(N/32) chunks per group segment), ``ans_params_device`` (device of the float32 Gaussian
     pmf evaluation in update_state; None = the module's device, like the reference; "cpu" reproduces a
-    CPU-run reference table bit for bit), ``ctx_precision`` ("fp32" = exact FP32 FMA kernel, "tf32x3" = tcgen05 tensor
-    cores with error-compensated TF32 products, "auto" = fp32 in the lanes=1 compatibility mode and tf32x3 otherwise;
-    encoder and decoder must agree) and ``ctx_accumulators`` (k-blocks of 32 accumulated in tensor memory before a
+    CPU-run reference table bit for bit), ``ctx_precision`` ("fp32" = exact FP32 FMA kernel, "tf32x3" / "fp16x3" = tcgen05
+    tensor cores with error-compensated TF32 / FP16 products (both within 1e-5 of fp32; fp16x3 falls back to tf32x3 when an
+    activation reaches 4000 in magnitude and records that in the stream), "auto" = fp32 in the lanes=1 compatibility mode and
+    fp16x3 otherwise; a multi-lane stream tells the decoder which tensor mode wrote it, fp32 and the tensor modes do not mix) and ``ctx_accumulators`` (k-blocks of 32 accumulated in tensor memory before a
     partial sum is drained into the FP32 register accumulator)."""
 
     def __init__(self, *args, in_channels=256, channel_groups=1, default_topo_group_method="none",
