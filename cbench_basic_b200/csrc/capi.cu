@@ -1,5 +1,6 @@
 // extern "C" entry points (include/basic_b200.h) and the host-side orchestration of the kernels.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <condition_variable>
@@ -128,6 +129,7 @@ struct basic_coder {
     std::vector<cudaEvent_t> out_events;  // one per chunk of the last device-to-host delivery into host_out
     int out_chunks = 0;                   // chunks of that delivery still to be awaited (0 = host_out is complete)
     cudaEvent_t in_event = nullptr;  // completion of the last upload out of host_in
+    cudaStream_t copy_stream = nullptr;  // the upload runs beside whatever is already queued on the caller's stream
     // cache for cache=1 / flush()
     std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
     std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
@@ -292,7 +294,21 @@ int reserve_pinned(uint8_t **buf, size_t *cap, size_t bytes)
 // coder's pinned staging buffer, from where basic_coder_last_output hands them out without another device trip.
 int finish_out(basic_coder *c);
 constexpr int64_t kHostChunk = 1 << 20;  // granularity of the pipelined host copies
-constexpr int kHostThreads = 4;
+constexpr int kHostThreadsMax = 8;
+// host threads of the staging copies: BASIC_HOST_THREADS, else up to 4 but no more than this rank's share of the cores
+// (LOCAL_WORLD_SIZE ranks per node under torchrun); 1 = the calling thread only
+static const int kHostThreads = [] {
+    const char *e = getenv("BASIC_HOST_THREADS");
+    int v = 4;
+    if (e) v = atoi(e);
+    else {
+        const char *l = getenv("LOCAL_WORLD_SIZE");
+        const int ranks = l ? std::max(1, atoi(l)) : 1;
+        const int cores = (int)std::thread::hardware_concurrency();
+        if (cores > 0) v = std::min(4, std::max(1, cores / ranks));
+    }
+    return v < 1 ? 1 : v > kHostThreadsMax ? kHostThreadsMax : v;
+}();
 
 // A few persistent host threads for the staging copies (a 16 MB memcpy on one core costs more than its bus transfer).
 // run(nt, fn) executes fn(t) for t = 0 .. nt - 1 (t = 0 on the caller) and returns when all are done; one job at a time.
@@ -506,6 +522,7 @@ void basic_coder_destroy(basic_coder *c)
     if (c->host_out) cudaFreeHost(c->host_out);
     if (c->host_in) cudaFreeHost(c->host_in);
     if (c->in_event) cudaEventDestroy(c->in_event);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (cudaEvent_t e : c->out_events) cudaEventDestroy(e);
     if (c->tt) tans_delete(c->tt);
     delete c;
@@ -712,28 +729,39 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
         BASIC_CUDA(cudaStreamSynchronize(s));
     } else if (len) {
         if (!c->in_event) BASIC_CUDA(cudaEventCreateWithFlags(&c->in_event, cudaEventDisableTiming));
+        if (!c->copy_stream) BASIC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         BASIC_CUDA(cudaEventSynchronize(c->in_event));  // an earlier upload out of host_in may still be in flight
         // staged through pinned memory chunk by chunk: every chunk goes on the bus as soon as it is copied, the host
-        // copies run on a few threads (the GPU keeps working on what is already queued on `s`)
+        // copies run on a few threads, and the upload has its own stream: what the caller has already queued on `s`
+        // (the y path: the first group's context model) runs beside it; `s` waits for the upload from here on.
+        // (every decoding call ends with a synchronisation of `s`, so nothing is still reading stream_dev)
         const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
         const int nt = std::min(kHostThreads, chunks);
+        cudaStream_t up = c->copy_stream;
         const std::function<void(int)> work = [&](int t) {
             if (t > 0) cudaSetDevice(c->device);
             for (int k = t; k < chunks; k += nt) {
                 const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
                 memcpy(c->host_in + at, encoded + at, (size_t)nb);
-                cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + at, c->host_in + at, (size_t)nb, cudaMemcpyHostToDevice, s);
+                cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + at, c->host_in + at, (size_t)nb, cudaMemcpyHostToDevice, up);
             }
         };
         if (nt <= 1) work(0);
         else HostPool::get().run(nt, work);
         BASIC_CUDA(cudaGetLastError());
-        BASIC_CUDA(cudaEventRecord(c->in_event, s));
+        BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, up));
+        BASIC_CUDA(cudaEventRecord(c->in_event, up));
+        BASIC_CUDA(cudaStreamWaitEvent(s, c->in_event, 0));
+        c->stream_len = len;
+        c->stream_lanes = lanes;
+        c->stream_set = true;
+        goto staged;
     }
     BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, s));
     c->stream_len = len;
     c->stream_lanes = lanes;
     c->stream_set = true;
+staged:
     if (lanes == BASIC_LANES_REFERENCE) {
         c->stream_pos = -1;  // state is initialised by the first decode_stream launch
     } else {
