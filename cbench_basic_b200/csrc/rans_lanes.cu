@@ -70,7 +70,9 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
     const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
     const int prec = P.precision;
     const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
-    const uint32_t xmax_bits = 1u << (32 - bp);
+    const int tpu = 16 / (int)bp;  // escape tokens per unit
+    // n / bp, n / maxb, n / tpu for n < 64 as multiply + shift (exact there; a runtime integer division is ~25 instructions)
+    const uint32_t r_bp = (65536u + bp - 1) / bp, r_maxb = (65536u + maxb - 1) / maxb, r_tpu = (65536u + tpu - 1) / tpu;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     // chunks are dealt round-robin over CTAs first so that few chunks still spread over all SMs
@@ -127,18 +129,34 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                 } else if (v < 0 || v > maxv) { if (active) st |= 2; v = 0; }
                 const uint32_t start = tv.cdf[mt.cdf_base + v];
                 const uint32_t freq = (uint16_t)(tv.cdf[mt.cdf_base + v + 1] - start);
-                // --- escape tokens: sub-steps last to first (oracle: bls_encode_chunk)
+                // --- escape units, last to first (oracle: bls_encode_slice): the token list (count tokens, then the
+                // digits) goes through the state in units of up to tpu = 16 / bp tokens, one renormalisation check each
                 if (__any_sync(kFull, esc)) {
                     int nd = 0, ncnt = 0, ntok = 0;
                     if (esc) {
-                        nd = raw ? (int)((32 - __clz(raw) + bp - 1) / bp) : 0;
-                        ncnt = nd / (int)maxb + 1;
+                        nd = (int)(((32 - __clz(raw) + bp - 1) * r_bp) >> 16);  // digits of raw (0 for raw = 0)
+                        ncnt = (int)(((uint32_t)nd * r_maxb) >> 16) + 1;
                         ntok = ncnt + nd;
                     }
-                    const int maxtok = (int)__reduce_max_sync(kFull, (unsigned)ntok);
-                    for (int u = maxtok - 1; u >= 0; --u) {
-                        const bool part = ntok > u;
-                        const bool emit = part && x >= xmax_bits;
+                    const int nunits = (int)(((uint32_t)(ntok + tpu - 1) * r_tpu) >> 16);
+                    const int maxunits = (int)__reduce_max_sync(kFull, (unsigned)nunits);
+                    for (int u = maxunits - 1; u >= 0; --u) {
+                        const bool part = nunits > u;
+                        // the unit: tokens [u * tpu, min((u + 1) * tpu, ntok)), first token in the low bits
+                        uint32_t unit = 0;
+                        int wbits = 0;
+                        if (part) {
+                            const int t0 = u * tpu, cnt = min(tpu, ntok - t0);
+                            for (int i = 0; i < cnt; ++i) {
+                                const int t = t0 + i;
+                                uint32_t tok;
+                                if (t >= ncnt) tok = (raw >> ((t - ncnt) * bp)) & maxb;
+                                else tok = t < ncnt - 1 ? maxb : (uint32_t)(nd - (ncnt - 1) * (int)maxb);
+                                unit |= tok << (bp * i);
+                            }
+                            wbits = (int)bp * cnt;
+                        }
+                        const bool emit = part && x >= (1u << (32 - wbits));
                         const unsigned em = __ballot_sync(kFull, emit);
                         pos -= __popc(em);
                         if (emit) {
@@ -146,17 +164,12 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                             if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
                             x >>= 16;
                         }
-                        if (part) {
-                            uint32_t tok;
-                            if (u >= ncnt) tok = (raw >> ((u - ncnt) * bp)) & maxb;
-                            else tok = u < ncnt - 1 ? maxb : (uint32_t)(nd - (ncnt - 1) * (int)maxb);
-                            x = (x << bp) | tok;
-                        }
+                        if (part) x = (x << wbits) | unit;
                     }
                 }
                 // --- the symbol itself
-                const unsigned long long x_max = ((unsigned long long)(kRansL >> prec) << 16) * freq;
-                const bool emit = active && x >= x_max;
+                // x >= ((L >> prec) << 16) * freq = freq << (32 - prec), without the 64-bit product
+                const bool emit = active && (x >> (32 - prec)) >= freq;
                 const unsigned em = __ballot_sync(kFull, emit);
                 pos -= __popc(em);
                 if (emit) {
@@ -276,6 +289,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     const int prec = P.precision;
     const uint32_t pmask = (1u << prec) - 1;
     const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
+    const int tpu = 16 / (int)bp;  // escape tokens per unit
     const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2 + seg_slices;
     const uint32_t *states = end_word + n_chunks;
     const long long words_at = kSegHdr + 4ll * seg_slices + 4ll * n_chunks + 128ll * n_chunks;
@@ -371,10 +385,25 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                     int phase = 0;
                     uint32_t nb = 0, raw = 0, jj = 0;
                     while (__any_sync(kFull, in)) {
-                        uint32_t val = 0;
-                        if (in) { val = x & maxb; x >>= bp; }
+                        // one unit: parse up to tpu tokens out of the low 16 bits (x >= 2^16 here), pop exactly those
+                        const bool was = in;
+                        if (in) {
+                            int used = 0;
+                            for (int i = 0; i < tpu && in; ++i, ++used) {
+                                const uint32_t val = (x >> (bp * i)) & maxb;
+                                if (phase == 0) {
+                                    nb += val;
+                                    if (val != maxb) { phase = 1; if (nb == 0) in = false; }
+                                    else if (nb > 64) { in = false; st |= 4; }
+                                } else {
+                                    if (jj * bp < 32) raw |= val << (jj * bp);
+                                    if (++jj == nb) in = false;
+                                }
+                            }
+                            x >>= bp * used;
+                        }
                         ensure();
-                        const bool need = in && x < kRansL;
+                        const bool need = was && x < kRansL;
                         const unsigned nm = __ballot_sync(kFull, need);
                         if (need) {
                             const uint32_t at = wp + __popc(nm & lt_mask);
@@ -383,16 +412,6 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                             x = (x << 16) | word;
                         }
                         wp += __popc(nm);
-                        if (in) {
-                            if (phase == 0) {
-                                nb += val;
-                                if (val != maxb) { phase = 1; if (nb == 0) in = false; }
-                                else if (nb > 64) { in = false; st |= 4; }
-                            } else {
-                                if (jj * bp < 32) raw |= val << (jj * bp);
-                                if (++jj == nb) in = false;
-                            }
-                        }
                     }
                     if (esc) {
                         const int32_t v2 = (int32_t)(raw >> 1);

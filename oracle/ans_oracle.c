@@ -578,6 +578,13 @@ int orc_tans_decode(const orc_tans_tables *tb, const uint8_t *enc, int64_t len, 
  *    interleaved lanes sharing one word stream.  Within a chunk, local symbol j belongs to lane
  *    (j % 128) / 4 and is coded at step (j / 128) * 4 + (j % 4).
  *
+ *    Escapes: the reference's token list (count in unary base 2^bp - 1, then the bp-bit digits LSB first,
+ *    rans64.cpp:293-335) is coded through the lane's own state, but in UNITS of up to floor(16 / bp) consecutive tokens:
+ *    unit k holds tokens [k * tpu, min((k + 1) * tpu, ntok)), first token in the low bits, and is pushed / popped as one
+ *    (bp * count)-bit quantity with one renormalisation check -- a typical escape (count + up to three digits) is one
+ *    warp-wide event instead of up to four.  A state is >= 2^16 at every unit boundary, so the decoder can parse the
+ *    tokens of a unit (and with them the unit's width) from the low 16 bits before it pops them.
+ *
  *    Segment layout (little endian): u32 n_chunks | u32 n_slices | u32 chunk_syms[n_slices] | u32 end_word[n_chunks]
  *    (cumulative word count up to and including chunk k) | u32 state[n_chunks][32] | u16 words of chunk 0, chunk 1, ...
  *    | zero pad to 4 bytes.  Slices: see orc_bls_encode_slices.
@@ -585,7 +592,22 @@ int orc_tans_decode(const orc_tans_tables *tb, const uint8_t *enc, int64_t len, 
 #define BLS_LANES 32
 #define BLS_L (1u << 16)
 
-typedef struct { int m; uint32_t tok[48]; } bls_esc;
+typedef struct { int m; uint32_t tok[48]; } bls_esc;  /* m = UNITS after bls_pack_units: tok[k] = unit value, wid[k] its bits */
+typedef struct { int wid[48]; } bls_wid;
+
+/* token list -> units of up to 16 / bp tokens (first token in the low bits); returns the number of units */
+static int bls_pack_units(int ntok, int bp, uint32_t *tok, int *wid)
+{
+    const int tpu = 16 / bp;
+    int nu = 0;
+    for (int t0 = 0; t0 < ntok; t0 += tpu, ++nu) {
+        const int cnt = ntok - t0 < tpu ? ntok - t0 : tpu;
+        uint32_t v = 0;
+        for (int i = 0; i < cnt; ++i) v |= tok[t0 + i] << (bp * i);
+        tok[nu] = v; wid[nu] = bp * cnt;   /* in place: nu <= t0 */
+    }
+    return nu;
+}
 
 static inline int64_t bls_local_index(int64_t step, int lane) { return (step >> 2) * 128 + lane * 4 + (step & 3); }
 
@@ -597,6 +619,7 @@ static int bls_encode_slice(const orc_rans64_tables *tb, const int32_t *sym, con
                             uint16_t *wbuf, int64_t *pp, uint32_t *x)
 {
     bls_esc *esc = (bls_esc *)malloc(sizeof(bls_esc) * BLS_LANES);
+    bls_wid *ew = (bls_wid *)malloc(sizeof(bls_wid) * BLS_LANES);
     uint32_t start[BLS_LANES], freq[BLS_LANES];
     int active[BLS_LANES];
     int64_t p = *pp;
@@ -618,22 +641,22 @@ static int bls_encode_slice(const orc_rans64_tables *tb, const int32_t *sym, con
             if (tb->bypass) {
                 if (value < 0) { raw = (uint32_t)(-2 * value - 1); value = max_value; }
                 else if (value >= max_value) { raw = (uint32_t)(2 * (value - max_value)); value = max_value; }
-                if (value == max_value) esc[l].m = escape_tokens(raw, bp, esc[l].tok);
+                if (value == max_value) esc[l].m = bls_pack_units(escape_tokens(raw, bp, esc[l].tok), bp, esc[l].tok, ew[l].wid);
             } else if (value < 0 || value > max_value) { rc = ORC_ERR_RANGE; break; }
             start[l] = (uint32_t)cdf[value]; freq[l] = (uint32_t)(cdf[value + 1] - cdf[value]);
             if (esc[l].m > maxm) maxm = esc[l].m;
         }
         if (rc) break;
-        /* escape sub-steps, last to first; inside one event words are laid out in ascending lane order */
+        /* escape units, last to first; inside one event words are laid out in ascending lane order */
         for (int u = maxm - 1; u >= 0; --u) {
             int cnt = 0;
-            for (int l = 0; l < BLS_LANES; ++l) if (esc[l].m > u && x[l] >= (BLS_L << (16 - bp))) cnt++;
+            for (int l = 0; l < BLS_LANES; ++l) if (esc[l].m > u && x[l] >= (BLS_L << (16 - ew[l].wid[u]))) cnt++;
             if (p < cnt) { rc = ORC_ERR_CAPACITY; break; }
             p -= cnt; int r = 0;
             for (int l = 0; l < BLS_LANES; ++l) {
                 if (esc[l].m <= u) continue;
-                if (x[l] >= (BLS_L << (16 - bp))) { wbuf[p + r++] = (uint16_t)x[l]; x[l] >>= 16; }
-                x[l] = (x[l] << bp) | esc[l].tok[u];
+                if (x[l] >= (BLS_L << (16 - ew[l].wid[u]))) { wbuf[p + r++] = (uint16_t)x[l]; x[l] >>= 16; }
+                x[l] = (x[l] << ew[l].wid[u]) | esc[l].tok[u];
             }
         }
         if (rc) break;
@@ -649,6 +672,7 @@ static int bls_encode_slice(const orc_rans64_tables *tb, const int32_t *sym, con
         }
     }
     free(esc);
+    free(ew);
     *pp = p;
     return rc;
 }
@@ -753,16 +777,25 @@ static int bls_decode_slice(const orc_rans64_tables *tb, const uint16_t *w, int6
         }
         for (int l = 0; l < BLS_LANES; ++l)
             if (cc[l] >= 0 && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
-        /* escape sub-steps */
+        /* escape units: every escaping lane parses up to 16 / bp tokens from the low 16 bits of its state (>= 2^16 here),
+         * pops exactly those, then the lanes renormalise in lane order */
         while (any) {
-            uint32_t val[BLS_LANES];
-            for (int l = 0; l < BLS_LANES; ++l) if (escl[l]) { val[l] = x[l] & maxb; x[l] >>= bp; }
-            for (int l = 0; l < BLS_LANES; ++l) if (escl[l] && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
+            int was[BLS_LANES];
+            for (int l = 0; l < BLS_LANES; ++l) {
+                was[l] = escl[l];
+                if (!escl[l]) continue;
+                int used = 0;
+                for (int i = 0; i < 16 / bp && escl[l]; ++i, ++used) {
+                    const uint32_t val = (x[l] >> (bp * i)) & maxb;
+                    if (phase[l] == 0) { nb[l] += val; if (val != maxb) { phase[l] = 1; if (nb[l] == 0) escl[l] = 0; } }
+                    else { if (jj[l] * bp < 32) raw[l] |= val << (jj[l] * bp); if (++jj[l] == nb[l]) escl[l] = 0; }
+                }
+                x[l] >>= bp * used;
+            }
+            for (int l = 0; l < BLS_LANES; ++l) if (was[l] && x[l] < BLS_L) x[l] = (x[l] << 16) | w[wp++];
             any = 0;
             for (int l = 0; l < BLS_LANES; ++l) {
-                if (!escl[l]) continue;
-                if (phase[l] == 0) { nb[l] += val[l]; if (val[l] != maxb) { phase[l] = 1; if (nb[l] == 0) escl[l] = 0; } }
-                else { raw[l] |= val[l] << (jj[l] * bp); if (++jj[l] == nb[l]) escl[l] = 0; }
+                if (!was[l]) continue;
                 if (escl[l]) any = 1;
                 else { int32_t v = (int32_t)(raw[l] >> 1); value[l] = (raw[l] & 1) ? -v - 1 : v + maxv[l]; }
             }
