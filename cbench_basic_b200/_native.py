@@ -20,7 +20,7 @@ SYMBOLS = [
     "basic_coder_decode_stream", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
     "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_map", "basic_ctx_num_stages",
     "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
-    "basic_ypath_decode", "basic_profile_enable", "basic_profile_read", "basic_launch_count",
+    "basic_ypath_decode", "basic_profile_enable", "basic_profile_read", "basic_debug_mma_bench", "basic_launch_count",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.basic_ypath_decode.argtypes = [vp, vp, u8p, i64, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, vp]
     L.basic_profile_enable.argtypes = [C.c_int]
     L.basic_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
+    L.basic_debug_mma_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     L.basic_launch_count.argtypes = [C.c_int]
     L.basic_launch_count.restype = i64
     _lib = L

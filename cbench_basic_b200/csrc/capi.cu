@@ -45,6 +45,7 @@ size_t ctx_cl_elems(int B, int channels, int HW);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
 int ctx_precision(const CtxModel &);
+int mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles);
 void ctx_set_run_precision(CtxModel &, int);
 int ctx_range_flag_clear(CtxModel &, cudaStream_t);
 int ctx_range_flag_read(CtxModel &, cudaStream_t, int *);
@@ -472,6 +473,11 @@ int basic_profile_read(double *ms, int64_t *spans)
     g_prof_spans.clear();
     cudaGetLastError();
     return BASIC_OK;
+}
+
+int basic_debug_mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles)
+{
+    return mma_bench(mode, ts, n_cols, iters, same_acc, cycles);
 }
 
 int64_t basic_launch_count(int reset)

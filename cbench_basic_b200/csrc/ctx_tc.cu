@@ -670,7 +670,82 @@ k_absmax(const float *__restrict__ w, long long n, unsigned int *out)
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Micro-benchmark (tools/mma_bench.py, basic_debug_mma_bench): back-to-back tcgen05.mma of one shape from one warp,
+// operands = whatever the shared / tensor memory holds; cycles per MMA between the first issue and the commit's arrival.
+template <int MODE, bool TS>
+__global__ void __launch_bounds__(128, 1)
+k_mma_bench(int n_cols, int iters, int same_acc, long long *out)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) unsigned long long bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;  // fp16 1.0 pairs
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | ((MODE ? 0u : 2u) << 7) | ((MODE ? 0u : 2u) << 10) | ((uint32_t)(n_cols >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
+        const uint64_t adesc = smem_desc<MODE>(s_base), bdesc = smem_desc<MODE>(s_base + 16384);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (elect_one()) {
+                const uint32_t d = tmem_base + (same_acc ? 0u : (uint32_t)((i & 1) * n_cols));
+                if constexpr (TS) umma_ts<MODE>(d, tmem_base + 448, bdesc, idesc, i ? 1u : 0u);
+                else {
+                    if constexpr (MODE == 0)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(i ? 1u : 0u) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(i ? 1u : 0u) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (elect_one()) umma_commit(smem_u32(&bar));
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        if (lane == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
+
+int mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles)
+{
+    long long *d = nullptr;
+    BASIC_CUDA(cudaMalloc(&d, 16));
+    const int smem = 96 * 1024;
+#define BASIC_MB(M, T)                                                                                         \
+    do {                                                                                                       \
+        BASIC_CUDA(cudaFuncSetAttribute(k_mma_bench<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        k_mma_bench<M, T><<<1, 128, smem>>>(n_cols, iters, same_acc, d);                                       \
+    } while (0)
+    if (mode == 0 && ts) BASIC_MB(0, true);
+    else if (mode == 0) BASIC_MB(0, false);
+    else if (ts) BASIC_MB(1, true);
+    else BASIC_MB(1, false);
+#undef BASIC_MB
+    BASIC_CUDA(cudaDeviceSynchronize());
+    BASIC_CUDA(cudaMemcpy(cycles, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return BASIC_OK;
+}
 
 int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv, int Cin, int k2, int c_src0, int c_src1, int mode,
                     cudaStream_t stream)

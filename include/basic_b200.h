@@ -156,6 +156,10 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
 int basic_profile_enable(int on);
 int basic_profile_read(double *ms, int64_t *spans);
 
+/* Debug aid (tools/mma_bench.py): cycles[0] = issue, cycles[1] = issue + completion of `iters` back-to-back
+ * tcgen05.mma (M = 128, N = n_cols; mode 0 = tf32 K 8, 1 = f16 K 16; ts = A operand in tensor memory) on one SM. */
+int basic_debug_mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles);
+
 /* Counters for bench.py ("gpu_launches"): kernels launched by this library since the last reset. */
 int64_t basic_launch_count(int reset);
 
