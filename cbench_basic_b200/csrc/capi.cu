@@ -27,9 +27,9 @@ int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64
                       uint32_t *, uint32_t *, int32_t *, int *, int, cudaStream_t);
 int launch_estimate_bits(const RansTables &, int, int, const int32_t *, const int32_t *, int64_t, float *, cudaStream_t);
 int launch_quantize_index(const float *, const float *, const int32_t *, int64_t, int, int, int, const float *, int, int32_t *,
-                          int32_t *, float *, int, cudaStream_t, int params_cl = 0);
+                          int32_t *, float *, int, cudaStream_t, int params_cl = 0, const int32_t *perm = nullptr);
 int launch_dequantize(const int32_t *, const float *, const int32_t *, int64_t, int, int, int, float *, int, cudaStream_t,
-                      int params_cl = 0);
+                      int params_cl = 0, const int32_t *perm = nullptr);
 
 struct CtxModel;
 CtxModel *ctx_new(int C, int G, int k, int device, int sm_count);
@@ -45,6 +45,7 @@ size_t ctx_cl_elems(int B, int channels, int HW);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
 int ctx_precision(const CtxModel &);
+const int32_t *ctx_perm(const CtxModel &);
 int mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles);
 void ctx_set_run_precision(CtxModel &, int);
 int ctx_range_flag_clear(CtxModel &, cudaStream_t);
@@ -1045,7 +1046,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             if (cnt == 0) continue;
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                            sym + done, idx + done, buf, c->sm_count, s, tc ? 1 : 0));
+                                            sym + done, idx + done, buf, c->sm_count, s, tc ? 1 : 0, tc ? ctx_perm(*model->m) : nullptr));
             if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
             done += (size_t)cnt;
         }
@@ -1171,7 +1172,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (cnt > 0) {
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
-                                            nullptr, idx, nullptr, c->sm_count, s, tc ? 1 : 0));
+                                            nullptr, idx, nullptr, c->sm_count, s, tc ? 1 : 0, tc ? ctx_perm(*model->m) : nullptr));
         }
         if (lanes == BASIC_LANES_REFERENCE) {
             if (cnt == 0) continue;
@@ -1188,7 +1189,8 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         }
         if (cnt > 0) {
             ProfScope ps(PROF_GAUSS, s);
-            BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s, tc ? 1 : 0));
+            BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s, tc ? 1 : 0,
+                                        tc ? ctx_perm(*model->m) : nullptr));
             if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf, buf_cl, B, C, s));
         }
     }

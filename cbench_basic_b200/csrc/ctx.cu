@@ -11,6 +11,8 @@
 // Deterministic (fixed K order, no atomics): the decoder recomputes bit-identical parameters.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace basic {
@@ -368,6 +370,20 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
     BASIC_CUDA(cudaMemcpy(m.d_cell_tap.p, cell_tap.data(), cell_tap.size() * 4, cudaMemcpyHostToDevice));
     BASIC_CUDA(cudaMemcpy(m.d_cell_grp.p, cell_grp.data(), cell_grp.size() * 4, cudaMemcpyHostToDevice));
     BASIC_CUDA(cudaMemcpy(m.d_positions.p, positions.data(), positions.size() * 4, cudaMemcpyHostToDevice));
+    // slot order of the tensor path's activation layout: stage-major by the coding group of channel group 0, raster inside
+    std::vector<int32_t> perm((size_t)HW), iperm((size_t)HW);
+    {
+        static const bool identity = getenv("BASIC_TC_NOPERM") && atoi(getenv("BASIC_TC_NOPERM"));  // A/B aid: raster slots
+        int32_t slot = 0;
+        for (int s = 0; s < S; ++s)
+            for (int p = 0; p < HW; ++p)
+                if (tg[p] == s) { perm[p] = slot; iperm[slot] = p; ++slot; }
+        if (identity) for (int p = 0; p < HW; ++p) perm[p] = iperm[p] = p;
+    }
+    BASIC_TRY(m.d_perm.reserve((size_t)HW * 4 + 16));
+    BASIC_TRY(m.d_iperm.reserve((size_t)HW * 4 + 16));
+    BASIC_CUDA(cudaMemcpy(m.d_perm.p, perm.data(), (size_t)HW * 4, cudaMemcpyHostToDevice));
+    BASIC_CUDA(cudaMemcpy(m.d_iperm.p, iperm.data(), (size_t)HW * 4, cudaMemcpyHostToDevice));
     return BASIC_OK;
 }
 
@@ -400,12 +416,14 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, const Packe
 
 bool ctx_uses_tc(const CtxModel &m, int B) { return tc_model_eligible(m, B); }
 int ctx_precision(const CtxModel &m) { return m.precision; }
+const int32_t *ctx_perm(const CtxModel &m) { return m.d_perm.as<int32_t>(); }
 // blocked channels-last copy in the operand format of the mode the next stage calls run in (floats, or split16)
 int ctx_to_cl(CtxModel &m, const float *src, float *dst, int B, int channels, cudaStream_t s)
 {
     const bool f16 = m.run_precision == BASIC_CTX_FP16X3;
     if (f16) BASIC_TRY(m.range_flag.reserve(16));
-    return launch_nchw_to_cl(src, dst, B, channels, m.H * m.W, s, f16 ? 1 : 0, f16 ? m.range_flag.as<int>() : nullptr);
+    return launch_nchw_to_cl(src, dst, B, channels, m.H * m.W, m.d_iperm.as<int32_t>(), s, f16 ? 1 : 0,
+                             f16 ? m.range_flag.as<int>() : nullptr);
 }
 void ctx_set_run_precision(CtxModel &m, int p)
 {
@@ -466,12 +484,12 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
     const int f16 = tc && m.run_precision == BASIC_CTX_FP16X3;
     if (tc && !buf_cl) {
         BASIC_TRY(m.cl_buf.reserve(cl_elems(B, m.C, HW) * sizeof(float)));
-        BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, stream, f16, m.range_flag.as<int>()));
+        BASIC_TRY(launch_nchw_to_cl(buf, m.cl_buf.as<float>(), B, m.C, HW, m.d_iperm.as<int32_t>(), stream, f16, m.range_flag.as<int>()));
         buf_cl = m.cl_buf.as<float>();
     }
     if (tc && !prior_cl && (m.has_merger || true)) {
         BASIC_TRY(m.cl_prior.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));
-        BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, stream, f16, m.range_flag.as<int>()));
+        BASIC_TRY(launch_nchw_to_cl(prior, m.cl_prior.as<float>(), B, m.c_ctx, HW, m.d_iperm.as<int32_t>(), stream, f16, m.range_flag.as<int>()));
         prior_cl = m.cl_prior.as<float>();
     }
     // tensor path: the parameters leave the last layer in blocked channels-last floats (full-line stores); the y-path
@@ -492,6 +510,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
     auto base_args = [&](int og, int ncells) {
         LayerArgs a = {};
         a.cell_hw = m.d_cell_hw.as<int32_t>();
+        a.perm = m.d_perm.as<int32_t>();
         a.cell_tap = m.d_cell_tap.as<uint32_t>();
         a.cell_grp = m.d_cell_grp.as<uint32_t>();
         a.ncells = ncells;
@@ -519,7 +538,7 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         BASIC_TRY(launch_layer(m, a, m.p_ctx, m.q_ctx, og, st, tc, stream));
     }
     auto finish = [&]() -> int {  // public stage API on the tensor path: NCHW copy of the parameters
-        if (tc && !params_cl) return launch_cl_to_nchw(m.cl_params.as<float>(), params, B, m.c_ctx, HW, stream);
+        if (tc && !params_cl) return launch_cl_to_nchw(m.cl_params.as<float>(), params, B, m.c_ctx, HW, m.d_iperm.as<int32_t>(), stream);
         return BASIC_OK;
     };
     if (!m.has_merger) return finish();
@@ -569,7 +588,7 @@ void ctx_delete(CtxModel *m)
     DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
-                      &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool};
+                      &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -38,6 +38,8 @@ struct CtxModel {
     DevBuf d_cell_tap;   // uint32 [ncells][G]        visible 5x5 taps per input channel group
     DevBuf d_cell_grp;   // uint32 [ncells]           bit j: in-group j visible through "<="
     DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
+    DevBuf d_perm;       // int32 [H*W]               position -> slot of the tensor path's activation layout (stage-major)
+    DevBuf d_iperm;      // int32 [H*W]               slot -> position
     // activations (grow-only)
     DevBuf a_ctx, a_m1, a_m2;
     int act_B = 0;
@@ -67,6 +69,7 @@ struct Source {          // one block of K coming from an NCHW activation tensor
 struct LayerArgs {
     // rows = B x cells(stage, out-group)
     const int32_t *cell_hw;
+    const int32_t *perm;        // tensor path: position -> slot of the blocked channels-last layout
     const uint32_t *cell_tap;   // conv only
     const uint32_t *cell_grp;   // dense only
     int ncells, cell_base;      // cells of this (stage, out-group) start at cell_base
@@ -103,13 +106,15 @@ struct LayerArgs {
 // Activation layout of the tensor-core path ("blocked channels-last"): element (b, hw, c) of a [B, channels, HW] tensor
 // lives at (((b * NB + hw / 32) * (channels / 4) + c / 4) * 32 + hw % 32) * 4 + c % 4, NB = ceil(HW / 32): the 4-channel
 // chunks of 32 neighbouring positions are 512 contiguous bytes, so a warp whose lanes are neighbouring positions reads
-// or writes whole lines per 128-bit access (plain channels-last costs one line per lane).
+// or writes whole lines per 128-bit access (plain channels-last costs one line per lane).  `hw` above is not the raster
+// position but its SLOT: positions are renumbered stage-major (by the coding group of channel group 0, then raster order;
+// CtxModel::d_perm), so the rows of one coding group -- what a warp of the GEMM kernel holds -- are neighbouring slots.
 inline size_t cl_elems(int B, int channels, int HW) { return (size_t)B * ((HW + 31) / 32) * 32 * channels; }
 bool tc_model_eligible(const CtxModel &m, int B);
-int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split = 0,
-                      int *range_flag = nullptr);
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, const int32_t *iperm, cudaStream_t stream,
+                      int split = 0, int *range_flag = nullptr);
 int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream);
-int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream);
+int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, const int32_t *iperm, cudaStream_t stream);
 int pack_weights_tc(PackedW &dst, const float *w_dev /* [N][Korig] state_dict layout */, int N, int G, int is_conv, int Cin,
                     int k2, int c_src0, int c_src1, int mode, cudaStream_t stream);
 

@@ -398,13 +398,14 @@ k_layer_tc(LayerArgs a)
             if (tid == 128) stamp(lt, 3);
             // ---- per-row facts of this tile
             const int row = (t / n_ntiles) * BM + r;
-            int rb = -1, rhw = 0;
+            int rb = -1, rhw = 0, rslot = 0;
             uint32_t rgrp = 0;
             uint32_t *my_mask = reinterpret_cast<uint32_t *>(smem + OFF_MASK) + grp * (MAX_G * BM) + r;  // [g * BM]: private to this thread
             if (row < rows) {
                 rb = row / a.ncells;
                 const int cell = a.cell_base + (row - rb * a.ncells);
                 rhw = a.cell_hw[cell];
+                rslot = __ldg(a.perm + rhw);
                 if (a.is_conv) for (int j = 0; j < G; ++j) my_mask[j * BM] = a.cell_tap[(size_t)cell * G + j];
                 else rgrp = a.cell_grp[cell];
             }
@@ -413,14 +414,12 @@ k_layer_tc(LayerArgs a)
             const long long rbz = rb < 0 ? 0 : rb;
             const int NB = (HW + 31) >> 5;
             const int nq0 = (a.is_conv ? a.Cin : a.src0.channels) >> 2, nq1 = a.src1.channels >> 2;
+            int last_shift = 0, last_slot = rslot;  // tap whose slot was looked up last (shift 0 = the row's own position)
             // gathers the 32 k of k-block i for this thread's row into registers (masked elements = 0)
             auto gather = [&](int i, float(&v)[BK]) {
                 const uint4 e = s_list[i];
-                const int hw2 = rhw + (int)(short)(e.y & 0xffffu);  // the tap's position (inside the image whenever the tap is visible)
                 const bool s1 = e.z & 1u;
                 const int tap = (int)((e.z >> 1) & 31u), nvalid = (int)((e.z >> 8) & 15u);
-                const float *p = (s1 ? a.src1.ptr : a.src0.ptr) +
-                                 ((rbz * NB + (hw2 >> 5)) * (s1 ? nq1 : nq0) + (int)(e.y >> 16)) * 128 + (hw2 & 31) * 4;
                 uint32_t vis = 0;  // bit j: chunk j (channels c0 + 4j .. + 3) is loaded
                 if (!((e.z >> 16) & 1u)) vis = 0xffu;  // ungrouped source: always visible
                 else {
@@ -433,7 +432,16 @@ k_layer_tc(LayerArgs a)
                 }
                 vis &= (1u << nvalid) - 1u;
                 if (rb < 0 || (a.debug & 1)) vis = 0;
-                // eight 4-channel chunks, 512 bytes apart; the warp's lanes are neighbouring positions of one or two blocks
+                // slot of the tap's position (inside the image whenever the tap is visible; 1x1 layers: the row's own slot)
+                const int shift = (int)(short)(e.y & 0xffffu);
+                if ((shift != last_shift || (a.debug & 64)) && vis != 0) {  // consecutive k-blocks of one tap share the lookup
+                    last_slot = __ldg(a.perm + rhw + shift);
+                    last_shift = shift;
+                }
+                const int slot = vis == 0 ? rslot : last_slot;
+                const float *p = (s1 ? a.src1.ptr : a.src0.ptr) +
+                                 ((rbz * NB + (slot >> 5)) * (s1 ? nq1 : nq0) + (int)(e.y >> 16)) * 128 + (slot & 31) * 4;
+                // eight 4-channel chunks, 512 bytes apart; the warp's lanes (rows of one coding group) are neighbouring slots
 #pragma unroll
                 for (int j = 0; j < BK / 4; ++j) {
                     const float4 t4 = ((vis >> j) & 1u) ? __ldg(reinterpret_cast<const float4 *>(p + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,10 +528,11 @@ k_layer_tc(LayerArgs a)
             if (tid == 384) stamp(lt, 5);
             const int nt = t % n_ntiles;
             const int row = (t / n_ntiles) * BM + r;
-            int rb = -1, rhw = 0;
+            int rb = -1, rhw = 0, rslot = 0;
             if (row < rows) {
                 rb = row / a.ncells;
                 rhw = a.cell_hw[a.cell_base + (row - rb * a.ncells)];
+                rslot = __ldg(a.perm + rhw);
             }
             float acc[BN];
 #pragma unroll
@@ -560,7 +569,7 @@ k_layer_tc(LayerArgs a)
                 // one or two 512-byte blocks (n_count % 4 == 0 on this path)
                 if (rb >= 0) {
                     const int NB = (HW + 31) >> 5;
-                    float *op = a.out + (((long long)rb * NB + (rhw >> 5)) * (a.Ntot >> 2) + ((a.n_begin + nt * BN) >> 2)) * 128 + (rhw & 31) * 4;
+                    float *op = a.out + (((long long)rb * NB + (rslot >> 5)) * (a.Ntot >> 2) + ((a.n_begin + nt * BN) >> 2)) * 128 + (rslot & 31) * 4;
                     const float *bp = s_bias + nt * BN;
                     const float *srow_c = reinterpret_cast<const float *>(smem + OFF_OUT + r * OUT_ROW);
                     const float *ap = a.add ? a.add + (long long)rb * ohw + rhw + (long long)(a.n_begin + nt * BN) * HW : nullptr;
@@ -807,19 +816,21 @@ bool tc_model_eligible(const CtxModel &m, int B)
 // (both sides coalesced); positions past HW in the last block are written as zeros.  split = 1: 3xFP16 operand
 // format (split16) instead of the floats themselves.
 __global__ void __launch_bounds__(256)
-k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW, int split, int *range_flag)
+k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW, int split, int *range_flag,
+             const int32_t *__restrict__ iperm)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, blk = blockIdx.x, hw0 = blk * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float *s = src + (size_t)b * channels * HW;
+    const int hw = hw0 + tx < HW ? iperm[hw0 + tx] : -1;  // the position stored in slot hw0 + tx
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i, hw = hw0 + tx;
-        tile[ty + 8 * i][tx] = (c < channels && hw < HW) ? s[(size_t)c * HW + hw] : 0.f;
+        const int c = c0 + ty + 8 * i;
+        tile[ty + 8 * i][tx] = (c < channels && hw >= 0) ? s[(size_t)c * HW + hw] : 0.f;
     }
     __syncthreads();
-    // thread = (chunk ty of 4 channels, position tx): one 16-byte chunk each, a warp writes 512 contiguous bytes
+    // thread = (chunk ty of 4 channels, slot tx): one 16-byte chunk each, a warp writes 512 contiguous bytes
     if (c0 + ty * 4 < channels) {
         float *d = dst + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2) + ty) * 128 + tx * 4;
         const float4 x = make_float4(tile[ty * 4 + 0][tx], tile[ty * 4 + 1][tx], tile[ty * 4 + 2][tx], tile[ty * 4 + 3][tx]);
@@ -835,7 +846,7 @@ k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channel
 
 // blocked channels-last (floats) -> [B, channels, HW]: the inverse of k_nchw_to_cl, for the public stage API
 __global__ void __launch_bounds__(256)
-k_cl_to_nchw(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
+k_cl_to_nchw(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW, const int32_t *__restrict__ iperm)
 {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, blk = blockIdx.x, hw0 = blk * 32, c0 = blockIdx.y * 32;
@@ -846,27 +857,29 @@ k_cl_to_nchw(const float *__restrict__ src, float *__restrict__ dst, int channel
     }
     __syncthreads();
     float *d = dst + (size_t)b * channels * HW;
+    const int hw = hw0 + tx < HW ? iperm[hw0 + tx] : -1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i, hw = hw0 + tx;
-        if (c < channels && hw < HW) d[(size_t)c * HW + hw] = tile[ty + 8 * i][tx];
+        const int c = c0 + ty + 8 * i;
+        if (c < channels && hw >= 0) d[(size_t)c * HW + hw] = tile[ty + 8 * i][tx];
     }
 }
 
-int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream)
+int launch_cl_to_nchw(const float *src, float *dst, int B, int channels, int HW, const int32_t *iperm, cudaStream_t stream)
 {
     if (B == 0) return BASIC_OK;
     dim3 grid((HW + 31) / 32, (channels + 31) / 32, B);
-    k_cl_to_nchw<<<grid, 256, 0, stream>>>(src, dst, channels, HW);
+    k_cl_to_nchw<<<grid, 256, 0, stream>>>(src, dst, channels, HW, iperm);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
 
-int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, cudaStream_t stream, int split, int *range_flag)
+int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, const int32_t *iperm, cudaStream_t stream, int split,
+                      int *range_flag)
 {
     if (B == 0) return BASIC_OK;
     dim3 grid((HW + 31) / 32, (channels + 31) / 32, B);
-    k_nchw_to_cl<<<grid, 256, 0, stream>>>(src, dst, channels, HW, split, range_flag);
+    k_nchw_to_cl<<<grid, 256, 0, stream>>>(src, dst, channels, HW, split, range_flag, iperm);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

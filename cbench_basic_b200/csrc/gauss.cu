@@ -25,7 +25,8 @@ __device__ inline int scale_index(float sigma, const float *__restrict__ tab, in
 __global__ void __launch_bounds__(256)
 k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, const int32_t *__restrict__ positions,
                  long long n_pos, int B, int C, int HW, const float *__restrict__ scale_table, int n_scales,
-                 int32_t *__restrict__ symbols, int32_t *__restrict__ indexes, float *__restrict__ yhat, int params_cl)
+                 int32_t *__restrict__ symbols, int32_t *__restrict__ indexes, float *__restrict__ yhat, int params_cl,
+                 const int32_t *__restrict__ perm)
 {
     __shared__ float tab[256];
     for (int i = threadIdx.x; i < n_scales; i += blockDim.x) tab[i] = scale_table[i];
@@ -39,7 +40,7 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
         const int c = p / HW;
         float mean, sigma;
         if (params_cl) {  // blocked channels-last parameters of the tensor path (ctx.cuh): (mean, scale) are neighbours
-            const int hw = p - c * HW;
+            const int hw = perm[p - c * HW];  // slot of the position
             const float2 ms = *reinterpret_cast<const float2 *>(
                 params + ((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2);
             mean = ms.x;
@@ -60,7 +61,7 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
 
 __global__ void __launch_bounds__(256)
 k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ params, const int32_t *__restrict__ positions,
-             long long n_pos, int B, int C, int HW, float *__restrict__ yhat, int params_cl)
+             long long n_pos, int B, int C, int HW, float *__restrict__ yhat, int params_cl, const int32_t *__restrict__ perm)
 {
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
@@ -69,7 +70,7 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
         const long long k = e - b * n_pos;
         const int p = positions ? positions[k] : (int)k;
         const int c = p / HW;
-        const int hw = p - c * HW;
+        const int hw = params_cl ? perm[p - c * HW] : 0;  // slot of the position
         const float mean = params_cl ? params[((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2]
                                      : params[b * 2 * chw + p + (long long)c * HW];
         // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
@@ -81,26 +82,26 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
 
 int launch_quantize_index(const float *y, const float *params, const int32_t *positions, int64_t n_pos, int B, int C, int HW,
                           const float *d_scale_table, int n_scales, int32_t *symbols, int32_t *indexes, float *yhat,
-                          int sm_count, cudaStream_t stream, int params_cl)
+                          int sm_count, cudaStream_t stream, int params_cl, const int32_t *perm)
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
     k_quantize_index<<<(int)blocks, 256, 0, stream>>>(y, params, positions, n_pos, B, C, HW, d_scale_table, n_scales, symbols,
-                                                      indexes, yhat, params_cl);
+                                                      indexes, yhat, params_cl, perm);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
 
 int launch_dequantize(const int32_t *symbols, const float *params, const int32_t *positions, int64_t n_pos, int B, int C,
-                      int HW, float *yhat, int sm_count, cudaStream_t stream, int params_cl)
+                      int HW, float *yhat, int sm_count, cudaStream_t stream, int params_cl, const int32_t *perm)
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat, params_cl);
+    k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat, params_cl, perm);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
