@@ -422,6 +422,7 @@ k_layer_tc(LayerArgs a)
                 const int tap = (int)((e.z >> 1) & 31u), nvalid = (int)((e.z >> 8) & 15u);
                 uint32_t vis = 0;  // bit j: chunk j (channels c0 + 4j .. + 3) is loaded
                 if (!((e.z >> 16) & 1u)) vis = 0xffu;  // ungrouped source: always visible
+                else if (G == 1) vis = (a.is_conv ? ((my_mask[0] >> tap) & 1u) : (rgrp & 1u)) ? 0xffu : 0u;  // one group: all or nothing
                 else {
 #pragma unroll
                     for (int j = 0; j < BK / 4; ++j) {
