@@ -352,13 +352,14 @@ def run_ours(args, rank, world, local_rank):
             ceil = {"fp16x3": "3 FP16 MMAs per product: ceiling = bf16/fp16 peak / 3 (frac 0.333)",
                     "tf32x3": "3 TF32 MMAs per product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)",
                     "fp32": "FP32 FMA pipe, not the tensor pipe"}[mode]
-            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1b_ncu_full_k_layer_tc_fp16x3.csv, cold
+            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1c_ncu_full_k_layer_tc_fp16x3.csv, cold
             # caches under ncu) x 2 passes per step, for the cfg2 geometry only; algorithmic bytes = activations once
-            traffic = 2 * 1436.1e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
+            traffic = 2 * 351.2e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
             roofline = {"kernel": kname, "bound": "tensor", "achieved": ach,
                         "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
-                        "traffic_note": "bytes per step (16 launches), ncu --set full, cold L2; algorithmic = 2 x 0.59 GB "
-                                        "(every activation read and written once per pass)",
+                        "traffic_note": "DRAM bytes per step (16 launches), ncu --set full, cold L2; algorithmic = 2 x 0.59 GB "
+                                        "(every activation read and written once per pass; most of the writes and "
+                                        "re-reads stay in the 126 MB L2)",
                         "ms_per_step": ctx_ms, "launches_per_step": phases["context_model"]["spans_per_step"] * 4,
                         "share_of_step": ctx_ms / ms, "peak_source": peak_src,
                         "note": "algorithmic FLOPs = 2*77.56*C^2 per latent position and pass (dense-equivalent, each position once; "
