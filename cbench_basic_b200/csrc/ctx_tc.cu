@@ -256,10 +256,13 @@ __device__ inline float h_lo(uint32_t p) { return __half2float(__ushort_as_half(
 __device__ inline float h_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
 
 // ------------------------------------------------------------------------------------------------- the kernel
-template <int MODE>
+// DBG = 1: the instrumented build (BASIC_TC_DEBUG switches, BASIC_TC_TIMELINE stamps); the production build has none of it
+template <int MODE, int DBG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_layer_tc(LayerArgs a)
 {
+    const int dbg = DBG ? a.debug : 0;                    // (constant 0 / NULL in the production build: every debug and
+    long long *const tline = DBG ? a.timeline : nullptr;  //  timeline branch folds away)
     constexpr int STAGES = Cfg<MODE>::STAGES, STAGE_BYTES = Cfg<MODE>::STAGE_BYTES, TILE_BYTES = Cfg<MODE>::TILE_BYTES;
     constexpr int A_COLS = Cfg<MODE>::A_COLS, SLOTS = Cfg<MODE>::SLOTS, A_COL0 = Cfg<MODE>::A_COL0;
     extern __shared__ unsigned char smem_raw[];
@@ -310,10 +313,10 @@ k_layer_tc(LayerArgs a)
     const uint32_t tmem_base = *s_tmem;
     // debug timeline: slot j of local tile lt of this CTA
     auto stamp_v = [&](int lt, int j, long long v) {
-        if (a.timeline && lt < 16) a.timeline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = v;
+        if (tline && lt < 16) tline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = v;
     };
     auto stamp = [&](int lt, int j) {
-        if (a.timeline && lt < 16) a.timeline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = clock64();
+        if (tline && lt < 16) tline[((size_t)blockIdx.x * 16 + lt) * 16 + j] = clock64();
     };
 
     if (wg == 0) {
@@ -330,7 +333,7 @@ k_layer_tc(LayerArgs a)
                     mbar_wait(bar_empty(s), par);
                     const unsigned char *src = wsrc + (size_t)s_list[i].x * (2 * TILE_BYTES);
                     if (elect_one()) {
-                        if (a.debug & 2) mbar_arrive(bar_full(s));
+                        if (dbg & 2) mbar_arrive(bar_full(s));
                         else {
                             mbar_arrive_expect_tx(bar_full(s), 2 * TILE_BYTES);
                             bulk_g2s(s_base + OFF_STAGES + s * STAGE_BYTES, src, 2 * TILE_BYTES, bar_full(s));
@@ -349,18 +352,18 @@ k_layer_tc(LayerArgs a)
                 long long w_full = 0, w_slot = 0, w_issue = 0;
                 for (int i = 0; i < n_kb; ++i) {
                     const bool seg_first = in_seg == 0, seg_last = in_seg == seg_kb - 1 || i == n_kb - 1;
-                    const long long c0 = a.timeline ? clock64() : 0;
+                    const long long c0 = tline ? clock64() : 0;
                     if (seg_first) {  // the slot must have been drained (fresh barrier: passes)
                         mbar_wait(bar_slot_empty(slot), slot_par);
                     }
-                    const long long c1 = a.timeline ? clock64() : 0;
+                    const long long c1 = tline ? clock64() : 0;
                     mbar_wait(bar_full(s), par);
                     tc_fence_after();
-                    const long long c2 = a.timeline ? clock64() : 0;
+                    const long long c2 = tline ? clock64() : 0;
                     if (elect_one()) {
                         const uint64_t bh0 = desc0 + (uint64_t)(s * (STAGE_BYTES >> 4));
                         const uint32_t d = tmem_base + (uint32_t)(slot * BN), a0 = tmem_base + (uint32_t)(A_COL0 + s * 2 * A_COLS);
-                        if (!(a.debug & 4)) {
+                        if (!(dbg & 4)) {
 #pragma unroll
                             for (int ks = 0; ks < Cfg<MODE>::KSTEPS; ++ks) {  // one k-step = 32 bytes of K in either mode
                                 const uint64_t bh = bh0 + (uint64_t)(ks * 2), bl = bh + (uint64_t)(TILE_BYTES >> 4);
@@ -374,7 +377,7 @@ k_layer_tc(LayerArgs a)
                         if (seg_last) umma_commit(bar_slot_full(slot));  // segment complete -> drain warps
                     }
                     __syncwarp();
-                    if (a.timeline) { w_slot += c1 - c0; w_full += c2 - c1; w_issue += clock64() - c2; }
+                    if (tline) { w_slot += c1 - c0; w_full += c2 - c1; w_issue += clock64() - c2; }
                     if (i == 0 && lane == 0) stamp(lt, 1);
                     if (++s == STAGES) { s = 0; par ^= 1; }
                     if (seg_last) {
@@ -409,12 +412,19 @@ k_layer_tc(LayerArgs a)
                 if (a.is_conv) for (int j = 0; j < G; ++j) my_mask[j * BM] = a.cell_tap[(size_t)cell * G + j];
                 else rgrp = a.cell_grp[cell];
             }
-            // sources are blocked channels-last (ctx.cuh): chunk c4 of position hw of image b starts at
-            // ((b * NB + hw / 32) * (channels / 4) + c4) * 128 + (hw % 32) * 4
+            // sources are blocked channels-last (ctx.cuh): chunk c4 of slot s of image b starts at
+            // ((b * NB + s / 32) * (channels / 4) + c4) * 128 + (s % 32) * 4.  Per tile and source the row's own base
+            // pointer; the conv recomputes it when the tap (and with it the slot) changes
             const long long rbz = rb < 0 ? 0 : rb;
             const int NB = (HW + 31) >> 5;
             const int nq0 = (a.is_conv ? a.Cin : a.src0.channels) >> 2, nq1 = a.src1.channels >> 2;
-            int last_shift = 0, last_slot = rslot;  // tap whose slot was looked up last (shift 0 = the row's own position)
+            auto slot_base = [&](const float *ptr, int nq, int slot) {
+                return ptr + ((rbz * NB + (slot >> 5)) * nq) * 128 + (slot & 31) * 4;
+            };
+            const float *base0 = slot_base(a.src0.ptr, nq0, rslot);
+            const float *base1 = a.src1.ptr ? slot_base(a.src1.ptr, nq1, rslot) : nullptr;
+            int last_shift = 0;              // conv: tap whose slot was looked up last (shift 0 = the row's own position)
+            const float *tap_base = base0;   // ... and the row's base pointer at that tap
             // gathers the 32 k of k-block i for this thread's row into registers (masked elements = 0)
             auto gather = [&](int i, float(&v)[BK]) {
                 const uint4 e = s_list[i];
@@ -432,16 +442,14 @@ k_layer_tc(LayerArgs a)
                     }
                 }
                 vis &= (1u << nvalid) - 1u;
-                if (rb < 0 || (a.debug & 1)) vis = 0;
-                // slot of the tap's position (inside the image whenever the tap is visible; 1x1 layers: the row's own slot)
+                if (rb < 0 || (dbg & 1)) vis = 0;
+                // row base at the tap's position (inside the image whenever the tap is visible; 1x1 layers: the row's own slot)
                 const int shift = (int)(short)(e.y & 0xffffu);
-                if ((shift != last_shift || (a.debug & 64)) && vis != 0) {  // consecutive k-blocks of one tap share the lookup
-                    last_slot = __ldg(a.perm + rhw + shift);
+                if ((shift != last_shift || (dbg & 64)) && vis != 0) {  // consecutive k-blocks of one tap share the lookup
+                    tap_base = slot_base(a.src0.ptr, nq0, __ldg(a.perm + rhw + shift));
                     last_shift = shift;
                 }
-                const int slot = vis == 0 ? rslot : last_slot;
-                const float *p = (s1 ? a.src1.ptr : a.src0.ptr) +
-                                 ((rbz * NB + (slot >> 5)) * (s1 ? nq1 : nq0) + (int)(e.y >> 16)) * 128 + (slot & 31) * 4;
+                const float *p = (s1 ? base1 : (shift ? tap_base : base0)) + (int)(e.y >> 16) * 128;
                 // eight 4-channel chunks, 512 bytes apart; the warp's lanes (rows of one coding group) are neighbouring slots
 #pragma unroll
                 for (int j = 0; j < BK / 4; ++j) {
@@ -453,11 +461,11 @@ k_layer_tc(LayerArgs a)
             long long w_empty = 0, w_st = 0, w_g = 0;
             auto publish = [&](int i, const float(&v)[BK]) {
                 const int it = it0 + i, s = it % STAGES, round = it / STAGES;
-                const long long c0 = a.timeline ? clock64() : 0;
+                const long long c0 = tline ? clock64() : 0;
                 mbar_wait(bar_empty(s), (round & 1) ^ 1);
-                const long long c1 = a.timeline ? clock64() : 0;
+                const long long c1 = tline ? clock64() : 0;
                 w_empty += c1 - c0;
-                if (a.debug & 16) { mbar_arrive(bar_full(s)); return; }
+                if (dbg & 16) { mbar_arrive(bar_full(s)); return; }
                 tc_fence_after();  // the MMAs that read this stage's TMEM columns have completed (tcgen05.commit)
                 const uint32_t col = lane_base + (uint32_t)(A_COL0 + s * 2 * A_COLS);
                 if constexpr (MODE == 0) {
@@ -485,16 +493,16 @@ k_layer_tc(LayerArgs a)
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_full(s));
-                if (a.timeline) w_st += clock64() - c1;
+                if (tline) w_st += clock64() - c1;
             };
             // this group's k-blocks of the tile: i = i_first, i_first + NGROUPS, ...; the loads of the next one are in
             // flight while the current one is split and stored
             const int i_first = ((grp - it0) % NGROUPS + NGROUPS) % NGROUPS;
             float v0[BK], v1[BK], v2[BK];
             auto gather_t = [&](int i, float(&v)[BK]) {
-                const long long c0 = a.timeline ? clock64() : 0;
+                const long long c0 = tline ? clock64() : 0;
                 gather(i, v);
-                if (a.timeline) w_g += clock64() - c0;
+                if (tline) w_g += clock64() - c0;
             };
             // three register buffers: the loads of this group's next two k-blocks are in flight while one is published
             constexpr int NG = NGROUPS;
@@ -541,13 +549,13 @@ k_layer_tc(LayerArgs a)
             long long w_sf = 0;
             for (int seg = 0; seg < n_seg; ++seg, ++segg) {
                 const int slot = segg % SLOTS;
-                const long long c0 = a.timeline ? clock64() : 0;
+                const long long c0 = tline ? clock64() : 0;
                 mbar_wait(bar_slot_full(slot), (segg / SLOTS) & 1);
-                if (a.timeline) w_sf += clock64() - c0;
+                if (tline) w_sf += clock64() - c0;
                 tc_fence_after();
 #pragma unroll
                 for (int cc = 0; cc < BN / 32; ++cc) {
-                    if (a.debug & 8) break;
+                    if (dbg & 8) break;
                     uint32_t tt[32];
                     tmem_ld32(lane_base + (uint32_t)(slot * BN + cc * 32), tt);
                     tmem_ld_wait();
@@ -931,8 +939,10 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
     static bool attr_done = false;
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done = true;
     }
     const long long tiles = (long long)((a.n_count + BN - 1) / BN) * ((rows + BM - 1) / BM);
@@ -970,8 +980,14 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
         cudaMemset(tl_buf, 0, (size_t)grid.x * 16 * 16 * sizeof(long long));
         b.timeline = tl_buf;
     }
-    if (b.mode) k_layer_tc<1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-    else k_layer_tc<0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    const bool instrumented = b.debug != 0 || b.timeline != nullptr;
+    if (instrumented) {
+        if (b.mode) k_layer_tc<1, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+        else k_layer_tc<0, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    } else {
+        if (b.mode) k_layer_tc<1, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+        else k_layer_tc<0, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
+    }
     BASIC_LAUNCHED();
     if (tl) {
         std::vector<long long> h((size_t)grid.x * 16 * 16);
