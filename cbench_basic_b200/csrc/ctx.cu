@@ -427,6 +427,7 @@ int ctx_to_cl(CtxModel &m, const float *src, float *dst, int B, int channels, cu
 }
 void ctx_set_run_precision(CtxModel &m, int p)
 {
+    if (p == BASIC_CTX_FP16X3 && !tc_fp16_ok(m)) p = BASIC_CTX_TF32X3;  // (channel counts not in 8-channel chunk pairs)
     if (m.run_precision != p) m.act_B = 0;  // (FP32 and the tensor modes keep their activations in different layouts)
     m.run_precision = p;
 }
@@ -601,6 +602,8 @@ int ctx_set_precision(CtxModel &m, int precision, int nacc)
         return value_error("unknown context-model precision");
     if (nacc < 1 || nacc > 64) return value_error("segment length must be 1..64 k-blocks");
     if (m.precision != precision) m.act_B = 0;  // the two paths keep their activations in different layouts
+    // 3xFP16 needs channel counts in 8-channel chunk pairs; otherwise the model runs (and says so: ctx_precision) in 3xTF32
+    if (precision == BASIC_CTX_FP16X3 && m.c_ctx && !tc_fp16_ok(m)) precision = BASIC_CTX_TF32X3;
     m.precision = precision;
     m.run_precision = precision;
     m.nacc = nacc;

@@ -111,6 +111,7 @@ struct LayerArgs {
 // CtxModel::d_perm), so the rows of one coding group -- what a warp of the GEMM kernel holds -- are neighbouring slots.
 inline size_t cl_elems(int B, int channels, int HW) { return (size_t)B * ((HW + 31) / 32) * 32 * channels; }
 bool tc_model_eligible(const CtxModel &m, int B);
+bool tc_fp16_ok(const CtxModel &m);
 int launch_nchw_to_cl(const float *src, float *dst, int B, int channels, int HW, const int32_t *iperm, cudaStream_t stream,
                       int split = 0, int *range_flag = nullptr);
 int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream);

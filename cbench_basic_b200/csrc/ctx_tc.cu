@@ -236,21 +236,23 @@ __device__ inline uint32_t pack_h2(float lo, float hi)
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-// Four consecutive channels -> the 16-byte chunk of the 3xFP16 activation format: X = 16 x, hi = fp16(X), lo = fp16(X - hi);
-// words {hi(c0, c1), hi(c2, c3), lo(c0, c1), lo(c2, c3)} are the TMEM columns the MMA reads, so a producer moves them
-// from global memory to tensor memory without touching them.  Returns max |x| for the range flag.
+// Eight consecutive channels -> the two 16-byte chunks of the 3xFP16 activation format (split16): X = 16 x,
+// hi = fp16(X), lo = fp16(X - hi); chunk 2m = {hi(c0,c1), hi(c2,c3), hi(c4,c5), hi(c6,c7)}, chunk 2m + 1 = the same of lo.
+// The words are the TMEM columns the MMA reads and a k-block's eight chunk loads land in column order (hi 0..15, lo 0..15),
+// so a producer moves them from global memory to tensor memory with no instruction in between.  amax: max |x| (range flag).
 __device__ inline float h_lo(uint32_t p);
 __device__ inline float h_hi(uint32_t p);
-__device__ inline uint4 split16(float4 x, float &amax)
+__device__ inline void split16(float4 x0, float4 x1, float &amax, uint4 &hi, uint4 &lo)
 {
-    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
-    const float a = x.x * kActScale, b = x.y * kActScale, c = x.z * kActScale, d = x.w * kActScale;
-    uint4 r;
-    r.x = pack_h2(a, b);
-    r.y = pack_h2(c, d);
-    r.z = pack_h2(a - h_lo(r.x), b - h_hi(r.x));
-    r.w = pack_h2(c - h_lo(r.y), d - h_hi(r.y));
-    return r;
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x0.z), fabsf(x0.w))));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x1.x), fabsf(x1.y)), fmaxf(fabsf(x1.z), fabsf(x1.w))));
+    const float a = x0.x * kActScale, b = x0.y * kActScale, c = x0.z * kActScale, d = x0.w * kActScale;
+    const float e = x1.x * kActScale, f = x1.y * kActScale, g = x1.z * kActScale, h = x1.w * kActScale;
+    hi.x = pack_h2(a, b); hi.y = pack_h2(c, d); hi.z = pack_h2(e, f); hi.w = pack_h2(g, h);
+    lo.x = pack_h2(a - h_lo(hi.x), b - h_hi(hi.x));
+    lo.y = pack_h2(c - h_lo(hi.y), d - h_hi(hi.y));
+    lo.z = pack_h2(e - h_lo(hi.z), f - h_hi(hi.z));
+    lo.w = pack_h2(g - h_lo(hi.w), h - h_hi(hi.w));
 }
 __device__ inline float h_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xffffu))); }
 __device__ inline float h_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
@@ -454,7 +456,10 @@ k_layer_tc(LayerArgs a)
 #pragma unroll
                 for (int j = 0; j < BK / 4; ++j) {
                     const float4 t4 = ((vis >> j) & 1u) ? __ldg(reinterpret_cast<const float4 *>(p + j * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * j + 0] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+                    // MODE 1: even chunks are hi columns, odd chunks lo columns -> registers in TMEM column order
+                    constexpr int kDummy = 0;
+                    const int d = MODE ? ((j & 1) ? 16 + 4 * (j >> 1) : 4 * (j >> 1)) + kDummy : 4 * j;
+                    v[d + 0] = t4.x; v[d + 1] = t4.y; v[d + 2] = t4.z; v[d + 3] = t4.w;
                 }
             };
             // splits k-block i into hi = tf32(v), lo = v - hi and stores both into the stage's TMEM columns
@@ -480,15 +485,11 @@ k_layer_tc(LayerArgs a)
                         tmem_st16(col + A_COLS + half * 16, h);
                     }
                 } else {
-                    // the activations arrive already split (split16): chunk j = {hi cols 2j, 2j + 1, lo cols 2j, 2j + 1}
-                    uint32_t h[16], l[16];
+                    // the activations arrive already split (split16) and in column order: hi columns 0..15, lo columns 0..15
+                    uint32_t h[BK];
 #pragma unroll
-                    for (int j = 0; j < BK / 4; ++j) {
-                        h[2 * j] = __float_as_uint(v[4 * j]); h[2 * j + 1] = __float_as_uint(v[4 * j + 1]);
-                        l[2 * j] = __float_as_uint(v[4 * j + 2]); l[2 * j + 1] = __float_as_uint(v[4 * j + 3]);
-                    }
-                    tmem_st16(col, h);
-                    tmem_st16(col + A_COLS, l);
+                    for (int q = 0; q < BK; ++q) h[q] = __float_as_uint(v[q]);
+                    tmem_st32(col, h);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -582,8 +583,7 @@ k_layer_tc(LayerArgs a)
                     const float *bp = s_bias + nt * BN;
                     const float *srow_c = reinterpret_cast<const float *>(smem + OFF_OUT + r * OUT_ROW);
                     const float *ap = a.add ? a.add + (long long)rb * ohw + rhw + (long long)(a.n_begin + nt * BN) * HW : nullptr;
-#pragma unroll 8
-                    for (int q = 0; q < n_left; q += 4) {
+                    auto finish4 = [&](int q) {
                         float4 val = *reinterpret_cast<const float4 *>(srow_c + q);
                         const float4 bv = *reinterpret_cast<const float4 *>(bp + q);
                         val.x += bv.x; val.y += bv.y; val.z += bv.z; val.w += bv.w;
@@ -595,8 +595,19 @@ k_layer_tc(LayerArgs a)
                             val.x = val.x > 0.f ? val.x : val.x * kSlope; val.y = val.y > 0.f ? val.y : val.y * kSlope;
                             val.z = val.z > 0.f ? val.z : val.z * kSlope; val.w = val.w > 0.f ? val.w : val.w * kSlope;
                         }
-                        if (MODE == 1 && !a.out_f32) *reinterpret_cast<uint4 *>(op + q * 32) = split16(val, amax);  // the next layer's operand format
-                        else *reinterpret_cast<float4 *>(op + q * 32) = val;
+                        return val;
+                    };
+                    if (MODE == 1 && !a.out_f32) {  // the next layer's operand format: eight channels -> a hi and a lo chunk
+#pragma unroll 4
+                        for (int q = 0; q < n_left; q += 8) {
+                            uint4 hi, lo;
+                            split16(finish4(q), finish4(q + 4), amax, hi, lo);
+                            *reinterpret_cast<uint4 *>(op + q * 32) = hi;
+                            *reinterpret_cast<uint4 *>(op + (q + 4) * 32) = lo;
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int q = 0; q < n_left; q += 4) *reinterpret_cast<float4 *>(op + q * 32) = finish4(q);
                     }
                 }
             } else if (rb >= 0) {
@@ -821,6 +832,13 @@ bool tc_model_eligible(const CtxModel &m, int B)
     return (long long)B * m.G * m.H * m.W / m.S >= 64;
 }
 
+// 3xFP16 keeps activations in 8-channel chunk pairs: every channel count (per visibility group) must be a multiple of 8
+bool tc_fp16_ok(const CtxModel &m)
+{
+    auto ok8 = [&](int channels) { return channels % m.G == 0 && (channels / m.G) % 8 == 0; };
+    return ok8(m.C) && ok8(m.c_ctx) && (!m.has_merger || (ok8(m.c_m1) && ok8(m.c_m2)));
+}
+
 // [B, channels, HW] -> blocked channels-last (ctx.cuh), 32 positions x 32 channels per CTA through shared memory
 // (both sides coalesced); positions past HW in the last block are written as zeros.  split = 1: 3xFP16 operand
 // format (split16) instead of the floats themselves.
@@ -842,13 +860,17 @@ k_nchw_to_cl(const float *__restrict__ src, float *__restrict__ dst, int channel
     // thread = (chunk ty of 4 channels, slot tx): one 16-byte chunk each, a warp writes 512 contiguous bytes
     if (c0 + ty * 4 < channels) {
         float *d = dst + (((size_t)b * gridDim.x + blk) * (channels >> 2) + (c0 >> 2) + ty) * 128 + tx * 4;
-        const float4 x = make_float4(tile[ty * 4 + 0][tx], tile[ty * 4 + 1][tx], tile[ty * 4 + 2][tx], tile[ty * 4 + 3][tx]);
-        if (split) {
+        if (split) {  // chunk pair m = ty / 2 holds channels 8m .. 8m + 7: the even chunk their hi halves, the odd one the lo halves
+            const int m8 = (ty >> 1) * 8;
+            const float4 x0 = make_float4(tile[m8 + 0][tx], tile[m8 + 1][tx], tile[m8 + 2][tx], tile[m8 + 3][tx]);
+            const float4 x1 = make_float4(tile[m8 + 4][tx], tile[m8 + 5][tx], tile[m8 + 6][tx], tile[m8 + 7][tx]);
             float amax = 0.f;
-            *reinterpret_cast<uint4 *>(d) = split16(x, amax);
+            uint4 hi, lo;
+            split16(x0, x1, amax, hi, lo);
+            *reinterpret_cast<uint4 *>(d) = (ty & 1) ? lo : hi;
             if (!(amax < kActLimit) && range_flag) atomicOr(range_flag, 1);
         } else {
-            *reinterpret_cast<float4 *>(d) = x;
+            *reinterpret_cast<float4 *>(d) = make_float4(tile[ty * 4 + 0][tx], tile[ty * 4 + 1][tx], tile[ty * 4 + 2][tx], tile[ty * 4 + 3][tx]);
         }
     }
 }
