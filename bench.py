@@ -372,9 +372,9 @@ def run_ours(args, rank, world, local_rank):
             ceil = {"fp16x3": "3 FP16 MMAs per product: ceiling = bf16/fp16 peak / 3 (frac 0.333)",
                     "tf32x3": "3 TF32 MMAs per product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)",
                     "fp32": "FP32 FMA pipe, not the tensor pipe"}[mode]
-            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1c_ncu_full_k_layer_tc_fp16x3.csv, cold
+            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1d_ncu_full_k_layer_tc_fp16x3.csv, cold
             # caches under ncu) x 2 passes per step, for the cfg2 geometry only; algorithmic bytes = activations once
-            traffic = 2 * 351.2e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
+            traffic = 2 * 346.6e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
             roofline = {"kernel": kname, "bound": "tensor", "achieved": ach,
                         "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                         "traffic_note": "DRAM bytes per step (16 launches), ncu --set full, cold L2; algorithmic = 2 x 0.59 GB "
