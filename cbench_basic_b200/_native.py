@@ -139,7 +139,7 @@ def last_output(handle):
     return out
 
 
-PHASES = ("context_model", "quantise", "coder_encode", "coder_decode")
+PHASES = ("context_model", "quantise", "coder_encode", "coder_decode", "host_set_stream", "host_staging")
 
 
 def profile(on):

@@ -1,5 +1,7 @@
 // extern "C" entry points (include/basic_b200.h) and the host-side orchestration of the kernels.
 #include <algorithm>
+#include <chrono>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -67,6 +69,13 @@ int tans_decode(TansTables &, const uint8_t *d_enc, int64_t len, const int32_t *
 enum { PROF_CTX = 0, PROF_GAUSS = 1, PROF_ENCODE = 2, PROF_DECODE = 3, PROF_N = 8 };
 struct ProfSpan { int cat; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;
+static double g_host_ms[PROF_N] = {0};  // host wall time of a few sections, slots 4.. (read with the device phases)
+struct HostScope {
+    int slot;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostScope(int s) : slot(s), t0(std::chrono::steady_clock::now()) {}
+    ~HostScope() { if (g_prof_on) g_host_ms[slot] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 static std::vector<ProfSpan> g_prof_spans;
 static std::vector<cudaEvent_t> g_prof_pool;
 static cudaEvent_t prof_event()
@@ -461,7 +470,7 @@ int basic_profile_enable(int on)
 
 int basic_profile_read(double *ms, int64_t *spans)
 {
-    for (int i = 0; i < PROF_N; ++i) { ms[i] = 0.0; spans[i] = 0; }
+    for (int i = 0; i < PROF_N; ++i) { ms[i] = g_host_ms[i]; g_host_ms[i] = 0.0; spans[i] = 0; }
     for (auto &sp : g_prof_spans) {
         float t = 0.f;
         if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&t, sp.e0, sp.e1) == cudaSuccess) {
@@ -725,6 +734,7 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
     DeviceGuard guard(c->device);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (len < 0) return value_error("negative length");
+    HostScope hs_set(4);
     // host copy in pinned memory (segment directories are parsed on the host; the upload runs asynchronously)
     if (c->in_event && (size_t)len + 64 > c->host_in_cap) BASIC_CUDA(cudaEventSynchronize(c->in_event));
     BASIC_TRY(reserve_pinned(&c->host_in, &c->host_in_cap, (size_t)len + 64));
@@ -745,16 +755,41 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
         const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
         const int nt = std::min(kHostThreads, chunks);
         cudaStream_t up = c->copy_stream;
-        const std::function<void(int)> work = [&](int t) {
-            if (t > 0) cudaSetDevice(c->device);
-            for (int k = t; k < chunks; k += nt) {
-                const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
-                memcpy(c->host_in + at, encoded + at, (size_t)nb);
-                cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + at, c->host_in + at, (size_t)nb, cudaMemcpyHostToDevice, up);
-            }
+        // workers only copy; the calling thread issues the uploads in chunk order as they become ready (CUDA calls from
+        // several threads on one stream serialise in the driver and cost more than they save)
+        std::vector<std::atomic<int>> ready((size_t)chunks);
+        for (auto &r : ready) r.store(0, std::memory_order_relaxed);
+        auto copy_chunk = [&](int k) {
+            const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
+            memcpy(c->host_in + at, encoded + at, (size_t)nb);
+            ready[(size_t)k].store(1, std::memory_order_release);
         };
-        if (nt <= 1) work(0);
-        else HostPool::get().run(nt, work);
+        auto upload_chunk = [&](int k) {
+            const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
+            cudaMemcpyAsync(c->stream_dev.as<uint8_t>() + at, c->host_in + at, (size_t)nb, cudaMemcpyHostToDevice, up);
+        };
+        HostScope hs_copy(5);
+        if (nt <= 1) {
+            for (int k = 0; k < chunks; ++k) { copy_chunk(k); upload_chunk(k); }
+        } else {
+            // chunks are handed out dynamically (a worker that wakes up late just takes fewer); the calling thread copies too
+            // and, between its own chunks, uploads whatever prefix is ready
+            std::atomic<int> next{0};
+            const std::function<void(int)> work = [&](int t) {
+                if (t > 0) {
+                    for (int k; (k = next.fetch_add(1, std::memory_order_relaxed)) < chunks;) copy_chunk(k);
+                    return;
+                }
+                int issued = 0;
+                while (issued < chunks) {
+                    const int k = next.load(std::memory_order_relaxed) < chunks ? next.fetch_add(1, std::memory_order_relaxed) : chunks;
+                    if (k < chunks) copy_chunk(k);
+                    while (issued < chunks && ready[(size_t)issued].load(std::memory_order_acquire)) upload_chunk(issued++);
+                    if (k >= chunks && issued < chunks && !ready[(size_t)issued].load(std::memory_order_acquire)) std::this_thread::yield();
+                }
+            };
+            HostPool::get().run(nt, work);
+        }
         BASIC_CUDA(cudaGetLastError());
         BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, up));
         BASIC_CUDA(cudaEventRecord(c->in_event, up));
