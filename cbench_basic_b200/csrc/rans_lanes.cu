@@ -71,7 +71,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
     const int prec = P.precision;
     const uint32_t bp = (uint32_t)P.bypass_precision, maxb = (1u << bp) - 1;
     const int tpu = 16 / (int)bp;  // escape tokens per unit
-    // n / bp, n / maxb, n / tpu for n < 64 as multiply + shift (exact there; a runtime integer division is ~25 instructions)
+    // n / bp, n / maxb, n / tpu for n < 160 as multiply + shift (exact there, checked for every bp; a runtime integer division is ~25 instructions)
     const uint32_t r_bp = (65536u + bp - 1) / bp, r_maxb = (65536u + maxb - 1) / maxb, r_tpu = (65536u + tpu - 1) / tpu;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;

@@ -132,7 +132,7 @@ int orc_rans64_encode(const orc_rans64_tables *tb, const int32_t *symbols, const
     uint64_t x = R64_L;
     int64_t p = cap_words;
     const int prec = tb->precision, bp = tb->bypass_precision;
-    uint32_t tok[48];
+    uint32_t tok[96];
     for (int64_t i = n - 1; i >= 0; --i) {
         const int32_t c = indexes[i];
         if (c < 0 || c >= tb->T) return ORC_ERR_RANGE;
@@ -460,7 +460,7 @@ int orc_tans_encode(const orc_tans_tables *tb, const int32_t *symbols, const int
     uint64_t state = 1ull << tb->tableLog;
     const int bp = tb->bypass_precision;
     const size_t tsz = (size_t)1 << tb->tableLog;
-    uint32_t tok[48];
+    uint32_t tok[96];
     for (int64_t i = n - 1; i >= 0; --i) {
         const int32_t c = indexes[i];
         if (c < 0 || c >= tb->T) return ORC_ERR_RANGE;
@@ -592,8 +592,8 @@ int orc_tans_decode(const orc_tans_tables *tb, const uint8_t *enc, int64_t len, 
 #define BLS_LANES 32
 #define BLS_L (1u << 16)
 
-typedef struct { int m; uint32_t tok[48]; } bls_esc;  /* m = UNITS after bls_pack_units: tok[k] = unit value, wid[k] its bits */
-typedef struct { int wid[48]; } bls_wid;
+typedef struct { int m; uint32_t tok[96]; } bls_esc;  /* m = UNITS after bls_pack_units: tok[k] = unit value, wid[k] its bits */
+typedef struct { int wid[96]; } bls_wid;
 
 /* token list -> units of up to 16 / bp tokens (first token in the low bits); returns the number of units */
 static int bls_pack_units(int ntok, int bp, uint32_t *tok, int *wid)

@@ -204,6 +204,25 @@ def test_multilane_escape_heavy_and_ragged(A, cv):
         assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
 
 
+@pytest.mark.parametrize("bp", [1, 2, 3, 4, 5, 8])
+def test_multilane_escape_units_any_bypass_precision(A, cv, bp):
+    """Escape tokens travel in units of floor(16 / bypass_precision) tokens (oracle/ans_oracle.c section 4): every unit
+    width, one-unit and many-unit escapes (|value| up to 2^30), byte-identical to the CPU specification and lossless."""
+    rng = np.random.default_rng(100 + bp)
+    n = 6000
+    idx = rng.integers(0, 8, n).astype(np.int32)
+    sym = rng.integers(-600, 600, n).astype(np.int32)
+    sym[::5] = rng.integers(-(2 ** 30), 2 ** 30, sym[::5].size)
+    sym[1::7] = rng.integers(-40000, 40000, sym[1::7].size)
+    enc, dec = _mk(A, cv, "b_offsets", lanes=96, bypass_precision=bp)
+    oenc = O.Rans64Encoder(bypass_coding=True, bypass_precision=bp)
+    oenc.init_params(cv["a_freqs"], cv["a_nsym"], cv["b_offsets"])
+    bs = enc.encode_with_indexes(sym, idx)
+    chunk = struct.unpack_from("<I", bs, 12)[0]
+    assert bs[4:] == oenc.encode_lanes(sym, idx, chunk)
+    assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
+
+
 def test_multilane_rejects_garbage(A, gauss):
     from cbench_basic_b200 import _native
     _, dec, _, _ = _gauss_pair(A, gauss, 64)

@@ -212,6 +212,25 @@ def test_lanes_slices_round_trip(cv):
     assert len(many) <= ref + 4 * 136 + 8 * 4 + 16 + 8 * 4 * 64     # + idle tail blocks cost nothing but word rounding
 
 
+@pytest.mark.parametrize("bp", [1, 2, 3, 4, 5, 8])
+def test_lanes_escape_units_round_trip(cv, bp):
+    """Escape units of the multi-lane format for every bypass precision: lossless, and the same number of escape bits
+    as the token-by-token code of the lanes=1 stream (size within the flush overhead)."""
+    rng = np.random.default_rng(bp)
+    n = 5000
+    idx = rng.integers(0, 8, n).astype(np.int32)
+    sym = rng.integers(-600, 600, n).astype(np.int32)
+    sym[::5] = rng.integers(-(2 ** 30), 2 ** 30, sym[::5].size)
+    enc, dec = O.Rans64Encoder(bypass_coding=True, bypass_precision=bp), O.Rans64Decoder(bypass_coding=True, bypass_precision=bp)
+    for c in (enc, dec):
+        c.init_params(cv["a_freqs"], cv["a_nsym"], cv["b_offsets"])
+    bs = enc.encode_lanes(sym, idx, 512)
+    out, used = dec.decode_lanes(bs, idx, 512)
+    assert used == len(bs) and np.array_equal(out, sym)
+    ref = len(enc.encode_with_indexes(sym, idx))
+    assert len(bs) <= ref + (-(-n // 512)) * 136 + 16
+
+
 @pytest.mark.parametrize("chunk", [128, 512, 4096])
 def test_lanes_round_trip_and_size(cv, chunk):
     enc, dec = _pair(cv, "b_offsets", bypass_coding=True)
