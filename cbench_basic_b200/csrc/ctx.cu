@@ -206,6 +206,120 @@ k_bias_prior(const float *__restrict__ prior, const float *__restrict__ bias, lo
     }
 }
 
+// Few-row stages (scanline-like maps: a stage is one position per image): the tiled kernel above would stream whole weight
+// matrices through 128-row tiles that hold one row.  Here a CTA owns 32 output channels (lane = channel: the K-major
+// weights are read in full 128-byte lines), gathers the <= kRowsMax masked input rows into shared memory once, and its 8
+// warps split K (k = warp, warp + 8, ..., eight loads in flight each).  Deterministic: fixed k order per warp, the eight
+// partial sums are added in warp order.
+constexpr int kRowsMax = 4, kGemvWarps = 8;
+
+__global__ void __launch_bounds__(kGemvWarps * 32)
+k_layer_rows(LayerArgs a)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int rows = a.B * a.ncells;          // <= kRowsMax
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.x * 32 + lane;     // relative to n_begin
+    // total K in weight order: conv = taps x Cin, dense = src0 channels then src1 channels
+    const int K0 = a.is_conv ? a.ksize * a.ksize * a.Cin : a.src0.channels;
+    const int K = K0 + (a.is_conv || !a.src1.ptr ? 0 : a.src1.channels);
+    float *A = sm;                            // [rows][K]
+    float *part = sm + (size_t)rows * K;      // [kGemvWarps][kRowsMax][32]
+    __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
+    __shared__ uint32_t s_tapor;
+    if (tid < kRowsMax) {
+        const int row = tid;
+        if (row < rows) {
+            const int b = row / a.ncells, cell = a.cell_base + (row - b * a.ncells);
+            s_b[row] = b; s_cell[row] = cell; s_hw[row] = a.cell_hw[cell];
+        }
+    }
+    if (tid == 0) s_tapor = 0;
+    __syncthreads();
+    // ---- gather (masked elements = 0); loops are arranged so that nothing divides per element
+    if (a.is_conv) {
+        const int k2 = a.ksize * a.ksize, pad = a.ksize / 2, cpg = a.Cin / a.G;
+        const long long chw = (long long)a.Cin * a.HW;
+        for (int r = 0; r < rows; ++r) {
+            const float *src = a.src0.ptr + (long long)s_b[r] * chw + s_hw[r];
+            for (int tap = 0; tap < k2; ++tap) {
+                const int shift = (tap / a.ksize - pad) * a.W_img + (tap % a.ksize - pad);
+                uint32_t any = 0;
+                for (int g = 0; g < a.G; ++g) {
+                    const bool vis = (a.cell_tap[(size_t)s_cell[r] * a.G + g] >> tap) & 1u;
+                    any |= vis;
+                    float *dst = A + (size_t)r * K + (size_t)tap * a.Cin + g * cpg;
+                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? src[(long long)(g * cpg + c) * a.HW + shift] : 0.f;
+                }
+                if (any && tid == 0) atomicOr(&s_tapor, 1u << tap);
+            }
+        }
+    } else {
+        for (int r = 0; r < rows; ++r) {
+            const uint32_t grp = a.cell_grp[s_cell[r]];
+            int kbase = 0;
+            for (int si = 0; si < 2; ++si) {
+                const Source sc = si == 0 ? a.src0 : a.src1;
+                if (!sc.ptr || sc.channels == 0) continue;
+                const int ng = sc.groups > 0 ? sc.groups : 1, cpg = sc.channels / ng;
+                const float *src = sc.ptr + (long long)s_b[r] * sc.channels * a.HW + s_hw[r];
+                for (int g = 0; g < ng; ++g) {
+                    const bool vis = sc.groups == 0 || ((grp >> g) & 1u);
+                    float *dst = A + (size_t)r * K + kbase + g * cpg;
+                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? src[(long long)(g * cpg + c) * a.HW] : 0.f;
+                }
+                kbase += sc.channels;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- this warp's share of K, segment by segment (conv: one segment per tap, dead taps skipped; dense: one segment)
+    float acc[kRowsMax];
+#pragma unroll
+    for (int r = 0; r < kRowsMax; ++r) acc[r] = 0.f;
+    const bool n_ok = n < a.n_count;
+    const float *wcol = a.wt + a.n_begin + (n_ok ? n : 0);
+    const uint32_t tapor = a.is_conv ? s_tapor : 1u;
+    const int nseg = a.is_conv ? a.ksize * a.ksize : 1, seglen = a.is_conv ? a.Cin : K;
+    for (int seg = 0; seg < nseg; ++seg) {
+        if (!((tapor >> seg) & 1u)) continue;
+        const int kb = seg * seglen;
+        for (int c0 = warp; c0 < seglen; c0 += kGemvWarps * 8) {
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * kGemvWarps;
+                wv[u] = c < seglen ? __ldg(wcol + (size_t)(kb + c) * a.Ntot) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * kGemvWarps;
+                if (c < seglen) {
+#pragma unroll
+                    for (int r = 0; r < kRowsMax; ++r)
+                        if (r < rows) acc[r] = fmaf(A[(size_t)r * K + kb + c], wv[u], acc[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsMax; ++r) part[(warp * kRowsMax + r) * 32 + lane] = acc[r];
+    __syncthreads();
+    // ---- reduce in warp order + epilogue: thread = (row, channel)
+    for (int o = tid; o < rows * 32; o += blockDim.x) {
+        const int r = o >> 5, l = o & 31, nn = blockIdx.x * 32 + l;
+        if (nn >= a.n_count) continue;
+        float v = 0.f;
+        for (int w8 = 0; w8 < kGemvWarps; ++w8) v += part[(w8 * kRowsMax + r) * 32 + l];
+        const int ch = a.n_begin + nn;
+        const long long oo = ((long long)s_b[r] * a.Ntot + ch) * a.HW + s_hw[r];
+        v += a.bias ? a.bias[ch] : 0.f;
+        if (a.add) v += a.add[oo];
+        if (a.lrelu) v = v > 0.f ? v : v * kSlope;
+        a.out[oo] = v;
+    }
+}
+
 // weight re-layout: src [N][K] (state_dict, conv flattened as c*k2+tap) -> dst K-major [K'][N]
 __global__ void k_transpose_w(const float *__restrict__ src, float *__restrict__ dst, int N, int Cin, int k2)
 {
@@ -408,6 +522,20 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, const Packe
     a.out_scale = f16 ? 1.f / (16.f * pk.scale) : 1.f;  // powers of two: exact
     a.range_flag = f16 ? m.range_flag.as<int>() : nullptr;
     if (tc) return launch_layer_tc(m, a, stream);
+    if (rows <= kRowsMax) {
+        const int K = a.is_conv ? a.ksize * a.ksize * a.Cin : a.src0.channels + (a.src1.ptr ? a.src1.channels : 0);
+        const size_t smem = ((size_t)rows * K + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
+        if (smem <= 200 * 1024) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                BASIC_CUDA(cudaFuncSetAttribute(k_layer_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_done = true;
+            }
+            k_layer_rows<<<(a.n_count + 31) / 32, kGemvWarps * 32, smem, stream>>>(a);
+            BASIC_LAUNCHED();
+            return BASIC_OK;
+        }
+    }
     dim3 grid((rows + BM - 1) / BM, (a.n_count + BN - 1) / BN);
     k_layer<<<grid, NT, 0, stream>>>(a);
     BASIC_LAUNCHED();
