@@ -308,6 +308,11 @@ k_layer_tc(LayerArgs a)
     // ---- the k-block list every role walks (built on the host, launch_layer_tc): k-blocks no row of this
     // (stage, out-group) can see -- masked taps, invisible channel groups -- are not in it
     for (int i = tid; i < a.n_kb; i += NTHREADS) s_list[i] = a.kb_list[i];
+    // programmatic dependent launch: the next layer's kernel may start its own prologue as soon as SMs free up, and this one
+    // waits here -- after its prologue (barriers, TMEM, list, bias: nothing a previous kernel writes) -- for the kernels
+    // before it to have completed (their activations are read / overwritten from here on)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1003,13 +1008,20 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
         b.timeline = tl_buf;
     }
     const bool instrumented = b.debug != 0 || b.timeline != nullptr;
-    if (instrumented) {
-        if (b.mode) k_layer_tc<1, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-        else k_layer_tc<0, 1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-    } else {
-        if (b.mode) k_layer_tc<1, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-        else k_layer_tc<0, 0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(b);
-    }
+    // launched with programmatic stream serialisation: the kernel's griddepcontrol.wait orders it after its predecessors
+    static const bool pdl = !(getenv("BASIC_TC_NOPDL") && atoi(getenv("BASIC_TC_NOPDL")));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    auto kfn = instrumented ? (b.mode ? k_layer_tc<1, 1> : k_layer_tc<0, 1>) : (b.mode ? k_layer_tc<1, 0> : k_layer_tc<0, 0>);
+    BASIC_CUDA(cudaLaunchKernelEx(&cfg, kfn, b));
     BASIC_LAUNCHED();
     if (tl) {
         std::vector<long long> h((size_t)grid.x * 16 * 16);
