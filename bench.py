@@ -285,8 +285,8 @@ def run_ours(args, rank, world, local_rank):
     out_host = torch.empty(B, C_, H, W, dtype=torch.float32).pin_memory()
 
     def step_e2e():   # pinned host buffers in, host bytes / pinned host tensor out: H2D / D2H inside the timed region
-        bs = coder.encode(yp.to(dev, non_blocking=True), prior=pp.to(dev, non_blocking=True))
-        out = coder.decode(bs, prior=pp.to(dev, non_blocking=True))
+        bs = coder.encode(yp, prior=pp)        # pinned host tensors: the library uploads them (prior first, y beside the
+        out = coder.decode(bs, prior=pp)       # first group's context model; the stream's staging beside the prior)
         out_host.copy_(out, non_blocking=False)
         return bs, out_host
 

@@ -141,6 +141,7 @@ struct basic_coder {
     int out_chunks = 0;                   // chunks of that delivery still to be awaited (0 = host_out is complete)
     cudaEvent_t in_event = nullptr;  // completion of the last upload out of host_in
     cudaStream_t copy_stream = nullptr;  // the upload runs beside whatever is already queued on the caller's stream
+    cudaEvent_t ev_start = nullptr, ev_prior = nullptr, ev_y = nullptr;  // host inputs of the y path uploaded on copy_stream
     // cache for cache=1 / flush()
     std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
     std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
@@ -174,6 +175,40 @@ int to_device(const T *p, size_t count, DevBuf &staging, cudaStream_t s, const T
     BASIC_TRY(staging.reserve(count * sizeof(T) + 16));
     BASIC_CUDA(cudaMemcpyAsync(staging.p, p, count * sizeof(T), cudaMemcpyHostToDevice, s));
     *out = staging.as<T>();
+    return BASIC_OK;
+}
+
+// Host inputs of the y path: uploaded on the coder's copy stream (prior first, then y), so that the caller's stream only
+// waits for what the next kernel needs -- the first group's context model runs while y is still on the bus, and in the
+// decoder the stream's staging copy runs while the prior is.  Device inputs pass through.
+int upload_inputs(basic_coder *c, const float *y, size_t n_y, const float *prior, size_t n_prior, cudaStream_t s,
+                  const float **d_y, const float **d_prior, bool *y_pending)
+{
+    *y_pending = false;
+    const bool y_host = y && !is_device_ptr(y), p_host = prior && !is_device_ptr(prior);
+    *d_y = y;
+    *d_prior = prior;
+    if (!y_host && !p_host) return BASIC_OK;
+    if (!c->copy_stream) BASIC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&c->ev_start, &c->ev_prior, &c->ev_y})
+        if (!*e) BASIC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (p_host) BASIC_TRY(c->prior_dev.reserve(n_prior * sizeof(float) + 16));
+    if (y_host) BASIC_TRY(c->y_dev.reserve(n_y * sizeof(float) + 16));
+    // the staging buffers may still be read by what an earlier call queued on `s`
+    BASIC_CUDA(cudaEventRecord(c->ev_start, s));
+    BASIC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+    if (p_host) {
+        BASIC_CUDA(cudaMemcpyAsync(c->prior_dev.p, prior, n_prior * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+        BASIC_CUDA(cudaEventRecord(c->ev_prior, c->copy_stream));
+        BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_prior, 0));
+        *d_prior = c->prior_dev.as<float>();
+    }
+    if (y_host) {
+        BASIC_CUDA(cudaMemcpyAsync(c->y_dev.p, y, n_y * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+        BASIC_CUDA(cudaEventRecord(c->ev_y, c->copy_stream));
+        *d_y = c->y_dev.as<float>();
+        *y_pending = true;  // the caller makes `s` wait for ev_y before the first kernel that reads y
+    }
     return BASIC_OK;
 }
 
@@ -539,6 +574,7 @@ void basic_coder_destroy(basic_coder *c)
     if (c->host_in) cudaFreeHost(c->host_in);
     if (c->in_event) cudaEventDestroy(c->in_event);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (cudaEvent_t e : {c->ev_start, c->ev_prior, c->ev_y}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->out_events) cudaEventDestroy(e);
     if (c->tt) tans_delete(c->tt);
     delete c;
@@ -1038,8 +1074,8 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     const int HW = H * W;
     const size_t n = (size_t)B * C * HW;
     const float *d_y, *d_prior;
-    BASIC_TRY(to_device(y, n, c->y_dev, s, &d_y));
-    BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
+    bool y_pending = false;
+    BASIC_TRY(upload_inputs(c, y, n, prior, 2 * n, s, &d_y, &d_prior, &y_pending));
     float *buf = c->buf.as<float>(), *params = c->params.as<float>();
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     const float *params_src = params;
@@ -1079,6 +1115,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             const int64_t cnt = (int64_t)B * n_pos;
             slice_n.push_back(cnt);
             if (cnt == 0) continue;
+            if (y_pending) {  // y was uploaded beside the first group's context model
+                BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_y, 0));
+                y_pending = false;
+            }
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(d_y, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                             sym + done, idx + done, buf, c->sm_count, s, tc ? 1 : 0, tc ? ctx_perm(*model->m) : nullptr));
@@ -1137,8 +1177,9 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int HW = H * W;
     const size_t n = (size_t)B * C * HW;
-    const float *d_prior;
-    BASIC_TRY(to_device(prior, 2 * n, c->prior_dev, s, &d_prior));
+    const float *d_prior, *d_none;
+    bool none_pending = false;
+    BASIC_TRY(upload_inputs(c, nullptr, 0, prior, 2 * n, s, &d_none, &d_prior, &none_pending));
     float *buf = c->buf.as<float>(), *params = c->params.as<float>();
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));

@@ -236,6 +236,14 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         tg32 = np.ascontiguousarray(tg[0].numpy(), dtype=np.int32)
         N.check(N.lib().basic_ctx_set_map(self._ctx, tg32.ctypes.data, tg32.shape[1], tg32.shape[2]))
 
+    def _operand(self, t):
+        """float32, contiguous; a CPU tensor stays where it is: the C ABI takes host pointers and uploads them on its own
+        copy stream, overlapped with the first kernels (pinned memory makes that asynchronous)."""
+        t = t.detach()
+        if t.device.type == "cpu":
+            return t.to(dtype=torch.float32).contiguous()
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
     # ------------------------------------------------------------------------------------------ coding
     def encode(self, input, *args, prior=None, pgm=None, quantizer_params=None, return_yhat=False, **kwargs) -> bytes:
         assert hasattr(self, "ans_encoder"), "Not Initialized! Should call self.update_state() before coding!"
@@ -249,12 +257,11 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                 prior = prior.narrow(dim, 0, size)
         B, Cc, H, W = input.shape
         assert Cc == self.in_channels and prior.shape[1] == 2 * Cc
-        y = input.detach().to(device=self.device, dtype=torch.float32).contiguous()
-        p = prior.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        y, p = self._operand(input), self._operand(prior)
         self._set_map(self._get_pgm(input.shape, pgm))
         h = self.ans_encoder.handle
         out_len = C.c_int64(0)
-        yhat = torch.empty_like(y) if return_yhat else None
+        yhat = torch.empty(y.shape, dtype=torch.float32, device=self.device) if return_yhat else None
         # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object
         N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
                                            C.byref(out_len), yhat.data_ptr() if return_yhat else None,
@@ -284,7 +291,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                 prior = prior.narrow(dim, 0, size)
         H, W = spatial
         Cc = self.in_channels
-        p = prior.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        p = self._operand(prior)
         self._set_map(self._get_pgm((B, Cc, H, W), pgm))
         enc = np.frombuffer(byte_string, dtype=np.uint8, offset=ptr)
         yhat = torch.empty(B, Cc, H, W, dtype=torch.float32, device=self.device)

@@ -293,6 +293,22 @@ def test_ypath_round_trip_properties_large():
     assert len(b0) <= len(b1) * 1.005 + 300
 
 
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_host_tensor_inputs_equal_device_inputs(precision):
+    """Pinned or pageable CPU tensors go to the C ABI as host pointers (uploaded on the coder's copy stream, overlapped
+    with the first kernels): same stream, same reconstruction as device inputs; repeated calls reuse the staging buffers."""
+    c = _random_case(96, 1, 3, 16, 24, 33)
+    coder = make_coder(c, 0, "checkerboard", ctx_precision=precision)
+    y, p = c["y"].contiguous(), c["prior"].contiguous()
+    ref = coder.encode(y.cuda(), prior=p.cuda())
+    for yy, pp in ((y.pin_memory(), p.pin_memory()), (y, p), (y.pin_memory(), p.cuda())):
+        for _ in range(2):
+            bs, yh = coder.encode(yy, prior=pp, return_yhat=True)
+            assert bs == ref
+            out = coder.decode(bs, prior=pp)
+            assert out.is_cuda and torch.equal(out, yh * 1.0 + 0.0)
+
+
 def test_mean_scale_4k_320ch_tiles():
     """BASELINE configs[4] geometry: 135 x 240 x 320 latent, mean-scale coder (tiling is exact there), coded as
     row-band tiles; every tile decodes on its own and the union equals the untiled result."""
