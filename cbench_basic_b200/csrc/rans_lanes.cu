@@ -26,15 +26,66 @@ constexpr int kMaxWarps = 16;  // ... and when there are more (throughput mode: 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSegHdr = 8;  // u32 n_chunks | u32 n_slices, followed by u32 chunk_syms[n_slices]
 
-__device__ inline const TableView stage_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
-                                                bool to_smem, unsigned char *smem)
+// Table access of the coding kernels.  SM = true: the blob was staged into shared memory and is read with ld.shared
+// through 32-bit window addresses (a generic pointer that may be global or shared compiles to generic loads plus 64-bit
+// address arithmetic on the state's dependency chain -- it was 40 % of the decoder's step); SM = false: tables larger
+// than the shared memory of an SM stay in HBM / L2 and are read through the read-only path.
+// The loads are plain (non-volatile) asm: the tables never change after staging, so the compiler may hoist them off the
+// chain; init() orders them behind the staging barrier.
+template <bool SM> struct Tab;
+template <> struct Tab<true> {
+    typedef uint32_t addr_t;
+    uint32_t meta, cdf, lut;
+    __device__ void init(const void *, unsigned char *smem, size_t meta_bytes, size_t cdf16_bytes)
+    {
+        uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
+        asm volatile("" : "+r"(b)::"memory");
+        meta = b;
+        cdf = b + (uint32_t)meta_bytes;
+        lut = cdf + (uint32_t)cdf16_bytes;
+    }
+    __device__ uint4 meta_at(int c) const
+    {
+        uint4 v;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(meta + (uint32_t)c * 16u));
+        return v;
+    }
+    __device__ addr_t cdf_at(uint32_t entry) const { return cdf + 2u * entry; }
+    __device__ addr_t lut_at(uint32_t entry) const { return lut + 2u * entry; }
+    template <int OFF> static __device__ uint32_t ld16(addr_t a)
+    {
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+        return v;
+    }
+};
+template <> struct Tab<false> {
+    typedef const unsigned char *addr_t;
+    const unsigned char *meta, *cdf, *lut;
+    __device__ void init(const void *blob, unsigned char *, size_t meta_bytes, size_t cdf16_bytes)
+    {
+        meta = reinterpret_cast<const unsigned char *>(blob);
+        cdf = meta + meta_bytes;
+        lut = cdf + cdf16_bytes;
+    }
+    __device__ uint4 meta_at(int c) const { return __ldg(reinterpret_cast<const uint4 *>(meta) + c); }
+    __device__ addr_t cdf_at(uint32_t entry) const { return cdf + 2ull * entry; }
+    __device__ addr_t lut_at(uint32_t entry) const { return lut + 2ull * entry; }
+    template <int OFF> static __device__ uint32_t ld16(addr_t a) { return __ldg(reinterpret_cast<const uint16_t *>(a + OFF)); }
+};
+
+template <bool SM> __device__ inline Tab<SM> stage_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
+                                                          unsigned char *smem)
 {
-    if (!to_smem) return make_view(blob, meta_bytes, cdf16_bytes);
-    const uint4 *src = reinterpret_cast<const uint4 *>(blob);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    return make_view(smem, meta_bytes, cdf16_bytes);
+    if (SM) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    Tab<SM> t;
+    t.init(blob, smem, meta_bytes, cdf16_bytes);
+    return t;
 }
 
 struct SliceDesc {  // one slice of a segment: `n` symbols starting at `off` in the operand arrays
@@ -58,13 +109,14 @@ struct LaneParams {
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
 // Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
+template <bool SM>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
              uint32_t *__restrict__ states, int *status)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem, smem);
+    const Tab<SM> tb = stage_tables<SM>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
@@ -112,29 +164,40 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
 #pragma unroll
             for (int q = 0; q < 4; ++q) { sy[q] = syn[q]; ix[q] = ixn[q]; }
             if (blk > 0) load_ops(blk - 1, syn, ixn);  // one block ahead: off the dependency chain
+            // --- everything that does not depend on the state, for the block's four symbols at once: table lookups,
+            // escape classification, the reciprocal of the frequency.  What is left per symbol is the state's own chain.
+            uint32_t start[4], freq[4], raw[4];
+            float rcp[4];
+            bool esc[4];
 #pragma unroll
-            for (int q = 3; q >= 0; --q) {
+            for (int q = 0; q < 4; ++q) {
                 const bool active = j0 + q < m;
                 int32_t c = ix[q];
                 if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
-                const TableMeta mt = tv.meta[c];
-                const int32_t maxv = (int32_t)mt.cdf_size - 2;
-                int32_t v = sy[q] - mt.offset;
-                uint32_t raw = 0;
-                bool esc = false;
+                const uint4 mt = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                const int32_t maxv = (int32_t)(mt.z & 0xffffu) - 2;
+                int32_t v = sy[q] - (int32_t)mt.w;
+                raw[q] = 0;
+                esc[q] = false;
                 if (P.bypass) {
-                    if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = maxv; }
-                    else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
-                    esc = active && v == maxv;
+                    if (v < 0) { raw[q] = (uint32_t)(-2 * v - 1); v = maxv; }
+                    else if (v >= maxv) { raw[q] = (uint32_t)(2 * (v - maxv)); v = maxv; }
+                    esc[q] = active && v == maxv;
                 } else if (v < 0 || v > maxv) { if (active) st |= 2; v = 0; }
-                const uint32_t start = tv.cdf[mt.cdf_base + v];
-                const uint32_t freq = (uint16_t)(tv.cdf[mt.cdf_base + v + 1] - start);
+                const typename Tab<SM>::addr_t at = tb.cdf_at(mt.x + (uint32_t)v);
+                start[q] = Tab<SM>::template ld16<0>(at);
+                freq[q] = (uint16_t)(Tab<SM>::template ld16<2>(at) - start[q]);
+                rcp[q] = __frcp_rn(__uint2float_rz(freq[q]));
+            }
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {
+                const bool active = j0 + q < m;
                 // --- escape units, last to first (oracle: bls_encode_slice): the token list (count tokens, then the
                 // digits) goes through the state in units of up to tpu = 16 / bp tokens, one renormalisation check each
-                if (__any_sync(kFull, esc)) {
+                if (__any_sync(kFull, esc[q])) {
                     int nd = 0, ncnt = 0, ntok = 0;
-                    if (esc) {
-                        nd = (int)(((32 - __clz(raw) + bp - 1) * r_bp) >> 16);  // digits of raw (0 for raw = 0)
+                    if (esc[q]) {
+                        nd = (int)(((32 - __clz(raw[q]) + bp - 1) * r_bp) >> 16);  // digits of raw (0 for raw = 0)
                         ncnt = (int)(((uint32_t)nd * r_maxb) >> 16) + 1;
                         ntok = ncnt + nd;
                     }
@@ -150,7 +213,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                             for (int i = 0; i < cnt; ++i) {
                                 const int t = t0 + i;
                                 uint32_t tok;
-                                if (t >= ncnt) tok = (raw >> ((t - ncnt) * bp)) & maxb;
+                                if (t >= ncnt) tok = (raw[q] >> ((t - ncnt) * bp)) & maxb;
                                 else tok = t < ncnt - 1 ? maxb : (uint32_t)(nd - (ncnt - 1) * (int)maxb);
                                 unit |= tok << (bp * i);
                             }
@@ -169,7 +232,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                 }
                 // --- the symbol itself
                 // x >= ((L >> prec) << 16) * freq = freq << (32 - prec), without the 64-bit product
-                const bool emit = active && (x >> (32 - prec)) >= freq;
+                const bool emit = active && (x >> (32 - prec)) >= freq[q];
                 const unsigned em = __ballot_sync(kFull, emit);
                 pos -= __popc(em);
                 if (emit) {
@@ -182,15 +245,15 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                     // one of it (exact general division when the invariant does not hold: prec < 16)
                     uint32_t qt, rem;
                     if (prec == 16) {
-                        qt = __float2uint_rz(__fdividef(__uint2float_rz(x), __uint2float_rz(freq)));
-                        rem = x - qt * freq;
-                        if ((int32_t)rem < 0) { --qt; rem += freq; }
-                        else if (rem >= freq) { ++qt; rem -= freq; }
+                        qt = __float2uint_rz(__uint2float_rz(x) * rcp[q]);
+                        rem = x - qt * freq[q];
+                        if ((int32_t)rem < 0) { --qt; rem += freq[q]; }
+                        else if (rem >= freq[q]) { ++qt; rem -= freq[q]; }
                     } else {
-                        qt = x / freq;
-                        rem = x - qt * freq;
+                        qt = x / freq[q];
+                        rem = x - qt * freq[q];
                     }
-                    x = (qt << prec) + rem + start;
+                    x = (qt << prec) + rem + start[q];
                 }
             }
         }
@@ -271,6 +334,7 @@ __device__ inline void cp_async4(uint32_t smem_dst, const void *gsrc)
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <bool SM>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
              int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
@@ -281,8 +345,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
     uint32_t *ring32 = reinterpret_cast<uint32_t *>(smem) + (threadIdx.x >> 5) * kRingUnits;
     const uint16_t *ring16 = reinterpret_cast<const uint16_t *>(ring32);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring32);
-    const TableView tv = stage_tables(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, P.tables_in_smem,
-                                      smem + (blockDim.x >> 5) * kRingUnits * 4);
+    const Tab<SM> tb = stage_tables<SM>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + (blockDim.x >> 5) * kRingUnits * 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks;
@@ -324,9 +387,12 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
         cp_async_wait<1>();
         __syncwarp();
         ready_u = fill_u - kGroupUnits;
-        // before an event that may consume up to 32 words: make sure they have landed
+        // Words must have landed before the events that consume them.  The check runs once per block of four coding
+        // steps (up to 128 words) and once per escape sub-step (up to 32 words); both keep 160 words ahead, so that the
+        // steps of a block are still covered after any number of escape sub-steps in between.  Unread words never
+        // exceed 3 groups = 384 of the ring's 512 units.
         auto ensure = [&]() {
-            if (((wp + 32) >> 1) + 1 > ready_u) {
+            if (((wp + 160) >> 1) + 1 > ready_u) {
                 cp_async_wait<0>();
                 __syncwarp();
                 ready_u = fill_u;
@@ -353,20 +419,40 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
             const bool full4 = vec_ok && j0 + 3 < m;
             const int32_t ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
             if (blk + 1 < nblocks) ixn = load_ix(blk + 1);  // one block ahead: off the dependency chain
+            // table records of the block's four symbols: known from the indexes alone, fetched before the chain starts
+            uint4 mt[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int32_t c = ix[q];
+                if ((uint32_t)c >= (uint32_t)P.T) { if (j0 + q < m) st |= 1; c = 0; }
+                mt[q] = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+            }
+            ensure();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const bool active = j0 + q < m;
-                int32_t c = ix[q];
-                if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
-                const TableMeta mt = tv.meta[c];
-                const uint16_t *cd = tv.cdf + mt.cdf_base;
-                const int nsyms = (int)mt.cdf_size - 1, maxv = nsyms - 1;
+                const typename Tab<SM>::addr_t cd = tb.cdf_at(mt[q].x);
+                const int nsyms = (int)(mt[q].z & 0xffffu) - 1, maxv = nsyms - 1;
                 const uint32_t cum = x & pmask;
-                int s = tv.lut[mt.lut_base + (cum >> mt.lut_shift)];
-                while (s + 1 < nsyms && cd[s + 1] <= cum) ++s;
-                const uint32_t start = cd[s], freq = (uint16_t)(cd[s + 1] - start);
+                // chain: bucket LUT -> four CDF entries at once (the answer is among the first three candidates unless
+                // the bucket sits in a tail of width-1 symbols) -> multiply -> ballot -> word
+                int s = (int)Tab<SM>::template ld16<0>(tb.lut_at(mt[q].y + (cum >> ((mt[q].z >> 16) & 0xffu))));
+                const typename Tab<SM>::addr_t e = cd + 2 * s;
+                const uint32_t c0 = Tab<SM>::template ld16<0>(e), c1 = Tab<SM>::template ld16<2>(e);
+                const uint32_t c2 = Tab<SM>::template ld16<4>(e), c3 = Tab<SM>::template ld16<6>(e);
+                const bool a1 = s + 1 < nsyms && c1 <= cum;
+                const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
+                const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
+                uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
+                s += (int)a1 + (int)a2;
+                if (a3) {
+                    ++s;
+                    while (s + 1 < nsyms && Tab<SM>::template ld16<2>(cd + 2 * s) <= cum) ++s;
+                    start = Tab<SM>::template ld16<0>(cd + 2 * s);
+                    next = Tab<SM>::template ld16<2>(cd + 2 * s);
+                }
+                const uint32_t freq = (uint16_t)(next - start);
                 if (active) x = freq * (x >> prec) + cum - start;
-                ensure();
                 {
                     const bool need = active && x < kRansL;
                     const unsigned nm = __ballot_sync(kFull, need);
@@ -418,7 +504,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                         value = (raw & 1) ? -v2 - 1 : v2 + maxv;
                     }
                 }
-                res[q] = value + mt.offset;
+                res[q] = value + (int32_t)mt[q].w;
             }
             if (full4) {
                 *reinterpret_cast<int4 *>(out + base + j0) = make_int4(res[0], res[1], res[2], res[3]);
@@ -523,9 +609,10 @@ static int set_attrs()
 {
     static bool attr_done = false;
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        const int dec_smem = kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit;
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         attr_done = true;
     }
     return BASIC_OK;
@@ -543,8 +630,9 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
     if (n_chunks > 0) {
-        k_bls_encode<<<grid_for(n_chunks, sm_count), warps_for(n_chunks, sm_count, smem) * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words,
-                                                                                 d_first, d_states, d_status);
+        const dim3 grid(grid_for(n_chunks, sm_count)), block(warps_for(n_chunks, sm_count, smem) * 32);
+        if (smem > 0) k_bls_encode<true><<<grid, block, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
+        else k_bls_encode<false><<<grid, block, 0, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
         BASIC_LAUNCHED();
     }
     k_bls_scan<<<1, 1024, 0, stream>>>(nullptr, n_chunks, n_slices, sl, d_first, cap_words, reinterpret_cast<uint32_t *>(d_seg_out),
@@ -569,8 +657,13 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
     const int nw = warps_for(n_chunks, sm_count, smem);
-    k_bls_decode<<<grid_for(n_chunks, sm_count), nw * 32, smem + nw * kRingUnits * 4, stream>>>(
-        P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
+    const dim3 grid(grid_for(n_chunks, sm_count)), block(nw * 32);
+    if (smem > 0)
+        k_bls_decode<true><<<grid, block, smem + nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0,
+                                                                                slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
+    else
+        k_bls_decode<false><<<grid, block, nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0,
+                                                                          slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
