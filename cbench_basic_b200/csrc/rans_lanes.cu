@@ -194,6 +194,31 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                 const bool active = j0 + q < m;
                 // --- escape units, last to first (oracle: bls_encode_slice): the token list (count tokens, then the
                 // digits) goes through the state in units of up to tpu = 16 / bp tokens, one renormalisation check each
+                if (bp == 4) {
+                    // bypass_precision 4 (the reference's default): a 32-bit payload has at most 8 digits, so there is one
+                    // count token and the whole token list is the 36-bit string  nd | raw << 4 ; unit u = its bits [16u, 16u + 16)
+                    if (__any_sync(kFull, esc[q])) {
+                        const int nd = esc[q] ? (35 - __clz(raw[q])) >> 2 : 0;
+                        const int ntok = esc[q] ? nd + 1 : 0;
+                        const int nunits = (ntok + 3) >> 2;
+                        const unsigned long long toks = (unsigned long long)nd | ((unsigned long long)raw[q] << 4);
+                        const int maxunits = (int)__reduce_max_sync(kFull, (unsigned)nunits);
+                        for (int u = maxunits - 1; u >= 0; --u) {
+                            const bool part = nunits > u;
+                            const int wbits = part ? 4 * min(4, ntok - 4 * u) : 0;
+                            const uint32_t unit = (uint32_t)(toks >> (16 * u)) & 0xffffu;
+                            const bool emit = part && x >= (1u << (32 - wbits));
+                            const unsigned em = __ballot_sync(kFull, emit);
+                            pos -= __popc(em);
+                            if (emit) {
+                                const int at = pos + __popc(em & lt_mask);
+                                if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
+                                x >>= 16;
+                            }
+                            if (part) x = (x << wbits) | unit;
+                        }
+                    }
+                } else
                 if (__any_sync(kFull, esc[q])) {
                     int nd = 0, ncnt = 0, ntok = 0;
                     if (esc[q]) {
@@ -466,6 +491,49 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                 }
                 int32_t value = s;
                 const bool esc = active && P.bypass && s == maxv;
+                if (bp == 4) {
+                    // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count
+                    // token), followed by the digits, least significant first, four tokens per unit
+                    if (__any_sync(kFull, esc)) {
+                        bool in = esc, first = true;
+                        uint32_t nb = 0, raw = 0, jj = 0;
+                        while (__any_sync(kFull, in)) {
+                            const bool was = in;
+                            if (in) {
+                                uint32_t cnt, used, bits = x;
+                                if (first) {
+                                    nb = x & 15u;
+                                    if (nb > 8) { st |= 4; nb = 0; }  // no encoder writes this
+                                    cnt = min(3u, nb);
+                                    used = cnt + 1;
+                                    bits = x >> 4;
+                                    first = false;
+                                } else {
+                                    cnt = min(4u, nb - jj);
+                                    used = cnt;
+                                }
+                                raw |= (bits & ((1u << (4 * cnt)) - 1)) << (4 * jj);
+                                jj += cnt;
+                                x >>= 4 * used;
+                                in = jj < nb;
+                            }
+                            ensure();
+                            const bool need = was && x < kRansL;
+                            const unsigned nm = __ballot_sync(kFull, need);
+                            if (need) {
+                                const uint32_t at = wp + __popc(nm & lt_mask);
+                                uint32_t word = 0;
+                                if (at < wend) word = ring16[at & (2 * kRingUnits - 1)]; else st |= 4;
+                                x = (x << 16) | word;
+                            }
+                            wp += __popc(nm);
+                        }
+                        if (esc) {
+                            const int32_t v2 = (int32_t)(raw >> 1);
+                            value = (raw & 1) ? -v2 - 1 : v2 + maxv;
+                        }
+                    }
+                } else
                 if (__any_sync(kFull, esc)) {
                     bool in = esc;
                     int phase = 0;
