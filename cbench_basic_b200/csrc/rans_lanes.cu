@@ -109,7 +109,7 @@ struct LaneParams {
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
 // Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
-template <bool SM>
+template <bool SM, bool BP4>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
@@ -194,7 +194,7 @@ k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *_
                 const bool active = j0 + q < m;
                 // --- escape units, last to first (oracle: bls_encode_slice): the token list (count tokens, then the
                 // digits) goes through the state in units of up to tpu = 16 / bp tokens, one renormalisation check each
-                if (bp == 4) {
+                if (BP4) {
                     // bypass_precision 4 (the reference's default): a 32-bit payload has at most 8 digits, so there is one
                     // count token and the whole token list is the 36-bit string  nd | raw << 4 ; unit u = its bits [16u, 16u + 16)
                     if (__any_sync(kFull, esc[q])) {
@@ -359,7 +359,7 @@ __device__ inline void cp_async4(uint32_t smem_dst, const void *gsrc)
 __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool SM>
+template <bool SM, bool BP4>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
              int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
@@ -491,7 +491,7 @@ k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_
                 }
                 int32_t value = s;
                 const bool esc = active && P.bypass && s == maxv;
-                if (bp == 4) {
+                if (BP4) {
                     // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count
                     // token), followed by the digits, least significant first, four tokens per unit
                     if (__any_sync(kFull, esc)) {
@@ -677,10 +677,13 @@ static int set_attrs()
 {
     static bool attr_done = false;
     if (!attr_done) {
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
         const int dec_smem = kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit;
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
-        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         attr_done = true;
     }
     return BASIC_OK;
@@ -699,8 +702,11 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     BASIC_TRY(set_attrs());
     if (n_chunks > 0) {
         const dim3 grid(grid_for(n_chunks, sm_count)), block(warps_for(n_chunks, sm_count, smem) * 32);
-        if (smem > 0) k_bls_encode<true><<<grid, block, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
-        else k_bls_encode<false><<<grid, block, 0, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
+        // instantiations: tables in shared memory or not x bypass_precision 4 (the reference's default; its escape code is a
+        // fraction of the general one -- the kernels are instruction-fetch sensitive with one warp per scheduler)
+        auto kern = smem > 0 ? (bypass_precision == 4 ? k_bls_encode<true, true> : k_bls_encode<true, false>)
+                             : (bypass_precision == 4 ? k_bls_encode<false, true> : k_bls_encode<false, false>);
+        kern<<<grid, block, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
         BASIC_LAUNCHED();
     }
     k_bls_scan<<<1, 1024, 0, stream>>>(nullptr, n_chunks, n_slices, sl, d_first, cap_words, reinterpret_cast<uint32_t *>(d_seg_out),
@@ -726,12 +732,10 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     BASIC_TRY(set_attrs());
     const int nw = warps_for(n_chunks, sm_count, smem);
     const dim3 grid(grid_for(n_chunks, sm_count)), block(nw * 32);
-    if (smem > 0)
-        k_bls_decode<true><<<grid, block, smem + nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0,
-                                                                                slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
-    else
-        k_bls_decode<false><<<grid, block, nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0,
-                                                                          slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
+    auto kern = smem > 0 ? (bypass_precision == 4 ? k_bls_decode<true, true> : k_bls_decode<true, false>)
+                         : (bypass_precision == 4 ? k_bls_decode<false, true> : k_bls_decode<false, false>);
+    kern<<<grid, block, smem + nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1,
+                                                              d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
