@@ -290,10 +290,15 @@ def run_ours(args, rank, world, local_rank):
         out_host.copy_(out, non_blocking=False)
         return bs, out_host
 
-    # correctness of what is timed: lossless + matches encoder-side reconstruction
+    # correctness of what is timed: lossless + matches encoder-side reconstruction (|rint(y - m) + m - y| reaches 0.5 plus a
+    # float rounding of the sum: rank 2's inputs hit 0.50000012)
     bs, yhat_enc = coder.encode(yd, prior=pd, return_yhat=True)
     out = coder.decode(bs, prior=pd)
-    assert torch.equal(out, yhat_enc * 1.0 + 0.0) and float((out - yd).abs().max()) <= 0.5, "round trip failed"
+    if not (torch.equal(out, yhat_enc * 1.0 + 0.0) and float((out - yd).abs().max()) <= 0.5 + 1e-5):
+        bad = (out != yhat_enc).nonzero()
+        raise AssertionError(f"round trip failed on rank {rank}: {bad.shape[0]} elements differ from the encoder's reconstruction "
+                             f"(first {bad[0].tolist() if bad.shape[0] else None}, images {sorted(set(bad[:, 0].tolist()))[:8]}), "
+                             f"max|out - y| {float((out - yd).abs().max())}, max|yhat_enc - y| {float((yhat_enc - yd).abs().max())}")
     stream_bytes = len(bs)
 
     def timed(fn, steps, warmup):

@@ -275,7 +275,7 @@ def test_ypath_multilane_container_matches_cpu_spec():
     out, used = o.dec.decode_lanes_slices(bs[4:], gidx, slice_n)
     assert used == len(bs) - 4 and np.array_equal(out, gsym)
     yhat = coder.decode(bs, prior=c["prior"].cuda())
-    assert float((yhat.cpu() - c["y"]).abs().max()) <= 0.5
+    assert float((yhat.cpu() - c["y"]).abs().max()) <= 0.5 + 1e-5
 
 
 def test_ypath_round_trip_properties_large():
@@ -289,7 +289,7 @@ def test_ypath_round_trip_properties_large():
     assert torch.equal(yh0, yh1)
     d1, d0 = coder1.decode(b1, prior=p), coder0.decode(b0, prior=p)
     assert torch.equal(d0, d1) and torch.equal(d0, yh0 * 1.0 + 0.0)
-    assert float((d0 - y).abs().max()) <= 0.5
+    assert float((d0 - y).abs().max()) <= 0.5 + 1e-5
     assert len(b0) <= len(b1) * 1.005 + 300
 
 
