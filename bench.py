@@ -263,6 +263,9 @@ def run_ours(args, rank, world, local_rank):
     from cbench_basic_b200 import _native as N, sharding
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # before any pinned allocation or library thread exists: stay on the CPUs next to this rank's GPU
+    numa = sharding.bind_to_gpu_numa(local_rank, local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world))) \
+        if not os.environ.get("BASIC_NO_BIND") else {"bound": False, "disabled": True}
     B, C_, H, W, method, ctx, desc = WORKLOADS[args.workload]
     y, prior, w = make_inputs(args.workload, rank)
     coder = build_coder(args.workload, w, args.lanes, dev)
@@ -433,7 +436,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": pix_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_coder": coder_roof, "phases": phases,
-            "coder_lane_sweep": sweep, "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes]}
+            "coder_lane_sweep": sweep, "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes],
+            "cpu_binding_rank0": numa}
     print(json.dumps(line), flush=True)
 
 

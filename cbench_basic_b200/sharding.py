@@ -13,6 +13,57 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index: int, local_rank: int = 0, local_world_size: int = 1) -> dict:
+    """One process per GPU: pin the calling (main) thread -- and with it every thread and pinned allocation made later --
+    to the CPUs of the NUMA node its GPU hangs off (/sys/bus/pci/devices/<bus id>/local_cpulist).  The stream of every
+    coding call crosses PCIe through pinned host memory and is copied by a few host threads; with processes floating
+    over both sockets the staging buffers land on the far node for half of the ranks.  Ranks that share a node split
+    its CPUs between them.  Returns what was done (for logs); a no-op where sysfs has no topology (-1 / one node)."""
+    import os
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        info["pci"] = bus
+        info["numa_node"] = int(open(base + "/numa_node").read())
+        local = _parse_cpulist(open(base + "/local_cpulist").read())
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        info["allowed"] = len(allowed)
+        info["local"] = len(cpus)
+        if not cpus or len(cpus) == len(allowed):
+            return info
+        # ranks whose GPUs share the node take disjoint slices of it
+        peers = []
+        for d in range(torch.cuda.device_count()):
+            q = torch.cuda.get_device_properties(d)
+            qb = f"/sys/bus/pci/devices/{q.pci_domain_id:04x}:{q.pci_bus_id:02x}:{q.pci_device_id:02x}.0/numa_node"
+            if int(open(qb).read()) == info["numa_node"]:
+                peers.append(d)
+        peers = peers[:max(1, local_world_size)] if device_index in peers[:max(1, local_world_size)] else peers
+        if device_index in peers and len(cpus) >= 2 * len(peers):
+            per = len(cpus) // len(peers)
+            at = peers.index(device_index) * per
+            cpus = cpus[at:at + per]
+        os.sched_setaffinity(0, cpus)
+        info["bound"] = True
+        info["cpus"] = len(cpus)
+    except Exception as e:  # no sysfs / no permission: run unbound
+        info["error"] = repr(e)
+    return info
+
+
 def partition(n_units: int, world_size: int, rank: int) -> range:
     """Contiguous block of units owned by `rank` (sizes differ by at most one)."""
     base, rem = divmod(n_units, world_size)
