@@ -53,6 +53,7 @@ int mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *
 void ctx_set_run_precision(CtxModel &, int);
 int ctx_range_flag_clear(CtxModel &, cudaStream_t);
 int ctx_range_flag_read(CtxModel &, cudaStream_t, int *);
+int ctx_range_flag_copy(CtxModel &, cudaStream_t, int *);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
 
@@ -1195,19 +1196,27 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     if (fp16) BASIC_TRY(ctx_range_flag_clear(*model->m, s));
     BASIC_TRY(run_groups());
     g_trace.mark("groups queued", s);
+    auto fallback_tf32 = [&]() -> int {
+        fp16 = false;
+        ctx_set_run_precision(*model->m, BASIC_CTX_TF32X3);
+        const int rc = run_groups();
+        ctx_set_run_precision(*model->m, ctx_precision(*model->m));
+        return rc;
+    };
+    // the flag is read with the coder's own first synchronisation (multi-lane: the size estimate) instead of a separate one;
+    // a raised flag -- rare -- then costs the coding pass that was already queued
+    int *h_flag = reinterpret_cast<int *>(static_cast<char *>(c->pinned) + 128);
+    bool flag_pending = false;
     if (fp16) {
-        int flag = 0;
-        BASIC_TRY(ctx_range_flag_read(*model->m, s, &flag));
-        g_trace.mark("flag read", s);
-        if (flag) {
-            if (lanes == BASIC_LANES_REFERENCE)
+        if (lanes == BASIC_LANES_REFERENCE) {
+            int flag = 0;
+            BASIC_TRY(ctx_range_flag_read(*model->m, s, &flag));
+            if (flag)
                 return value_error("context-model activation outside the 3xFP16 range and a lanes=1 stream cannot record the "
                                    "fallback: use ctx_precision tf32x3 or fp32");
-            fp16 = false;
-            ctx_set_run_precision(*model->m, BASIC_CTX_TF32X3);
-            const int rc = run_groups();
-            ctx_set_run_precision(*model->m, ctx_precision(*model->m));
-            BASIC_TRY(rc);
+        } else {
+            BASIC_TRY(ctx_range_flag_copy(*model->m, s, h_flag));
+            flag_pending = true;
         }
     }
     if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
@@ -1222,9 +1231,15 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     // multi-lane container: magic | one segment with one slice per coding group (lane states carried across groups)
     BASIC_TRY(c->segs.reserve(64));
     int64_t seg_len = 0;
-    {
-        ProfScope ps(PROF_ENCODE, s);
-        BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));
+    for (int pass = 0; pass < 2; ++pass) {
+        {
+            ProfScope ps(PROF_ENCODE, s);
+            BASIC_TRY(encode_segment(c, sym, idx, S, slice_n.data(), lanes, 4, s, &seg_len));  // synchronises `s`
+        }
+        if (!(flag_pending && *h_flag)) break;
+        flag_pending = false;  // outside the 3xFP16 range: everything again in 3xTF32, container magic "BLS1"
+        BASIC_TRY(fallback_tf32());
+        if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     }
     g_trace.mark("segment coded", s);
     BASIC_CUDA(cudaMemcpyAsync(c->segs.p, fp16 ? &kMagic2 : &kMagic, 4, cudaMemcpyHostToDevice, s));
@@ -1248,7 +1263,9 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     bool none_pending = false;
     g_trace.mark("enter", s);
     BASIC_TRY(upload_inputs(c, nullptr, 0, prior, 2 * n, s, &d_none, &d_prior, &none_pending));
-    float *buf = c->buf.as<float>(), *params = c->params.as<float>();
+    // the reconstruction is built in place when the caller's output lives on the device
+    const bool direct = is_device_ptr(yhat_out) && (reinterpret_cast<uintptr_t>(yhat_out) & 255) == 0;
+    float *buf = direct ? yhat_out : c->buf.as<float>(), *params = c->params.as<float>();
     int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
     BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
     const float *params_src = params;
@@ -1343,7 +1360,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     if (lanes != BASIC_LANES_REFERENCE) c->stream_pos += si.len;
     g_trace.mark("all queued", s);
     BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
+    if (!direct) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     g_trace.mark("yhat copied", s);
     BASIC_CUDA(cudaStreamSynchronize(s));
     g_trace.mark("synced", (cudaStream_t)-1);

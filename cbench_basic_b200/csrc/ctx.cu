@@ -574,6 +574,14 @@ int ctx_range_flag_read(CtxModel &m, cudaStream_t s, int *flag)
     BASIC_CUDA(cudaStreamSynchronize(s));
     return BASIC_OK;
 }
+// Queues the copy of the flag into pinned host memory; the value is valid after the caller's next synchronisation of `s`.
+int ctx_range_flag_copy(CtxModel &m, cudaStream_t s, int *pinned_flag)
+{
+    *pinned_flag = 0;
+    if (!m.range_flag.p) return BASIC_OK;
+    BASIC_CUDA(cudaMemcpyAsync(pinned_flag, m.range_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return BASIC_OK;
+}
 size_t ctx_cl_elems(int B, int channels, int HW) { return cl_elems(B, channels, HW); }
 
 // One autoregressive step (see include/basic_b200.h basic_ctx_stage_params).  buf / prior are NCHW; the tensor path
