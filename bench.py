@@ -361,7 +361,10 @@ def run_ours(args, rank, world, local_rank):
         if dec_ms > 0:
             ach = (8 + cbytes) * n_sym / (dec_ms * 1e-3) / 1e9  # 4 B index + 4 B symbol + c stream bytes per symbol
             coder_roof = {"kernel": "k_bls_decode (multi-lane rANS decode, one launch per coding group)", "bound": "hbm",
-                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                          "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                          # dram__bytes of the two launches of a step (profiles/r1e_ncu_full_k_bls_coder.csv): indexes + stream
+                          # are read once; the decoded symbols (28 MB) stay in L2 for the dequantiser
+                          "traffic": 45.6e6 if (args.workload == "cfg2" and args.lanes == 0) else None,
                           "decode_ms_per_step": dec_ms, "launches_per_step": phases["coder_decode"]["spans_per_step"],
                           "encode_phase_ms_per_step": enc_ms, "bytes_per_symbol": 8 + cbytes,
                           "decode_msym_s": n_sym / dec_ms / 1e3, "encode_msym_s": n_sym / enc_ms / 1e3 if enc_ms > 0 else None,
@@ -380,9 +383,9 @@ def run_ours(args, rank, world, local_rank):
             ceil = {"fp16x3": "3 FP16 MMAs per product: ceiling = bf16/fp16 peak / 3 (frac 0.333)",
                     "tf32x3": "3 TF32 MMAs per product: ceiling = tf32 peak / 3 = bf16 peak / 6 (frac 0.167)",
                     "fp32": "FP32 FMA pipe, not the tensor pipe"}[mode]
-            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1d_ncu_full_k_layer_tc_fp16x3.csv, cold
+            # dram__bytes_read + write of the 8 launches of one pass (profiles/r1e_ncu_full_k_layer_tc_fp16x3.csv, cold
             # caches under ncu) x 2 passes per step, for the cfg2 geometry only; algorithmic bytes = activations once
-            traffic = 2 * 346.6e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
+            traffic = 2 * 342.7e6 if (args.workload == "cfg2" and mode == "fp16x3") else None
             roofline = {"kernel": kname, "bound": "tensor", "achieved": ach,
                         "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                         "traffic_note": "DRAM bytes per step (16 launches), ncu --set full, cold L2; algorithmic = 2 x 0.59 GB "
