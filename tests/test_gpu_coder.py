@@ -223,6 +223,32 @@ def test_multilane_escape_units_any_bypass_precision(A, cv, bp):
     assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
 
 
+@pytest.mark.parametrize("bp", [4, 2])
+def test_multilane_tables_larger_than_shared_memory(A, bp):
+    """400 tables x 512 symbols = 411 KB of CDFs: the table image does not fit an SM's shared memory, the kernels read it
+    through L2 instead (rans_lanes.cu Tab<false>; both escape instantiations).  Same bytes as the CPU specification."""
+    rng = np.random.default_rng(77 + bp)
+    T, M, n = 400, 512, 40_000
+    freqs = rng.integers(1, 1024, (T, M)).astype(np.int32)
+    nsym, offs = np.full(T, M, np.int32), rng.integers(-300, 1, T).astype(np.int32)
+    idx = rng.integers(0, T, n).astype(np.int32)
+    sym = (rng.integers(0, M + 40, n) + offs[idx] - 20).astype(np.int32)       # a few percent escapes on both sides
+    sym[::97] = rng.integers(-(2 ** 28), 2 ** 28, sym[::97].size)
+    enc, dec = A.Rans64Encoder(lanes=640, bypass_precision=bp), A.Rans64Decoder(lanes=640, bypass_precision=bp)
+    oenc = O.Rans64Encoder(bypass_coding=True, bypass_precision=bp)
+    for c in (enc, dec, oenc):
+        c.init_params(freqs, nsym, offs)
+    bs = enc.encode_with_indexes(sym, idx)
+    chunk = struct.unpack_from("<I", bs, 12)[0]
+    assert bs[4:] == oenc.encode_lanes(sym, idx, chunk)
+    assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
+    e1, d1 = A.Rans64Encoder(lanes=1, bypass_precision=bp), A.Rans64Decoder(lanes=1, bypass_precision=bp)
+    for c in (e1, d1):
+        c.init_params(freqs, nsym, offs)
+    ref = oenc.encode_with_indexes(sym, idx)
+    assert e1.encode_with_indexes(sym, idx) == ref and np.array_equal(d1.decode_with_indexes(ref, idx), sym)
+
+
 def test_multilane_rejects_garbage(A, gauss):
     from cbench_basic_b200 import _native
     _, dec, _, _ = _gauss_pair(A, gauss, 64)
