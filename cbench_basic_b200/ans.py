@@ -190,12 +190,41 @@ class _DecoderMixin:
 class Rans64Encoder(_EncoderMixin, _Rans64):
     _role = N.ROLE_BOTH
 
+    def encode_batch(self, symbols, indexes):
+        """[B, n] symbols / indexes -> B reference (lanes=1) streams, coded by one CTA each in a single launch -- what
+        B calls of encode_with_indexes return (the z node codes one stream per image)."""
+        sym, idx = _Arg(symbols, self.device), _Arg(indexes, self.device)
+        if sym.shape != idx.shape or len(sym.shape) != 2:
+            raise ValueError("symbols and indexes must be [n_streams, n] arrays of the same shape")
+        B, n = sym.shape
+        lens = (C.c_int64 * max(B, 1))()
+        N.check(N.lib().basic_coder_encode_batch(self._h, sym.ptr, idx.ptr, n, B, None, 0, lens, _stream(sym, idx)))
+        blob = N.last_output(self._h)
+        out, at = [], 0
+        for b in range(B):
+            out.append(blob[at:at + lens[b]])
+            at += lens[b]
+        return out
+
     def peek_cache(self):
         raise NotImplementedError("peek_cache exposes the reference's internal symbol list; not provided")
 
 
 class Rans64Decoder(_DecoderMixin, _Rans64):
     _role = N.ROLE_BOTH
+
+    def decode_batch(self, streams, indexes):
+        """B reference (lanes=1) streams + [B, n] indexes -> [B, n] symbols in a single launch (one CTA per stream)."""
+        idx = _Arg(indexes, self.device)
+        if len(idx.shape) != 2 or idx.shape[0] != len(streams):
+            raise ValueError("indexes must be [n_streams, n]")
+        B, n = idx.shape
+        lens = (C.c_int64 * max(B, 1))(*[len(s) for s in streams])
+        enc = np.frombuffer(b"".join(bytes(s) for s in streams), dtype=np.uint8)
+        out, optr = self._out_like(idx, indexes)
+        N.check(N.lib().basic_coder_decode_batch(self._h, enc.ctypes.data if enc.size else 0, lens, B, idx.ptr, n, optr,
+                                                 _stream(idx)))
+        return out
 
 
 class _Tans(_Coder):

@@ -21,9 +21,10 @@ int rans_tables_from_freqs(RansTables &, const int32_t *, int, int, const int32_
 int rans_tables_from_cdfs(RansTables &, const int32_t *, int, int, const int32_t *, const int32_t *, int, cudaStream_t);
 int pmf_to_cdf_device(const float *, int, int, int32_t *);
 int launch_rans64_encode(const RansTables &, const int32_t *, const int32_t *, int64_t, int, int, uint32_t *, int64_t,
-                         long long *, int *, cudaStream_t);
+                         long long *, int *, cudaStream_t, int n_streams = 1);
 int launch_rans64_decode(const RansTables &, const uint32_t *, int64_t, void *, int, const int32_t *, int64_t, int, int,
-                         int32_t *, int *, cudaStream_t);
+                         int32_t *, int *, cudaStream_t, int n_streams = 1, const long long *d_off = nullptr,
+                         const long long *d_nwords = nullptr);
 int launch_bls_encode(const RansTables &, int, int, const int32_t *, const int32_t *, int, const void *, int, uint16_t *, int,
                       uint32_t *, uint32_t *, unsigned char *, long long *, int *, int, cudaStream_t);
 int launch_bls_decode(const RansTables &, int, int, const unsigned char *, int64_t, const int32_t *, int64_t, int, int, int, int,
@@ -165,7 +166,7 @@ struct basic_coder {
     DevBuf d_scale;
     // scratch
     DevBuf in_a, in_b, out_i32, words, first, states, segs, small, stream_dev, y_dev, prior_dev, buf, params, sym_all, idx_all,
-        yhat_stage, slices_dev, carry_x, carry_wp, buf_cl, prior_cl;
+        yhat_stage, slices_dev, carry_x, carry_wp, buf_cl, prior_cl, batch_first, batch_meta, batch_state;
     void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
     // pinned host staging (grow-only): encoded output kept for basic_coder_last_output, and the stream being decoded
     uint8_t *host_out = nullptr, *host_in = nullptr;
@@ -626,7 +627,8 @@ void basic_coder_destroy(basic_coder *c)
     DeviceGuard guard(c->device);
     DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
                       &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
-                      &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp, &c->buf_cl, &c->prior_cl};
+                      &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp, &c->buf_cl, &c->prior_cl, &c->batch_first,
+                      &c->batch_meta, &c->batch_state};
     for (DevBuf *b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->host_out) cudaFreeHost(c->host_out);
@@ -977,6 +979,104 @@ int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, cons
     }
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     return basic_coder_decode_stream(c, indexes, n, out, stream);
+}
+
+// ---- batches of independent reference streams (the z node: one lanes=1 stream per image, compressai_coder.py:233,242) --
+// n_streams runs of n symbols each ([n_streams, n] row-major, host or device) -> n_streams reference rANS64 streams, coded
+// by one CTA each in ONE launch.  The streams are delivered back to back (into `out`, or with out == NULL into the coder's
+// pinned buffer: basic_coder_last_output); out_lens (host, [n_streams]) receives their byte lengths.
+int basic_coder_encode_batch(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, int n_streams, uint8_t *out,
+                             int64_t out_cap, int64_t *out_lens, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind != BASIC_KIND_RANS64) return value_error("batched streams are a rANS call");
+    if (n < 0 || n_streams < 0 || !out_lens) return value_error("negative size");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    BASIC_TRY(finish_out(c));
+    c->last_len = 0;
+    if (n_streams == 0) return BASIC_OK;
+    const int32_t *d_sym, *d_idx;
+    BASIC_TRY(to_device(symbols, (size_t)n * n_streams, c->in_a, s, &d_sym));
+    BASIC_TRY(to_device(indexes, (size_t)n * n_streams, c->in_b, s, &d_idx));
+    BASIC_TRY(c->small.reserve(sizeof(Small)));
+    BASIC_TRY(c->batch_first.reserve(sizeof(long long) * (size_t)n_streams));
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    std::vector<long long> first((size_t)n_streams);
+    int64_t cap_words = 0;
+    for (int attempt = 0;; ++attempt) {
+        cap_words = attempt == 0 ? n + n / 4 + 64 : 12 * n + 64;
+        BASIC_TRY(c->segs.reserve((size_t)cap_words * 4 * (size_t)n_streams));
+        BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
+        BASIC_TRY(launch_rans64_encode(c->rt, d_sym, d_idx, n, c->bypass, (int)c->bypass_precision, c->segs.as<uint32_t>(), cap_words,
+                                       c->batch_first.as<long long>(), &ds->status, s, n_streams));
+        BASIC_CUDA(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaMemcpyAsync(first.data(), c->batch_first.p, sizeof(long long) * (size_t)n_streams, cudaMemcpyDeviceToHost, s));
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        if ((hs->status & 4) && !(hs->status & 3) && attempt == 0) continue;  // escape-heavy input: retry, worst-case size
+        BASIC_TRY(status_error(hs->status));
+        break;
+    }
+    int64_t total = 0;
+    for (int b = 0; b < n_streams; ++b) { out_lens[b] = (cap_words - first[(size_t)b]) * 4; total += out_lens[b]; }
+    uint8_t *dst = out;
+    if (out) {
+        if (total > out_cap) { set_error("output buffer too small"); return BASIC_ERR_CAPACITY; }
+    } else {
+        BASIC_TRY(reserve_pinned(&c->host_out, &c->host_out_cap, (size_t)total));
+        dst = c->host_out;
+        c->last_len = total;
+    }
+    int64_t at = 0;
+    for (int b = 0; b < n_streams; ++b) {
+        const uint32_t *src = c->segs.as<uint32_t>() + (int64_t)b * cap_words + first[(size_t)b];
+        if (out_lens[b]) BASIC_CUDA(cudaMemcpyAsync(dst + at, src, (size_t)out_lens[b], cudaMemcpyDefault, s));
+        at += out_lens[b];
+    }
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return BASIC_OK;
+}
+
+// The mirror: `encoded` holds n_streams reference streams back to back (host or device), lens (host) their byte lengths;
+// every stream decodes n symbols with its row of indexes ([n_streams, n]) into its row of out.
+int basic_coder_decode_batch(basic_coder *c, const uint8_t *encoded, const int64_t *lens, int n_streams, const int32_t *indexes,
+                             int64_t n, int32_t *out, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (c->kind != BASIC_KIND_RANS64) return value_error("batched streams are a rANS call");
+    if (n < 0 || n_streams < 0 || (n_streams && !lens)) return value_error("negative size");
+    if (n_streams == 0 || n == 0) return BASIC_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<long long> meta(2 * (size_t)n_streams);  // word offsets | word counts
+    int64_t total = 0;
+    for (int b = 0; b < n_streams; ++b) {
+        if (lens[b] < 0 || (lens[b] & 3)) return value_error("a reference rANS64 stream is a whole number of 32-bit words");
+        meta[(size_t)b] = total / 4;
+        meta[(size_t)n_streams + b] = lens[b] / 4;
+        total += lens[b];
+    }
+    const int32_t *d_idx;
+    BASIC_TRY(to_device(indexes, (size_t)n * n_streams, c->in_b, s, &d_idx));
+    BASIC_TRY(c->stream_dev.reserve((size_t)total + 64));
+    if (total) BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)total, cudaMemcpyDefault, s));
+    BASIC_TRY(c->batch_meta.reserve(sizeof(long long) * meta.size()));
+    BASIC_CUDA(cudaMemcpyAsync(c->batch_meta.p, meta.data(), sizeof(long long) * meta.size(), cudaMemcpyHostToDevice, s));
+    BASIC_TRY(c->batch_state.reserve(16 * (size_t)n_streams));
+    BASIC_TRY(c->small.reserve(sizeof(Small)));
+    int32_t *d_out = out;
+    const bool out_dev = is_device_ptr(out);
+    if (!out_dev) { BASIC_TRY(c->out_i32.reserve((size_t)n * n_streams * 4 + 16)); d_out = c->out_i32.as<int32_t>(); }
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    BASIC_TRY(launch_rans64_decode(c->rt, c->stream_dev.as<uint32_t>(), 0, c->batch_state.p, 1, d_idx, n, c->bypass,
+                                   (int)c->bypass_precision, d_out, &ds->status, s, n_streams, c->batch_meta.as<long long>(),
+                                   c->batch_meta.as<long long>() + n_streams));
+    BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!out_dev) BASIC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * n_streams * 4, cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    c->stream_set = false;  // stream_dev was reused
+    return status_error(hs->status);
 }
 
 // ------------------------------------------------------------------------------- Gaussian conditional

@@ -44,17 +44,36 @@ __device__ inline void enc_sym_init(EncSym &s, uint32_t start, uint32_t freq, ui
     }
 }
 
-// One CTA.  Words are written back-to-front into out_words[cap_words]; *first_word receives the index of
-// the first word, status: bit0 = index out of range, bit1 = symbol out of range with bypass off,
-// bit2 = capacity exceeded.  state_io: running state for cached/segmented encodes (nullptr = fresh).
+// Tables of the lanes=1 kernels: staged into dynamic shared memory when they fit (the serial thread's chain is
+// record -> LUT -> CDF -> CDF, four dependent loads per symbol: out of L2 that was most of the decoder's time).
+__device__ inline TableView stage_compat_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
+                                                int to_smem, unsigned char *dyn)
+{
+    if (!to_smem) return make_view(blob, meta_bytes, cdf16_bytes);
+    const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+    uint4 *dst = reinterpret_cast<uint4 *>(dyn);
+    for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return make_view(dyn, meta_bytes, cdf16_bytes);
+}
+
+// One CTA per stream (blockIdx.x = stream b of a batch of equally long streams: the z node codes one stream per image).
+// Words are written back-to-front into out_words[b * cap_words .. (b + 1) * cap_words); first_word[b] receives the index
+// (inside that region) of the first word, status: bit0 = index out of range, bit1 = symbol out of range with bypass off,
+// bit2 = capacity exceeded.
 __global__ void __launch_bounds__(kThreads)
 k_rans64_encode(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, long long n,
-                const void *__restrict__ blob, size_t meta_bytes, size_t cdf16_bytes, int T, int precision, int bypass,
-                int bypass_precision, uint32_t *__restrict__ out_words, long long cap_words, long long *first_word,
-                int *status)
+                const void *__restrict__ blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes, int tables_in_smem, int T,
+                int precision, int bypass, int bypass_precision, uint32_t *__restrict__ out_words, long long cap_words,
+                long long *first_word, int *status)
 {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    symbols += (long long)blockIdx.x * n;
+    indexes += (long long)blockIdx.x * n;
+    out_words += (long long)blockIdx.x * cap_words;
+    first_word += blockIdx.x;
     __shared__ EncSym sm[kEncTile];
-    const TableView tv = make_view(blob, meta_bytes, cdf16_bytes);
+    const TableView tv = stage_compat_tables(blob, blob_bytes, meta_bytes, cdf16_bytes, tables_in_smem, dyn_smem);
     const int tid = threadIdx.x;
     unsigned long long x = kL64;
     long long p = cap_words;
@@ -146,16 +165,24 @@ __device__ inline uint32_t getbits64(unsigned long long &x, const uint32_t *__re
     return v;
 }
 
-// One CTA: thread 0 walks the stream, everybody stages indexes in / symbols out through shared memory.
+// One CTA per stream: thread 0 walks the stream, everybody stages indexes in / symbols out through shared memory.
+// Batch of equally long symbol runs (blockIdx.x = b): stream b is words[stream_off[b] .. + stream_nwords[b]) (both arrays
+// NULL for a single stream of `nwords` words), its state state[b], its operands indexes / out + b * n.
 __global__ void __launch_bounds__(kThreads)
-k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, DecState *state, int init_state,
-                const int32_t *__restrict__ indexes, long long n, const void *__restrict__ blob, size_t meta_bytes,
-                size_t cdf16_bytes, int T, int precision, int bypass, int bypass_precision, int32_t *__restrict__ out,
-                int *status)
+k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, const long long *__restrict__ stream_off,
+                const long long *__restrict__ stream_nwords, DecState *state, int init_state,
+                const int32_t *__restrict__ indexes, long long n, const void *__restrict__ blob, size_t blob_bytes, size_t meta_bytes,
+                size_t cdf16_bytes, int tables_in_smem, int T, int precision, int bypass, int bypass_precision,
+                int32_t *__restrict__ out, int *status)
 {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    if (stream_off) { words += stream_off[blockIdx.x]; nwords = stream_nwords[blockIdx.x]; }
+    state += blockIdx.x;
+    indexes += (long long)blockIdx.x * n;
+    out += (long long)blockIdx.x * n;
     __shared__ int32_t s_idx[kTile];
     __shared__ int32_t s_out[kTile];
-    const TableView tv = make_view(blob, meta_bytes, cdf16_bytes);
+    const TableView tv = stage_compat_tables(blob, blob_bytes, meta_bytes, cdf16_bytes, tables_in_smem, dyn_smem);
     const int tid = threadIdx.x;
     unsigned long long x = 0;
     long long pos = 0;
@@ -217,24 +244,50 @@ k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, DecState *
 
 }  // namespace
 
+// the table image goes to shared memory when it fits beside the kernel's static tiles
+static int compat_table_smem(const RansTables &tb, size_t static_bytes)
+{
+    return tb.blob_bytes + static_bytes + 2048 <= 227 * 1024 ? (int)tb.blob_bytes : 0;
+}
+static int compat_attrs()
+{
+    static bool attr_done = false;
+    if (!attr_done) {
+        BASIC_CUDA(cudaFuncSetAttribute(k_rans64_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(sizeof(EncSym) * kEncTile)));
+        BASIC_CUDA(cudaFuncSetAttribute(k_rans64_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(2 * sizeof(int32_t) * kTile)));
+        attr_done = true;
+    }
+    return BASIC_OK;
+}
+
+// n_streams equally long runs of n symbols each, coded as independent streams by one CTA each; stream b's words end at
+// d_words + (b + 1) * cap_words and start at d_first[b] inside its region.
 int launch_rans64_encode(const RansTables &tb, const int32_t *d_sym, const int32_t *d_idx, int64_t n, int bypass,
                          int bypass_precision, uint32_t *d_words, int64_t cap_words, long long *d_first, int *d_status,
-                         cudaStream_t stream)
+                         cudaStream_t stream, int n_streams)
 {
-    k_rans64_encode<<<1, kThreads, 0, stream>>>(d_sym, d_idx, n, tb.blob.p, tb.meta_bytes, tb.cdf16_bytes, tb.T,
-                                                tb.precision, bypass, bypass_precision, d_words, cap_words, d_first,
-                                                d_status);
+    BASIC_TRY(compat_attrs());
+    if (n_streams < 1) return BASIC_OK;
+    const int smem = compat_table_smem(tb, sizeof(EncSym) * kEncTile);
+    k_rans64_encode<<<n_streams, kThreads, smem, stream>>>(d_sym, d_idx, n, tb.blob.p, tb.blob_bytes, tb.meta_bytes, tb.cdf16_bytes,
+                                                           smem > 0, tb.T, tb.precision, bypass, bypass_precision, d_words,
+                                                           cap_words, d_first, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
 
+// d_off / d_nwords: per-stream word offsets and lengths of a batch (device arrays), or NULL for one stream of `nwords`.
 int launch_rans64_decode(const RansTables &tb, const uint32_t *d_words, int64_t nwords, void *d_state, int init_state,
                          const int32_t *d_idx, int64_t n, int bypass, int bypass_precision, int32_t *d_out, int *d_status,
-                         cudaStream_t stream)
+                         cudaStream_t stream, int n_streams, const long long *d_off, const long long *d_nwords)
 {
-    k_rans64_decode<<<1, kThreads, 0, stream>>>(d_words, nwords, reinterpret_cast<DecState *>(d_state), init_state, d_idx,
-                                                n, tb.blob.p, tb.meta_bytes, tb.cdf16_bytes, tb.T, tb.precision, bypass,
-                                                bypass_precision, d_out, d_status);
+    BASIC_TRY(compat_attrs());
+    if (n_streams < 1) return BASIC_OK;
+    const int smem = compat_table_smem(tb, 2 * sizeof(int32_t) * kTile);
+    k_rans64_decode<<<n_streams, kThreads, smem, stream>>>(d_words, nwords, d_off, d_nwords, reinterpret_cast<DecState *>(d_state),
+                                                           init_state, d_idx, n, tb.blob.p, tb.blob_bytes, tb.meta_bytes,
+                                                           tb.cdf16_bytes, smem > 0, tb.T, tb.precision, bypass, bypass_precision,
+                                                           d_out, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

@@ -286,7 +286,16 @@ int rans_tables_from_cdfs(RansTables &tb, const int32_t *cdfs, int T, int M, con
 int pmf_to_cdf_device(const float *pmf, int n, int precision, int32_t *cdf_out)
 {
     if (n < 1) return value_error("empty pmf");
-    DevBuf d_pmf, d_cdf, d_err;
+    // grow-only scratch kept per thread and device (the z node converts one pmf per channel: a cudaMalloc / cudaFree
+    // triple per call made its update_state() take seconds)
+    static thread_local DevBuf d_pmf, d_cdf, d_err;
+    static thread_local int scratch_device = -1;
+    int dev = 0;
+    BASIC_CUDA(cudaGetDevice(&dev));
+    if (dev != scratch_device) {
+        d_pmf = DevBuf(); d_cdf = DevBuf(); d_err = DevBuf();  // (buffers of another device are left to that context)
+        scratch_device = dev;
+    }
     BASIC_TRY(d_pmf.reserve(sizeof(float) * n));
     BASIC_TRY(d_cdf.reserve(sizeof(int32_t) * (n + 1)));
     BASIC_TRY(d_err.reserve(sizeof(int)));
@@ -299,9 +308,6 @@ int pmf_to_cdf_device(const float *pmf, int n, int precision, int32_t *cdf_out)
     int err = 0;
     BASIC_CUDA(cudaMemcpy(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
     BASIC_CUDA(cudaMemcpy(cdf_out, d_cdf.p, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
-    d_pmf.release();
-    d_cdf.release();
-    d_err.release();
     if (err) return value_error("pmf_to_quantized_cdf: cannot normalise table");
     return BASIC_OK;
 }

@@ -19,8 +19,9 @@ Parity status: stream format and framing PINNED (golden vectors made with the re
 tests/golden/make_z_golden.py); the CDF construction out of the network parameters is **parity unpinned** -- compressai is
 absent from this image, so nothing can run the original.
 
-Every image is one lanes=1 stream (the reference's format); they are coded by the CUDA coder through the C ABI
-(`ans.Rans64Encoder / Rans64Decoder`, tables resident on the device).  Quantisation is two elementwise torch ops on the
+Every image is one lanes=1 stream (the reference's format); all images of a call are coded in ONE launch, one CTA per
+stream, through the C ABI (`basic_coder_encode_batch / _decode_batch`, tables resident on the device, staged into shared
+memory by every CTA).  Quantisation is two elementwise torch ops on the
 device (N_z = N / 16: not a hot spot).  No CPU fallback: without the library or a GPU the coder raises.
 """
 import io
@@ -172,7 +173,9 @@ class EntropyBottleneck(nn.Module):
         med = self._get_medians().to(dev).view(1, -1, *([1] * (x.dim() - 2)))
         sym = torch.round(x - med).to(torch.int32)
         idx = self._indexes(x.shape[0], x.shape[2:], dev)
-        return [self._enc.encode_with_indexes(sym[i].reshape(-1), idx[i].reshape(-1)) for i in range(x.shape[0])]
+        if x.shape[0] == 0:
+            return []
+        return self._enc.encode_batch(sym.reshape(x.shape[0], -1), idx.reshape(x.shape[0], -1))  # one CTA per image
 
     @torch.no_grad()
     def decompress(self, strings, size):
@@ -182,10 +185,10 @@ class EntropyBottleneck(nn.Module):
         spatial = tuple(int(s) for s in size)
         idx = self._indexes(len(strings), spatial, dev)
         med = self._get_medians().to(dev).view(1, -1, *([1] * len(spatial)))
-        out = torch.empty(len(strings), self.channels, *spatial, dtype=torch.float32, device=dev)
-        for i, s in enumerate(strings):
-            out[i] = self._dec.decode_with_indexes(s, idx[i]).to(torch.float32) + med[0]
-        return out
+        if len(strings) == 0:
+            return torch.empty(0, self.channels, *spatial, dtype=torch.float32, device=dev)
+        sym = self._dec.decode_batch(strings, idx.reshape(len(strings), -1))            # one CTA per image
+        return sym.view(len(strings), self.channels, *spatial).to(torch.float32) + med
 
 
 class CompressAIEntropyBottleneckPriorCoder(nn.Module):

@@ -92,6 +92,16 @@ int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, cons
 int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, int lanes, void *stream);
 int basic_coder_decode_stream(basic_coder *c, const int32_t *indexes, int64_t n, int32_t *out, void *stream);
 
+/* ---- batches of independent reference streams (the z node: compressai_coder.py:233,242 code one stream per image) --
+ * n_streams runs of n symbols each ([n_streams, n] row-major, host or device) become n_streams lanes=1 rANS64 streams in
+ * ONE launch (one CTA per stream), delivered back to back into `out` (or, with out == NULL, into the coder's pinned
+ * buffer: basic_coder_last_output / _take_output); out_lens: host int64 [n_streams], the byte length of every stream.
+ * basic_coder_decode_batch is the mirror: `encoded` = the streams back to back, lens = their lengths (host). */
+int basic_coder_encode_batch(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, int n_streams,
+                             uint8_t *out, int64_t out_cap, int64_t *out_lens, void *stream);
+int basic_coder_decode_batch(basic_coder *c, const uint8_t *encoded, const int64_t *lens, int n_streams,
+                             const int32_t *indexes, int64_t n, int32_t *out, void *stream);
+
 /* ---- Gaussian conditional: quantise + scale index (pgm_coder.py:802-821,927-941; torch_ans.py:105-159) -- */
 /* scale_table: host float [n_scales] (compressai_coder.py:23-30). */
 int basic_coder_set_scale_table(basic_coder *c, const float *scale_table, int n_scales);

@@ -154,6 +154,28 @@ def test_cache_and_flush_lanes1(A, cv):
     assert enc.flush() == cv["b_rans"].tobytes()      # == one stream over the concatenation (what _encode_with_pgm builds)
 
 
+def test_lanes1_batch_of_streams(A, cv, gauss):
+    """encode_batch / decode_batch: B independent reference streams in one launch (one CTA per stream) = what B single calls
+    give, byte for byte; numpy and CUDA-tensor operands; escapes; an empty batch."""
+    enc, dec = _mk(A, cv, "b_offsets")
+    data, idx = cv["a_data"].reshape(6, -1)[:, :3000].copy(), cv["a_idx"].reshape(6, -1)[:, :3000].copy()
+    data[2, ::50] = 100_000
+    data[4, 1::70] = -70_000
+    singles = [enc.encode_with_indexes(data[b], idx[b]) for b in range(6)]
+    assert enc.encode_batch(data, idx) == singles
+    assert np.array_equal(dec.decode_batch(singles, idx), data)
+    g_enc, g_dec, oenc, _ = _gauss_pair(A, gauss, 1)
+    sym, ix = _gauss_data(gauss, 24 * 18432, 3, geometric=True)
+    sym, ix = sym.reshape(24, -1), ix.reshape(24, -1)
+    bs = g_enc.encode_batch(torch.from_numpy(sym).cuda(), torch.from_numpy(ix).cuda())
+    assert bs == [oenc.encode_with_indexes(sym[b], ix[b]) for b in range(24)]
+    out = g_dec.decode_batch(bs, torch.from_numpy(ix).cuda())
+    assert out.is_cuda and torch.equal(out.cpu(), torch.from_numpy(sym))
+    assert enc.encode_batch(np.zeros((0, 5), np.int32), np.zeros((0, 5), np.int32)) == []
+    with pytest.raises(ValueError):
+        dec.decode_batch([singles[0][:-4]], idx[:1])               # a word short: truncated stream
+
+
 # ------------------------------------------------------------------------ multi-lane: format + lossless
 @pytest.mark.parametrize("lanes", [32, 64, 1000, 4096])
 def test_multilane_matches_cpu_spec_and_is_lossless(A, cv, lanes):
