@@ -113,6 +113,57 @@ __host__ __device__ inline TableView make_view(const void *blob, size_t meta_byt
     return v;
 }
 
+#ifdef __CUDACC__
+// Table access of the coding kernels.  SM = true: the blob was staged into shared memory and is read with ld.shared
+// through 32-bit window addresses (a generic pointer that may be global or shared compiles to generic loads plus 64-bit
+// address arithmetic on the state's dependency chain -- it was 40 % of the decoder's step); SM = false: tables larger
+// than the shared memory of an SM stay in HBM / L2 and are read through the read-only path.
+// The loads are plain (non-volatile) asm: the tables never change after staging, so the compiler may hoist them off the
+// chain; init() orders them behind the staging barrier.
+template <bool SM> struct Tab;
+template <> struct Tab<true> {
+    typedef uint32_t addr_t;
+    uint32_t meta, cdf, lut;
+    __device__ void init(const void *, unsigned char *smem, size_t meta_bytes, size_t cdf16_bytes)
+    {
+        uint32_t b = (uint32_t)__cvta_generic_to_shared(smem);
+        asm volatile("" : "+r"(b)::"memory");
+        meta = b;
+        cdf = b + (uint32_t)meta_bytes;
+        lut = cdf + (uint32_t)cdf16_bytes;
+    }
+    __device__ uint4 meta_at(int c) const
+    {
+        uint4 v;
+        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(meta + (uint32_t)c * 16u));
+        return v;
+    }
+    __device__ addr_t cdf_at(uint32_t entry) const { return cdf + 2u * entry; }
+    __device__ addr_t lut_at(uint32_t entry) const { return lut + 2u * entry; }
+    template <int OFF> static __device__ uint32_t ld16(addr_t a)
+    {
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF));
+        return v;
+    }
+};
+template <> struct Tab<false> {
+    typedef const unsigned char *addr_t;
+    const unsigned char *meta, *cdf, *lut;
+    __device__ void init(const void *blob, unsigned char *, size_t meta_bytes, size_t cdf16_bytes)
+    {
+        meta = reinterpret_cast<const unsigned char *>(blob);
+        cdf = meta + meta_bytes;
+        lut = cdf + cdf16_bytes;
+    }
+    __device__ uint4 meta_at(int c) const { return __ldg(reinterpret_cast<const uint4 *>(meta) + c); }
+    __device__ addr_t cdf_at(uint32_t entry) const { return cdf + 2ull * entry; }
+    __device__ addr_t lut_at(uint32_t entry) const { return lut + 2ull * entry; }
+    template <int OFF> static __device__ uint32_t ld16(addr_t a) { return __ldg(reinterpret_cast<const uint16_t *>(a + OFF)); }
+};
+
+#endif  // __CUDACC__
+
 static constexpr int kLanes = 32;             // lanes of one chunk = one warp
 static constexpr uint32_t kRansL = 1u << 16;  // multi-lane state lower bound
 static constexpr uint32_t kMagic = 0x31534C42u;   // "BLS1"

@@ -107,8 +107,10 @@ k_rans64_encode(const int32_t *__restrict__ symbols, const int32_t *__restrict__
         }
         __syncthreads();
         if (tid == 0) {
+            EncSym nxt = sm[cnt - 1];  // operands of the next symbol are fetched while the current one is coded
             for (int k = cnt - 1; k >= 0; --k) {
-                const EncSym s = sm[k];
+                const EncSym s = nxt;
+                if (k > 0) nxt = sm[k - 1];
                 if (s.shift_esc & 0x100) {  // escape tokens, pushed last to first (rans64.cpp:293-335)
                     const uint32_t raw = s.raw;
                     int nd = 0;
@@ -125,7 +127,7 @@ k_rans64_encode(const int32_t *__restrict__ symbols, const int32_t *__restrict__
                         x = (x << bp) | tok;
                     }
                 }
-                const unsigned long long x_max = ((kL64 >> precision) << 32) * (unsigned long long)s.freq;
+                const unsigned long long x_max = (unsigned long long)s.freq << (63 - precision);  // ((L >> prec) << 32) * freq
                 if (x >= x_max) {
                     if (p > 0) out_words[--p] = (uint32_t)x; else st |= 4;
                     x >>= 32;
@@ -151,29 +153,38 @@ struct DecState {
     long long pos;  // next word to read
 };
 
+// rans64.cpp:49-65 with the next word of the stream held in a register (`nw` = words[pos], fetched when the previous one
+// was consumed): the serial thread never waits for a global load inside a renormalisation.
+__device__ inline void pull_word(unsigned long long &x, const uint32_t *__restrict__ w, long long &pos, long long nwords,
+                                 uint32_t &nw, int &st)
+{
+    if (pos >= nwords) st |= 4;
+    x = (x << 32) | nw;
+    ++pos;
+    nw = pos < nwords ? w[pos] : 0u;
+}
+
 __device__ inline uint32_t getbits64(unsigned long long &x, const uint32_t *__restrict__ w, long long &pos,
-                                     long long nwords, uint32_t nb, int &st)
-{  // rans64.cpp:49-65
+                                     long long nwords, uint32_t nb, uint32_t &nw, int &st)
+{
     const uint32_t v = (uint32_t)(x & ((1u << nb) - 1));
     x >>= nb;
-    if (x < kL64) {
-        uint32_t word = 0;
-        if (pos < nwords) word = w[pos]; else st |= 4;
-        ++pos;
-        x = (x << 32) | word;
-    }
+    if (x < kL64) pull_word(x, w, pos, nwords, nw, st);
     return v;
 }
 
 // One CTA per stream: thread 0 walks the stream, everybody stages indexes in / symbols out through shared memory.
 // Batch of equally long symbol runs (blockIdx.x = b): stream b is words[stream_off[b] .. + stream_nwords[b]) (both arrays
 // NULL for a single stream of `nwords` words), its state state[b], its operands indexes / out + b * n.
+// The serial chain per symbol is  LUT -> four CDF entries at once -> 64-bit multiply-add -> (word from a register);  the
+// table record of the NEXT symbol is fetched while the current one is decoded (common.cuh Tab<SM>, ld.shared when the
+// image fits).
+template <bool SM>
 __global__ void __launch_bounds__(kThreads)
 k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, const long long *__restrict__ stream_off,
                 const long long *__restrict__ stream_nwords, DecState *state, int init_state,
                 const int32_t *__restrict__ indexes, long long n, const void *__restrict__ blob, size_t blob_bytes, size_t meta_bytes,
-                size_t cdf16_bytes, int tables_in_smem, int T, int precision, int bypass, int bypass_precision,
-                int32_t *__restrict__ out, int *status)
+                size_t cdf16_bytes, int T, int precision, int bypass, int bypass_precision, int32_t *__restrict__ out, int *status)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     if (stream_off) { words += stream_off[blockIdx.x]; nwords = stream_nwords[blockIdx.x]; }
@@ -182,16 +193,25 @@ k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, const long
     out += (long long)blockIdx.x * n;
     __shared__ int32_t s_idx[kTile];
     __shared__ int32_t s_out[kTile];
-    const TableView tv = stage_compat_tables(blob, blob_bytes, meta_bytes, cdf16_bytes, tables_in_smem, dyn_smem);
+    if (SM) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(dyn_smem);
+        for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    Tab<SM> tb;
+    tb.init(blob, dyn_smem, meta_bytes, cdf16_bytes);
     const int tid = threadIdx.x;
     unsigned long long x = 0;
     long long pos = 0;
+    uint32_t nw = 0;
     int st = 0;
     if (tid == 0) {
         if (init_state) {  // set_stream: rans64.hpp:104-111, Rans64DecInit rans64.h:106-115
             if (nwords >= 2) { x = (unsigned long long)words[0] | ((unsigned long long)words[1] << 32); pos = 2; }
             else st |= 4;
         } else { x = state->x; pos = state->pos; }
+        nw = pos < nwords ? words[pos] : 0u;
     }
     const uint32_t bp = (uint32_t)bypass_precision, maxb = (1u << bp) - 1;
     const uint32_t pmask = (1u << precision) - 1;
@@ -205,34 +225,44 @@ k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, const long
         }
         __syncthreads();
         if (tid == 0) {
+            uint4 rec = tb.meta_at(s_idx[0]);  // cdf_base | lut_base | cdf_size, lut_shift | offset
             for (int k = 0; k < cnt; ++k) {
-                const TableMeta m = tv.meta[s_idx[k]];
-                const uint16_t *cd = tv.cdf + m.cdf_base;
-                const int nsyms = (int)m.cdf_size - 1, maxv = nsyms - 1;
+                const uint4 m = rec;
+                if (k + 1 < cnt) rec = tb.meta_at(s_idx[k + 1]);
+                const typename Tab<SM>::addr_t cd = tb.cdf_at(m.x);
+                const int nsyms = (int)(m.z & 0xffffu) - 1, maxv = nsyms - 1;
                 const uint32_t cum = (uint32_t)x & pmask;
-                int s = tv.lut[m.lut_base + (cum >> m.lut_shift)];
-                while (s + 1 < nsyms && cd[s + 1] <= cum) ++s;
-                const uint32_t start = cd[s], freq = (uint16_t)(cd[s + 1] - start);
-                x = (unsigned long long)freq * (x >> precision) + cum - start;
-                if (x < kL64) {
-                    uint32_t word = 0;
-                    if (pos < nwords) word = words[pos]; else st |= 4;
-                    ++pos;
-                    x = (x << 32) | word;
+                int s = (int)Tab<SM>::template ld16<0>(tb.lut_at(m.y + (cum >> ((m.z >> 16) & 0xffu))));
+                const typename Tab<SM>::addr_t e = cd + 2 * s;
+                const uint32_t c0 = Tab<SM>::template ld16<0>(e), c1 = Tab<SM>::template ld16<2>(e);
+                const uint32_t c2 = Tab<SM>::template ld16<4>(e), c3 = Tab<SM>::template ld16<6>(e);
+                const bool a1 = s + 1 < nsyms && c1 <= cum;
+                const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
+                const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
+                uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
+                s += (int)a1 + (int)a2;
+                if (a3) {  // rans64.cpp:456-460 walks the table linearly; so does a bucket of width-1 symbols
+                    ++s;
+                    while (s + 1 < nsyms && Tab<SM>::template ld16<2>(cd + 2 * s) <= cum) ++s;
+                    start = Tab<SM>::template ld16<0>(cd + 2 * s);
+                    next = Tab<SM>::template ld16<2>(cd + 2 * s);
                 }
+                const uint32_t freq = (uint16_t)(next - start);
+                x = (unsigned long long)freq * (x >> precision) + cum - start;
+                if (x < kL64) pull_word(x, words, pos, nwords, nw, st);
                 int32_t value = s;
                 if (bypass && s == maxv) {
-                    uint32_t val = getbits64(x, words, pos, nwords, bp, st), nb = val;
-                    while (val == maxb && nb < 64) { val = getbits64(x, words, pos, nwords, bp, st); nb += val; }
+                    uint32_t val = getbits64(x, words, pos, nwords, bp, nw, st), nb = val;
+                    while (val == maxb && nb < 64) { val = getbits64(x, words, pos, nwords, bp, nw, st); nb += val; }
                     uint32_t raw = 0;
                     for (uint32_t j = 0; j < nb; ++j) {
-                        val = getbits64(x, words, pos, nwords, bp, st);
+                        val = getbits64(x, words, pos, nwords, bp, nw, st);
                         if (j * bp < 32) raw |= val << (j * bp);
                     }
                     value = (int32_t)(raw >> 1);
                     value = (raw & 1) ? -value - 1 : value + maxv;
                 }
-                s_out[k] = value + m.offset;
+                s_out[k] = value + (int32_t)m.w;
             }
         }
         __syncthreads();
@@ -254,7 +284,7 @@ static int compat_attrs()
     static bool attr_done = false;
     if (!attr_done) {
         BASIC_CUDA(cudaFuncSetAttribute(k_rans64_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(sizeof(EncSym) * kEncTile)));
-        BASIC_CUDA(cudaFuncSetAttribute(k_rans64_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(2 * sizeof(int32_t) * kTile)));
+        BASIC_CUDA(cudaFuncSetAttribute(k_rans64_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(2 * sizeof(int32_t) * kTile)));
         attr_done = true;
     }
     return BASIC_OK;
@@ -284,10 +314,10 @@ int launch_rans64_decode(const RansTables &tb, const uint32_t *d_words, int64_t 
     BASIC_TRY(compat_attrs());
     if (n_streams < 1) return BASIC_OK;
     const int smem = compat_table_smem(tb, 2 * sizeof(int32_t) * kTile);
-    k_rans64_decode<<<n_streams, kThreads, smem, stream>>>(d_words, nwords, d_off, d_nwords, reinterpret_cast<DecState *>(d_state),
-                                                           init_state, d_idx, n, tb.blob.p, tb.blob_bytes, tb.meta_bytes,
-                                                           tb.cdf16_bytes, smem > 0, tb.T, tb.precision, bypass, bypass_precision,
-                                                           d_out, d_status);
+    auto kern = smem > 0 ? k_rans64_decode<true> : k_rans64_decode<false>;
+    kern<<<n_streams, kThreads, smem, stream>>>(d_words, nwords, d_off, d_nwords, reinterpret_cast<DecState *>(d_state), init_state, d_idx,
+                                                n, tb.blob.p, tb.blob_bytes, tb.meta_bytes, tb.cdf16_bytes, tb.T, tb.precision, bypass,
+                                                bypass_precision, d_out, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
