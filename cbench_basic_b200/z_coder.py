@@ -70,8 +70,9 @@ class EntropyBottleneck(nn.Module):
     of the original, so a trained reference checkpoint loads)."""
 
     def __init__(self, channels, *args, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3), likelihood_bound=1e-9,
-                 entropy_coder_precision=16, device_index=0, **kwargs):
+                 entropy_coder_precision=16, device_index=0, lanes=1, **kwargs):
         super().__init__()
+        self.lanes = int(lanes)
         self.channels = int(channels)
         self.filters = tuple(int(f) for f in filters)
         self.init_scale = float(init_scale)
@@ -154,8 +155,8 @@ class EntropyBottleneck(nn.Module):
     def _push_tables(self):
         if self._quantized_cdf.numel() == 0:
             raise ValueError("Uninitialized CDFs. Run update() first")
-        self._enc = ans.Rans64Encoder(freq_precision=self.entropy_coder_precision, lanes=1, device=self.device_index)
-        self._dec = ans.Rans64Decoder(freq_precision=self.entropy_coder_precision, lanes=1, device=self.device_index)
+        self._enc = ans.Rans64Encoder(freq_precision=self.entropy_coder_precision, lanes=self.lanes, device=self.device_index)
+        self._dec = ans.Rans64Decoder(freq_precision=self.entropy_coder_precision, lanes=self.lanes, device=self.device_index)
         for c in (self._enc, self._dec):
             c.init_cdf_params(self._quantized_cdf.cpu().numpy(), self._cdf_length.cpu().numpy(), self._offset.cpu().numpy())
 
@@ -175,6 +176,8 @@ class EntropyBottleneck(nn.Module):
         idx = self._indexes(x.shape[0], x.shape[2:], dev)
         if x.shape[0] == 0:
             return []
+        if self.lanes != 1:  # our multi-lane container over the whole batch: u32 batch size | container
+            return [struct.pack("<I", x.shape[0]) + self._enc.encode_with_indexes(sym.reshape(-1), idx.reshape(-1))]
         return self._enc.encode_batch(sym.reshape(x.shape[0], -1), idx.reshape(x.shape[0], -1))  # one CTA per image
 
     @torch.no_grad()
@@ -183,6 +186,14 @@ class EntropyBottleneck(nn.Module):
             self._push_tables()
         dev = torch.device("cuda", self.device_index)
         spatial = tuple(int(s) for s in size)
+        if self.lanes != 1 and len(strings) == 1:
+            if len(strings[0]) < 4:
+                raise ValueError("z stream truncated")
+            (B,) = struct.unpack_from("<I", strings[0], 0)
+            idx = self._indexes(B, spatial, dev)
+            med = self._get_medians().to(dev).view(1, -1, *([1] * len(spatial)))
+            sym = self._dec.decode_with_indexes(strings[0][4:], idx.reshape(-1))
+            return sym.view(B, self.channels, *spatial).to(torch.float32) + med
         idx = self._indexes(len(strings), spatial, dev)
         med = self._get_medians().to(dev).view(1, -1, *([1] * len(spatial)))
         if len(strings) == 0:
@@ -196,9 +207,11 @@ class CompressAIEntropyBottleneckPriorCoder(nn.Module):
     update_state().  Training forward() (likelihoods, aux loss) stays with the reference module."""
 
     def __init__(self, entropy_bottleneck_channels=256, eps=1e-7, use_inner_aux_opt=False, use_bit_rate_loss=True,
-                 freeze_params=False, training_output_straight_through=False, device_index=0, **kwargs):
+                 freeze_params=False, training_output_straight_through=False, device_index=0, lanes=1, **kwargs):
         super().__init__()
-        self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels, device_index=device_index)
+        # lanes = 1: the reference's streams (one per image).  lanes = 0 / N: ONE multi-lane container (DESIGN.md section 4)
+        # over the whole batch inside the same write_body framing -- not readable by compressai, ~30x faster
+        self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels, device_index=device_index, lanes=lanes)
         self.eps = eps
         if freeze_params:
             for p in self.parameters():

@@ -136,3 +136,21 @@ def test_gpu_round_trip_with_gains_and_empty_batch():
     assert float((y_hat.cpu() * gains.view(1, -1, 1, 1) - x * gains.view(1, -1, 1, 1)).abs().max()) <= 0.5 + 1e-4
     empty = coder.encode(torch.zeros(0, C_, 3, 7).cuda())
     assert coder.decode(empty).shape == (0, C_, 3, 7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_multilane_z_container(zv, name):
+    """lanes = 0: the whole batch in one multi-lane container behind the same framing; same symbols as the reference
+    streams (y_hat identical), lossless, and not larger than the per-image streams plus the lane flush."""
+    C_ = zv[name + "/x"].shape[1]
+    coder = z_coder.CompressAIEntropyBottleneckPriorCoder(entropy_bottleneck_channels=C_, lanes=0)
+    eb = coder.entropy_bottleneck
+    eb.load_state_dict(dict(_sd(zv, name), target=eb.target.clone(), _offset=torch.from_numpy(zv[name + "/offset"]),
+                            _quantized_cdf=torch.from_numpy(zv[name + "/cdf"]), _cdf_length=torch.from_numpy(zv[name + "/cdf_length"])))
+    x = torch.from_numpy(zv[name + "/x"])
+    body = coder.encode(x.cuda())
+    strings, shape = z_coder.read_body(body)
+    assert len(strings) == 1 and strings[0][4:8] == b"BLS1" and tuple(shape) == tuple(x.shape[-2:])
+    assert torch.equal(coder.decode(body).cpu(), torch.from_numpy(zv[name + "/y_hat"]))
+    assert len(body) <= len(zv[name + "/body"]) + 200

@@ -5,7 +5,8 @@ sys.path.insert(0, REPO)
 from cbench_basic_b200 import z_coder
 from oracle import z_oracle as Z
 C_, B, H, W = 192, 24, 8, 12
-coder = z_coder.CompressAIEntropyBottleneckPriorCoder(entropy_bottleneck_channels=C_)
+lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+coder = z_coder.CompressAIEntropyBottleneckPriorCoder(entropy_bottleneck_channels=C_, lanes=lanes)
 eb = coder.entropy_bottleneck
 eb.load_state_dict(dict(Z.init_params(C_, seed=3), target=eb.target.clone(), _offset=torch.IntTensor(),
                         _quantized_cdf=torch.IntTensor(), _cdf_length=torch.IntTensor()))
@@ -20,4 +21,4 @@ torch.cuda.synchronize(); te = (time.perf_counter() - t) / 10
 t = time.perf_counter()
 for _ in range(10): y = coder.decode(bs)
 torch.cuda.synchronize(); td = (time.perf_counter() - t) / 10
-print(f"encode {te*1e3:.3f} ms, decode {td*1e3:.3f} ms, {len(bs)} bytes, {B*C_*H*W} symbols, max err {float((y - x).abs().max()):.3f}")
+print(f"lanes {lanes}: encode {te*1e3:.3f} ms, decode {td*1e3:.3f} ms, {len(bs)} bytes, {B*C_*H*W} symbols, max err {float((y - x).abs().max()):.3f}")
