@@ -152,8 +152,27 @@ def context_model(buf, tg, prior, w):
     return masked_conv(F.leaky_relu(m), tg, w["m3_w"], w["m3_b"], allow_same=True)
 
 
+def internal_merger(buf, tg, prior, w):
+    """The coder's own context_prediction + param_merger (no topo_group_context_model): pgm_coder.py:1177-1239 and
+    _merge_prior_params :1606-1638 -- three masked 1x1 convolutions over 2G channel groups [ctx groups (ids = map),
+    prior groups (id -1)], all with the <= rule, every out-group computed in every layer, the first G kept at the end."""
+    G = tg.shape[1]
+    ctx = masked_conv(buf, tg, w["ctx_w"], w["ctx_b"], allow_same=False)
+    cat_tg = torch.cat([tg, torch.zeros_like(tg) - 1], dim=1)
+    m = masked_conv(torch.cat([ctx, prior], dim=1), cat_tg, w["pm0_w"], w["pm0_b"], allow_same=True)
+    m = masked_conv(F.leaky_relu(m), cat_tg, w["pm2_w"], w["pm2_b"], allow_same=True)
+    m = masked_conv(F.leaky_relu(m), cat_tg, w["pm4_w"], w["pm4_b"], allow_same=True)
+    B, out = m.shape[0], ctx.shape[1]
+    return m.reshape(B, 2 * G, out // G, *m.shape[2:])[:, :G].reshape(B, out, *m.shape[2:])
+
+
 def weights_from_state_dict(sd, prefix="topo_group_context_model."):
     g = lambda k: sd[prefix + k].detach().float().cpu()
+    if prefix + "param_merger.0.weight" in sd:   # the internal variant
+        return {"ctx_w": g("context_prediction.weight"), "ctx_b": g("context_prediction.bias"),
+                "pm0_w": g("param_merger.0.weight"), "pm0_b": g("param_merger.0.bias"),
+                "pm2_w": g("param_merger.2.weight"), "pm2_b": g("param_merger.2.bias"),
+                "pm4_w": g("param_merger.4.weight"), "pm4_b": g("param_merger.4.bias")}
     return {"ctx_w": g("context_prediction.weight"), "ctx_b": g("context_prediction.bias"),
             "m1_w": g("param_merger_in.weight"), "m1_b": g("param_merger_in.bias"),
             "m2_w": g("param_merger_out.1.weight"), "m2_b": g("param_merger_out.1.bias"),
@@ -183,6 +202,8 @@ def params_for(buf, tg, prior, w):
     (pgm_coder.py:1606-1638 use_param_merger=False with map "none": ctx == bias == 0 at init; cfg 1)."""
     if w is None:
         return prior
+    if "pm0_w" in w:
+        return internal_merger(buf, tg, prior, w)
     if "m1_w" not in w:   # internal variant, use_param_merger=False: params = ctx + prior (pgm_coder.py:1634-1635)
         return masked_conv(buf, tg, w["ctx_w"], w["ctx_b"], allow_same=False) + prior
     return context_model(buf, tg, prior, w)

@@ -180,6 +180,36 @@ def test_ypath_matches_reference(yv, name):
         assert torch.equal(Y.params_for(c["yhat"], c["tg"], c["prior"], c["w"]), c["params_full"])
 
 
+ICASES = ["int_ckbd", "int_cwckbd", "int_raster"]
+
+
+def load_icase(iv, name):
+    C, G, B, H, W = [int(v) for v in iv[name + ".meta"]]
+    sd = {k[len(name) + 4:]: torch.from_numpy(iv[k]) for k in iv.files if k.startswith(name + ".sd.")}
+    get = lambda k: iv[f"{name}.{k}"]
+    return dict(C=C, G=G, B=B, H=H, W=W, sd=sd, w=Y.weights_from_state_dict(sd, prefix=""), method=str(get("method")),
+                y=torch.from_numpy(get("y")), prior=torch.from_numpy(get("prior")), tg=torch.from_numpy(get("tg")).long(),
+                bytes=get("bytes").tobytes(), yhat=torch.from_numpy(get("yhat")), params_full=torch.from_numpy(get("params_full")))
+
+
+@pytest.fixture(scope="module")
+def iv(golden_dir):
+    return np.load(os.path.join(golden_dir, "ypath_internal_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", ICASES)
+def test_internal_merger_matches_reference(iv, name):
+    """the coder's own context_prediction + param_merger over 2G channel groups (pgm_coder.py:1177-1239,
+    :1606-1638), golden vectors from the unmodified reference (tests/golden/make_internal_golden.py)."""
+    c = load_icase(iv, name)
+    o = Y.YPathOracle(c["C"], c["G"], c["w"])
+    o.update_state()
+    with torch.no_grad():
+        assert torch.equal(Y.params_for(c["yhat"], c["tg"], c["prior"], c["w"]), c["params_full"])
+        assert o.encode(c["y"], c["prior"], c["tg"]) == c["bytes"]
+        assert torch.equal(o.decode(c["bytes"], c["prior"], c["tg"]), c["yhat"])
+
+
 def test_group_maps(yv):
     for name, method in [("ckbd", "checkerboard"), ("cwckbd", "channelwise-checkerboard"), ("scanline", "scanline"),
                          ("raster", "raster2x2"), ("meanscale", "none")]:
