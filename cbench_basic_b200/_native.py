@@ -18,7 +18,7 @@ SYMBOLS = [
     "basic_coder_init_cdf_params", "basic_coder_cdfs_shape", "basic_coder_get_cdfs", "basic_pmf_to_quantized_cdf",
     "basic_coder_encode_bound", "basic_coder_encode", "basic_coder_flush", "basic_coder_last_output", "basic_coder_output_size", "basic_coder_take_output", "basic_coder_decode", "basic_coder_set_stream",
     "basic_coder_decode_stream", "basic_coder_encode_batch", "basic_coder_decode_batch", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
-    "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_map", "basic_ctx_num_stages",
+    "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_weights_internal", "basic_ctx_set_map", "basic_ctx_num_stages",
     "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
     "basic_ypath_decode", "basic_profile_enable", "basic_profile_read", "basic_debug_mma_bench", "basic_launch_count",
 ]
@@ -76,6 +76,7 @@ def lib():
     L.basic_ctx_destroy.argtypes = [vp]
     L.basic_ctx_destroy.restype = None
     L.basic_ctx_set_weights.argtypes = [vp] + [f32p] * 8
+    L.basic_ctx_set_weights_internal.argtypes = [vp] + [f32p] * 12 + [C.c_int]
     L.basic_ctx_set_map.argtypes = [vp, i32p, C.c_int, C.c_int]
     L.basic_ctx_num_stages.argtypes = [vp]
     L.basic_ctx_set_precision.argtypes = [vp, C.c_int, C.c_int]

@@ -40,6 +40,8 @@ CtxModel *ctx_new(int C, int G, int k, int device, int sm_count);
 void ctx_delete(CtxModel *);
 int ctx_set_weights(CtxModel &, const float *, const float *, const float *, const float *, const float *, const float *,
                     const float *, const float *);
+int ctx_set_weights_internal(CtxModel &, const float *, const float *, const float *, const float *, const float *, const float *,
+                             const float *, const float *, const float *, const float *, const float *, const float *, int);
 int ctx_set_map(CtxModel &, const int32_t *, int, int);
 int ctx_stage_params(CtxModel &, int, const float *, const float *, int, float *, cudaStream_t, const float *buf_cl = nullptr,
                      const float *prior_cl = nullptr, bool params_cl = false);
@@ -1150,6 +1152,15 @@ int basic_ctx_set_weights(basic_ctx *m, const float *ctx_w, const float *ctx_b, 
     if (!m) return value_error("null model");
     DeviceGuard guard(m->device);
     return ctx_set_weights(*m->m, ctx_w, ctx_b, m1_w, m1_b, m2_w, m2_b, m3_w, m3_b);
+}
+
+int basic_ctx_set_weights_internal(basic_ctx *m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b,
+                                   const float *m2_w, const float *m2_b, const float *m3_w, const float *m3_b, const float *p1_w,
+                                   const float *p1_b, const float *p2_w, const float *p2_b, int half)
+{
+    if (!m) return value_error("null model");
+    DeviceGuard guard(m->device);
+    return ctx_set_weights_internal(*m->m, ctx_w, ctx_b, m1_w, m1_b, m2_w, m2_b, m3_w, m3_b, p1_w, p1_b, p2_w, p2_b, half);
 }
 
 int basic_ctx_set_map(basic_ctx *m, const int32_t *tg, int H, int W)

@@ -381,6 +381,7 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
     m.c_m2 = m.c_ctx * 4 / 3;
     m.has_conv = ctx_w != nullptr;
     m.has_merger = m1_w != nullptr;
+    m.internal = false;
     if (m.has_merger && !(m1_b && m2_w && m2_b && m3_w && m3_b)) return value_error("merger weights incomplete");
     if (m.has_merger && !m.has_conv) return value_error("param merger needs the context convolution weights");
     if (m.has_merger && (m.c_m1 % m.G || m.c_m2 % m.G)) return value_error("2C*5/3 and 2C*4/3 must be divisible by channel_groups");
@@ -401,6 +402,44 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
         BASIC_TRY(upload_transposed(m.w_m3, m3_w, m.c_ctx, m.c_m2, 1, s));
         BASIC_TRY(upload(m.b_m3, m3_b, m.c_ctx, s));
     }
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    return BASIC_OK;
+}
+
+// The coder's internal context model (pgm_coder.py:1177-1239, _merge_prior_params :1606-1638): masked convolutions over 2G
+// channel groups -- G context groups carrying the map's ids and G prior groups with id -1 -- with the <= rule in every
+// layer, all 2G out-groups computed, the first G kept at the end.  With id -1 a prior out-group sees exactly the prior
+// in-groups, everywhere: the prior branch is a plain unmasked chain prior -> p1 -> p2 and the context branch is the usual
+// three layers whose second source is (prior | p1 | p2).  The caller passes the matrices already cut that way:
+//   m1_w [half, 4C] = rows of the context out-groups of layer 0 (columns: ctx 2C | prior 2C),   p1_w [half, 2C]
+//   m2_w [half, 2*half] (columns: context branch | prior branch),                                p2_w [half, half]
+//   m3_w [2C, 2*half]                                   with half = bottleneck / 2 (2C, or 4C with the expanded bottleneck)
+int ctx_set_weights_internal(CtxModel &m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b,
+                             const float *m2_w, const float *m2_b, const float *m3_w, const float *m3_b, const float *p1_w,
+                             const float *p1_b, const float *p2_w, const float *p2_b, int half)
+{
+    cudaStream_t s = 0;
+    const int C = m.C;
+    if (!(ctx_w && ctx_b && m1_w && m1_b && m2_w && m2_b && m3_w && m3_b && p1_w && p1_b && p2_w && p2_b))
+        return value_error("internal merger weights incomplete");
+    if (half < 1 || half % m.G || C % m.G) return value_error("channel counts must be divisible by channel_groups");
+    m.kb_count.clear();
+    m.c_ctx = 2 * C;
+    m.c_m1 = m.c_m2 = m.c_p = half;
+    m.has_conv = m.has_merger = m.internal = true;
+    m.act_B = 0;
+    BASIC_TRY(upload_transposed(m.w_ctx, ctx_w, m.c_ctx, C, m.k * m.k, s));
+    BASIC_TRY(upload(m.b_ctx, ctx_b, m.c_ctx, s));
+    BASIC_TRY(upload_transposed(m.w_m1, m1_w, half, 2 * m.c_ctx, 1, s));
+    BASIC_TRY(upload(m.b_m1, m1_b, half, s));
+    BASIC_TRY(upload_transposed(m.w_m2, m2_w, half, 2 * half, 1, s));
+    BASIC_TRY(upload(m.b_m2, m2_b, half, s));
+    BASIC_TRY(upload_transposed(m.w_m3, m3_w, m.c_ctx, 2 * half, 1, s));
+    BASIC_TRY(upload(m.b_m3, m3_b, m.c_ctx, s));
+    BASIC_TRY(upload_transposed(m.w_p1, p1_w, half, m.c_ctx, 1, s));
+    BASIC_TRY(upload(m.b_p1, p1_b, half, s));
+    BASIC_TRY(upload_transposed(m.w_p2, p2_w, half, half, 1, s));
+    BASIC_TRY(upload(m.b_p2, p2_b, half, s));
     BASIC_CUDA(cudaStreamSynchronize(s));
     return BASIC_OK;
 }
@@ -616,6 +655,10 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             BASIC_TRY(x1.reserve(cl_elems(B, m.c_m1, HW) * sizeof(float)));
             BASIC_TRY(x2.reserve(cl_elems(B, m.c_m2, HW) * sizeof(float)));
         }
+        if (m.internal) {
+            BASIC_TRY(m.a_p1.reserve(cl_elems(B, m.c_p, HW) * sizeof(float)));
+            BASIC_TRY(m.a_p2.reserve(cl_elems(B, m.c_p, HW) * sizeof(float)));
+        }
         m.act_B = B;
     }
     const int f16 = tc && m.run_precision == BASIC_CTX_FP16X3;
@@ -679,6 +722,26 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         return BASIC_OK;
     };
     if (!m.has_merger) return finish();
+    // internal merger: the prior branch at the positions of this stage's cells (unmasked 1x1 layers over the prior; a
+    // position shared by several channel groups of the stage is simply computed once per group)
+    if (m.internal) {
+        for (int pl = 0; pl < 2; ++pl)
+            for (int og = 0; og < G; ++og) {
+                const int ncells = st.cell_off[og + 1] - st.cell_off[og];
+                if (ncells == 0) continue;
+                LayerArgs a = base_args(og, ncells);
+                a.is_conv = 0;
+                a.src0 = pl == 0 ? Source{prior, m.c_ctx, 0, 0} : Source{m.a_p1.as<float>(), m.c_p, 0, 0};
+                a.src1 = Source{nullptr, 0, 0, 0};
+                a.wt = pl == 0 ? m.w_p1.as<float>() : m.w_p2.as<float>();
+                a.bias = pl == 0 ? m.b_p1.as<float>() : m.b_p2.as<float>();
+                a.Ntot = m.c_p; a.n_begin = 0; a.n_count = m.c_p;
+                a.out = pl == 0 ? m.a_p1.as<float>() : m.a_p2.as<float>();
+                a.out_cl = 0; a.lrelu = 1;
+                a.list_key = 0;
+                BASIC_TRY(launch_layer(m, a, m.p_m1, m.q_m1, og, st, false, stream));
+            }
+    }
     // the three 1x1 layers; within a stage, layer L+1 of a cell may read layer L of ANOTHER channel group of the
     // same stage at the same position, hence one launch wave per layer
     for (int layer = 1; layer <= 3; ++layer) {
@@ -694,10 +757,12 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
                 a.Ntot = m.c_m1; a.out = act1; a.out_cl = cl; a.lrelu = 1;
             } else if (layer == 2) {
                 a.src0 = Source{act1, m.c_m1, G, cl};
+                if (m.internal) a.src1 = Source{m.a_p1.as<float>(), m.c_p, 0, 0};
                 a.wt = m.w_m2.as<float>(); a.bias = m.b_m2.as<float>();
                 a.Ntot = m.c_m2; a.out = act2; a.out_cl = cl; a.lrelu = 1;
             } else {
                 a.src0 = Source{act2, m.c_m2, G, cl};
+                if (m.internal) a.src1 = Source{m.a_p2.as<float>(), m.c_p, 0, 0};
                 a.wt = m.w_m3.as<float>(); a.bias = m.b_m3.as<float>();
                 a.Ntot = m.c_ctx; a.out = params_out; a.out_cl = cl; a.out_f32 = 1; a.lrelu = 0;
             }
@@ -725,7 +790,8 @@ void ctx_delete(CtxModel *m)
     DevBuf *bufs[] = {&m->w_ctx, &m->b_ctx, &m->w_m1, &m->b_m1, &m->w_m2, &m->b_m2, &m->w_m3, &m->b_m3, &m->d_cell_hw,
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
-                      &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params};
+                      &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -21,6 +21,12 @@ struct CtxModel {
     // weights, K-major ("transposed"): wt[kk][o]
     DevBuf w_ctx, b_ctx;                // conv: kk = tap * C + c
     DevBuf w_m1, b_m1, w_m2, b_m2, w_m3, b_m3;
+    // the coder's INTERNAL merger (pgm_coder.py:1207-1239: 2G channel groups, the G "prior" groups with id -1): besides the
+    // context branch above (widths c_m1 = c_m2 = bottleneck / 2, layers 2 and 3 also read the prior branch) a prior branch
+    // prior -> p1 -> p2 of width c_p that no rule masks.  Exact FP32 kernels only.
+    bool internal = false;
+    int c_p = 0;
+    DevBuf w_p1, b_p1, w_p2, b_p2, a_p1, a_p2;
     // map
     int H = 0, W = 0, S = 0;
     std::vector<int32_t> h_tg;

@@ -828,6 +828,7 @@ int pack_weights_tc(PackedW &dst, const float *w_dev, int N, int G, int is_conv,
 bool tc_model_eligible(const CtxModel &m, int B)
 {
     if ((m.run_precision != BASIC_CTX_TF32X3 && m.run_precision != BASIC_CTX_FP16X3) || !m.has_conv || m.S < 1) return false;
+    if (m.internal) return false;  // the internal 2G-group merger runs on the exact FP32 kernels
     if (!m.has_merger && m.S == 1 && m.stages[0].tap_or == 0) return false;  // nothing to multiply: params = prior + bias
     if (m.G > MAX_G || m.k * m.k * ((m.C + BK - 1) / BK) > MAX_KB || m.k * m.k > 31) return false;
     if (std::max(m.c_ctx, std::max(m.c_m1, m.c_m2)) / m.G > MAX_BIAS) return false;

@@ -93,7 +93,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                  bypass_precision=4, data_precision=8, quantizer_type="uniform", quantizer_params=None,
                  fixed_input_shape=None, force_input_prior_shape_aligned=True, use_autoregressive_encode=True,
                  lower_bound_scale=0.11, scale_table=None, topo_group_predictor=None, lanes=0, ans_params_device=None,
-                 ctx_precision="auto", ctx_accumulators=4, **kwargs):
+                 ctx_precision="auto", ctx_accumulators=4, param_merger_expand_bottleneck=False, **kwargs):
         super().__init__()
         if use_joint_ar_model_impl:
             raise NotImplementedError("use_joint_ar_model_impl (CompressAI-style serial coder) is SURVEY row f4")
@@ -105,9 +105,6 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             raise NotImplementedError("only the default uniform quantiser [0, 128, 1] is accelerated")
         if not use_autoregressive_encode:
             raise NotImplementedError("use_autoregressive_encode=False")
-        if topo_group_context_model is None and use_param_merger:
-            raise NotImplementedError("the internal param_merger variant (pgm_coder.py:1207-1239) is not accelerated; "
-                                      "pass topo_group_context_model=... or use_param_merger=False")
         if default_topo_group_method not in topo_groups.METHODS:
             raise NotImplementedError(f"Unknown default_topo_group_method {default_topo_group_method}")
         self.in_channels = in_channels
@@ -133,11 +130,29 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             self.register_buffer("topo_group_predictor_cache", topo_group_predictor())   # pgm_coder.py:1097-1103
         self.topo_group_context_model = topo_group_context_model
         if topo_group_context_model is None:
-            self.context_prediction = nn.Conv2d(in_channels, 2 * in_channels, kernel_size, padding=kernel_size // 2)
+            # the coder's own context model (pgm_coder.py:1177-1239), parameter names of the reference
+            out = 2 * in_channels
+            self.context_prediction = nn.Conv2d(in_channels, out, kernel_size, padding=kernel_size // 2)
+            if use_param_merger:
+                # three masked 1x1 convolutions over 2G channel groups [context | prior], 4C -> bottleneck -> bottleneck -> 4C,
+                # the context half of the result kept (_merge_prior_params, :1606-1638); runs on the exact FP32 kernels
+                bott = out * 4 if param_merger_expand_bottleneck else out * 2
+                if (bott // 2) % self.channel_groups or in_channels % self.channel_groups:
+                    raise ValueError("channel counts must be divisible by channel_groups")
+                self.param_merger = nn.Sequential(nn.Conv2d(out * 2, bott, 1), nn.LeakyReLU(inplace=True),
+                                                  nn.Conv2d(bott, bott, 1), nn.LeakyReLU(inplace=True),
+                                                  nn.Conv2d(bott, out * 2, 1))
         self.register_buffer("_device_indicator", torch.zeros(1), persistent=False)
         self.out_channels = 2 * in_channels
         self.profile = {}          # wall-clock ms of the last calls, keyed like the reference's profiler scopes
         self._ctx_holder = _CtxHandle()
+
+    def _load_from_state_dict(self, state_dict, prefix, *a, **k):
+        # entries of a reference checkpoint that carry nothing for coding: the unused compatibility copy of the conv kernel
+        # (pgm_coder.py:1179-1181) and the LowerBound buffer (its value is the constructor's lower_bound_scale)
+        for key in ("conv_kernel_weight", "conv_kernel_bias", "lower_bound_scale.bound"):
+            state_dict.pop(prefix + key, None)
+        super()._load_from_state_dict(state_dict, prefix, *a, **k)
 
     # ------------------------------------------------------------------------------------------ plumbing
     @property
@@ -208,10 +223,21 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                          ptr(cm.param_merger_out[3].weight), ptr(cm.param_merger_out[3].bias)]
             else:
                 ptrs += [None] * 6
+        elif self.use_param_merger:
+            o = 2 * self.in_channels
+            pm0, pm2, pm4 = self.param_merger[0], self.param_merger[2], self.param_merger[4]
+            half = pm0.weight.shape[0] // 2
+            w0, w2, w4 = pm0.weight.reshape(2 * half, 2 * o), pm2.weight.reshape(2 * half, 2 * half), pm4.weight.reshape(2 * o, 2 * half)
+            ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias),
+                    ptr(w0[:half]), ptr(pm0.bias[:half]), ptr(w2[:half]), ptr(pm2.bias[:half]), ptr(w4[:o]), ptr(pm4.bias[:o]),
+                    ptr(w0[half:, o:]), ptr(pm0.bias[half:]), ptr(w2[half:, half:]), ptr(pm2.bias[half:])]
         else:
             ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias)] + [None] * 6
         torch.cuda.synchronize(self.device)
-        N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
+        if len(ptrs) == 12:
+            N.check(N.lib().basic_ctx_set_weights_internal(self._ctx, *ptrs, int(half)))
+        else:
+            N.check(N.lib().basic_ctx_set_weights(self._ctx, *ptrs))
         prec = self.ctx_precision
         if prec == "auto":
             prec = "fp32" if self.lanes == 1 else "fp16x3"

@@ -128,6 +128,17 @@ int basic_ctx_create(int C, int G, int kernel_size, int device, basic_ctx **out)
 void basic_ctx_destroy(basic_ctx *m);
 int basic_ctx_set_weights(basic_ctx *m, const float *ctx_w, const float *ctx_b, const float *m1_w, const float *m1_b,
                           const float *m2_w, const float *m2_b, const float *m3_w, const float *m3_b);
+/* The coder's INTERNAL context model (no topo_group_context_model: context_prediction + param_merger over 2G channel
+ * groups, pgm_coder.py:1177-1239, :1606-1638).  The G "prior" groups carry id -1, so they see exactly each other: the
+ * merger splits into an unmasked prior branch (prior -> p1 -> p2) and a context branch whose layers also read it.  The
+ * caller passes the reference's matrices cut accordingly (half = bottleneck / 2; rows / columns of param_merger.{0,2,4}):
+ *   m1_w = pm0[:half, :]  [half, 4C]     p1_w = pm0[half:, 2C:]   [half, 2C]
+ *   m2_w = pm2[:half, :]  [half, 2half]  p2_w = pm2[half:, half:] [half, half]
+ *   m3_w = pm4[:2C, :]    [2C, 2half]    (biases cut the same way).  Runs on the exact FP32 kernels. */
+int basic_ctx_set_weights_internal(basic_ctx *m, const float *ctx_w, const float *ctx_b, const float *m1_w,
+                                   const float *m1_b, const float *m2_w, const float *m2_b, const float *m3_w,
+                                   const float *m3_b, const float *p1_w, const float *p1_b, const float *p2_w,
+                                   const float *p2_b, int half);
 /* Group map for the next calls: tg int32 [G, H, W] (host or device), already tiled to H x W
  * (pgm_coder.py:1299-1414).  Builds the per-stage cell and position lists on the device. */
 int basic_ctx_set_map(basic_ctx *m, const int32_t *tg, int H, int W);

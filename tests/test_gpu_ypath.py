@@ -168,6 +168,44 @@ def test_ypath_golden(yv, name, lanes):
         assert len(bs) <= len(c["bytes"]) + 140 * (int(c["tg"].max()) + 1) * (1 if lanes == 0 else 2) + 8
 
 
+@pytest.mark.parametrize("name", ["int_ckbd", "int_cwckbd", "int_raster"])
+@pytest.mark.parametrize("lanes", [1, 0])
+def test_internal_merger_golden(iv, name, lanes):
+    """the coder's own context_prediction + param_merger (2G channel groups, no topo_group_context_model),
+    a reference state_dict loaded as it is.  lanes = 1: the reference's bytes; parameters within 1e-5; multi-lane lossless."""
+    from cbench_basic_b200.prior_coder import GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder
+    from tests.test_oracle_golden import load_icase
+    c = load_icase(iv, name)
+    coder = Coder(in_channels=c["C"], channel_groups=c["G"], default_topo_group_method=c["method"], lanes=lanes,
+                  ans_params_device="cpu")
+    sd = dict(c["sd"])
+    sd["conv_kernel_weight"] = torch.zeros_like(sd["context_prediction.weight"])     # a reference checkpoint has these too
+    sd["lower_bound_scale.bound"] = torch.tensor([0.11])
+    coder.load_state_dict(sd)
+    coder = coder.cuda().eval()
+    coder.update_state()
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    from cbench_basic_b200 import _native as N
+    params = torch.full((c["B"], 2 * c["C"], c["H"], c["W"]), float("nan"), device="cuda")
+    coder._set_map(c["tg"])
+    yhat_ref = c["yhat"].cuda().contiguous()
+    for g in range(int(c["tg"].max()) + 1):   # every cell at its own stage, from the full reconstruction
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, yhat_ref.data_ptr(), prior.data_ptr(), c["B"], params.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert not torch.isnan(params).any()
+    assert rel_err(params.cpu(), c["params_full"]) <= REL_TOL, rel_err(params.cpu(), c["params_full"])
+    bs = coder.encode(y, prior=prior)
+    yhat = coder.decode(bs, prior=prior)
+    if lanes == 1:
+        assert bs == c["bytes"]
+    assert_latents_match(yhat.cpu(), c["yhat"])
+
+
+@pytest.fixture(scope="module")
+def iv(golden_dir):
+    return np.load(os.path.join(golden_dir, "ypath_internal_vectors.npz"))
+
+
 @pytest.mark.parametrize("name,method", [("ckbd", "checkerboard"), ("cwckbd", "channelwise-checkerboard"),
                                          ("scanline", "scanline"), ("raster", "raster2x2"), ("meanscale", "none")])
 def test_default_maps_through_constructor(yv, name, method):
