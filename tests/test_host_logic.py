@@ -115,3 +115,16 @@ def test_sharded_encode_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_numa_binding_helper_is_safe_without_topology():
+    """sharding.bind_to_gpu_numa: cpulist parsing, and a no-op (never an exception, affinity untouched) where there is no
+    GPU / no sysfs topology -- the pool's boxes report numa_node = -1."""
+    import os
+    from cbench_basic_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = sharding.bind_to_gpu_numa(0)
+    assert isinstance(info, dict) and info["bound"] is False
+    assert os.sched_getaffinity(0) == before
