@@ -6,7 +6,10 @@
 #include <cstring>
 #include <string>
 #include <condition_variable>
+#if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
+#define BASIC_HAVE_SSE2 1
+#endif
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -369,6 +372,10 @@ static void copy_streaming(uint8_t *dst, const uint8_t *src, size_t n)
     size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
     if (head > n) head = n;
     if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+#ifndef BASIC_HAVE_SSE2
+    memcpy(dst, src, n);   // (other host architectures: plain copy)
+    return;
+#else
     const size_t blocks = n / 64;
     for (size_t i = 0; i < blocks; ++i) {
         const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 0);
@@ -384,6 +391,7 @@ static void copy_streaming(uint8_t *dst, const uint8_t *src, size_t n)
     }
     if (n & 63) memcpy(dst, src, n & 63);
     _mm_sfence();  // the stores are globally visible before the upload of the chunk is queued
+#endif
 }
 
 int reserve_pinned(uint8_t **buf, size_t *cap, size_t bytes)
