@@ -196,7 +196,7 @@ def run_reference(args, rank, world):
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 rANS states / int32 symbols; context model f32 in / f32 accumulate, products as 3xFP16 on tcgen05", "data": "synthetic",
+            "dtype": "u64 rANS state / int32 symbols (reference CPU coder); context model f32 on torch CPU", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "sample": f"{n_img} image per step"},
             "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port",
                              "sample": f"{n_img} of {B} images per step, encode+decode, torch CPU context model + reference coder "
@@ -458,6 +458,12 @@ def main():
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5
+        # all the host threads the box gives this process: torchrun exports OMP_NUM_THREADS=1, which would time the
+        # CPU arm on one core at N > 1 (rank 0 alone runs it, the other ranks exit)
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except Exception:
+            pass
         run_reference(args, rank, world)
         return
     if world > 1:
