@@ -209,6 +209,63 @@ def params_for(buf, tg, prior, w):
     return context_model(buf, tg, prior, w)
 
 
+# ---------------------------------------------------------------- CompressAI-style serial coder
+def joint_ar_weights_from_state_dict(sd, prefix=""):
+    g = lambda k: sd[prefix + k].detach().float().cpu()
+    return {"ctx_w": g("context_prediction.weight"), "ctx_b": g("context_prediction.bias"),
+            "e0_w": g("entropy_parameters.0.weight"), "e0_b": g("entropy_parameters.0.bias"),
+            "e2_w": g("entropy_parameters.2.weight"), "e2_b": g("entropy_parameters.2.bias"),
+            "e4_w": g("entropy_parameters.4.weight"), "e4_b": g("entropy_parameters.4.bias")}
+
+
+def _joint_ar_params(w, y_crop, p, conv_w):
+    """pgm_coder.py:1996-2008 / :2049-2059: 5x5 convolution on the crop, then the 1x1 entropy_parameters network on
+    cat(prior, ctx); scales = first half of the channels, means = second (mean_scale_split_method "chunk", inverse)."""
+    ctx_p = F.conv2d(y_crop, conv_w, bias=w["ctx_b"])
+    x = torch.cat((p, ctx_p), dim=1)
+    x = F.leaky_relu(F.conv2d(x, w["e0_w"], w["e0_b"]))
+    x = F.leaky_relu(F.conv2d(x, w["e2_w"], w["e2_b"]))
+    params = F.conv2d(x, w["e4_w"], w["e4_b"]).squeeze(-1).squeeze(-1)
+    scales, means = params.chunk(2, 1)
+    return means, scales
+
+
+def joint_ar_encode_symbols(y, prior, w, scale_table, k=5):
+    """use_joint_ar_model_impl, _encode_with_pgm (pgm_coder.py:1975-2027): pixel by pixel in raster order with the
+    causally masked kernel; stream order = pixel-major, then (b, c)."""
+    B, C, H, W = y.shape
+    pad = k // 2
+    y_hat = F.pad(y, (pad, pad, pad, pad))
+    mask = torch.ones_like(w["ctx_w"])
+    mask[:, :, k // 2, k // 2:] = 0
+    mask[:, :, k // 2 + 1:] = 0
+    mw = w["ctx_w"] * mask
+    data, idx = [], []
+    for h in range(H):
+        for x in range(W):
+            crop = y_hat[:, :, h:h + k, x:x + k]
+            means, scales = _joint_ar_params(w, crop, prior[:, :, h:h + 1, x:x + 1], mw)
+            sym = torch.round(crop[:, :, pad, pad] - means)
+            y_hat[:, :, h + pad, x + pad] = sym + means
+            data.append(sym)
+            idx.append(select_indexes(scales, scale_table))
+    return (torch.cat(data).numpy().astype(np.int32).reshape(-1), torch.cat(idx).numpy().astype(np.int32).reshape(-1),
+            y_hat[:, :, pad:pad + H, pad:pad + W].clone())
+
+
+def joint_ar_decode(decode_group, prior, w, scale_table, C, k=5):
+    """_pgm_generate (pgm_coder.py:2031-2066): the unmasked kernel on a buffer whose future is still zero."""
+    B, _, H, W = prior.shape
+    pad = k // 2
+    y_hat = torch.zeros(B, C, H + 2 * pad, W + 2 * pad)
+    for h in range(H):
+        for x in range(W):
+            means, scales = _joint_ar_params(w, y_hat[:, :, h:h + k, x:x + k], prior[:, :, h:h + 1, x:x + 1], w["ctx_w"])
+            sym = decode_group(select_indexes(scales, scale_table).numpy().astype(np.int32))
+            y_hat[:, :, h + pad, x + pad] = torch.from_numpy(np.asarray(sym)).float().reshape(B, C) + means
+    return y_hat[:, :, pad:pad + H, pad:pad + W].clone()
+
+
 # ------------------------------------------------------------------------------------------- the path
 def encode_symbols(y, prior, tg, w, scale_table):
     """pgm_coder.py:912-947 _encode_with_pgm: returns (symbols int32 [N], indexes int32 [N], y_hat) in the
@@ -269,3 +326,16 @@ class YPathOracle:
     def decode(self, data, prior, tg):
         self.dec.set_stream(data)
         return decode_symbols(self.dec.decode_stream, prior, tg, self.w, self.scale_table, self.C)
+
+
+class JointAROracle(YPathOracle):
+    """The CompressAI-style serial coder (use_joint_ar_model_impl=True): same tables and coder, the
+    pixel-by-pixel loops of pgm_coder.py:1975-2066."""
+
+    def encode(self, y, prior, tg=None):
+        sym, idx, _ = joint_ar_encode_symbols(y, prior, self.w, self.scale_table)
+        return self.enc.encode_with_indexes(sym, idx)
+
+    def decode(self, data, prior, tg=None):
+        self.dec.set_stream(data)
+        return joint_ar_decode(self.dec.decode_stream, prior, self.w, self.scale_table, self.C)

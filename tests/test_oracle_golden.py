@@ -210,6 +210,34 @@ def test_internal_merger_matches_reference(iv, name):
         assert torch.equal(o.decode(c["bytes"], c["prior"], c["tg"]), c["yhat"])
 
 
+JCASES = ["jar_a", "jar_b"]
+
+
+def load_jcase(jv, name):
+    C, B, H, W = [int(v) for v in jv[name + ".meta"]]
+    sd = {k[len(name) + 4:]: torch.from_numpy(jv[k]) for k in jv.files if k.startswith(name + ".sd.")}
+    get = lambda k: jv[f"{name}.{k}"]
+    return dict(C=C, B=B, H=H, W=W, sd=sd, w=Y.joint_ar_weights_from_state_dict(sd), y=torch.from_numpy(get("y")),
+                prior=torch.from_numpy(get("prior")), bytes=get("bytes").tobytes(), yhat=torch.from_numpy(get("yhat")))
+
+
+@pytest.fixture(scope="module")
+def jv(golden_dir):
+    return np.load(os.path.join(golden_dir, "ypath_jointar_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", JCASES)
+def test_joint_ar_matches_reference(jv, name):
+    """use_joint_ar_model_impl=True (pixel-by-pixel CompressAI-style coder), golden vectors from the
+    unmodified reference (tests/golden/make_jointar_golden.py)."""
+    c = load_jcase(jv, name)
+    o = Y.JointAROracle(c["C"], 1, c["w"])
+    o.update_state()
+    with torch.no_grad():
+        assert o.encode(c["y"], c["prior"]) == c["bytes"]
+        assert torch.equal(o.decode(c["bytes"], c["prior"]), c["yhat"])
+
+
 def test_group_maps(yv):
     for name, method in [("ckbd", "checkerboard"), ("cwckbd", "channelwise-checkerboard"), ("scanline", "scanline"),
                          ("raster", "raster2x2"), ("meanscale", "none")]:
