@@ -95,8 +95,8 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                  lower_bound_scale=0.11, scale_table=None, topo_group_predictor=None, lanes=0, ans_params_device=None,
                  ctx_precision="auto", ctx_accumulators=4, param_merger_expand_bottleneck=False, **kwargs):
         super().__init__()
-        if use_joint_ar_model_impl:
-            raise NotImplementedError("use_joint_ar_model_impl (CompressAI-style serial coder) is SURVEY row f4")
+        if use_joint_ar_model_impl and (channel_groups != 1 or topo_group_context_model is not None):
+            raise ValueError("use_joint_ar_model_impl needs channel_groups == 1 and the coder's own context model")
         if coder_type not in ("rans", "rans64"):
             # torch_ans.py:241-243 builds Tans* with table_log = freq_precision = 16, which the reference decoder
             # itself refuses (TANS_MAX_TABLELOG = 12); tANS is available through cbench_basic_b200.ans only.
@@ -114,6 +114,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self.default_topo_group_method = default_topo_group_method
         self.kernel_size = kernel_size
         self.use_param_merger = use_param_merger
+        self.use_joint_ar_model_impl = use_joint_ar_model_impl
         self.coder_type, self.freq_precision = coder_type, freq_precision
         self.use_bypass_coding, self.bypass_precision = use_bypass_coding, bypass_precision
         self.fixed_input_shape = fixed_input_shape
@@ -133,7 +134,15 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             # the coder's own context model (pgm_coder.py:1177-1239), parameter names of the reference
             out = 2 * in_channels
             self.context_prediction = nn.Conv2d(in_channels, out, kernel_size, padding=kernel_size // 2)
-            if use_param_merger:
+            if use_joint_ar_model_impl:
+                # CompressAI-style serial coder (pgm_coder.py:1204-1213, :1975-2066): pixel by pixel in raster
+                # order, causally masked 5x5 convolution, entropy_parameters(cat(prior, ctx)) with scales in the first half
+                # of its output and means in the second.  On the device that is the scanline map with the merger's first
+                # matrix read as [ctx | prior] columns and its last one as interleaved (mean, scale) rows (_upload_weights).
+                self.entropy_parameters = nn.Sequential(nn.Conv2d(out * 2, out * 5 // 3, 1), nn.LeakyReLU(inplace=True),
+                                                        nn.Conv2d(out * 5 // 3, out * 4 // 3, 1), nn.LeakyReLU(inplace=True),
+                                                        nn.Conv2d(out * 4 // 3, out, 1))
+            elif use_param_merger:
                 # three masked 1x1 convolutions over 2G channel groups [context | prior], 4C -> bottleneck -> bottleneck -> 4C,
                 # the context half of the result kept (_merge_prior_params, :1606-1638); runs on the exact FP32 kernels
                 bott = out * 4 if param_merger_expand_bottleneck else out * 2
@@ -223,6 +232,15 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                          ptr(cm.param_merger_out[3].weight), ptr(cm.param_merger_out[3].bias)]
             else:
                 ptrs += [None] * 6
+        elif self.use_joint_ar_model_impl:
+            o, Cc = 2 * self.in_channels, self.in_channels
+            e0, e2, e4 = self.entropy_parameters[0], self.entropy_parameters[2], self.entropy_parameters[4]
+            w0 = e0.weight.reshape(e0.weight.shape[0], 2 * o)
+            w0 = torch.cat([w0[:, o:], w0[:, :o]], dim=1)                       # cat(prior, ctx) -> [ctx | prior]
+            rows = torch.stack([torch.arange(Cc, 2 * Cc), torch.arange(0, Cc)], dim=1).reshape(-1)   # (mean_c, scale_c) pairs
+            w4 = e4.weight.reshape(o, -1)[rows]
+            ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias), ptr(w0), ptr(e0.bias),
+                    ptr(e2.weight), ptr(e2.bias), ptr(w4), ptr(e4.bias[rows])]
         elif self.use_param_merger:
             o = 2 * self.in_channels
             pm0, pm2, pm4 = self.param_merger[0], self.param_merger[2], self.param_merger[4]
@@ -252,6 +270,8 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
     def _get_pgm(self, input_shape, pgm=None):
         """pgm_coder.py:1498-1604 (eval branch): explicit map > cached predictor output > default method."""
         H, W = int(input_shape[-2]), int(input_shape[-1])
+        if self.use_joint_ar_model_impl:   # the serial coder ignores the map arguments (pgm_coder.py:1978-1985)
+            return topo_groups.default_map("scanline", 1, H, W)
         if pgm is None and self.topo_group_predictor is not None:
             pgm = self.topo_group_predictor_cache
         if pgm is None:

@@ -201,6 +201,33 @@ def test_internal_merger_golden(iv, name, lanes):
     assert_latents_match(yhat.cpu(), c["yhat"])
 
 
+@pytest.mark.parametrize("name", ["jar_a", "jar_b"])
+@pytest.mark.parametrize("lanes", [1, 0])
+def test_joint_ar_serial_coder_golden(jv, name, lanes):
+    """use_joint_ar_model_impl=True -- the reference codes pixel by pixel with a causally masked 5x5
+    convolution and entropy_parameters(cat(prior, ctx)); here it is the scanline map with remapped merger matrices.  A
+    reference state_dict loads as it is; lanes = 1 reproduces the reference's bytes."""
+    from cbench_basic_b200.prior_coder import GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder
+    from tests.test_oracle_golden import load_jcase
+    c = load_jcase(jv, name)
+    coder = Coder(in_channels=c["C"], use_joint_ar_model_impl=True, lanes=lanes, ans_params_device="cpu")
+    coder.load_state_dict(dict(c["sd"], conv_kernel_bias=torch.zeros(2 * c["C"])))
+    coder = coder.cuda().eval()
+    coder.update_state()
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+    if lanes == 1:
+        assert bs == c["bytes"]
+    yhat = coder.decode(bs, prior=prior)
+    assert torch.equal(yhat, yhat_enc * 1.0 + 0.0)
+    assert_latents_match(yhat.cpu(), c["yhat"])
+
+
+@pytest.fixture(scope="module")
+def jv(golden_dir):
+    return np.load(os.path.join(golden_dir, "ypath_jointar_vectors.npz"))
+
+
 @pytest.fixture(scope="module")
 def iv(golden_dir):
     return np.load(os.path.join(golden_dir, "ypath_internal_vectors.npz"))
