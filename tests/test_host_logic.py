@@ -128,3 +128,37 @@ def test_numa_binding_helper_is_safe_without_topology():
     info = sharding.bind_to_gpu_numa(0)
     assert isinstance(info, dict) and info["bound"] is False
     assert os.sched_getaffinity(0) == before
+
+
+def test_latent_codec_container_layout():
+    """HyperpriorLatentCodec: segments in generative order (z, y), u32 length before all but the last
+    (latent_graph.py:1260-1263 + bytes_ops.merge_bytes) -- with stub node coders, no GPU."""
+    import struct
+    import torch
+    from cbench_basic_b200.latent_codec import HyperpriorLatentCodec
+
+    class Stub(torch.nn.Module):
+        def __init__(self, tag):
+            super().__init__()
+            self.tag, self.seen = tag, []
+
+        def update_state(self):
+            self.seen.append("update")
+
+        def encode(self, x, prior=None):
+            self.seen.append(("enc", None if prior is None else float(prior.sum())))
+            return self.tag * int(x.numel())
+
+        def decode(self, b, prior=None):
+            self.seen.append(("dec", bytes(b), None if prior is None else float(prior.sum())))
+            return torch.full((1, 2), float(len(b)))
+
+    z, y = Stub(b"z"), Stub(b"y")
+    codec = HyperpriorLatentCodec(z, y, hyper_synthesis=lambda zh: zh * 2, hyper_analysis=lambda t: t[:, :3])
+    codec.update_state()
+    data = codec.encode(torch.ones(1, 5))
+    assert data == struct.pack("I", 3) + b"zzz" + b"yyyyy"
+    assert y.seen[-1] == ("enc", 12.0)                      # prior = h_s(z_hat) = 2 * [3, 3]
+    out = codec.decode(data)
+    assert z.seen[-1][:2] == ("dec", b"zzz") and y.seen[-1] == ("dec", b"yyyyy", 12.0) and float(out[0, 0]) == 5.0
+    assert list(codec.state_dict().keys()) == [] and set(codec.latent_node_entropy_coders.keys()) == {"z", "y"}

@@ -154,3 +154,34 @@ def test_gpu_multilane_z_container(zv, name):
     assert len(strings) == 1 and strings[0][4:8] == b"BLS1" and tuple(shape) == tuple(x.shape[-2:])
     assert torch.equal(coder.decode(body).cpu(), torch.from_numpy(zv[name + "/y_hat"]))
     assert len(body) <= len(zv[name + "/body"]) + 200
+
+
+@pytest.mark.gpu
+def test_gpu_hyperprior_latent_codec_round_trip():
+    """z -> h_s -> y on the device: both node coders, a random hyper-analysis / hyper-synthesis pair, the
+    reference's container (z segment with its u32 length, then y).  The decoder reproduces the encoder's y_hat."""
+    import struct
+    import torch.nn as nn
+    from cbench_basic_b200.latent_codec import HyperpriorLatentCodec
+    from cbench_basic_b200.prior_coder import (GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as YCoder,
+                                               TopoGroupDynamicMaskConv2dContextModel as Ctx)
+    torch.manual_seed(1)
+    C_, Cz, B, H, W = 24, 16, 3, 8, 12
+    zc = z_coder.CompressAIEntropyBottleneckPriorCoder(entropy_bottleneck_channels=Cz)
+    zc.entropy_bottleneck.load_state_dict(dict(Z.init_params(Cz, seed=5), target=zc.entropy_bottleneck.target.clone(),
+                                               _offset=torch.IntTensor(), _quantized_cdf=torch.IntTensor(),
+                                               _cdf_length=torch.IntTensor()))
+    yc = YCoder(in_channels=C_, default_topo_group_method="checkerboard",
+                topo_group_context_model=Ctx(in_channels=C_, out_channels=2 * C_), lanes=0)
+    h_a = nn.Conv2d(C_, Cz, 3, stride=2, padding=1)
+    h_s = nn.Sequential(nn.ConvTranspose2d(Cz, 2 * C_, 4, stride=2, padding=1))
+    codec = HyperpriorLatentCodec(zc, yc, hyper_synthesis=h_s, hyper_analysis=h_a).cuda().eval()
+    codec.update_state()
+    y = (3 * torch.randn(B, C_, H, W)).cuda()
+    data = codec.encode(y)
+    (zlen,) = struct.unpack_from("I", data, 0)
+    strings, shape = z_coder.read_body(data[4:4 + zlen])
+    assert len(strings) == B and tuple(shape) == (H // 2, W // 2) and data[4 + zlen:8 + zlen] in (b"BLS1", b"BLS2")
+    y_hat = codec.decode(data)
+    assert y_hat.shape == y.shape and float((y_hat - y).abs().max()) <= 0.5 + 1e-4
+    assert torch.equal(codec.decode(data), y_hat)
