@@ -30,6 +30,18 @@ def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):  # no
     return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
 
 
+def joint_ar_remap(e0_weight, e4_weight, e4_bias, in_channels):
+    """The serial coder's entropy_parameters network (pgm_coder.py:1204-1213, :2000-2003) in the layout of the masked-merger
+    kernels: its first matrix multiplies cat(prior, ctx) -- the kernels read [ctx | prior]; its last one emits scales in the
+    first C channels and means in the second ("chunk" split, inverse_mean_scale) -- the kernels emit (mean_c, scale_c) pairs.
+    Returns (first weight [N, 4C] with swapped column halves, last weight and bias with interleaved rows)."""
+    o, Cc = 2 * in_channels, in_channels
+    w0 = e0_weight.reshape(e0_weight.shape[0], 2 * o)
+    w0 = torch.cat([w0[:, o:], w0[:, :o]], dim=1)
+    rows = torch.stack([torch.arange(Cc, 2 * Cc), torch.arange(0, Cc)], dim=1).reshape(-1)
+    return w0, e4_weight.reshape(o, -1)[rows], e4_bias[rows]
+
+
 class _CtxHandle:
     """Owns a basic_ctx* (kept out of nn.Module attribute machinery so it can be freed at interpreter exit)."""
 
@@ -233,14 +245,10 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             else:
                 ptrs += [None] * 6
         elif self.use_joint_ar_model_impl:
-            o, Cc = 2 * self.in_channels, self.in_channels
             e0, e2, e4 = self.entropy_parameters[0], self.entropy_parameters[2], self.entropy_parameters[4]
-            w0 = e0.weight.reshape(e0.weight.shape[0], 2 * o)
-            w0 = torch.cat([w0[:, o:], w0[:, :o]], dim=1)                       # cat(prior, ctx) -> [ctx | prior]
-            rows = torch.stack([torch.arange(Cc, 2 * Cc), torch.arange(0, Cc)], dim=1).reshape(-1)   # (mean_c, scale_c) pairs
-            w4 = e4.weight.reshape(o, -1)[rows]
+            w0, w4, b4 = joint_ar_remap(e0.weight, e4.weight, e4.bias, self.in_channels)
             ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias), ptr(w0), ptr(e0.bias),
-                    ptr(e2.weight), ptr(e2.bias), ptr(w4), ptr(e4.bias[rows])]
+                    ptr(e2.weight), ptr(e2.bias), ptr(w4), ptr(b4)]
         elif self.use_param_merger:
             o = 2 * self.in_channels
             pm0, pm2, pm4 = self.param_merger[0], self.param_merger[2], self.param_merger[4]

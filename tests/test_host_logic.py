@@ -162,3 +162,62 @@ def test_latent_codec_container_layout():
     out = codec.decode(data)
     assert z.seen[-1][:2] == ("dec", b"zzz") and y.seen[-1] == ("dec", b"yyyyy", 12.0) and float(out[0, 0]) == 5.0
     assert list(codec.state_dict().keys()) == [] and set(codec.latent_node_entropy_coders.keys()) == {"z", "y"}
+
+
+def test_serial_coder_is_the_scanline_map_with_remapped_matrices(golden_dir):
+    """prior_coder.joint_ar_remap (row f4): the reference's pixel-by-pixel loop (oracle restatement, byte-identical to the
+    reference) and the masked-merger formulation the kernels run -- scanline map, [ctx | prior] columns, interleaved
+    (mean, scale) rows -- produce the same symbols, scale indexes and reconstruction."""
+    import numpy as np
+    import torch
+    from cbench_basic_b200.prior_coder import joint_ar_remap
+    from oracle import ypath_oracle as Y
+    jv = np.load(os.path.join(golden_dir, "ypath_jointar_vectors.npz"))
+    for name in ("jar_a", "jar_b"):
+        C_, B, H, W = [int(v) for v in jv[name + ".meta"]]
+        sd = {k[len(name) + 4:]: torch.from_numpy(jv[k]) for k in jv.files if k.startswith(name + ".sd.")}
+        w = Y.joint_ar_weights_from_state_dict(sd)
+        y, prior = torch.from_numpy(jv[name + ".y"]), torch.from_numpy(jv[name + ".prior"])
+        w0, w4, b4 = joint_ar_remap(w["e0_w"], w["e4_w"], w["e4_b"], C_)
+        wm = {"ctx_w": w["ctx_w"], "ctx_b": w["ctx_b"], "m1_w": w0.reshape(*w0.shape, 1, 1), "m1_b": w["e0_b"],
+              "m2_w": w["e2_w"], "m2_b": w["e2_b"], "m3_w": w4.reshape(*w4.shape, 1, 1), "m3_b": b4}
+        tg = Y.default_pgm("scanline", 1, H, W)
+        with torch.no_grad():
+            sym_a, idx_a, yhat_a = Y.joint_ar_encode_symbols(y, prior, w, Y.get_scale_table())
+            sym_b, idx_b, yhat_b = Y.encode_symbols(y, prior, tg, wm, Y.get_scale_table())
+        assert np.array_equal(sym_a, sym_b) and np.array_equal(idx_a, idx_b)
+        assert float((yhat_a - yhat_b).abs().max()) <= 1e-5
+
+
+def test_reference_state_dicts_load_into_every_coder_variant(golden_dir):
+    """Drop-in at the checkpoint level: the state_dict keys of the reference coder -- its internal context model with and
+    without the param merger, the serial coder's entropy_parameters, plus the entries that carry nothing for coding
+    (conv_kernel_*, lower_bound_scale.bound) -- load strictly (no GPU needed for that)."""
+    import numpy as np
+    import torch
+    from cbench_basic_b200.prior_coder import GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder
+
+    def ref_sd(npz, name, C_):
+        sd = {k[len(name) + 4:]: torch.from_numpy(npz[k]) for k in npz.files if k.startswith(name + ".sd.")}
+        sd.update({"conv_kernel_weight": torch.zeros(2 * C_, C_, 5, 5), "conv_kernel_bias": torch.zeros(2 * C_),
+                   "lower_bound_scale.bound": torch.tensor([0.11])})
+        return sd
+    iv = np.load(os.path.join(golden_dir, "ypath_internal_vectors.npz"))
+    C_, G = int(iv["int_cwckbd.meta"][0]), int(iv["int_cwckbd.meta"][1])
+    coder = Coder(in_channels=C_, channel_groups=G, default_topo_group_method="channelwise-checkerboard")
+    coder.load_state_dict(ref_sd(iv, "int_cwckbd", C_))
+    assert set(coder.state_dict()) == {"context_prediction.weight", "context_prediction.bias"} | \
+        {f"param_merger.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias")}
+    assert tuple(coder.param_merger[0].weight.shape) == (4 * C_, 4 * C_, 1, 1)
+    wide = Coder(in_channels=C_, channel_groups=G, param_merger_expand_bottleneck=True)
+    assert tuple(wide.param_merger[2].weight.shape) == (8 * C_, 8 * C_, 1, 1)
+    jv = np.load(os.path.join(golden_dir, "ypath_jointar_vectors.npz"))
+    Cj = int(jv["jar_a.meta"][0])
+    serial = Coder(in_channels=Cj, use_joint_ar_model_impl=True)
+    serial.load_state_dict(ref_sd(jv, "jar_a", Cj))
+    assert tuple(serial.entropy_parameters[0].weight.shape) == (2 * Cj * 5 // 3, 4 * Cj, 1, 1)
+    assert serial._get_pgm((1, Cj, 3, 4)).reshape(-1).tolist() == list(range(12))      # pixel = coding group
+    plain = Coder(in_channels=Cj, use_param_merger=False)
+    assert set(plain.state_dict()) == {"context_prediction.weight", "context_prediction.bias"}
+    with pytest.raises(ValueError):
+        Coder(in_channels=Cj, channel_groups=2, use_joint_ar_model_impl=True)
