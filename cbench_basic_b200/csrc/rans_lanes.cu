@@ -14,7 +14,12 @@
 //   Segment bytes: u32 n_chunks | u32 n_slices | u32 chunk_syms[n_slices] | u32 end_word[n_chunks] (cumulative) |
 //   u32 state[n_chunks][32] | u16 words | zero pad to 4 bytes.
 //
-// Tables (u16 CDFs + bucket LUTs, tables.cu) are staged once per CTA into shared memory.
+// Tables (u16 CDFs + bucket LUTs, tables.cu) are staged once per CTA into shared memory and read with ld.shared (common.cuh
+// Tab<SM>; images larger than an SM's shared memory are read through L2).  With the chunk count fixed by the 0.5 % bpp bar
+// a call lasts as long as ONE warp's dependency chain, so everything that does not depend on the state is fetched off the
+// chain: table records and encoder operands per 128-symbol block, four CDF probes at once in the decoder, escape payloads of
+// bypass_precision 4 as one 36-bit token string.  Kernels are instantiated per <tables in shared
+// memory, bypass_precision == 4>.
 #include "common.cuh"
 
 namespace basic {
