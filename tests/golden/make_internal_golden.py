@@ -20,12 +20,18 @@ import ref_shim  # noqa: E402
 
 def main():
     Coder, _ = ref_shim.load()
-    cases = [("int_ckbd", 24, 1, "checkerboard", 2, 6, 8, 10), ("int_cwckbd", 24, 2, "channelwise-checkerboard", 2, 5, 7, 11),
-             ("int_raster", 12, 1, "raster2x2", 1, 6, 6, 12)]
+    cases = [("int_ckbd", 24, 1, "checkerboard", 2, 6, 8, 10, False), ("int_cwckbd", 24, 2, "channelwise-checkerboard", 2, 5, 7, 11, False),
+             ("int_raster", 12, 1, "raster2x2", 1, 6, 6, 12, False)]
+    generate(Coder, cases, "ypath_internal_vectors.npz")
+    # the expanded bottleneck (param_merger_expand_bottleneck=True: 4C -> 8C -> 8C -> 4C), kept in its own file
+    generate(Coder, [("int_expand", 12, 2, "channelwise-checkerboard", 2, 4, 6, 13, True)], "ypath_internal_expand_vectors.npz")
+
+
+def generate(Coder, cases, filename):
     out = {}
-    for name, C, G, method, B, H, W, seed in cases:
+    for name, C, G, method, B, H, W, seed, expand in cases:
         torch.manual_seed(seed)
-        coder = Coder(in_channels=C, channel_groups=G, default_topo_group_method=method)
+        coder = Coder(in_channels=C, channel_groups=G, default_topo_group_method=method, param_merger_expand_bottleneck=expand)
         with torch.no_grad():   # the masked convolutions start from a structured init: perturb so every weight matters
             for prm in coder.parameters():
                 prm.add_(0.05 * torch.randn_like(prm))
@@ -47,7 +53,7 @@ def main():
         out[f"{name}.bytes"], out[f"{name}.yhat"] = np.frombuffer(bs, dtype=np.uint8), yh.numpy()
         out[f"{name}.params_full"] = params_full.numpy()
         print(name, "bytes", len(bs), "max|yhat-y|", float((yh - y).abs().max()))
-    np.savez_compressed(os.path.join(HERE, "ypath_internal_vectors.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, filename), **out)
 
 
 if __name__ == "__main__":

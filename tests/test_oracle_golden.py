@@ -238,6 +238,19 @@ def test_joint_ar_matches_reference(jv, name):
         assert torch.equal(o.decode(c["bytes"], c["prior"]), c["yhat"])
 
 
+def test_internal_merger_expanded_bottleneck_matches_reference(golden_dir):
+    """param_merger_expand_bottleneck=True (4C -> 8C -> 8C -> 4C, pgm_coder.py:1215): the oracle against the reference."""
+    ev = np.load(os.path.join(golden_dir, "ypath_internal_expand_vectors.npz"))
+    c = load_icase(ev, "int_expand")
+    assert tuple(c["w"]["pm2_w"].shape[:2]) == (8 * c["C"], 8 * c["C"])
+    o = Y.YPathOracle(c["C"], c["G"], c["w"])
+    o.update_state()
+    with torch.no_grad():
+        assert torch.equal(Y.params_for(c["yhat"], c["tg"], c["prior"], c["w"]), c["params_full"])
+        assert o.encode(c["y"], c["prior"], c["tg"]) == c["bytes"]
+        assert torch.equal(o.decode(c["bytes"], c["prior"], c["tg"]), c["yhat"])
+
+
 def test_group_maps(yv):
     for name, method in [("ckbd", "checkerboard"), ("cwckbd", "channelwise-checkerboard"), ("scanline", "scanline"),
                          ("raster", "raster2x2"), ("meanscale", "none")]:
