@@ -42,6 +42,13 @@ def lib():
                 raise NativeLibraryError(
                     f"cbench_basic_b200: CUDA library missing and could not be built ({e}). "
                     "There is no CPU fallback; run `python cbench_basic_b200/build.py`.") from e
+            # a library that does not match the sources is only used on request: results would not be those of HEAD
+            if os.environ.get("BASIC_ALLOW_STALE_LIB") != "1":
+                raise NativeLibraryError(
+                    f"cbench_basic_b200: {LIB_PATH} was built from other sources and could not be rebuilt ({e}). "
+                    "Run `python cbench_basic_b200/build.py`, or set BASIC_ALLOW_STALE_LIB=1 to load it anyway.") from e
+            import warnings
+            warnings.warn(f"cbench_basic_b200: loading a stale library ({e})")
     try:
         L = C.CDLL(LIB_PATH)
     except OSError as e:

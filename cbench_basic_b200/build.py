@@ -23,12 +23,27 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
 
 
+STAMP = os.path.join(OUT_DIR, "libbasic_b200.sources.sha256")
+
+
+def source_hash():
+    """sha256 over the kernel sources, the header and the flags: what the library was built from (mtimes do not survive a
+    checkout or the snapshot copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(SRC, f) for f in os.listdir(SRC)) + [os.path.join(HERE, "..", "include", "basic_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fd:
+            h.update(fd.read())
+    return h.hexdigest()
+
+
 def stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(HERE, "..", "include", "basic_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fd:
+        return fd.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -53,6 +68,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     subprocess.check_call([_nvcc(), "--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
                            "-o", LIB] + objs + ["-Xlinker", "--export-dynamic"])
+    with open(STAMP, "w") as fd:
+        fd.write(source_hash() + "\n")
     return LIB
 
 

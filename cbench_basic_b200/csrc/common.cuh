@@ -64,6 +64,21 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Function attributes (the opt-in to more than 48 KB of dynamic shared memory) are per device: one process may hold coders
+// on several GPUs.  first() is true once per (call site, current device).
+struct PerDeviceOnce {
+    unsigned long long done = 0;  // bit d = device d has been set up (the library is called from one host thread at a time)
+    bool first()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done & bit) return false;
+        done |= bit;
+        return true;
+    }
+};
+
 inline bool is_device_ptr(const void *p)
 {
     if (!p) return false;

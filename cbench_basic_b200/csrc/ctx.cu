@@ -565,10 +565,9 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, const Packe
         const int K = a.is_conv ? a.ksize * a.ksize * a.Cin : a.src0.channels + (a.src1.ptr ? a.src1.channels : 0);
         const size_t smem = ((size_t)rows * K + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
         if (smem <= 200 * 1024) {
-            static bool attr_done = false;
-            if (!attr_done) {
+            static PerDeviceOnce attr_once;
+            if (attr_once.first()) {
                 BASIC_CUDA(cudaFuncSetAttribute(k_layer_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_done = true;
             }
             k_layer_rows<<<(a.n_count + 31) / 32, kGemvWarps * 32, smem, stream>>>(a);
             BASIC_LAUNCHED();

@@ -965,13 +965,12 @@ int launch_layer_tc(CtxModel &m, const LayerArgs &a, cudaStream_t stream)
 {
     const int rows = a.B * a.ncells;
     if (rows == 0 || a.n_count == 0) return BASIC_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         BASIC_CUDA(cudaFuncSetAttribute(k_layer_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_done = true;
     }
     const long long tiles = (long long)((a.n_count + BN - 1) / BN) * ((rows + BM - 1) / BM);
     dim3 grid((unsigned)(tiles < m.sm_count ? tiles : m.sm_count));  // persistent: one CTA per SM

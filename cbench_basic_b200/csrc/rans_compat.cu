@@ -281,11 +281,10 @@ static int compat_table_smem(const RansTables &tb, size_t static_bytes)
 }
 static int compat_attrs()
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         BASIC_CUDA(cudaFuncSetAttribute(k_rans64_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(sizeof(EncSym) * kEncTile)));
         BASIC_CUDA(cudaFuncSetAttribute(k_rans64_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048 - (int)(2 * sizeof(int32_t) * kTile)));
-        attr_done = true;
     }
     return BASIC_OK;
 }

@@ -632,8 +632,8 @@ static int grid_for(int n_chunks, int sm_count)
 
 static int set_attrs()
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         const int dec_smem = kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit;
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
@@ -641,7 +641,6 @@ static int set_attrs()
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
-        attr_done = true;
     }
     return BASIC_OK;
 }

@@ -41,8 +41,8 @@ class HyperpriorLatentCodec(nn.Module):
             if self.hyper_analysis is None:
                 raise ValueError("z not given and no hyper_analysis module")
             z = self.hyper_analysis(y)
+        z_hat = coders["z"](z)                       # eval forward = the dequantised z the decoder will see (latent_graph.py:836)
         z_bytes = coders["z"].encode(z)
-        z_hat = coders["z"].decode(z_bytes)          # what the decoder will see, bit for bit
         prior = self.hyper_synthesis(z_hat)
         y_bytes = coders["y"].encode(y, prior=prior, **y_kwargs)
         return merge_bytes([z_bytes, y_bytes], num_segments=len(self.NODES))

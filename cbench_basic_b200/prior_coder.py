@@ -8,7 +8,12 @@ Same class names, constructor keywords (the ones that matter for coding), state_
 semantics (pgm_coder.py:544-618, :912-981, torch_ans.py:237-251).  The hot loop -- per group: context model,
 scale index, quantisation, ANS coding, write-back -- runs entirely in the CUDA library
 (basic_ypath_encode / basic_ypath_decode, include/basic_b200.h); Python only builds the group map and
-frames the bytes.  ``forward()`` (the training likelihood) is not part of the hot path and is not provided.
+frames the bytes.  ``forward()`` in eval mode returns what the reference returns there -- the dequantised input
+(pgm_coder.py:391-398, :539), which is what ``LatentGraphicalANSEntropyCoder._generative_process`` feeds to the next edge
+before it calls ``encode`` (latent_graph.py:836-841); the training likelihood stays with the reference module.  The module
+protocol the reference's harness uses on a coder (cache dicts, ``profiler.start_time_profile`` scopes, ``device``) comes from
+``module_api.CoderModuleBase``; ``reference_integration.bind()`` additionally derives the classes from the reference's own
+``NNTrainableModule``.
 """
 import ctypes as C
 import math
@@ -21,6 +26,7 @@ import torch.nn as nn
 
 from . import _native as N
 from . import ans, topo_groups
+from .module_api import CoderModuleBase
 
 SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
 
@@ -59,7 +65,7 @@ class _CtxHandle:
     __del__ = reset
 
 
-class TopoGroupDynamicMaskConv2dContextModel(nn.Module):
+class TopoGroupDynamicMaskConv2dContextModel(CoderModuleBase):
     """Weight container with the reference's parameter names (masked_conv.py:231-305): a 5x5 context
     convolution C -> 2C and the three 1x1 "param merger" convolutions 4C -> 10C/3 -> 8C/3 -> 2C, all with
     nn.Conv2d's default initialisation, so a reference state_dict loads unchanged.  Inference happens in the
@@ -87,7 +93,7 @@ class TopoGroupDynamicMaskConv2dContextModel(nn.Module):
         raise NotImplementedError("inference runs in the CUDA library (prior_coder.encode / decode)")
 
 
-class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
+class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
     """encode / decode / update_state of the reference coder of the same name (pgm_coder.py:983-2070).
 
     Extra keywords: ``lanes`` (1 = reference bitstream byte for byte; 0 = multi-lane container within 0.5 % of it,
@@ -113,9 +119,19 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             # torch_ans.py:241-243 builds Tans* with table_log = freq_precision = 16, which the reference decoder
             # itself refuses (TANS_MAX_TABLELOG = 12); tANS is available through cbench_basic_b200.ans only.
             raise NotImplementedError(f"Unknown coder type {coder_type}")
-        if quantizer_type != "uniform" or (quantizer_params is not None and list(quantizer_params) != [0.0, 128, 1.0]):
-            raise NotImplementedError("only the default uniform quantiser [0, 128, 1] is accelerated")
+        # torch_ans.py:32-56: "uniform" [zero point, levels, step] and "uniform_scale" [step]; the affine transform is an
+        # elementwise torch op around the fused call (identity, bit for bit, for the default [0, 128, 1])
+        if quantizer_type == "uniform":
+            quantizer_params = [0.0, 1 << data_precision - 1, 1.0] if quantizer_params is None else quantizer_params
+            assert len(quantizer_params) == 3
+        elif quantizer_type == "uniform_scale":
+            quantizer_params = [1.0] if quantizer_params is None else quantizer_params
+            assert len(quantizer_params) == 1
+        else:
+            raise NotImplementedError(f"Unknown quantizer_type {quantizer_type}")   # the reference's own transforms raise for these
         if not use_autoregressive_encode:
+            # pgm_coder.py:310-335 + :975: the encoder then truncates round(y) - mean while the decoder adds round(mean): the
+            # reference's own round trip is lossy there and no BaSIC configuration uses it
             raise NotImplementedError("use_autoregressive_encode=False")
         if default_topo_group_method not in topo_groups.METHODS:
             raise NotImplementedError(f"Unknown default_topo_group_method {default_topo_group_method}")
@@ -128,6 +144,8 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         self.use_param_merger = use_param_merger
         self.use_joint_ar_model_impl = use_joint_ar_model_impl
         self.coder_type, self.freq_precision = coder_type, freq_precision
+        self.quantizer_type, self.data_precision = quantizer_type, data_precision
+        self.register_buffer("quantizer_params", torch.as_tensor(quantizer_params, dtype=torch.float32), persistent=False)
         self.use_bypass_coding, self.bypass_precision = use_bypass_coding, bypass_precision
         self.fixed_input_shape = fixed_input_shape
         self.force_input_prior_shape_aligned = force_input_prior_shape_aligned
@@ -163,10 +181,9 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                 self.param_merger = nn.Sequential(nn.Conv2d(out * 2, bott, 1), nn.LeakyReLU(inplace=True),
                                                   nn.Conv2d(bott, bott, 1), nn.LeakyReLU(inplace=True),
                                                   nn.Conv2d(bott, out * 2, 1))
-        self.register_buffer("_device_indicator", torch.zeros(1), persistent=False)
         self.out_channels = 2 * in_channels
-        self.profile = {}          # wall-clock ms of the last calls, keyed like the reference's profiler scopes
         self._ctx_holder = _CtxHandle()
+        self._map_key = None       # (H, W, bytes of the group map) the library currently holds
 
     def _load_from_state_dict(self, state_dict, prefix, *a, **k):
         # entries of a reference checkpoint that carry nothing for coding: the unused compatibility copy of the conv kernel
@@ -185,6 +202,12 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             raise N.CudaError("cbench_basic_b200 coders run on CUDA devices only: move the module with .cuda() "
                               "(there is no CPU fallback)")
         return self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _sync(self):
+        torch.cuda.synchronize(self.device)
 
     def _get_ans_params(self):
         """torch_ans.py:284-310, the float32 torch calls verbatim (their rounding decides truncated counts)."""
@@ -226,6 +249,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
 
     def _upload_weights(self, dev):
         self._ctx_holder.reset()
+        self._map_key = None
         h = C.c_void_p()
         N.check(N.lib().basic_ctx_create(self.in_channels, self.channel_groups, self.kernel_size, dev, C.byref(h)))
         self._ctx_holder.h = h
@@ -259,7 +283,7 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
                     ptr(w0[half:, o:]), ptr(pm0.bias[half:]), ptr(w2[half:, half:]), ptr(pm2.bias[half:])]
         else:
             ptrs = [ptr(self.context_prediction.weight), ptr(self.context_prediction.bias)] + [None] * 6
-        torch.cuda.synchronize(self.device)
+        self._sync()
         if len(ptrs) == 12:
             N.check(N.lib().basic_ctx_set_weights_internal(self._ctx, *ptrs, int(half)))
         else:
@@ -287,8 +311,15 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
         return topo_groups.tile_map(pgm, self.channel_groups, H, W)
 
     def _set_map(self, tg):
+        """Hands the group map to the library -- once per (H, W, map): the cell lists, tap masks and position lists it derives
+        stay on the device between calls."""
         tg32 = np.ascontiguousarray(tg[0].numpy(), dtype=np.int32)
+        key = (tg32.shape, tg32.tobytes())
+        if key == self._map_key:
+            return
+        self._map_key = None
         N.check(N.lib().basic_ctx_set_map(self._ctx, tg32.ctypes.data, tg32.shape[1], tg32.shape[2]))
+        self._map_key = key
 
     def _operand(self, t):
         """float32, contiguous; a CPU tensor stays where it is: the C ABI takes host pointers and uploads them on its own
@@ -298,41 +329,78 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             return t.to(dtype=torch.float32).contiguous()
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
+    # ------------------------------------------------------------------------------------------ quantiser (torch_ans.py:105-180)
+    def _qparams(self, quantizer_params):
+        q = self.quantizer_params if quantizer_params is None else torch.as_tensor(quantizer_params, dtype=torch.float32)
+        if self.quantizer_type == "uniform":
+            zero, step = float(q[0]), float(q[2])
+        else:
+            zero, step = 0.0, float(q.reshape(-1)[0])
+        return zero, step
+
+    def _transform(self, x, quantizer_params=None):
+        zero, step = self._qparams(quantizer_params)
+        return x if (zero == 0.0 and step == 1.0) else (x - zero) / step
+
+    def _inverse_transform(self, x, quantizer_params=None):
+        zero, step = self._qparams(quantizer_params)
+        return x if (zero == 0.0 and step == 1.0) else x * step + zero
+
+    def _align_prior(self, prior, spatial):
+        """pgm_coder.py:571-577, :611-616: same spatial size, or the prior narrowed to the input's."""
+        if self.force_input_prior_shape_aligned:
+            assert tuple(spatial) == tuple(prior.shape[2:]), "Input and prior shape not aligned! Consider setting force_input_prior_shape_aligned = False, which may add a little overhead to the bitstream to save the input shape!"
+        else:
+            for dim, size in enumerate(spatial, 2):
+                prior = prior.narrow(dim, 0, size)
+        return prior
+
     # ------------------------------------------------------------------------------------------ coding
+    def forward(self, input, prior=None, pgm=None, quantizer_params=None, **kwargs):
+        """Eval mode of pgm_coder.py:391-539: returns ``input_dequant`` = dequantise(round(transform(input))) -- the tensor the
+        reference hands to the generative edges while it encodes (latent_graph.py:836-841).  The likelihood / rate terms of
+        that method feed training and the ``prior_entropy`` monitor only; they are not evaluated here."""
+        if self.training:
+            raise NotImplementedError("training likelihood (pgm_coder.py:391-539) is outside the accelerated hot path; "
+                                      "use the reference module for training and load its state_dict here for coding")
+        if prior is not None:
+            self._align_prior(prior, input.shape[2:])
+        with self.profiler.start_time_profile("time_data_preprocess_encode"):
+            return self._inverse_transform(torch.round(self._transform(input, quantizer_params)), quantizer_params)
+
     def encode(self, input, *args, prior=None, pgm=None, quantizer_params=None, return_yhat=False, **kwargs) -> bytes:
         assert hasattr(self, "ans_encoder"), "Not Initialized! Should call self.update_state() before coding!"
         if prior is None:
             raise ValueError("prior should not be None!")
-        t0 = time.perf_counter()
-        if self.force_input_prior_shape_aligned:
-            assert input.shape[2:] == prior.shape[2:], "Input and prior shape not aligned! Consider setting force_input_prior_shape_aligned = False, which may add a little overhead to the bitstream to save the input shape!"
-        else:
-            for dim, size in enumerate(input.shape[2:], 2):
-                prior = prior.narrow(dim, 0, size)
         B, Cc, H, W = input.shape
-        assert Cc == self.in_channels and prior.shape[1] == 2 * Cc
-        y, p = self._operand(input), self._operand(prior)
-        self._set_map(self._get_pgm(input.shape, pgm))
-        h = self.ans_encoder.handle
-        out_len = C.c_int64(0)
-        yhat = torch.empty(y.shape, dtype=torch.float32, device=self.device) if return_yhat else None
-        # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object
-        N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
-                                           C.byref(out_len), yhat.data_ptr() if return_yhat else None,
-                                           torch.cuda.current_stream(self.device).cuda_stream))
-        byte_string = N.last_output(h)
+        prior = self._align_prior(prior, (H, W))
+        if Cc != self.in_channels or tuple(prior.shape) != (B, 2 * Cc, H, W):
+            raise ValueError(f"expected input [B, {self.in_channels}, H, W] and prior [B, {2 * self.in_channels}, H, W], got "
+                             f"{tuple(input.shape)} and {tuple(prior.shape)}")
+        with self.profiler.start_time_profile("time_prior_preprocess_encode"):
+            y, p = self._operand(self._transform(input, quantizer_params)), self._operand(prior)
+            self._set_map(self._get_pgm(input.shape, pgm))
+        with self.profiler.start_time_profile("time_ans_encode"):
+            h = self.ans_encoder.handle
+            out_len = C.c_int64(0)
+            yhat = torch.empty(y.shape, dtype=torch.float32, device=self.device) if return_yhat else None
+            # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object
+            N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
+                                               C.byref(out_len), yhat.data_ptr() if return_yhat else None,
+                                               self._stream()))
+            byte_string = N.last_output(h)
         head = b""
         if self.fixed_input_shape is not None:
             assert B == self.fixed_input_shape[0] and tuple(input.shape[2:]) == tuple(self.fixed_input_shape[1:])
-        elif not (self.force_input_prior_shape_aligned and prior is not None):
+        elif not self.force_input_prior_shape_aligned:
             head = struct.pack("B", 3) + struct.pack("<H", B) + struct.pack("<H", H) + struct.pack("<H", W)  # :581-597
-        self.profile["time_ans_encode"] = (time.perf_counter() - t0) * 1e3
-        return (head + byte_string, yhat) if return_yhat else head + byte_string
+        if return_yhat:
+            return head + byte_string, self._inverse_transform(yhat, quantizer_params)
+        return head + byte_string
 
     def decode(self, byte_string: bytes, *args, prior=None, pgm=None, quantizer_params=None, **kwargs) -> torch.Tensor:
         assert hasattr(self, "ans_decoder"), "Not Initialized! Should call self.update_state() before coding!"
         assert prior is not None
-        t0 = time.perf_counter()
         if self.fixed_input_shape is not None:
             ptr, B, spatial = 0, self.fixed_input_shape[0], tuple(self.fixed_input_shape[1:])
         elif self.force_input_prior_shape_aligned:
@@ -341,26 +409,24 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(nn.Module):
             nd = struct.unpack("B", byte_string[:1])[0]
             flat = [struct.unpack("<H", byte_string[1 + 2 * i:3 + 2 * i])[0] for i in range(nd)]
             ptr, B, spatial = 1 + 2 * nd, flat[0], tuple(flat[1:])
-            for dim, size in enumerate(spatial, 2):
-                prior = prior.narrow(dim, 0, size)
+        prior = self._align_prior(prior, spatial)
         H, W = spatial
         Cc = self.in_channels
-        p = self._operand(prior)
-        self._set_map(self._get_pgm((B, Cc, H, W), pgm))
-        enc = np.frombuffer(byte_string, dtype=np.uint8, offset=ptr)
-        yhat = torch.empty(B, Cc, H, W, dtype=torch.float32, device=self.device)
-        N.check(N.lib().basic_ypath_decode(self.ans_decoder.handle, self._ctx, enc.ctypes.data if enc.size else None, enc.size,
-                                           p.data_ptr(), B, Cc, H, W, self.lanes, yhat.data_ptr(),
-                                           torch.cuda.current_stream(self.device).cuda_stream))
-        self.profile["pgm_generate_coding"] = (time.perf_counter() - t0) * 1e3
-        return yhat
+        if tuple(prior.shape) != (B, 2 * Cc, H, W):
+            raise ValueError(f"expected prior [{B}, {2 * Cc}, {H}, {W}], got {tuple(prior.shape)}")
+        with self.profiler.start_time_profile("time_prior_preprocess_decode"):
+            p = self._operand(prior)
+            self._set_map(self._get_pgm((B, Cc, H, W), pgm))
+        with self.profiler.start_time_profile("pgm_generate_coding"):
+            enc = np.frombuffer(byte_string, dtype=np.uint8, offset=ptr)
+            yhat = torch.empty(B, Cc, H, W, dtype=torch.float32, device=self.device)
+            N.check(N.lib().basic_ypath_decode(self.ans_decoder.handle, self._ctx, enc.ctypes.data if enc.size else None, enc.size,
+                                               p.data_ptr(), B, Cc, H, W, self.lanes, yhat.data_ptr(),
+                                               self._stream()))
+        return self._inverse_transform(yhat, quantizer_params)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("training likelihood (pgm_coder.py:391-539) is outside the accelerated hot path; "
-                                  "use the reference module for training and load its state_dict here for coding")
 
-
-class CombinedNNTrainablePGMPriorCoder(nn.Module):
+class CombinedNNTrainablePGMPriorCoder(CoderModuleBase):
     """BaSIC "dynamic entropy coder" dispatch (pgm_coder.py:632-715): picks one sub-coder by blend_weight.argmax()."""
 
     def __init__(self, coders, *args, fix_weight=False, **kwargs):
@@ -375,6 +441,12 @@ class CombinedNNTrainablePGMPriorCoder(nn.Module):
         if blend_weight is None:
             blend_weight = torch.softmax(self.default_blend_weight, dim=0)
         return self.coders[int(blend_weight.argmax().item())]
+
+    def forward(self, input, prior=None, blend_weight=None, **kwargs):
+        """Eval branch of pgm_coder.py:651-696: the selected sub-coder's forward."""
+        if self.training:
+            raise NotImplementedError("training forward stays with the reference module")
+        return self._pick(blend_weight)(input, prior=prior, **kwargs)
 
     def encode(self, input, *args, prior=None, blend_weight=None, **kwargs) -> bytes:
         return self._pick(blend_weight).encode(input, prior=prior, **kwargs)

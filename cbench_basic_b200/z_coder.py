@@ -33,6 +33,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ans
+from .module_api import CoderModuleBase
 
 
 # ---------------------------------------------------------------------------------------------------- framing
@@ -78,7 +79,7 @@ class EntropyBottleneck(nn.Module):
         self.init_scale = float(init_scale)
         self.tail_mass = float(tail_mass)
         self.entropy_coder_precision = int(entropy_coder_precision)
-        self.device_index = int(device_index)
+        self._device_index = int(device_index)
         filters = (1,) + self.filters + (1,)
         scale = self.init_scale ** (1 / (len(self.filters) + 1))
         for i in range(len(self.filters) + 1):
@@ -96,6 +97,15 @@ class EntropyBottleneck(nn.Module):
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
         self._enc = self._dec = None
+
+    @property
+    def device_index(self):
+        """The GPU the coder objects live on: the module's own device once it has been moved to CUDA (what the reference's
+        harness does with the whole codec), else the constructor's ``device_index``."""
+        d = self.quantiles.device
+        if d.type == "cuda":
+            return d.index if d.index is not None else torch.cuda.current_device()
+        return self._device_index
 
     def _load_from_state_dict(self, state_dict, prefix, *a, **k):
         # later compressai releases keep the same tensors in ParameterLists (matrices.0, biases.0, factors.0)
@@ -152,6 +162,11 @@ class EntropyBottleneck(nn.Module):
         self._push_tables()
         return True
 
+    def _coders(self):
+        if self._enc is None or self._enc.device != self.device_index:
+            self._push_tables()
+        return self._enc, self._dec
+
     def _push_tables(self):
         if self._quantized_cdf.numel() == 0:
             raise ValueError("Uninitialized CDFs. Run update() first")
@@ -167,8 +182,7 @@ class EntropyBottleneck(nn.Module):
     @torch.no_grad()
     def compress(self, x):
         """One lanes=1 stream per image: symbols = round(x - median), table = channel (EntropyModel.compress)."""
-        if self._enc is None:
-            self._push_tables()
+        enc, _ = self._coders()
         dev = torch.device("cuda", self.device_index)
         x = x.detach().to(device=dev, dtype=torch.float32)
         med = self._get_medians().to(dev).view(1, -1, *([1] * (x.dim() - 2)))
@@ -177,13 +191,12 @@ class EntropyBottleneck(nn.Module):
         if x.shape[0] == 0:
             return []
         if self.lanes != 1:  # our multi-lane container over the whole batch: u32 batch size | container
-            return [struct.pack("<I", x.shape[0]) + self._enc.encode_with_indexes(sym.reshape(-1), idx.reshape(-1))]
-        return self._enc.encode_batch(sym.reshape(x.shape[0], -1), idx.reshape(x.shape[0], -1))  # one CTA per image
+            return [struct.pack("<I", x.shape[0]) + enc.encode_with_indexes(sym.reshape(-1), idx.reshape(-1))]
+        return enc.encode_batch(sym.reshape(x.shape[0], -1), idx.reshape(x.shape[0], -1))  # one CTA per image
 
     @torch.no_grad()
     def decompress(self, strings, size):
-        if self._dec is None:
-            self._push_tables()
+        _, dec = self._coders()
         dev = torch.device("cuda", self.device_index)
         spatial = tuple(int(s) for s in size)
         if self.lanes != 1 and len(strings) == 1:
@@ -192,19 +205,20 @@ class EntropyBottleneck(nn.Module):
             (B,) = struct.unpack_from("<I", strings[0], 0)
             idx = self._indexes(B, spatial, dev)
             med = self._get_medians().to(dev).view(1, -1, *([1] * len(spatial)))
-            sym = self._dec.decode_with_indexes(strings[0][4:], idx.reshape(-1))
+            sym = dec.decode_with_indexes(strings[0][4:], idx.reshape(-1))
             return sym.view(B, self.channels, *spatial).to(torch.float32) + med
         idx = self._indexes(len(strings), spatial, dev)
         med = self._get_medians().to(dev).view(1, -1, *([1] * len(spatial)))
         if len(strings) == 0:
             return torch.empty(0, self.channels, *spatial, dtype=torch.float32, device=dev)
-        sym = self._dec.decode_batch(strings, idx.reshape(len(strings), -1))            # one CTA per image
+        sym = dec.decode_batch(strings, idx.reshape(len(strings), -1))            # one CTA per image
         return sym.view(len(strings), self.channels, *spatial).to(torch.float32) + med
 
 
-class CompressAIEntropyBottleneckPriorCoder(nn.Module):
+class CompressAIEntropyBottleneckPriorCoder(CoderModuleBase):
     """compressai_coder.py:87-248: encode(input, channel_gains=) -> bytes, decode(bytes, channel_gains_inv=) -> Tensor,
-    update_state().  Training forward() (likelihoods, aux loss) stays with the reference module."""
+    update_state(), and the eval-mode forward() -- the dequantised latent the reference's latent graph hands to h_s while it
+    encodes (latent_graph.py:836-841).  Training forward() (likelihoods, aux loss) stays with the reference module."""
 
     def __init__(self, entropy_bottleneck_channels=256, eps=1e-7, use_inner_aux_opt=False, use_bit_rate_loss=True,
                  freeze_params=False, training_output_straight_through=False, device_index=0, lanes=1, **kwargs):
@@ -236,5 +250,16 @@ class CompressAIEntropyBottleneckPriorCoder(nn.Module):
             y_hat = self._channelwise_mul(y_hat, channel_gains_inv)
         return y_hat
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("training likelihoods (compressai_coder.py:203-227) are outside the accelerated path")
+    def forward(self, input, *args, channel_gains=None, channel_gains_inv=None, **kwargs):
+        """Eval mode of compressai_coder.py:203-227: ``entropy_bottleneck(input)[0]`` outside training is
+        quantize(x, "dequantize", medians) = round(x - median) + median -- exactly what decode() returns for encode(input).
+        The likelihoods only feed the rate loss / the ``prior_entropy`` monitor and are not evaluated."""
+        if self.training:
+            raise NotImplementedError("training likelihoods (compressai_coder.py:203-227) are outside the accelerated path")
+        if channel_gains is not None:
+            input = self._channelwise_mul(input, channel_gains)
+        med = self.entropy_bottleneck._get_medians().to(input.device).view(1, -1, *([1] * (input.dim() - 2)))
+        y_hat = torch.round(input - med) + med
+        if channel_gains_inv is not None:
+            y_hat = self._channelwise_mul(y_hat, channel_gains_inv)
+        return y_hat

@@ -312,3 +312,22 @@ def test_tans_limits_mirror_reference(A):
         A.TansDecoder(table_log=16, max_symbol_value=255).init_params(f[:, :100], np.array([100]), np.array([0]))
     with pytest.raises(ValueError, match="generic"):
         A.TansEncoder(table_log=10, max_symbol_value=255).init_params(f, np.array([600]), np.array([0]))
+
+
+# ----------------------------------------------------------------------------------------------- several GPUs, one process
+def test_coders_on_two_devices_in_one_process(A, gauss):
+    """The opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: coders created on cuda:0 and
+    cuda:1 by the same process must both launch (tables image 155 KB) and agree byte for byte."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sym, idx = _gauss_data(gauss, 50_000, seed=5, geometric=True)
+    out = []
+    for dev in (0, 1):
+        for lanes in (1, 0):
+            enc, dec = A.Rans64Encoder(lanes=lanes, device=dev), A.Rans64Decoder(lanes=lanes, device=dev)
+            for c in (enc, dec):
+                c.init_params(gauss["freqs"], gauss["nsym"], gauss["offsets"])
+            bs = enc.encode_with_indexes(sym, idx)
+            assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
+            out.append(bs)
+    assert out[0] == out[2] and out[1] == out[3]

@@ -201,6 +201,37 @@ def test_internal_merger_golden(iv, name, lanes):
     assert_latents_match(yhat.cpu(), c["yhat"])
 
 
+@pytest.mark.parametrize("lanes", [1, 0])
+def test_internal_merger_expand_bottleneck_golden(golden_dir, lanes):
+    """param_merger_expand_bottleneck=True (pgm_coder.py:1216-1222: the merger's hidden width is 8C instead of 4C) on the CUDA
+    path against the unmodified reference's vectors (tests/golden/make_internal_golden.py): bytes at lanes = 1, parameters
+    within 1e-5, multi-lane lossless."""
+    from cbench_basic_b200.prior_coder import GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder as Coder
+    from cbench_basic_b200 import _native as N
+    from tests.test_oracle_golden import load_icase
+    ev = np.load(os.path.join(golden_dir, "ypath_internal_expand_vectors.npz"))
+    c = load_icase(ev, "int_expand")
+    coder = Coder(in_channels=c["C"], channel_groups=c["G"], default_topo_group_method=c["method"], lanes=lanes,
+                  ans_params_device="cpu", param_merger_expand_bottleneck=True)
+    coder.load_state_dict(dict(c["sd"]))
+    coder = coder.cuda().eval()
+    coder.update_state()
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    params = torch.full((c["B"], 2 * c["C"], c["H"], c["W"]), float("nan"), device="cuda")
+    coder._set_map(c["tg"])
+    yhat_ref = c["yhat"].cuda().contiguous()
+    for g in range(int(c["tg"].max()) + 1):
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, g, yhat_ref.data_ptr(), prior.data_ptr(), c["B"], params.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert not torch.isnan(params).any()
+    assert rel_err(params.cpu(), c["params_full"]) <= REL_TOL, rel_err(params.cpu(), c["params_full"])
+    bs = coder.encode(y, prior=prior)
+    yhat = coder.decode(bs, prior=prior)
+    if lanes == 1:
+        assert bs == c["bytes"]
+    assert_latents_match(yhat.cpu(), c["yhat"])
+
+
 @pytest.mark.parametrize("name", ["jar_a", "jar_b"])
 @pytest.mark.parametrize("lanes", [1, 0])
 def test_joint_ar_serial_coder_golden(jv, name, lanes):

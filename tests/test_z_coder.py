@@ -1,8 +1,8 @@
 """z-node factorized-prior coder (cbench_basic_b200/z_coder.py).
 
 Pinned by tests/golden/z_vectors.npz (made with the reference's own cbench.rans coder and write_body framing,
-tests/golden/make_z_golden.py): stream bytes, framing, tables -> streams.  The pmf evaluation out of the network parameters
-restates compressai 1.2.3 (not installed): parity unpinned, checked only against the oracle's restatement."""
+tests/golden/make_z_golden.py): stream bytes, framing, tables -> streams.  The density network is pinned to the reference's in-tree copy of it
+(z_pmf_vectors.npz, make_z_pmf_golden.py); the three lines that turn its logits into a pmf restate compressai 1.2.3."""
 import os
 
 import numpy as np
@@ -43,6 +43,23 @@ def test_oracle_matches_golden(zv, name):
     assert body == zv[name + "/body"].tobytes()
     back, shape = Z.read_body(body)
     assert torch.equal(Z.decompress(sd, tables, back, shape), torch.from_numpy(zv[name + "/y_hat"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cumulative_logits_match_reference_network(name):
+    """The density network of the z node (the step whose original lives in compressai): the product's and the oracle's
+    evaluation against the reference's own in-tree copy of that network (cbench/nn/layers/param_generator.py:158-199), run
+    by tests/golden/make_z_pmf_golden.py on seeded parameters at the sample points update() uses.  Bit-exact on the CPU."""
+    pv = np.load(os.path.join(os.path.dirname(GOLDEN), "z_pmf_vectors.npz"))
+    sd = _sd(pv, name)
+    samples = torch.from_numpy(pv[name + "/samples"])
+    C = samples.shape[0]
+    eb = z_coder.EntropyBottleneck(C)
+    eb.load_state_dict(sd, strict=False)
+    for shift, key in ((-0.5, "lower"), (0.5, "upper")):
+        ref = torch.from_numpy(pv[f"{name}/{key}"])
+        assert torch.equal(eb._logits_cumulative(samples + shift), ref)
+        assert torch.equal(Z.logits_cumulative(sd, samples + shift), ref)
 
 
 @pytest.mark.parametrize("name", CASES)
