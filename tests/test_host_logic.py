@@ -145,6 +145,10 @@ def test_latent_codec_container_layout():
         def update_state(self):
             self.seen.append("update")
 
+        def forward(self, x, prior=None):                    # latent_graph.py:836: forward before encode
+            self.seen.append("fwd")
+            return torch.full((1, 2), float(x.numel()))
+
         def encode(self, x, prior=None):
             self.seen.append(("enc", None if prior is None else float(prior.sum())))
             return self.tag * int(x.numel())
@@ -159,6 +163,7 @@ def test_latent_codec_container_layout():
     data = codec.encode(torch.ones(1, 5))
     assert data == struct.pack("I", 3) + b"zzz" + b"yyyyy"
     assert y.seen[-1] == ("enc", 12.0)                      # prior = h_s(z_hat) = 2 * [3, 3]
+    assert z.seen == ["update", "fwd", ("enc", None)]
     out = codec.decode(data)
     assert z.seen[-1][:2] == ("dec", b"zzz") and y.seen[-1] == ("dec", b"yyyyy", 12.0) and float(out[0, 0]) == 5.0
     assert list(codec.state_dict().keys()) == [] and set(codec.latent_node_entropy_coders.keys()) == {"z", "y"}
