@@ -20,48 +20,11 @@
 // chain: table records and encoder operands per 128-symbol block, four CDF probes at once in the decoder, escape payloads of
 // bypass_precision 4 as one 36-bit token string.  Kernels are instantiated per <tables in shared
 // memory, bypass_precision == 4>.
-#include "common.cuh"
+#include "rans_lanes.cuh"
 
 namespace basic {
 
 namespace {
-
-constexpr int kWarps = 8;      // warps per CTA when the chunks fit 8 per SM
-constexpr int kMaxWarps = 16;  // ... and when there are more (throughput mode: 16 x 148 chunks resident)
-constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSegHdr = 8;  // u32 n_chunks | u32 n_slices, followed by u32 chunk_syms[n_slices]
-
-template <bool SM> __device__ inline Tab<SM> stage_tables(const void *blob, size_t blob_bytes, size_t meta_bytes, size_t cdf16_bytes,
-                                                          unsigned char *smem)
-{
-    if (SM) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (size_t i = threadIdx.x; i < blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
-        __syncthreads();
-    }
-    Tab<SM> t;
-    t.init(blob, smem, meta_bytes, cdf16_bytes);
-    return t;
-}
-
-struct SliceDesc {  // one slice of a segment: `n` symbols starting at `off` in the operand arrays
-    long long off, n;
-    int cs, pad;
-};
-
-struct LaneParams {
-    const void *blob;
-    size_t blob_bytes, meta_bytes, cdf16_bytes;
-    int tables_in_smem;
-    int T, precision, bypass, bypass_precision;
-    long long n;            // symbols in the slice being coded (decoder) / unused (encoder)
-    int chunk_syms;         // chunk_syms of that slice, multiple of 128
-    const int *n_chunks_dev;  // device scalar (the auto mode decides it on the device); nullptr -> n_chunks
-    int n_chunks;
-    int n_slices;           // encoder: slices of the segment, walked last to first
-    const SliceDesc *slices;
-};
 
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
@@ -308,13 +271,6 @@ k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, int n_slices, const uint
 // them through a private shared-memory ring filled by cp.async two groups ahead: the state update chain never
 // waits on a global load.  Ring = kRingUnits u32 units (2 words each), filled in groups of kGroupUnits.
 constexpr int kRingUnits = 512, kGroupUnits = 128;
-
-__device__ inline void cp_async4(uint32_t smem_dst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool SM, bool BP4>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
@@ -592,6 +548,14 @@ k_estimate_bits(LaneParams P, const int32_t *__restrict__ symbols, const int32_t
 
 }  // namespace
 
+// rans_pair.cu
+bool pair_kernels_apply(const RansTables &tb, int bypass_precision);
+int launch_pair_encode(const RansTables &tb, const LaneParams &P, const int32_t *d_sym, const int32_t *d_idx, uint16_t *d_scratch,
+                       int cap_words, uint32_t *d_first, uint32_t *d_states, int *d_status, int sm_count, cudaStream_t stream);
+int launch_pair_decode(const RansTables &tb, const LaneParams &P, const unsigned char *d_seg, int64_t seg_cap, const int32_t *d_idx,
+                       int seg_slices, int slice, uint32_t *d_carry_x, uint32_t *d_carry_wp, int32_t *d_out, int *d_status,
+                       int sm_count, cudaStream_t stream);
+
 static int smem_for(const RansTables &tb) { return tb.blob_bytes <= (size_t)kMaxSmemTables ? (int)tb.blob_bytes : 0; }
 static constexpr int kRingBytes = kMaxWarps * kRingUnits * 4;
 // warps per CTA: 8 while every chunk gets its own resident warp, 16 beyond that (more lanes in flight per SM)
@@ -656,7 +620,9 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     const LaneParams P = make_params(tb, bypass, bypass_precision, 0, 128, n_chunks, n_slices, sl);
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
-    if (n_chunks > 0) {
+    if (n_chunks > 0 && smem > 0 && pair_kernels_apply(tb, bypass_precision)) {
+        BASIC_TRY(launch_pair_encode(tb, P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status, sm_count, stream));
+    } else if (n_chunks > 0) {
         const dim3 grid(grid_for(n_chunks, sm_count)), block(warps_for(n_chunks, sm_count, smem) * 32);
         // instantiations: tables in shared memory or not x bypass_precision 4 (the reference's default; its escape code is a
         // fraction of the general one -- the kernels are instruction-fetch sensitive with one warp per scheduler)
@@ -685,6 +651,8 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     if (n_chunks <= 0) return BASIC_OK;
     const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, 0, nullptr);
     const int smem = smem_for(tb);
+    if (smem > 0 && pair_kernels_apply(tb, bypass_precision))
+        return launch_pair_decode(tb, P, d_seg, seg_cap, d_idx, seg_slices, slice, d_carry_x, d_carry_wp, d_out, d_status, sm_count, stream);
     BASIC_TRY(set_attrs());
     const int nw = warps_for(n_chunks, sm_count, smem);
     const dim3 grid(grid_for(n_chunks, sm_count)), block(nw * 32);

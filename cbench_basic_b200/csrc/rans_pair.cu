@@ -1,0 +1,554 @@
+// Multi-lane interleaved rANS as MAIN / HELPER warp pairs -- the kernels of the default configuration (tables resident in
+// shared memory, bypass_precision 4).  Same container, byte for byte, as rans_lanes.cu and the CPU specification
+// (oracle/ans_oracle.c section 4).
+//
+// Why pairs: the 0.5 % size bar fixes the number of chunks (= warps that carry a state), so a coding call lasts as long as
+// ONE warp needs for its chunk: steps x the length of the state's dependency chain, with the instructions the same warp has
+// to issue around the chain added on top (one warp per scheduler: nothing else hides them).  Here the warp that owns the
+// states (main) issues the chain and nothing else; a second warp (helper) does everything that does not depend on the state:
+//   decoder helper: loads the indexes, fetches the table records, writes per-symbol lookup operands into a shared-memory
+//                   ring one block (4 steps) ahead, streams the renormalisation words global -> shared (cp.async), and
+//                   moves the decoded symbols shared -> global with 128-bit stores;
+//   encoder helper: loads symbols and indexes, classifies escapes, looks up (start, freq), computes 1 / freq, and writes
+//                   one 16-byte operand record per symbol into the ring.
+// Hand-over is by monotonically increasing block counters in shared memory (st.release / ld.acquire, CTA scope).
+#include <cstdlib>
+
+#include "rans_lanes.cuh"
+
+namespace basic {
+
+namespace {
+
+constexpr int kPairs = 8;          // chunk slots per CTA: warps [0, kPairs) are the main warps, [kPairs, 2 kPairs) their helpers
+constexpr int kWordUnits = 512;    // word ring per slot: u32 units of two 16-bit words (2 KB)
+constexpr int kWordGroup = 128;    // ... filled in groups of this many units
+constexpr int kDecParBlocks = 2;   // decoder operand ring: blocks of 4 steps x 32 lanes x 16 B (2 KB each)
+constexpr int kEncParBlocks = 4;   // encoder operand ring
+constexpr int kOutBlocks = 2;      // decoder output ring: blocks of 4 steps x 32 lanes x 4 B
+constexpr int kCtrlBytes = 32;     // per slot: params_ready | out_done | stored | wp_pub | ready_w | w_epoch | pad | pad
+
+constexpr int kDecSlotBytes = kWordUnits * 4 + kDecParBlocks * 2048 + kOutBlocks * 512;
+constexpr int kEncSlotBytes = kEncParBlocks * 2048;
+
+__device__ inline void st_release(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ inline uint32_t ld_acquire(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ inline void st_relaxed(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ inline uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ inline void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ inline uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ inline void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ inline uint32_t lds16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+// spin until the counter at `addr` reaches `want` (warp-uniform: every lane polls the same word)
+__device__ inline uint32_t wait_ge(uint32_t addr, uint32_t want)
+{
+    uint32_t v = ld_acquire(addr);
+    while ((int32_t)(v - want) < 0) {
+        __nanosleep(20);
+        v = ld_acquire(addr);
+    }
+    return v;
+}
+
+enum { C_PARAMS = 0, C_DONE = 4, C_STORED = 8, C_WP = 12, C_READYW = 16, C_EPOCH = 20 };
+
+// ------------------------------------------------------------------------------------------------ decode
+__global__ void __launch_bounds__(kPairs * 64, 1)
+k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
+              int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
+              uint32_t *__restrict__ carry_wp, int *status)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp % kPairs;
+    const bool is_main = warp < kPairs;
+    unsigned char *slot_mem = smem + kPairs * kCtrlBytes + slot * kDecSlotBytes;
+    const uint32_t ctrl = (uint32_t)__cvta_generic_to_shared(smem + slot * kCtrlBytes);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(slot_mem);             // words
+    const uint32_t par_s = ring_s + kWordUnits * 4;                                   // operands
+    const uint32_t out_s = par_s + kDecParBlocks * 2048;                              // decoded symbols
+    if (threadIdx.x < kPairs * kCtrlBytes / 4) reinterpret_cast<uint32_t *>(smem)[threadIdx.x] = 0;
+    const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kDecSlotBytes));
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int n_chunks = P.n_chunks;
+    const int prec = P.precision;
+    const uint32_t pmask = (1u << prec) - 1;
+    const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2 + seg_slices;
+    const uint32_t *states = end_word + n_chunks;
+    const long long words_at = kSegHdr + 4ll * seg_slices + 4ll * n_chunks + 128ll * n_chunks;
+    const uint32_t *units = reinterpret_cast<const uint32_t *>(seg + words_at);  // 2 words per unit, 4-byte aligned
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
+    int st = 0;
+    uint32_t gb = 0;     // blocks of this slot so far (all its chunks): the counters in `ctrl` count in these
+    uint32_t seq = 0;    // chunks of this slot so far
+    for (int k = blockIdx.x + slot * gridDim.x; k < n_chunks; k += gridDim.x * kPairs) {
+        ++seq;
+        const long long base = (long long)k * P.chunk_syms;
+        const long long rem = P.n - base;
+        const int m = (int)(rem <= 0 ? 0 : rem < P.chunk_syms ? rem : P.chunk_syms);
+        const int nblocks = (m + 127) >> 7;
+        uint32_t wend = end_word[k], wbeg = k ? end_word[k - 1] : 0;
+        if (wend < wbeg || words_at + 2ll * wend > seg_cap) { st |= 4; wend = wbeg = 0; }  // corrupt directory
+        uint32_t wp = first_slice ? wbeg : carry_wp[k];  // absolute word index; a later slice continues where the previous stopped
+        if (wp < wbeg || wp > wend) { st |= 4; wp = wend; }
+        const uint32_t gb0 = gb;
+        if (is_main) {
+            // ================================================================================= main: the state's chain
+            uint32_t x = first_slice ? states[(size_t)k * 32 + lane] : carry_x[(size_t)k * 32 + lane];
+            wait_ge(ctrl + C_EPOCH, seq);               // the helper serves this chunk's words from now on
+            uint32_t ready_w = ld_acquire(ctrl + C_READYW);
+            // words must have landed before the events that consume them: 160 ahead at every block and escape sub-step
+            // (a block's four steps take up to 128, a sub-step up to 32)
+            auto ensure = [&]() {
+                const uint32_t need = wp + 160 < wend ? wp + 160 : wend;
+                if ((int32_t)(ready_w - need) < 0) {
+                    if (lane == 0) st_relaxed(ctrl + C_WP, wp);
+                    ready_w = wait_ge(ctrl + C_READYW, need);
+                }
+            };
+            for (int blk = 0; blk < nblocks; ++blk, ++gb) {
+                const int j0 = blk * 128 + lane * 4;
+                wait_ge(ctrl + C_PARAMS, gb + 1);
+                if (gb >= kOutBlocks) wait_ge(ctrl + C_STORED, gb + 1 - kOutBlocks);
+                const uint32_t pbase = par_s + (gb % kDecParBlocks) * 2048 + lane * 16;
+                const uint32_t obase = out_s + (gb % kOutBlocks) * 512 + lane * 4;
+                uint4 Pq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Pq[q] = lds128(pbase + q * 512);
+                ensure();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // operands: lut address | cdf address | lut shift, symbols << 8, active << 31 | offset
+                    const bool active = (int32_t)Pq[q].z < 0;
+                    const int nsyms = (int)((Pq[q].z >> 8) & 0xffffu), maxv = nsyms - 1;
+                    const uint32_t cum = x & pmask;
+                    int s = (int)lds16(Pq[q].x + ((cum >> (Pq[q].z & 31u)) << 1));
+                    const uint32_t e = Pq[q].y + 2u * (uint32_t)s;
+                    const uint32_t c0 = lds16(e), c1 = lds16(e + 2), c2 = lds16(e + 4), c3 = lds16(e + 6);
+                    const bool a1 = s + 1 < nsyms && c1 <= cum;
+                    const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
+                    const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
+                    uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
+                    s += (int)a1 + (int)a2;
+                    if (a3) {  // a bucket in a tail of width-1 symbols
+                        ++s;
+                        while (s + 1 < nsyms && lds16(Pq[q].y + 2u * (uint32_t)s + 2) <= cum) ++s;
+                        start = lds16(Pq[q].y + 2u * (uint32_t)s);
+                        next = lds16(Pq[q].y + 2u * (uint32_t)s + 2);
+                    }
+                    const uint32_t freq = (uint16_t)(next - start);
+                    if (active) x = freq * (x >> prec) + cum - start;
+                    {
+                        const bool need = active && x < kRansL;
+                        const unsigned nm = __ballot_sync(kFull, need);
+                        if (need) {
+                            const uint32_t at = wp + __popc(nm & lt_mask);
+                            uint32_t word = 0;
+                            if (at < wend) word = lds16(ring_s + ((at & (2 * kWordUnits - 1)) << 1)); else st |= 4;
+                            x = (x << 16) | word;
+                        }
+                        wp += __popc(nm);
+                    }
+                    int32_t value = s;
+                    const bool esc = active && P.bypass && s == maxv;
+                    // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count
+                    // token), followed by the digits, least significant first, four tokens per unit
+                    if (__any_sync(kFull, esc)) {
+                        bool in = esc, first = true;
+                        uint32_t nb = 0, raw = 0, jj = 0;
+                        while (__any_sync(kFull, in)) {
+                            const bool was = in;
+                            if (in) {
+                                uint32_t cnt, used, bits = x;
+                                if (first) {
+                                    nb = x & 15u;
+                                    if (nb > 8) { st |= 4; nb = 0; }  // no encoder writes this
+                                    cnt = min(3u, nb);
+                                    used = cnt + 1;
+                                    bits = x >> 4;
+                                    first = false;
+                                } else {
+                                    cnt = min(4u, nb - jj);
+                                    used = cnt;
+                                }
+                                raw |= (bits & ((1u << (4 * cnt)) - 1)) << (4 * jj);
+                                jj += cnt;
+                                x >>= 4 * used;
+                                in = jj < nb;
+                            }
+                            ensure();
+                            const bool need = was && x < kRansL;
+                            const unsigned nm = __ballot_sync(kFull, need);
+                            if (need) {
+                                const uint32_t at = wp + __popc(nm & lt_mask);
+                                uint32_t word = 0;
+                                if (at < wend) word = lds16(ring_s + ((at & (2 * kWordUnits - 1)) << 1)); else st |= 4;
+                                x = (x << 16) | word;
+                            }
+                            wp += __popc(nm);
+                        }
+                        if (esc) {
+                            const int32_t v2 = (int32_t)(raw >> 1);
+                            value = (raw & 1) ? -v2 - 1 : v2 + maxv;
+                        }
+                    }
+                    sts32(obase + q * 128, (uint32_t)(value + (int32_t)Pq[q].w));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    st_relaxed(ctrl + C_WP, wp);
+                    st_release(ctrl + C_DONE, gb + 1);
+                }
+            }
+            if (last_slice) {
+                if (wp != wend && lane == 0) st |= 4;
+            } else {
+                carry_x[(size_t)k * 32 + lane] = x;
+                if (lane == 0) carry_wp[k] = wp;
+            }
+        } else {
+            // ================================================================================= helper: everything else
+            const uint32_t u_lim = (wend + 1) >> 1;  // units holding words of this chunk end here
+            const uint32_t wp0 = wp;
+            uint32_t fill_u = wp0 >> 1, wp_known = wp0;
+            bool serving = false;                    // the word ring belongs to this chunk (the main warp left the previous one)
+            auto load_ix = [&](int blk) -> int4 {
+                const int j0 = blk * 128 + lane * 4;
+                if (vec_ok && j0 + 3 < m) return __ldg(reinterpret_cast<const int4 *>(indexes + base + j0));
+                int4 b;
+                b.x = j0 + 0 < m ? indexes[base + j0 + 0] : 0;
+                b.y = j0 + 1 < m ? indexes[base + j0 + 1] : 0;
+                b.z = j0 + 2 < m ? indexes[base + j0 + 2] : 0;
+                b.w = j0 + 3 < m ? indexes[base + j0 + 3] : 0;
+                return b;
+            };
+            int blk_par = 0, blk_out = 0;
+            int4 ixn = make_int4(0, 0, 0, 0);
+            if (nblocks > 0) ixn = load_ix(0);
+            while (blk_out < nblocks || !serving) {
+                const uint32_t done = ld_acquire(ctrl + C_DONE);
+                bool progress = false;
+                // --- lookup operands of the next block (its ring slot is free once the main warp left block - kDecParBlocks)
+                if (blk_par < nblocks && (int32_t)(gb0 + blk_par - done) < kDecParBlocks) {
+                    const int j0 = blk_par * 128 + lane * 4;
+                    const int32_t ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
+                    if (blk_par + 1 < nblocks) ixn = load_ix(blk_par + 1);
+                    const uint32_t pbase = par_s + ((gb0 + blk_par) % kDecParBlocks) * 2048 + lane * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool active = j0 + q < m;
+                        int32_t c = ix[q];
+                        if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
+                        const uint4 mt = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                        uint4 o;
+                        o.x = tb.lut_at(mt.y);
+                        o.y = tb.cdf_at(mt.x);
+                        o.z = ((mt.z >> 16) & 0xffu) | (((mt.z & 0xffffu) - 1u) << 8) | (active ? 0x80000000u : 0u);
+                        o.w = mt.w;
+                        sts128(pbase + q * 512, o);
+                    }
+                    __syncwarp();
+                    ++blk_par;
+                    if (lane == 0) st_release(ctrl + C_PARAMS, gb0 + blk_par);
+                    progress = true;
+                }
+                // --- renormalisation words: global -> ring, as far ahead as the ring allows
+                if ((int32_t)(done - gb0) >= 0) {
+                    if (!serving) {
+                        serving = true;
+                        if (lane == 0) {
+                            st_relaxed(ctrl + C_READYW, fill_u >= u_lim ? 0x7fffffffu : wp0);
+                            st_release(ctrl + C_EPOCH, seq);
+                        }
+                        progress = true;
+                    }
+                    const uint32_t pub = ld_acquire(ctrl + C_WP);   // (a value left by the previous chunk lies below wp0)
+                    if ((int32_t)(pub - wp_known) > 0 && pub <= wend) wp_known = pub;
+                    bool filled = false;
+                    while (fill_u < u_lim && fill_u + kWordGroup - (wp_known >> 1) <= (uint32_t)kWordUnits) {
+#pragma unroll
+                        for (int i = 0; i < kWordGroup / 32; ++i) {
+                            const uint32_t u = fill_u + i * 32 + lane;
+                            if (u < u_lim) cp_async4(ring_s + (u & (kWordUnits - 1)) * 4, units + u);
+                        }
+                        fill_u += kWordGroup;
+                        filled = true;
+                    }
+                    if (filled) {
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                        __syncwarp();
+                        if (lane == 0) st_release(ctrl + C_READYW, fill_u >= u_lim ? 0x7fffffffu : fill_u * 2);
+                        progress = true;
+                    }
+                }
+                // --- decoded symbols of a finished block: ring -> global
+                if (blk_out < nblocks && (int32_t)(done - (gb0 + blk_out)) > 0) {
+                    const int j0 = blk_out * 128 + lane * 4;
+                    const uint32_t obase = out_s + ((gb0 + blk_out) % kOutBlocks) * 512 + lane * 4;
+                    int4 r;
+                    r.x = (int32_t)lds32(obase);
+                    r.y = (int32_t)lds32(obase + 128);
+                    r.z = (int32_t)lds32(obase + 256);
+                    r.w = (int32_t)lds32(obase + 384);
+                    if (vec_ok && j0 + 3 < m) {
+                        *reinterpret_cast<int4 *>(out + base + j0) = r;
+                    } else {
+                        if (j0 + 0 < m) out[base + j0 + 0] = r.x;
+                        if (j0 + 1 < m) out[base + j0 + 1] = r.y;
+                        if (j0 + 2 < m) out[base + j0 + 2] = r.z;
+                        if (j0 + 3 < m) out[base + j0 + 3] = r.w;
+                    }
+                    __syncwarp();
+                    ++blk_out;
+                    if (lane == 0) st_release(ctrl + C_STORED, gb0 + blk_out);
+                    progress = true;
+                }
+                if (!progress) __nanosleep(40);
+            }
+            gb += nblocks;
+        }
+    }
+    if (st) atomicOr(status, st);
+}
+
+// ------------------------------------------------------------------------------------------------ encode
+// scratch layout as in rans_lanes.cu: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front;
+// outputs per chunk: first_word[k], states[k * 32 + lane].
+__global__ void __launch_bounds__(kPairs * 64, 1)
+k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
+              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word, uint32_t *__restrict__ states,
+              int *status)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp % kPairs;
+    const bool is_main = warp < kPairs;
+    const uint32_t ctrl = (uint32_t)__cvta_generic_to_shared(smem + slot * kCtrlBytes);
+    const uint32_t par_s = (uint32_t)__cvta_generic_to_shared(smem + kPairs * kCtrlBytes + slot * kEncSlotBytes);
+    if (threadIdx.x < kPairs * kCtrlBytes / 4) reinterpret_cast<uint32_t *>(smem)[threadIdx.x] = 0;
+    const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kEncSlotBytes));
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
+    const int prec = P.precision;
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
+    int st = 0;
+    uint32_t gb = 0;
+    for (int k = blockIdx.x + slot * gridDim.x; k < n_chunks; k += gridDim.x * kPairs) {
+        uint16_t *wbuf = scratch + (size_t)k * cap_words;
+        int pos = cap_words;  // warp-uniform
+        uint32_t x = kRansL;
+        for (int g = P.n_slices - 1; g >= 0; --g) {  // the encoder walks the chunk's symbols backwards
+            const SliceDesc sd = P.slices[g];
+            const long long rem = sd.n - (long long)k * sd.cs;
+            if (rem <= 0) continue;
+            const long long base = sd.off + (long long)k * sd.cs;
+            const int m = (int)(rem < sd.cs ? rem : sd.cs);
+            const int nblocks = (m + 127) >> 7;
+            if (is_main) {
+                for (int blk = nblocks - 1; blk >= 0; --blk, ++gb) {
+                    wait_ge(ctrl + C_PARAMS, gb + 1);
+                    const uint32_t pbase = par_s + (gb % kEncParBlocks) * 2048 + lane * 16;
+                    uint4 Pq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) Pq[q] = lds128(pbase + q * 512);
+#pragma unroll
+                    for (int q = 3; q >= 0; --q) {
+                        // operands: start | freq << 16, 1 / freq, escape payload, active | escape << 1
+                        const bool active = Pq[q].w & 1u, esc = Pq[q].w & 2u;
+                        const uint32_t start = Pq[q].x & 0xffffu, freq = Pq[q].x >> 16, raw = Pq[q].z;
+                        // --- escape units, last to first: the token list is the 36-bit string  nd | raw << 4 ; unit u = its
+                        // bits [16u, 16u + 16) (a 32-bit payload has at most 8 digits: one count token)
+                        if (__any_sync(kFull, esc)) {
+                            const int nd = esc ? (35 - __clz(raw)) >> 2 : 0;
+                            const int ntok = esc ? nd + 1 : 0;
+                            const int nunits = (ntok + 3) >> 2;
+                            const unsigned long long toks = (unsigned long long)nd | ((unsigned long long)raw << 4);
+                            const int maxunits = (int)__reduce_max_sync(kFull, (unsigned)nunits);
+                            for (int u = maxunits - 1; u >= 0; --u) {
+                                const bool part = nunits > u;
+                                const int wbits = part ? 4 * min(4, ntok - 4 * u) : 0;
+                                const uint32_t unit = (uint32_t)(toks >> (16 * u)) & 0xffffu;
+                                const bool emit = part && x >= (1u << (32 - wbits));
+                                const unsigned em = __ballot_sync(kFull, emit);
+                                pos -= __popc(em);
+                                if (emit) {
+                                    const int at = pos + __popc(em & lt_mask);
+                                    if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
+                                    x >>= 16;
+                                }
+                                if (part) x = (x << wbits) | unit;
+                            }
+                        }
+                        // --- the symbol itself: x >= freq << (32 - prec) -> emit a word
+                        const bool emit = active && (x >> (32 - prec)) >= freq;
+                        const unsigned em = __ballot_sync(kFull, emit);
+                        pos -= __popc(em);
+                        if (emit) {
+                            const int at = pos + __popc(em & lt_mask);
+                            if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
+                            x >>= 16;
+                        }
+                        if (active) {
+                            uint32_t qt, rm;
+                            if (prec == 16) {  // x < freq << 16 here: the float estimate of the quotient is within one
+                                qt = __float2uint_rz(__uint2float_rz(x) * __uint_as_float(Pq[q].y));
+                                rm = x - qt * freq;
+                                if ((int32_t)rm < 0) { --qt; rm += freq; }
+                                else if (rm >= freq) { ++qt; rm -= freq; }
+                            } else {
+                                qt = x / freq;
+                                rm = x - qt * freq;
+                            }
+                            x = (qt << prec) + rm + start;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) st_release(ctrl + C_DONE, gb + 1);
+                }
+            } else {
+                const bool vec_ok = ptr_ok && (sd.off & 3) == 0;
+                auto load_ops = [&](int blk, int4 &a, int4 &b) {
+                    const int j0 = blk * 128 + lane * 4;
+                    if (vec_ok && j0 + 3 < m) {
+                        a = __ldg(reinterpret_cast<const int4 *>(symbols + base + j0));
+                        b = __ldg(reinterpret_cast<const int4 *>(indexes + base + j0));
+                    } else {
+                        int32_t sy[4], ix[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool ok = j0 + q < m;
+                            sy[q] = ok ? symbols[base + j0 + q] : 0;
+                            ix[q] = ok ? indexes[base + j0 + q] : 0;
+                        }
+                        a = make_int4(sy[0], sy[1], sy[2], sy[3]);
+                        b = make_int4(ix[0], ix[1], ix[2], ix[3]);
+                    }
+                };
+                int4 syn = make_int4(0, 0, 0, 0), ixn = syn;
+                if (nblocks > 0) load_ops(nblocks - 1, syn, ixn);
+                for (int blk = nblocks - 1; blk >= 0; --blk, ++gb) {
+                    const int j0 = blk * 128 + lane * 4;
+                    const int32_t sy[4] = {syn.x, syn.y, syn.z, syn.w}, ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
+                    if (blk > 0) load_ops(blk - 1, syn, ixn);
+                    if (gb >= kEncParBlocks) wait_ge(ctrl + C_DONE, gb + 1 - kEncParBlocks);  // the ring slot is free again
+                    const uint32_t pbase = par_s + (gb % kEncParBlocks) * 2048 + lane * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool active = j0 + q < m;
+                        int32_t c = ix[q];
+                        if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
+                        const uint4 mt = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                        const int32_t maxv = (int32_t)(mt.z & 0xffffu) - 2;
+                        int32_t v = sy[q] - (int32_t)mt.w;
+                        uint32_t raw = 0;
+                        bool esc = false;
+                        if (P.bypass) {
+                            if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = maxv; }
+                            else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
+                            esc = active && v == maxv;
+                        } else if (v < 0 || v > maxv) { if (active) st |= 2; v = 0; }
+                        const uint32_t at = tb.cdf_at(mt.x + (uint32_t)v);
+                        const uint32_t start = lds16(at);
+                        const uint32_t freq = (uint16_t)(lds16(at + 2) - start);
+                        uint4 o;
+                        o.x = start | (freq << 16);
+                        o.y = __float_as_uint(__frcp_rn(__uint2float_rz(freq)));
+                        o.z = raw;
+                        o.w = (active ? 1u : 0u) | (esc ? 2u : 0u);
+                        sts128(pbase + q * 512, o);
+                    }
+                    __syncwarp();
+                    if (lane == 0) st_release(ctrl + C_PARAMS, gb + 1);
+                }
+            }
+        }
+        if (is_main) {
+            states[(size_t)k * 32 + lane] = x;
+            if (lane == 0) first_word[k] = (uint32_t)(pos < 0 ? 0 : pos);
+        }
+    }
+    if (st) atomicOr(status, st);
+}
+
+}  // namespace
+
+static constexpr int kSmemLimit = 232448;  // opt-in dynamic shared memory of one CTA on sm_100
+
+static int pair_smem(const RansTables &tb, int slot_bytes) { return kPairs * (kCtrlBytes + slot_bytes) + (int)tb.blob_bytes; }
+
+// The pair kernels serve the default configuration: bypass_precision 4 and a table image that fits beside the rings.
+bool pair_kernels_apply(const RansTables &tb, int bypass_precision)
+{
+    static const bool off = [] { const char *e = getenv("BASIC_CODER_PAIRS"); return e && e[0] == '0'; }();  // A/B switch
+    return !off && bypass_precision == 4 && tb.blob_bytes > 0 &&
+           pair_smem(tb, kDecSlotBytes > kEncSlotBytes ? kDecSlotBytes : kEncSlotBytes) <= kSmemLimit;
+}
+
+static int pair_attrs()
+{
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
+        BASIC_CUDA(cudaFuncSetAttribute(k_pair_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        BASIC_CUDA(cudaFuncSetAttribute(k_pair_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    }
+    return BASIC_OK;
+}
+
+static int pair_grid(int n_chunks, int sm_count)
+{
+    int g = n_chunks < sm_count ? n_chunks : sm_count;  // chunks are dealt over CTAs first: few chunks still spread over all SMs
+    return g < 1 ? 1 : g;
+}
+
+int launch_pair_encode(const RansTables &tb, const LaneParams &P, const int32_t *d_sym, const int32_t *d_idx, uint16_t *d_scratch,
+                       int cap_words, uint32_t *d_first, uint32_t *d_states, int *d_status, int sm_count, cudaStream_t stream)
+{
+    BASIC_TRY(pair_attrs());
+    k_pair_encode<<<pair_grid(P.n_chunks, sm_count), kPairs * 64, pair_smem(tb, kEncSlotBytes), stream>>>(
+        P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+int launch_pair_decode(const RansTables &tb, const LaneParams &P, const unsigned char *d_seg, int64_t seg_cap, const int32_t *d_idx,
+                       int seg_slices, int slice, uint32_t *d_carry_x, uint32_t *d_carry_wp, int32_t *d_out, int *d_status,
+                       int sm_count, cudaStream_t stream)
+{
+    BASIC_TRY(pair_attrs());
+    k_pair_decode<<<pair_grid(P.n_chunks, sm_count), kPairs * 64, pair_smem(tb, kDecSlotBytes), stream>>>(
+        P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+}  // namespace basic
