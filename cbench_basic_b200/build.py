@@ -13,7 +13,8 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libbasic_b200.so")
 SOURCES = ["capi.cu", "tables.cu", "rans_compat.cu", "rans_lanes.cu", "rans_pair.cu", "gauss.cu", "ctx.cu", "ctx_tc.cu", "tans.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"] + \
+             [f"-D{d}" for d in os.environ.get("BASIC_NVCC_DEFS", "").split(",") if d]   # debug builds (kernel timing switches)
 
 
 def _nvcc():

@@ -334,7 +334,8 @@ int encode_segment(basic_coder *c, const int32_t *d_sym, const int32_t *d_idx, i
     if (n_slices) BASIC_CUDA(cudaMemcpyAsync(c->slices_dev.p, sl.data(), sizeof(SliceDesc) * (size_t)n_slices, cudaMemcpyHostToDevice, s));
     const size_t hdr = 8 + 4 * (size_t)n_slices + (size_t)n_chunks * 132;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int64_t cap_words64 = attempt == 0 ? cs_sum + cs_sum / 4 + 64 : 12 * cs_sum + 64;
+        // (+ 512: the pair kernel checks the room for a whole block of four steps at once)
+        int64_t cap_words64 = (attempt == 0 ? cs_sum + cs_sum / 4 + 64 : 12 * cs_sum + 64) + 512;
         cap_words64 = (cap_words64 + 7) & ~(int64_t)7;
         if (cap_words64 > 0x7fffffff) return value_error("chunk too large: use more lanes");
         const int cap_words = (int)cap_words64;
@@ -635,7 +636,7 @@ void basic_coder_destroy(basic_coder *c)
 {
     if (!c) return;
     DeviceGuard guard(c->device);
-    DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
+    DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->rt.enc, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
                       &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
                       &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp, &c->buf_cl, &c->prior_cl, &c->batch_first,
                       &c->batch_meta, &c->batch_state};

@@ -106,6 +106,8 @@ struct RansTables {
     std::vector<int32_t> h_sizes, h_offsets;  // host mirrors (sizes are known without a device round trip)
     DevBuf cdf32;                              // int32 [T, stride], the reference's _cdfs (zero padded)
     DevBuf blob;                               // packed: TableMeta[T] | u16 cdf[...] | u16 lut[...]
+    DevBuf enc;                                // uint4 per CDF entry (same numbering as the u16 CDFs): the encoder's operands of that symbol
+                                               // start' | m = ceil(2^32 / f) | f | 0  (rans_pair.cu); read through L2
     size_t blob_bytes = 0, meta_bytes = 0, cdf16_bytes = 0, lut_bytes = 0;
     uint32_t total_cdf = 0, total_lut = 0;
     bool ready = false;

@@ -651,7 +651,9 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     if (n_chunks <= 0) return BASIC_OK;
     const LaneParams P = make_params(tb, bypass, bypass_precision, n, chunk_syms, n_chunks, 0, nullptr);
     const int smem = smem_for(tb);
-    if (smem > 0 && pair_kernels_apply(tb, bypass_precision))
+    // pairs while every chunk gets its own resident main warp (the lane count the size bar allows); beyond that -- lanes chosen
+    // freely, throughput mode -- sixteen state-carrying warps per SM do better than eight pairs
+    if (smem > 0 && n_chunks <= 8 * sm_count && pair_kernels_apply(tb, bypass_precision))
         return launch_pair_decode(tb, P, d_seg, seg_cap, d_idx, seg_slices, slice, d_carry_x, d_carry_wp, d_out, d_status, sm_count, stream);
     BASIC_TRY(set_attrs());
     const int nw = warps_for(n_chunks, sm_count, smem);

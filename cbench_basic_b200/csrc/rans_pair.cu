@@ -12,6 +12,7 @@
 //   encoder helper: loads symbols and indexes, classifies escapes, looks up (start, freq), computes 1 / freq, and writes
 //                   one 16-byte operand record per symbol into the ring.
 // Hand-over is by monotonically increasing block counters in shared memory (st.release / ld.acquire, CTA scope).
+#include <cstdio>
 #include <cstdlib>
 
 #include "rans_lanes.cuh"
@@ -25,8 +26,9 @@ constexpr int kWordUnits = 512;    // word ring per slot: u32 units of two 16-bi
 constexpr int kWordGroup = 128;    // ... filled in groups of this many units
 constexpr int kDecParBlocks = 2;   // decoder operand ring: blocks of 4 steps x 32 lanes x 16 B (2 KB each)
 constexpr int kEncParBlocks = 4;   // encoder operand ring
+constexpr int kEncHelpers = 2;     // encoder: helper warps per main warp; helper h prepares the blocks with (block number) % kEncHelpers == h
 constexpr int kOutBlocks = 2;      // decoder output ring: blocks of 4 steps x 32 lanes x 4 B
-constexpr int kCtrlBytes = 32;     // per slot: params_ready | out_done | stored | wp_pub | ready_w | w_epoch | pad | pad
+constexpr int kCtrlBytes = 64;     // per slot: params_ready | out_done | stored | wp_pub | ready_w | w_epoch | pad | pad | flags of the ring's blocks [8]
 
 constexpr int kDecSlotBytes = kWordUnits * 4 + kDecParBlocks * 2048 + kOutBlocks * 512;
 constexpr int kEncSlotBytes = kEncParBlocks * 2048;
@@ -34,6 +36,16 @@ constexpr int kEncSlotBytes = kEncParBlocks * 2048;
 __device__ inline void st_release(uint32_t addr, uint32_t v)
 {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// Per-block hand-over flags.  st.release.cta compiles to MEMBAR.ALL.CTA + ST, and the membar waits for EVERY memory
+// operation of the warp still in flight -- the helper's operand prefetch from global memory, the main warp's word stores --
+// which put a full global-memory round trip into every block (measured: 1500 of a helper's 1650 cycles per block).  The
+// data handed over lives in shared memory only and is written by the same warp that raises the flag: shared-memory stores of
+// one warp are performed in program order, so __syncwarp() (all lanes' data stores issued) followed by a plain store of the
+// flag is sufficient; the asm is volatile with a memory clobber, so the compiler keeps the order too.
+__device__ inline void st_flag(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ inline uint32_t ld_acquire(uint32_t addr)
 {
@@ -64,24 +76,31 @@ __device__ inline uint32_t lds32(uint32_t addr)
 __device__ inline void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ inline uint32_t lds16(uint32_t addr)
 {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");  // zero-extended
     return v;
 }
+// The helper keeps ONE block of operands in registers ahead of its work; what hides the DRAM latency (a block of four steps
+// is shorter than a trip to HBM) is a prefetch into L2 several blocks further ahead.
+constexpr int kPrefetchBlocks = 12;
+__device__ inline void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // spin until the counter at `addr` reaches `want` (warp-uniform: every lane polls the same word)
 __device__ inline uint32_t wait_ge(uint32_t addr, uint32_t want)
 {
     uint32_t v = ld_acquire(addr);
     while ((int32_t)(v - want) < 0) {
-        __nanosleep(20);
-        v = ld_acquire(addr);
+        v = ld_acquire(addr);   // (no nanosleep: its granularity is far above a block's duration)
     }
     return v;
 }
 
-enum { C_PARAMS = 0, C_DONE = 4, C_STORED = 8, C_WP = 12, C_READYW = 16, C_EPOCH = 20 };
+enum { C_PARAMS = 0, C_DONE = 4, C_STORED = 8, C_WP = 12, C_READYW = 16, C_EPOCH = 20, C_FLAGS = 32 };
 
 // ------------------------------------------------------------------------------------------------ decode
+// One coding step of the main warp.  Operand record Q (written by the helper): lut address | cdf address |
+// lut shift, symbols << 8, active << 31 | offset.  Everything the common case needs is straight-line predicated code: the
+// single warp of a scheduler pays the full latency of every dependent instruction and of every branch.
 __global__ void __launch_bounds__(kPairs * 64, 1)
 k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
               int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
@@ -100,8 +119,7 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
     const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kDecSlotBytes));
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks;
-    const int prec = P.precision;
-    const uint32_t pmask = (1u << prec) - 1;
+    const bool bypass = P.bypass != 0;
     const uint32_t *end_word = reinterpret_cast<const uint32_t *>(seg) + 2 + seg_slices;
     const uint32_t *states = end_word + n_chunks;
     const long long words_at = kSegHdr + 4ll * seg_slices + 4ll * n_chunks + 128ll * n_chunks;
@@ -135,8 +153,15 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                     ready_w = wait_ge(ctrl + C_READYW, need);
                 }
             };
+            // one renormalisation event: the lanes below L take consecutive words in lane order
+            auto refill = [&](bool need) {
+                const unsigned nm = __ballot_sync(kFull, need);
+                const uint32_t at = wp + __popc(nm & lt_mask);
+                const uint32_t word = lds16(ring_s + ((at & (2 * kWordUnits - 1)) << 1));
+                x = need ? (x << 16) | word : x;
+                wp += __popc(nm);
+            };
             for (int blk = 0; blk < nblocks; ++blk, ++gb) {
-                const int j0 = blk * 128 + lane * 4;
                 wait_ge(ctrl + C_PARAMS, gb + 1);
                 if (gb >= kOutBlocks) wait_ge(ctrl + C_STORED, gb + 1 - kOutBlocks);
                 const uint32_t pbase = par_s + (gb % kDecParBlocks) * 2048 + lane * 16;
@@ -147,39 +172,65 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                 ensure();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    // operands: lut address | cdf address | lut shift, symbols << 8, active << 31 | offset
-                    const bool active = (int32_t)Pq[q].z < 0;
-                    const int nsyms = (int)((Pq[q].z >> 8) & 0xffffu), maxv = nsyms - 1;
-                    const uint32_t cum = x & pmask;
-                    int s = (int)lds16(Pq[q].x + ((cum >> (Pq[q].z & 31u)) << 1));
-                    const uint32_t e = Pq[q].y + 2u * (uint32_t)s;
+                    const uint4 Q = Pq[q];
+                    const bool active = (int32_t)Q.z < 0;
+                    const int maxv = (int)((Q.z >> 8) & 0xffffu) - 1;      // the escape symbol = last coded symbol
+                    const uint32_t cum = x & 0xffffu;
+                    int s = (int)lds16(Q.x + ((cum >> (Q.z & 31u)) << 1));
+                    const uint32_t e = Q.y + 2u * (uint32_t)s;
                     const uint32_t c0 = lds16(e), c1 = lds16(e + 2), c2 = lds16(e + 4), c3 = lds16(e + 6);
-                    const bool a1 = s + 1 < nsyms && c1 <= cum;
-                    const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
-                    const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
+                    const int d = maxv - s;                                // symbols above the candidate
+                    const bool a1 = d > 0 && c1 <= cum;
+                    const bool a2 = a1 && d > 1 && c2 <= cum;
+                    const bool a3 = a2 && d > 2 && c3 <= cum;
                     uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
                     s += (int)a1 + (int)a2;
-                    if (a3) {  // a bucket in a tail of width-1 symbols
-                        ++s;
-                        while (s + 1 < nsyms && lds16(Pq[q].y + 2u * (uint32_t)s + 2) <= cum) ++s;
-                        start = lds16(Pq[q].y + 2u * (uint32_t)s);
-                        next = lds16(Pq[q].y + 2u * (uint32_t)s + 2);
+                    const bool rare = active && (a3 || (bypass && s == maxv));
+                    if (!__any_sync(kFull, rare)) {
+                        // ---- the common step
+                        const uint32_t freq = (next - start) & 0xffffu;
+                        const uint32_t xn = freq * (x >> 16) + (cum - start);
+                        x = active ? xn : x;
+                        refill(active && x < kRansL);
+                        sts32(obase + q * 128, (uint32_t)(s + (int32_t)Q.w));
+                        continue;
                     }
-                    const uint32_t freq = (uint16_t)(next - start);
-                    if (active) x = freq * (x >> prec) + cum - start;
-                    {
-                        const bool need = active && x < kRansL;
-                        const unsigned nm = __ballot_sync(kFull, need);
-                        if (need) {
-                            const uint32_t at = wp + __popc(nm & lt_mask);
-                            uint32_t word = 0;
-                            if (at < wend) word = lds16(ring_s + ((at & (2 * kWordUnits - 1)) << 1)); else st |= 4;
-                            x = (x << 16) | word;
+                    // ---- a lane sits in a tail of narrow symbols (eight more entries per round) and / or decoded an escape
+                    if (__any_sync(kFull, a3)) {
+                        bool more = a3;
+                        int sc = s + 1;            // cdf[sc] <= cum is known for the lanes still searching
+                        uint32_t lo = c3;
+                        while (__any_sync(kFull, more)) {
+                            const uint32_t e8 = Q.y + 2u * (uint32_t)sc;
+                            uint32_t cc[9];
+#pragma unroll
+                            for (int i = 1; i <= 8; ++i) cc[i] = lds16(e8 + 2 * i);
+                            cc[0] = lo;
+                            int adv = 0;
+                            bool run = more;
+#pragma unroll
+                            for (int i = 1; i <= 8; ++i) {
+                                run = run && sc + i <= maxv && cc[i] <= cum;
+                                adv += (int)run;
+                            }
+                            uint32_t st_ = cc[0], nx_ = cc[1];
+#pragma unroll
+                            for (int i = 1; i <= 7; ++i) if (adv >= i) { st_ = cc[i]; nx_ = cc[i + 1]; }
+                            if (more) {
+                                sc += adv;
+                                lo = cc[8];
+                                if (adv < 8) { s = sc; start = st_; next = nx_; more = false; }
+                            }
                         }
-                        wp += __popc(nm);
+                    }
+                    {
+                        const uint32_t freq = (next - start) & 0xffffu;
+                        const uint32_t xn = freq * (x >> 16) + (cum - start);
+                        x = active ? xn : x;
+                        refill(active && x < kRansL);
                     }
                     int32_t value = s;
-                    const bool esc = active && P.bypass && s == maxv;
+                    const bool esc = active && bypass && s == maxv;
                     // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count
                     // token), followed by the digits, least significant first, four tokens per unit
                     if (__any_sync(kFull, esc)) {
@@ -206,27 +257,21 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                                 in = jj < nb;
                             }
                             ensure();
-                            const bool need = was && x < kRansL;
-                            const unsigned nm = __ballot_sync(kFull, need);
-                            if (need) {
-                                const uint32_t at = wp + __popc(nm & lt_mask);
-                                uint32_t word = 0;
-                                if (at < wend) word = lds16(ring_s + ((at & (2 * kWordUnits - 1)) << 1)); else st |= 4;
-                                x = (x << 16) | word;
-                            }
-                            wp += __popc(nm);
+                            refill(was && x < kRansL);
+                            if (wp > wend) { st |= 4; wp = wend; in = false; }   // truncated / corrupt stream
                         }
                         if (esc) {
                             const int32_t v2 = (int32_t)(raw >> 1);
                             value = (raw & 1) ? -v2 - 1 : v2 + maxv;
                         }
                     }
-                    sts32(obase + q * 128, (uint32_t)(value + (int32_t)Pq[q].w));
+                    sts32(obase + q * 128, (uint32_t)(value + (int32_t)Q.w));
                 }
+                if (wp > wend) { st |= 4; wp = wend; }   // reads past the chunk's words: truncated / corrupt stream
                 __syncwarp();
                 if (lane == 0) {
                     st_relaxed(ctrl + C_WP, wp);
-                    st_release(ctrl + C_DONE, gb + 1);
+                    st_flag(ctrl + C_DONE, gb + 1);
                 }
             }
             if (last_slice) {
@@ -254,6 +299,8 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
             int blk_par = 0, blk_out = 0;
             int4 ixn = make_int4(0, 0, 0, 0);
             if (nblocks > 0) ixn = load_ix(0);
+            for (int b = 1 + (lane >> 2); b < kPrefetchBlocks && b < nblocks; b += 8) prefetch_l2(indexes + base + b * 128 + (lane & 3) * 32);
+            for (uint32_t u = fill_u + lane * 32; u < u_lim && u < fill_u + 3 * kWordGroup; u += 32 * 32) prefetch_l2(units + u);
             while (blk_out < nblocks || !serving) {
                 const uint32_t done = ld_acquire(ctrl + C_DONE);
                 bool progress = false;
@@ -262,7 +309,10 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                     const int j0 = blk_par * 128 + lane * 4;
                     const int32_t ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
                     if (blk_par + 1 < nblocks) ixn = load_ix(blk_par + 1);
+                    if (lane < 4 && blk_par + kPrefetchBlocks < nblocks)   // four 128-byte lines per block
+                        prefetch_l2(indexes + base + (blk_par + kPrefetchBlocks) * 128 + lane * 32);
                     const uint32_t pbase = par_s + ((gb0 + blk_par) % kDecParBlocks) * 2048 + lane * 16;
+                    uint4 rec[4];   // (lookups first, stores after: see the encoder)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const bool active = j0 + q < m;
@@ -274,11 +324,13 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                         o.y = tb.cdf_at(mt.x);
                         o.z = ((mt.z >> 16) & 0xffu) | (((mt.z & 0xffffu) - 1u) << 8) | (active ? 0x80000000u : 0u);
                         o.w = mt.w;
-                        sts128(pbase + q * 512, o);
+                        rec[q] = o;
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sts128(pbase + q * 512, rec[q]);
                     __syncwarp();
                     ++blk_par;
-                    if (lane == 0) st_release(ctrl + C_PARAMS, gb0 + blk_par);
+                    if (lane == 0) st_flag(ctrl + C_PARAMS, gb0 + blk_par);
                     progress = true;
                 }
                 // --- renormalisation words: global -> ring, as far ahead as the ring allows
@@ -302,6 +354,8 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                         }
                         fill_u += kWordGroup;
                         filled = true;
+                        if (lane < kWordGroup / 32 && fill_u + kWordGroup + lane * 32 < u_lim)   // the group after the next: into L2
+                            prefetch_l2(units + fill_u + kWordGroup + lane * 32);
                     }
                     if (filled) {
                         cp_async_commit();
@@ -330,10 +384,9 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                     }
                     __syncwarp();
                     ++blk_out;
-                    if (lane == 0) st_release(ctrl + C_STORED, gb0 + blk_out);
+                    if (lane == 0) st_flag(ctrl + C_STORED, gb0 + blk_out);
                     progress = true;
                 }
-                if (!progress) __nanosleep(40);
             }
             gb += nblocks;
         }
@@ -344,8 +397,19 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout as in rans_lanes.cu: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front;
 // outputs per chunk: first_word[k], states[k * 32 + lane].
-__global__ void __launch_bounds__(kPairs * 64, 1)
-k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
+//
+// Operand record of one symbol (helper -> main): start' | m | f, escape << 31 | escape payload, with
+//   m = ceil(2^32 / f): x < f << 16 after the renormalisation, so umulhi(x, m) is the quotient or one more (fixed up with the
+//       sign of the remainder): two integer multiplies instead of int -> float -> int conversions on the chain;
+//   f = 1: m = 2^32 - 1 gives x - 1 with remainder 1, and start' = start + 65535 makes the new state come out right;
+//   a position past the end of the chunk is the identity symbol f = 2^16, start = 0 (never emits, leaves x unchanged).
+__device__ inline void stg16_if(uint16_t *ptr, uint32_t v, bool p)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u16 [%0], %1;\n\t}" ::"l"(ptr), "h"((uint16_t)v), "r"((uint32_t)p) : "memory");
+}
+
+__global__ void __launch_bounds__(kPairs * 32 * (1 + kEncHelpers), 1)
+k_pair_encode(LaneParams P, const uint4 *__restrict__ enc_tab, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
               uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word, uint32_t *__restrict__ states,
               int *status)
 {
@@ -353,16 +417,20 @@ k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = warp % kPairs;
     const bool is_main = warp < kPairs;
+    const uint32_t hid = is_main ? 0u : (uint32_t)(warp / kPairs - 1);   // which of the slot's helpers
     const uint32_t ctrl = (uint32_t)__cvta_generic_to_shared(smem + slot * kCtrlBytes);
     const uint32_t par_s = (uint32_t)__cvta_generic_to_shared(smem + kPairs * kCtrlBytes + slot * kEncSlotBytes);
     if (threadIdx.x < kPairs * kCtrlBytes / 4) reinterpret_cast<uint32_t *>(smem)[threadIdx.x] = 0;
     const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kEncSlotBytes));
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
-    const int prec = P.precision;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
     uint32_t gb = 0;
+#ifdef PAIR_TIMING
+    long long t_wait = 0, t_work = 0;
+    const long long t_start = clock64();
+#endif
     for (int k = blockIdx.x + slot * gridDim.x; k < n_chunks; k += gridDim.x * kPairs) {
         uint16_t *wbuf = scratch + (size_t)k * cap_words;
         int pos = cap_words;  // warp-uniform
@@ -375,67 +443,82 @@ k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *
             const int m = (int)(rem < sd.cs ? rem : sd.cs);
             const int nblocks = (m + 127) >> 7;
             if (is_main) {
+                // ============================================================================= main: the state's chain
                 for (int blk = nblocks - 1; blk >= 0; --blk, ++gb) {
-                    wait_ge(ctrl + C_PARAMS, gb + 1);
+#ifdef PAIR_TIMING
+                    const long long t_w0 = clock64();
+#endif
+                    // the ring slot carries its own sequence word: (block number + 1) | a symbol of the block escapes << 31
+                    uint32_t flag = ld_acquire(ctrl + C_FLAGS + (gb % kEncParBlocks) * 4);
+                    while ((flag & 0x7fffffffu) != gb + 1) {
+                        flag = ld_acquire(ctrl + C_FLAGS + (gb % kEncParBlocks) * 4);
+                    }
+#ifdef PAIR_TIMING
+                    const long long t_w1 = clock64();
+                    t_wait += t_w1 - t_w0;
+#endif
                     const uint32_t pbase = par_s + (gb % kEncParBlocks) * 2048 + lane * 16;
+                    const uint32_t has_esc = flag >> 31;
                     uint4 Pq[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) Pq[q] = lds128(pbase + q * 512);
-#pragma unroll
-                    for (int q = 3; q >= 0; --q) {
-                        // operands: start | freq << 16, 1 / freq, escape payload, active | escape << 1
-                        const bool active = Pq[q].w & 1u, esc = Pq[q].w & 2u;
-                        const uint32_t start = Pq[q].x & 0xffffu, freq = Pq[q].x >> 16, raw = Pq[q].z;
-                        // --- escape units, last to first: the token list is the 36-bit string  nd | raw << 4 ; unit u = its
-                        // bits [16u, 16u + 16) (a 32-bit payload has at most 8 digits: one count token)
-                        if (__any_sync(kFull, esc)) {
-                            const int nd = esc ? (35 - __clz(raw)) >> 2 : 0;
-                            const int ntok = esc ? nd + 1 : 0;
-                            const int nunits = (ntok + 3) >> 2;
-                            const unsigned long long toks = (unsigned long long)nd | ((unsigned long long)raw << 4);
-                            const int maxunits = (int)__reduce_max_sync(kFull, (unsigned)nunits);
-                            for (int u = maxunits - 1; u >= 0; --u) {
-                                const bool part = nunits > u;
-                                const int wbits = part ? 4 * min(4, ntok - 4 * u) : 0;
-                                const uint32_t unit = (uint32_t)(toks >> (16 * u)) & 0xffffu;
-                                const bool emit = part && x >= (1u << (32 - wbits));
-                                const unsigned em = __ballot_sync(kFull, emit);
-                                pos -= __popc(em);
-                                if (emit) {
-                                    const int at = pos + __popc(em & lt_mask);
-                                    if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
-                                    x >>= 16;
-                                }
-                                if (part) x = (x << wbits) | unit;
-                            }
-                        }
-                        // --- the symbol itself: x >= freq << (32 - prec) -> emit a word
-                        const bool emit = active && (x >> (32 - prec)) >= freq;
+                    // room for everything a block can emit (4 steps x (1 symbol + 3 escape units) x 32 words): checked here,
+                    // not per word; on overflow the words are dropped and the call is repeated with a worst-case buffer
+                    const bool room = pos >= 4 * 4 * 32;
+                    if (!room) st |= 4;
+                    // the symbol itself: a word goes out when x >= f << 16, then x = (x / f << 16) + x % f + start
+                    auto put = [&](const uint4 &Q, uint32_t f) {
+                        const uint32_t t = x >> 16;
+                        const bool emit = t >= f;
                         const unsigned em = __ballot_sync(kFull, emit);
-                        pos -= __popc(em);
-                        if (emit) {
-                            const int at = pos + __popc(em & lt_mask);
-                            if (at >= 0) wbuf[at] = (uint16_t)x; else st |= 4;
-                            x >>= 16;
-                        }
-                        if (active) {
-                            uint32_t qt, rm;
-                            if (prec == 16) {  // x < freq << 16 here: the float estimate of the quotient is within one
-                                qt = __float2uint_rz(__uint2float_rz(x) * __uint_as_float(Pq[q].y));
-                                rm = x - qt * freq;
-                                if ((int32_t)rm < 0) { --qt; rm += freq; }
-                                else if (rm >= freq) { ++qt; rm -= freq; }
-                            } else {
-                                qt = x / freq;
-                                rm = x - qt * freq;
+                        pos -= room ? __popc(em) : 0;
+                        stg16_if(wbuf + pos + __popc(em & lt_mask), x, emit && room);
+                        x = emit ? t : x;
+                        uint32_t qt = __umulhi(x, Q.y);
+                        const int32_t rm = (int32_t)(x - qt * f);
+                        const int32_t neg = rm >> 31;      // -1: the estimate was one too large
+                        qt += (uint32_t)neg;
+                        x = (qt << 16) + (uint32_t)(rm + (neg & (int32_t)f)) + Q.x;
+                    };
+                    if (!has_esc) {
+#pragma unroll
+                        for (int q = 3; q >= 0; --q) put(Pq[q], Pq[q].z);
+                    } else {
+#pragma unroll
+                        for (int q = 3; q >= 0; --q) {
+                            const bool esc = (int32_t)Pq[q].z < 0;
+                            const uint32_t raw = Pq[q].w;
+                            // escape units, last to first: the token list is the 36-bit string  nd | raw << 4 ; unit u = its
+                            // bits [16u, 16u + 16) (a 32-bit payload has at most 8 digits: one count token)
+                            if (__any_sync(kFull, esc)) {
+                                const int nd = esc ? (35 - __clz(raw)) >> 2 : 0;
+                                const int ntok = esc ? nd + 1 : 0;
+                                const int nunits = (ntok + 3) >> 2;
+                                const unsigned long long toks = (unsigned long long)nd | ((unsigned long long)raw << 4);
+                                const int maxunits = (int)__reduce_max_sync(kFull, (unsigned)nunits);
+                                for (int u = maxunits - 1; u >= 0; --u) {
+                                    const bool part = nunits > u;
+                                    const int wbits = part ? 4 * min(4, ntok - 4 * u) : 0;
+                                    const uint32_t unit = (uint32_t)(toks >> (16 * u)) & 0xffffu;
+                                    const bool emit = part && x >= (1u << (32 - wbits));
+                                    const unsigned em = __ballot_sync(kFull, emit);
+                                    pos -= room ? __popc(em) : 0;
+                                    stg16_if(wbuf + pos + __popc(em & lt_mask), x, emit && room);
+                                    x = emit ? x >> 16 : x;
+                                    x = part ? (x << wbits) | unit : x;
+                                }
                             }
-                            x = (qt << prec) + rm + start;
+                            put(Pq[q], Pq[q].z & 0x1ffffu);
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) st_release(ctrl + C_DONE, gb + 1);
+                    if (lane == 0) st_flag(ctrl + C_DONE, gb + 1);
+#ifdef PAIR_TIMING
+                    t_work += clock64() - t_w1;
+#endif
                 }
             } else {
+                // ============================================================================= helper: operands
                 const bool vec_ok = ptr_ok && (sd.off & 3) == 0;
                 auto load_ops = [&](int blk, int4 &a, int4 &b) {
                     const int j0 = blk * 128 + lane * 4;
@@ -454,14 +537,31 @@ k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *
                         b = make_int4(ix[0], ix[1], ix[2], ix[3]);
                     }
                 };
+                // this helper's blocks of the slice: every kEncHelpers-th, starting with the first whose number matches
                 int4 syn = make_int4(0, 0, 0, 0), ixn = syn;
-                if (nblocks > 0) load_ops(nblocks - 1, syn, ixn);
+                const int first = nblocks - 1 - (int)((hid + kEncHelpers - gb % kEncHelpers) % kEncHelpers);
+                if (first >= 0) load_ops(first, syn, ixn);
+                for (int b = nblocks - 2 - (lane >> 3); b >= 0 && b > nblocks - 1 - kPrefetchBlocks; b -= 4)
+                    prefetch_l2(((lane & 4) ? indexes : symbols) + base + b * 128 + (lane & 3) * 32);
                 for (int blk = nblocks - 1; blk >= 0; --blk, ++gb) {
+                    if (gb % kEncHelpers != hid) continue;
                     const int j0 = blk * 128 + lane * 4;
                     const int32_t sy[4] = {syn.x, syn.y, syn.z, syn.w}, ix[4] = {ixn.x, ixn.y, ixn.z, ixn.w};
-                    if (blk > 0) load_ops(blk - 1, syn, ixn);
+                    if (blk >= kEncHelpers) load_ops(blk - kEncHelpers, syn, ixn);
+                    if (lane < 8 && blk >= kPrefetchBlocks)   // four 128-byte lines of symbols, four of indexes
+                        prefetch_l2((lane < 4 ? symbols : indexes) + base + (blk - kPrefetchBlocks) * 128 + (lane & 3) * 32);
+#ifdef PAIR_TIMING
+                    const long long t_h0 = clock64();
+#endif
                     if (gb >= kEncParBlocks) wait_ge(ctrl + C_DONE, gb + 1 - kEncParBlocks);  // the ring slot is free again
+#ifdef PAIR_TIMING
+                    const long long t_h1 = clock64();
+                    t_wait += t_h1 - t_h0;
+#endif
                     const uint32_t pbase = par_s + (gb % kEncParBlocks) * 2048 + lane * 16;
+                    bool any_esc = false;
+                    uint4 rec[4];   // all four lookups first, the stores after them: a store (a compiler barrier) between two
+                                    // lookups would serialise their L2 round trips
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const bool active = j0 + q < m;
@@ -477,18 +577,22 @@ k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *
                             else if (v >= maxv) { raw = (uint32_t)(2 * (v - maxv)); v = maxv; }
                             esc = active && v == maxv;
                         } else if (v < 0 || v > maxv) { if (active) st |= 2; v = 0; }
-                        const uint32_t at = tb.cdf_at(mt.x + (uint32_t)v);
-                        const uint32_t start = lds16(at);
-                        const uint32_t freq = (uint16_t)(lds16(at + 2) - start);
-                        uint4 o;
-                        o.x = start | (freq << 16);
-                        o.y = __float_as_uint(__frcp_rn(__uint2float_rz(freq)));
-                        o.z = raw;
-                        o.w = (active ? 1u : 0u) | (esc ? 2u : 0u);
-                        sts128(pbase + q * 512, o);
+                        // the symbol's precomputed operands (tables.cu; 16 bytes through L2 -- the four loads of a block overlap)
+                        uint4 o = __ldg(enc_tab + mt.x + (uint32_t)v);
+                        o.z |= esc ? 0x80000000u : 0u;
+                        o.w = raw;
+                        if (!active) { o.x = 0; o.y = 65536u; o.z = 65536u; o.w = 0; }
+                        any_esc |= esc;
+                        rec[q] = o;
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sts128(pbase + q * 512, rec[q]);
+                    const bool blk_esc = __any_sync(kFull, any_esc);
                     __syncwarp();
-                    if (lane == 0) st_release(ctrl + C_PARAMS, gb + 1);
+                    if (lane == 0) st_flag(ctrl + C_FLAGS + (gb % kEncParBlocks) * 4, (gb + 1) | (blk_esc ? 0x80000000u : 0u));
+#ifdef PAIR_TIMING
+                    t_work += clock64() - t_h1;
+#endif
                 }
             }
         }
@@ -497,6 +601,11 @@ k_pair_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *
             if (lane == 0) first_word[k] = (uint32_t)(pos < 0 ? 0 : pos);
         }
     }
+#ifdef PAIR_TIMING
+    if (blockIdx.x == 0 && slot == 0 && lane == 0 && gb)
+        printf("[pair encode] warp %d (%s): blocks %u, total %lld cycles, waiting %lld, working %lld = %lld per own block\n", warp,
+               is_main ? "main" : "helper", gb, clock64() - t_start, t_wait, t_work, t_work / (gb / (is_main ? 1 : kEncHelpers) + 1));
+#endif
     if (st) atomicOr(status, st);
 }
 
@@ -510,7 +619,7 @@ static int pair_smem(const RansTables &tb, int slot_bytes) { return kPairs * (kC
 bool pair_kernels_apply(const RansTables &tb, int bypass_precision)
 {
     static const bool off = [] { const char *e = getenv("BASIC_CODER_PAIRS"); return e && e[0] == '0'; }();  // A/B switch
-    return !off && bypass_precision == 4 && tb.blob_bytes > 0 &&
+    return !off && bypass_precision == 4 && tb.precision == 16 && tb.blob_bytes > 0 &&
            pair_smem(tb, kDecSlotBytes > kEncSlotBytes ? kDecSlotBytes : kEncSlotBytes) <= kSmemLimit;
 }
 
@@ -534,8 +643,8 @@ int launch_pair_encode(const RansTables &tb, const LaneParams &P, const int32_t 
                        int cap_words, uint32_t *d_first, uint32_t *d_states, int *d_status, int sm_count, cudaStream_t stream)
 {
     BASIC_TRY(pair_attrs());
-    k_pair_encode<<<pair_grid(P.n_chunks, sm_count), kPairs * 64, pair_smem(tb, kEncSlotBytes), stream>>>(
-        P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
+    k_pair_encode<<<pair_grid(P.n_chunks, sm_count), kPairs * 32 * (1 + kEncHelpers), pair_smem(tb, kEncSlotBytes), stream>>>(
+        P, tb.enc.as<uint4>(), d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

@@ -144,13 +144,21 @@ k_pmf_to_cdf(const float *__restrict__ pmf, int n, int precision, int32_t *__res
 // One CTA per table: u16 CDF + bucket LUT + metadata.
 __global__ void __launch_bounds__(256)
 k_pack_tables(const int32_t *__restrict__ cdfs, int stride, const TableMeta *__restrict__ meta_in,
-              TableMeta *__restrict__ meta_out, uint16_t *__restrict__ cdf16, uint16_t *__restrict__ lut, int precision)
+              TableMeta *__restrict__ meta_out, uint16_t *__restrict__ cdf16, uint16_t *__restrict__ lut, int precision,
+              uint4 *__restrict__ enc)
 {
     const int t = blockIdx.x;
     const TableMeta m = meta_in[t];
     const int32_t *row = cdfs + (size_t)t * stride;
     if (threadIdx.x == 0) meta_out[t] = m;
-    for (int i = threadIdx.x; i < m.cdf_size; i += blockDim.x) cdf16[m.cdf_base + i] = (uint16_t)row[i];
+    for (int i = threadIdx.x; i < m.cdf_size; i += blockDim.x) {
+        cdf16[m.cdf_base + i] = (uint16_t)row[i];
+        // the multi-lane encoder's operands of symbol i (rans_pair.cu): the state update x -> (x / f << 16) + x % f + start as
+        // two integer multiplies with m = ceil(2^32 / f); f = 1: m = 2^32 - 1 yields x - 1 with remainder 1, corrected by start'
+        uint32_t start = (uint32_t)row[i], f = i + 1 < m.cdf_size ? (uint32_t)(row[i + 1] - row[i]) : 1u;
+        if (f == 0 || f > 65536u) f = 1;
+        enc[m.cdf_base + i] = make_uint4(f == 1 ? start + 65535u : start, f == 1 ? 0xffffffffu : 0xffffffffu / f + 1u, f, 0u);
+    }
     const int nb = 1 << (precision - m.lut_shift);
     const int nsyms = m.cdf_size - 1;
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
@@ -203,6 +211,7 @@ int rans_tables_pack(RansTables &tb, cudaStream_t stream)
     tb.total_cdf = cdf_total;
     tb.total_lut = lut_total;
     BASIC_TRY(tb.blob.reserve(tb.blob_bytes));
+    BASIC_TRY(tb.enc.reserve((size_t)cdf_total * sizeof(uint4)));
     BASIC_CUDA(cudaMemsetAsync(tb.blob.p, 0, tb.blob_bytes, stream));
     DevBuf tmp;
     BASIC_TRY(tmp.reserve(sizeof(TableMeta) * T));
@@ -211,7 +220,8 @@ int rans_tables_pack(RansTables &tb, cudaStream_t stream)
     k_pack_tables<<<T, 256, 0, stream>>>(tb.cdf32.as<int32_t>(), tb.stride, tmp.as<TableMeta>(),
                                          reinterpret_cast<TableMeta *>(b),
                                          reinterpret_cast<uint16_t *>(b + tb.meta_bytes),
-                                         reinterpret_cast<uint16_t *>(b + tb.meta_bytes + tb.cdf16_bytes), tb.precision);
+                                         reinterpret_cast<uint16_t *>(b + tb.meta_bytes + tb.cdf16_bytes), tb.precision,
+                                         tb.enc.as<uint4>());
     BASIC_LAUNCHED();
     BASIC_CUDA(cudaStreamSynchronize(stream));
     tmp.release();
