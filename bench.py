@@ -425,8 +425,24 @@ def run_ours(args, rank, world, local_rank):
     coder = build_coder(args.workload, w, args.lanes, dev)
     yd, pd = y.to(dev), prior.to(dev)
     if args.rates == "trained":
-        if method == "combined":
-            raise SystemExit("--rates trained is defined per single coder")
+        if method == "combined" or not ctx:
+            raise SystemExit("--rates trained needs a single coder with a context model")
+        # A random-init network predicts scales around zero (everything lands in the narrowest table: 0.001 bpp when y is drawn
+        # from the model, 13.7 bpp when it is not).  A trained model's scales spread over the lower third of the table: the last
+        # layer's scale rows are rescaled so that the predicted scales are ~ N(0.25, 0.35^2), then y is drawn from the model.
+        import ctypes as C
+        params = torch.zeros(B, 2 * C_, H, W, device=dev)
+        coder._set_map(coder._get_pgm((B, C_, H, W)))
+        N.check(N.lib().basic_ctx_stage_params(coder._ctx, 0, torch.zeros_like(yd).data_ptr(), pd.data_ptr(), B, params.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream))
+        raw = params[:, 1::2][:, :, 0::2, 0::2]      # (checkerboard stage 0 owns the even-even positions among others)
+        gain = 0.35 / float(raw.std())
+        w = dict(w)
+        w["m3_w"] = w["m3_w"].clone()
+        w["m3_b"] = w["m3_b"].clone()
+        w["m3_w"][1::2] *= gain
+        w["m3_b"][1::2] = w["m3_b"][1::2] * gain + (0.25 - gain * float(raw.mean()))
+        coder = build_coder(args.workload, w, args.lanes, dev)
         yd = calibrated_inputs(coder, pd, 77 + rank)
         y = yd.cpu()
     yp, pp = y.pin_memory(), prior.pin_memory()

@@ -62,6 +62,9 @@ int ctx_range_flag_read(CtxModel &, cudaStream_t, int *);
 int ctx_range_flag_copy(CtxModel &, cudaStream_t, int *);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
+bool ctx_scan_supported(const CtxModel &, int B);
+int ctx_scan_run(CtxModel &, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t);
 
 struct TansTables;
 TansTables *tans_new();
@@ -1266,6 +1269,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     // (refreshed after every group's write-back)
     if (model) ctx_set_run_precision(*model->m, ctx_precision(*model->m));
     const bool tc = model && ctx_uses_tc(*model->m, B);
+    const bool scan = model && ctx_scan_supported(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1284,6 +1288,23 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         if (tc) {  // (in the operand format of the current mode: redone by the 3xTF32 fallback)
             BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
             BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
+        }
+        if (scan) {
+            // many-stage map (scanline, the serial JointAR coder): ONE persistent launch walks every stage -- context model,
+            // scale indexes, quantisation and the y_hat write-back (ctx.cu k_scan_stages)
+            if (y_pending) {
+                BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_y, 0));
+                y_pending = false;
+            }
+            for (int g = 0; g < S; ++g) {
+                const int32_t *pos = nullptr;
+                int64_t n_pos = 0;
+                BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
+                slice_n.push_back((int64_t)B * n_pos);
+                done += (size_t)B * n_pos;
+            }
+            ProfScope ps(PROF_CTX, s);
+            return ctx_scan_run(*model->m, 0, S, buf, d_prior, B, params, d_y, sym, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s);
         }
         for (int g = 0; g < S; ++g) {
             const int32_t *pos = nullptr;
@@ -1407,6 +1428,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         ctx_set_run_precision(*model->m, prec);
     }
     const bool tc = model && ctx_uses_tc(*model->m, B);
+    const bool scan = model && ctx_scan_supported(*model->m, B);   // many-stage map: one fused launch per stage (ctx.cu k_scan_stages)
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1420,7 +1442,8 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     // memory and upload it while the GPU is busy
     if (model) {
         ProfScope ps(PROF_CTX, s);
-        BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
+        if (scan) BASIC_TRY(ctx_scan_run(*model->m, 0, 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s));
+        else BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
     }
     g_trace.mark("g0 queued", s);
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
@@ -1445,14 +1468,15 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (model) {
             if (g > 0) {
                 ProfScope ps(PROF_CTX, s);
-                BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
+                if (scan) BASIC_TRY(ctx_scan_run(*model->m, g, g + 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s));
+                else BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
             }
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
         } else {
             params_src = d_prior;
         }
         const int64_t cnt = slice_n[g];
-        if (cnt > 0) {
+        if (cnt > 0 && !scan) {   // (the fused stage launch has written the indexes already)
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_quantize_index(nullptr, params_src, pos, n_pos, B, C, HW, c->d_scale.as<float>(), (int)c->h_scale.size(),
                                             nullptr, idx, nullptr, c->sm_count, s, tc ? 1 : 0, tc ? ctx_perm(*model->m) : nullptr));

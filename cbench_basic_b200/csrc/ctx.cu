@@ -211,22 +211,44 @@ k_bias_prior(const float *__restrict__ prior, const float *__restrict__ bias, lo
 // weights are read in full 128-byte lines), gathers the <= kRowsMax masked input rows into shared memory once, and its 8
 // warps split K (k = warp, warp + 8, ..., eight loads in flight each).  Deterministic: fixed k order per warp, the eight
 // partial sums are added in warp order.
-constexpr int kRowsMax = 4, kGemvWarps = 8;
+constexpr int kRowsMax = 4, kGemvWarps = 8, kGemvInFlight = 8;
 
-__global__ void __launch_bounds__(kGemvWarps * 32)
-k_layer_rows(LayerArgs a)
+// What the last layer's epilogue does with its (mean, scale) pairs when the stage kernel also quantises (k_scan_stages):
+// the arithmetic of gauss.cu's k_quantize_index / k_dequantize, element for element.
+struct RowsQuant {
+    const float *y;            // encoder: the latents [B, C, HW]; NULL = decoder (indexes only)
+    float *buf;                // encoder: y_hat written back for the later stages
+    int32_t *sym, *idx;        // this stage's slice of the stream: element (b, c, cell i) at b * (C * ncells) + c * ncells + i
+    const float *scale_table;
+    int n_scales, C;
+};
+
+__device__ inline int scale_index_dev(float sigma, const float *__restrict__ tab, int n)
 {
-    extern __shared__ __align__(16) float sm[];
+    if (!(fabsf(sigma) <= 3.402823466e38f)) return 0;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tab[mid] < sigma) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0;
+    if (lo == n) return n - 1;
+    const float d0 = fabsf(__fsub_rn(sigma, tab[lo - 1])), d1 = fabsf(__fsub_rn(sigma, tab[lo]));
+    return d0 <= d1 ? lo - 1 : lo;
+}
+
+__device__ __forceinline__ void layer_rows_cta(const LayerArgs &a, const int cta, float *sm, int *s_b, int *s_hw, int *s_cell,
+                                               uint32_t *s_tapor_p, const RowsQuant *qz)
+{
+    uint32_t &s_tapor = *s_tapor_p;
     const int rows = a.B * a.ncells;          // <= kRowsMax
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = blockIdx.x * 32 + lane;     // relative to n_begin
+    const int n = cta * 32 + lane;            // relative to n_begin
     // total K in weight order: conv = taps x Cin, dense = src0 channels then src1 channels
     const int K0 = a.is_conv ? a.ksize * a.ksize * a.Cin : a.src0.channels;
     const int K = K0 + (a.is_conv || !a.src1.ptr ? 0 : a.src1.channels);
     float *A = sm;                            // [rows][K]
     float *part = sm + (size_t)rows * K;      // [kGemvWarps][kRowsMax][32]
-    __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
-    __shared__ uint32_t s_tapor;
     if (tid < kRowsMax) {
         const int row = tid;
         if (row < rows) {
@@ -249,7 +271,8 @@ k_layer_rows(LayerArgs a)
                     const bool vis = (a.cell_tap[(size_t)s_cell[r] * a.G + g] >> tap) & 1u;
                     any |= vis;
                     float *dst = A + (size_t)r * K + (size_t)tap * a.Cin + g * cpg;
-                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? src[(long long)(g * cpg + c) * a.HW + shift] : 0.f;
+                    // (__ldcg: in the persistent stage kernel other CTAs wrote these during the same launch -- never through L1)
+                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? __ldcg(src + (long long)(g * cpg + c) * a.HW + shift) : 0.f;
                 }
                 if (any && tid == 0) atomicOr(&s_tapor, 1u << tap);
             }
@@ -266,7 +289,7 @@ k_layer_rows(LayerArgs a)
                 for (int g = 0; g < ng; ++g) {
                     const bool vis = sc.groups == 0 || ((grp >> g) & 1u);
                     float *dst = A + (size_t)r * K + kbase + g * cpg;
-                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? src[(long long)(g * cpg + c) * a.HW] : 0.f;
+                    for (int c = tid; c < cpg; c += blockDim.x) dst[c] = vis ? __ldcg(src + (long long)(g * cpg + c) * a.HW) : 0.f;
                 }
                 kbase += sc.channels;
             }
@@ -284,15 +307,17 @@ k_layer_rows(LayerArgs a)
     for (int seg = 0; seg < nseg; ++seg) {
         if (!((tapor >> seg) & 1u)) continue;
         const int kb = seg * seglen;
-        for (int c0 = warp; c0 < seglen; c0 += kGemvWarps * 8) {
-            float wv[8];
+        // kGemvInFlight weight loads (128-byte lines from L2) in flight per warp: with eight the 12 - 20 CTAs of a layer drew
+        // ~25 GB/s each; the order of the additions (ascending k per warp) does not depend on the batch size
+        for (int c0 = warp; c0 < seglen; c0 += kGemvWarps * kGemvInFlight) {
+            float wv[kGemvInFlight];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kGemvInFlight; ++u) {
                 const int c = c0 + u * kGemvWarps;
                 wv[u] = c < seglen ? __ldg(wcol + (size_t)(kb + c) * a.Ntot) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kGemvInFlight; ++u) {
                 const int c = c0 + u * kGemvWarps;
                 if (c < seglen) {
 #pragma unroll
@@ -306,17 +331,96 @@ k_layer_rows(LayerArgs a)
     for (int r = 0; r < kRowsMax; ++r) part[(warp * kRowsMax + r) * 32 + lane] = acc[r];
     __syncthreads();
     // ---- reduce in warp order + epilogue: thread = (row, channel)
-    for (int o = tid; o < rows * 32; o += blockDim.x) {
-        const int r = o >> 5, l = o & 31, nn = blockIdx.x * 32 + l;
-        if (nn >= a.n_count) continue;
+    for (int o = tid; o < rows * 32; o += blockDim.x) {   // (rows * 32 <= 128: a whole warp per row, no divergence inside it)
+        const int r = o >> 5, l = o & 31, nn = cta * 32 + l;
+        const bool ok = nn < a.n_count;
         float v = 0.f;
         for (int w8 = 0; w8 < kGemvWarps; ++w8) v += part[(w8 * kRowsMax + r) * 32 + l];
-        const int ch = a.n_begin + nn;
+        const int ch = a.n_begin + (ok ? nn : 0);
         const long long oo = ((long long)s_b[r] * a.Ntot + ch) * a.HW + s_hw[r];
         v += a.bias ? a.bias[ch] : 0.f;
-        if (a.add) v += a.add[oo];
+        if (a.add && ok) v += a.add[oo];
         if (a.lrelu) v = v > 0.f ? v : v * kSlope;
-        a.out[oo] = v;
+        if (ok) a.out[oo] = v;
+        if (qz) {  // channel 2c = mean, 2c + 1 = scale (neighbouring lanes): the even lane codes latent channel c
+            const float sigma = __shfl_down_sync(0xffffffffu, v, 1);
+            if (ok && !(l & 1)) {
+                const int c = ch >> 1, b = s_b[r], i = s_cell[r] - a.cell_base;
+                const long long e = (long long)b * qz->C * a.ncells + (long long)c * a.ncells + i;
+                qz->idx[e] = scale_index_dev(sigma, qz->scale_table, qz->n_scales);
+                if (qz->y) {
+                    const long long yo = ((long long)b * qz->C + c) * a.HW + s_hw[r];
+                    const float sq = rintf(__fsub_rn(qz->y[yo], v));  // torch.round: half to even
+                    qz->sym[e] = (int32_t)sq;
+                    qz->buf[yo] = __fadd_rn(sq, v);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGemvWarps * 32)
+k_layer_rows(LayerArgs a)
+{
+    extern __shared__ __align__(16) float sm[];
+    __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
+    __shared__ uint32_t s_tapor;
+    layer_rows_cta(a, blockIdx.x, sm, s_b, s_hw, s_cell, &s_tapor, nullptr);
+}
+
+// ---- many-stage maps (scanline: one position per stage, 1536 stages for a Kodak-shape image; the serial JointAR coder):
+// one PERSISTENT kernel walks the stages -- per stage the four layers of the context model, each the deterministic GEMV of
+// k_layer_rows (same code, same summation order: the results are those of the per-layer launches bit for bit), the
+// quantiser in the last layer's epilogue, and a grid-wide barrier between layers (a layer reads what other CTAs of the
+// previous one wrote).  The encoder knows y, so its whole pass is ONE launch; the decoder launches it per stage (the coder
+// sits between two stages).  Weights (11 MB FP32) stay in L2.  One channel group only (G = 1).
+struct ScanArgs {
+    LayerArgs layer[4];          // conv, m1, m2, m3 with the stage-independent fields filled in
+    const int2 *stage_cells;     // per stage: first cell, cells
+    int g0, g1;                  // stages [g0, g1)
+    RowsQuant qz;                // sym / idx point at the slice of stage g0
+    unsigned *barrier;           // zeroed before the launch
+    int ctas;                    // CTAs of the launch = 32-channel blocks of the widest layer
+};
+
+__device__ inline void grid_barrier(unsigned *counter, unsigned nblocks, unsigned &epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned target = epoch * nblocks;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGemvWarps * 32)
+k_scan_stages(const __grid_constant__ ScanArgs S)
+{
+    extern __shared__ __align__(16) float sm[];
+    __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
+    __shared__ uint32_t s_tapor;
+    unsigned epoch = 0;
+    const int cta = blockIdx.x;
+    RowsQuant qz = S.qz;
+    for (int g = S.g0; g < S.g1; ++g) {
+        const int2 sc = S.stage_cells[g];
+        const long long slice = (long long)S.layer[0].B * qz.C * sc.y;
+#pragma unroll 1
+        for (int L = 0; L < 4; ++L) {
+            LayerArgs a = S.layer[L];
+            a.cell_base = sc.x;
+            a.ncells = sc.y;
+            if (sc.y > 0 && cta * 32 < a.n_count) layer_rows_cta(a, cta, sm, s_b, s_hw, s_cell, &s_tapor, L == 3 ? &qz : nullptr);
+            if (L < 3 || g + 1 < S.g1) grid_barrier(S.barrier, (unsigned)S.ctas, epoch);
+        }
+        qz.sym += slice;
+        qz.idx += slice;
     }
 }
 
@@ -514,6 +618,16 @@ int ctx_set_map(CtxModel &m, const int32_t *tg_any, int H, int W)
             for (int c = g * cpg; c < (g + 1) * cpg; ++c)
                 for (int i = st.cell_off[g]; i < st.cell_off[g + 1]; ++i)
                     positions[at++] = c * HW + cell_hw[st.cells_at + i];
+    }
+    {   // per stage: first cell and cell count (the persistent stage kernel of many-stage maps, one channel group)
+        std::vector<int2> sc((size_t)S);
+        m.max_stage_cells = 0;
+        for (int s2 = 0; s2 < S; ++s2) {
+            sc[(size_t)s2] = make_int2((int)m.stages[(size_t)s2].cells_at, m.stages[(size_t)s2].cell_off[G]);
+            m.max_stage_cells = std::max(m.max_stage_cells, m.stages[(size_t)s2].cell_off[G]);
+        }
+        BASIC_TRY(m.d_stage_cells.reserve(sc.size() * sizeof(int2) + 16));
+        BASIC_CUDA(cudaMemcpy(m.d_stage_cells.p, sc.data(), sc.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     BASIC_TRY(m.d_cell_hw.reserve(cell_hw.size() * 4 + 16));
     BASIC_TRY(m.d_cell_tap.reserve(cell_tap.size() * 4 + 16));
@@ -775,6 +889,69 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
     return finish();
 }
 
+// ---- the persistent stage kernel (k_scan_stages): when it applies and how it is launched
+bool ctx_scan_supported(const CtxModel &m, int B)
+{
+    if (!m.has_conv || !m.has_merger || m.internal || m.G != 1 || m.S < 8 || !m.d_stage_cells.p) return false;
+    if (tc_model_eligible(m, B)) return false;
+    if ((long long)B * m.max_stage_cells > kRowsMax) return false;
+    const size_t smem = ((size_t)kRowsMax * m.k * m.k * m.C + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
+    return smem <= 200 * 1024 && m.c_m1 >= m.c_ctx && m.c_m1 >= m.c_m2;
+}
+
+// Stages [g0, g1): parameters into `params` (NCHW), scale indexes (and, with y, symbols + the y_hat write-back into buf) into
+// the stream slices starting at idx / sym.  One launch.
+int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t stream)
+{
+    if (g0 < 0 || g1 > m.S || g0 >= g1) return value_error("stage range out of bounds");
+    const int HW = m.H * m.W;
+    if (m.act_B < B || !m.a_ctx.p) {
+        BASIC_TRY(m.a_ctx.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));
+        BASIC_TRY(m.a_m1.reserve(cl_elems(B, m.c_m1, HW) * sizeof(float)));
+        BASIC_TRY(m.a_m2.reserve(cl_elems(B, m.c_m2, HW) * sizeof(float)));
+        m.act_B = B;
+    }
+    BASIC_TRY(m.scan_barrier.reserve(64));
+    BASIC_CUDA(cudaMemsetAsync(m.scan_barrier.p, 0, 64, stream));
+    ScanArgs S = {};
+    for (int L = 0; L < 4; ++L) {
+        LayerArgs &a = S.layer[L];
+        a.cell_hw = m.d_cell_hw.as<int32_t>();
+        a.perm = m.d_perm.as<int32_t>();
+        a.cell_tap = m.d_cell_tap.as<uint32_t>();
+        a.cell_grp = m.d_cell_grp.as<uint32_t>();
+        a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = 1;
+        a.n_begin = 0;
+    }
+    LayerArgs &c0 = S.layer[0], &l1 = S.layer[1], &l2 = S.layer[2], &l3 = S.layer[3];
+    c0.is_conv = 1; c0.ksize = m.k; c0.Cin = m.C;
+    c0.src0 = Source{buf, m.C, 1, 0};
+    c0.wt = m.w_ctx.as<float>(); c0.bias = m.b_ctx.as<float>();
+    c0.Ntot = c0.n_count = m.c_ctx; c0.out = m.a_ctx.as<float>();
+    l1.src0 = Source{m.a_ctx.as<float>(), m.c_ctx, 1, 0};
+    l1.src1 = Source{prior, m.c_ctx, 0, 0};
+    l1.wt = m.w_m1.as<float>(); l1.bias = m.b_m1.as<float>();
+    l1.Ntot = l1.n_count = m.c_m1; l1.out = m.a_m1.as<float>(); l1.lrelu = 1;
+    l2.src0 = Source{m.a_m1.as<float>(), m.c_m1, 1, 0};
+    l2.wt = m.w_m2.as<float>(); l2.bias = m.b_m2.as<float>();
+    l2.Ntot = l2.n_count = m.c_m2; l2.out = m.a_m2.as<float>(); l2.lrelu = 1;
+    l3.src0 = Source{m.a_m2.as<float>(), m.c_m2, 1, 0};
+    l3.wt = m.w_m3.as<float>(); l3.bias = m.b_m3.as<float>();
+    l3.Ntot = l3.n_count = m.c_ctx; l3.out = params; l3.out_f32 = 1;
+    S.stage_cells = m.d_stage_cells.as<int2>();
+    S.g0 = g0; S.g1 = g1;
+    S.qz = RowsQuant{y, buf, sym, idx, d_scale_table, n_scales, m.C};
+    S.barrier = m.scan_barrier.as<unsigned>();
+    S.ctas = (m.c_m1 + 31) / 32;
+    const size_t smem = ((size_t)kRowsMax * m.k * m.k * m.C + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_scan_stages<<<S.ctas, kGemvWarps * 32, smem, stream>>>(S);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
 CtxModel *ctx_new(int C, int G, int k, int device, int sm_count)
 {
     CtxModel *m = new CtxModel();
@@ -790,7 +967,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -44,6 +44,9 @@ struct CtxModel {
     DevBuf d_cell_tap;   // uint32 [ncells][G]        visible 5x5 taps per input channel group
     DevBuf d_cell_grp;   // uint32 [ncells]           bit j: in-group j visible through "<="
     DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
+    DevBuf d_stage_cells;  // int2 [S]                first cell, cells of every stage (persistent stage kernel, G = 1)
+    int max_stage_cells = 0;
+    DevBuf scan_barrier;   // grid barrier counter of the persistent stage kernel
     DevBuf d_perm;       // int32 [H*W]               position -> slot of the tensor path's activation layout (stage-major)
     DevBuf d_iperm;      // int32 [H*W]               slot -> position
     // activations (grow-only)
