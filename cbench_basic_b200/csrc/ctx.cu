@@ -13,6 +13,8 @@
 
 #include <cstdlib>
 
+#include <cstdio>
+
 #include "ctx.cuh"
 
 namespace basic {
@@ -238,7 +240,7 @@ __device__ inline int scale_index_dev(float sigma, const float *__restrict__ tab
 }
 
 __device__ __forceinline__ void layer_rows_cta(const LayerArgs &a, const int cta, float *sm, int *s_b, int *s_hw, int *s_cell,
-                                               uint32_t *s_tapor_p, const RowsQuant *qz)
+                                               uint32_t *s_tapor_p)
 {
     uint32_t &s_tapor = *s_tapor_p;
     const int rows = a.B * a.ncells;          // <= kRowsMax
@@ -342,20 +344,6 @@ __device__ __forceinline__ void layer_rows_cta(const LayerArgs &a, const int cta
         if (a.add && ok) v += a.add[oo];
         if (a.lrelu) v = v > 0.f ? v : v * kSlope;
         if (ok) a.out[oo] = v;
-        if (qz) {  // channel 2c = mean, 2c + 1 = scale (neighbouring lanes): the even lane codes latent channel c
-            const float sigma = __shfl_down_sync(0xffffffffu, v, 1);
-            if (ok && !(l & 1)) {
-                const int c = ch >> 1, b = s_b[r], i = s_cell[r] - a.cell_base;
-                const long long e = (long long)b * qz->C * a.ncells + (long long)c * a.ncells + i;
-                qz->idx[e] = scale_index_dev(sigma, qz->scale_table, qz->n_scales);
-                if (qz->y) {
-                    const long long yo = ((long long)b * qz->C + c) * a.HW + s_hw[r];
-                    const float sq = rintf(__fsub_rn(qz->y[yo], v));  // torch.round: half to even
-                    qz->sym[e] = (int32_t)sq;
-                    qz->buf[yo] = __fadd_rn(sq, v);
-                }
-            }
-        }
     }
 }
 
@@ -365,22 +353,36 @@ k_layer_rows(LayerArgs a)
     extern __shared__ __align__(16) float sm[];
     __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
     __shared__ uint32_t s_tapor;
-    layer_rows_cta(a, blockIdx.x, sm, s_b, s_hw, s_cell, &s_tapor, nullptr);
+    layer_rows_cta(a, blockIdx.x, sm, s_b, s_hw, s_cell, &s_tapor);
 }
 
 // ---- many-stage maps (scanline: one position per stage, 1536 stages for a Kodak-shape image; the serial JointAR coder):
-// one PERSISTENT kernel walks the stages -- per stage the four layers of the context model, each the deterministic GEMV of
-// k_layer_rows (same code, same summation order: the results are those of the per-layer launches bit for bit), the
-// quantiser in the last layer's epilogue, and a grid-wide barrier between layers (a layer reads what other CTAs of the
-// previous one wrote).  The encoder knows y, so its whole pass is ONE launch; the decoder launches it per stage (the coder
-// sits between two stages).  Weights (11 MB FP32) stay in L2.  One channel group only (G = 1).
+// one PERSISTENT kernel walks the stages.  Per stage the four layers of the context model are matrix-vector products
+// (rows = batch x cells of the stage <= 4): every CTA gathers the layer's input vectors into shared memory, every warp
+// owns two neighbouring output channels and streams their weight rows (N-major copies of the matrices, 128-bit loads, L2
+// resident) against them, lanes striding over K, then a butterfly sum -- about two instructions per multiply-add (the
+// 32-channel GEMV of k_layer_rows needs ~15: its CTAs drew 5 bytes per cycle).  The last layer's pair is (mean, scale) of
+// one latent channel, so the quantiser runs in its epilogue.  A grid-wide barrier separates the layers.  The encoder knows
+// y: its whole pass is ONE launch; the decoder launches the kernel once per stage (the coder sits between two stages).
+// Deterministic (fixed summation order); one channel group only (G = 1).
+constexpr int kScanWarps = 8, kScanCtas = 40, kScanInFlight = 6;   // (6 x 2 x 512-byte weight loads in flight per warp)
+//   // 320 warps = channel pairs of the widest layer at C = 192
+
 struct ScanArgs {
-    LayerArgs layer[4];          // conv, m1, m2, m3 with the stage-independent fields filled in
+    const float *w[4];           // N-major: conv [2C][k2][C], dense [N][K]
+    const float *bias[4];
+    int N[4], K[4];              // K[0] = k2 * C
+    int C, ksize, HW, W_img, B;
     const int2 *stage_cells;     // per stage: first cell, cells
+    const int32_t *cell_hw;
+    const uint32_t *cell_tap, *cell_grp;
+    float *buf;                  // y_hat [B, C, HW]
+    const float *prior;          // [B, 2C, HW]
+    float *act[3];               // ctx, m1, m2 outputs [B, N, HW]
+    float *params;               // [B, 2C, HW]
     int g0, g1;                  // stages [g0, g1)
     RowsQuant qz;                // sym / idx point at the slice of stage g0
     unsigned *barrier;           // zeroed before the launch
-    int ctas;                    // CTAs of the launch = 32-channel blocks of the widest layer
 };
 
 __device__ inline void grid_barrier(unsigned *counter, unsigned nblocks, unsigned &epoch)
@@ -399,28 +401,152 @@ __device__ inline void grid_barrier(unsigned *counter, unsigned nblocks, unsigne
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kGemvWarps * 32)
+__global__ void __launch_bounds__(kScanWarps * 32)
 k_scan_stages(const __grid_constant__ ScanArgs S)
 {
-    extern __shared__ __align__(16) float sm[];
-    __shared__ int s_b[kRowsMax], s_hw[kRowsMax], s_cell[kRowsMax];
-    __shared__ uint32_t s_tapor;
+    extern __shared__ __align__(16) float A[];   // [rows][K] of the current layer
+    __shared__ int s_b[kRowsMax], s_hw[kRowsMax];
+    __shared__ uint32_t s_tap[kRowsMax], s_grp[kRowsMax];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * kScanWarps + warp;          // this warp's channel pair in every layer
+    const int k2 = S.ksize * S.ksize, pad = S.ksize / 2, C = S.C;
     unsigned epoch = 0;
-    const int cta = blockIdx.x;
     RowsQuant qz = S.qz;
     for (int g = S.g0; g < S.g1; ++g) {
         const int2 sc = S.stage_cells[g];
-        const long long slice = (long long)S.layer[0].B * qz.C * sc.y;
+        const int rows = S.B * sc.y;                         // <= kRowsMax
+        const long long slice = (long long)S.B * qz.C * sc.y;
+        if (tid < rows) {
+            const int b = tid / sc.y, cell = sc.x + (tid - b * sc.y);
+            s_b[tid] = b; s_hw[tid] = S.cell_hw[cell]; s_tap[tid] = S.cell_tap[cell]; s_grp[tid] = S.cell_grp[cell];
+        }
+        __syncthreads();
+        uint32_t tap_or = 0;
+        for (int r = 0; r < rows; ++r) tap_or |= s_tap[r];
 #pragma unroll 1
         for (int L = 0; L < 4; ++L) {
-            LayerArgs a = S.layer[L];
-            a.cell_base = sc.x;
-            a.ncells = sc.y;
-            if (sc.y > 0 && cta * 32 < a.n_count) layer_rows_cta(a, cta, sm, s_b, s_hw, s_cell, &s_tapor, L == 3 ? &qz : nullptr);
-            if (L < 3 || g + 1 < S.g1) grid_barrier(S.barrier, (unsigned)S.ctas, epoch);
+            const int K = S.K[L], N = S.N[L];
+            // ---- gather the input vectors (other CTAs wrote them during this launch: L2 loads, never L1)
+            if (L == 0) {
+                for (int r = 0; r < rows; ++r) {
+                    const float *src = S.buf + (long long)s_b[r] * C * S.HW + s_hw[r];
+                    const uint32_t vis = s_tap[r];
+                    for (int c = tid; c < C; c += blockDim.x) {
+                        float v[25];
+#pragma unroll
+                        for (int t = 0; t < 25; ++t) {   // all taps of a channel in flight at once
+                            const int shift = (t / S.ksize - pad) * S.W_img + (t % S.ksize - pad);
+                            v[t] = (t < k2 && ((vis >> t) & 1u)) ? __ldcg(src + (long long)c * S.HW + shift) : 0.f;
+                        }
+#pragma unroll
+                        for (int t = 0; t < 25; ++t) if (t < k2) A[(size_t)r * K + t * C + c] = v[t];
+                    }
+                }
+            } else {
+                const float *src0 = S.act[L - 1];
+                const int c0n = S.N[L - 1];
+                for (int r = 0; r < rows; ++r) {
+                    const bool vis = s_grp[r] & 1u;
+                    const long long at = (long long)s_b[r] * c0n * S.HW + s_hw[r];
+                    for (int c = tid; c < c0n; c += blockDim.x) A[(size_t)r * K + c] = vis ? __ldcg(src0 + at + (long long)c * S.HW) : 0.f;
+                    if (L == 1) {   // the prior: always visible
+                        const long long ap = (long long)s_b[r] * (K - c0n) * S.HW + s_hw[r];
+                        for (int c = tid; c < K - c0n; c += blockDim.x) A[(size_t)r * K + c0n + c] = __ldcg(S.prior + ap + (long long)c * S.HW);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- two output channels per warp
+            if (2 * gw < N && rows > 0) {
+                const int n0 = 2 * gw;
+                const float4 *w0 = reinterpret_cast<const float4 *>(S.w[L] + (size_t)n0 * K);
+                const float4 *w1 = reinterpret_cast<const float4 *>(S.w[L] + (size_t)(n0 + 1) * K);
+                float acc0[kRowsMax], acc1[kRowsMax];
+#pragma unroll
+                for (int r = 0; r < kRowsMax; ++r) acc0[r] = acc1[r] = 0.f;
+                const int nseg = L == 0 ? k2 : 1, seg4 = (L == 0 ? C : K) >> 2;   // conv: one segment per tap, dead taps skipped
+                for (int seg = 0; seg < nseg; ++seg) {
+                    if (L == 0 && !((tap_or >> seg) & 1u)) continue;
+                    const int base4 = seg * seg4;
+                    for (int i0 = lane; i0 < seg4; i0 += 32 * kScanInFlight) {
+                        float4 x0[kScanInFlight], x1[kScanInFlight];
+#pragma unroll
+                        for (int u = 0; u < kScanInFlight; ++u) {
+                            const int i = i0 + 32 * u;
+                            const bool ok = i < seg4;
+                            x0[u] = ok ? __ldg(w0 + base4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            x1[u] = ok ? __ldg(w1 + base4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kScanInFlight; ++u) {
+                            const int i = i0 + 32 * u;
+                            if (i < seg4) {
+#pragma unroll
+                                for (int r = 0; r < kRowsMax; ++r) {
+                                    if (r < rows) {
+                                        const float4 av = *reinterpret_cast<const float4 *>(A + (size_t)r * K + 4 * (base4 + i));
+                                        acc0[r] = fmaf(av.x, x0[u].x, acc0[r]); acc0[r] = fmaf(av.y, x0[u].y, acc0[r]);
+                                        acc0[r] = fmaf(av.z, x0[u].z, acc0[r]); acc0[r] = fmaf(av.w, x0[u].w, acc0[r]);
+                                        acc1[r] = fmaf(av.x, x1[u].x, acc1[r]); acc1[r] = fmaf(av.y, x1[u].y, acc1[r]);
+                                        acc1[r] = fmaf(av.z, x1[u].z, acc1[r]); acc1[r] = fmaf(av.w, x1[u].w, acc1[r]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRowsMax; ++r) {
+                    if (r < rows) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
+                            acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    const float b0 = S.bias[L][n0], b1 = S.bias[L][n0 + 1];
+                    float *out = L < 3 ? S.act[L] : S.params;
+                    for (int r = 0; r < rows; ++r) {
+                        float v0 = acc0[r] + b0, v1 = acc1[r] + b1;
+                        if (L == 1 || L == 2) {
+                            v0 = v0 > 0.f ? v0 : v0 * kSlope;
+                            v1 = v1 > 0.f ? v1 : v1 * kSlope;
+                        }
+                        const long long oo = ((long long)s_b[r] * N + n0) * S.HW + s_hw[r];
+                        out[oo] = v0;
+                        out[oo + S.HW] = v1;
+                        if (L == 3) {   // (mean, scale) of latent channel gw: scale index, symbol, y_hat
+                            const int c = gw, b = s_b[r], i = r - b * sc.y;
+                            const long long e = (long long)b * qz.C * sc.y + (long long)c * sc.y + i;
+                            qz.idx[e] = scale_index_dev(v1, qz.scale_table, qz.n_scales);
+                            if (qz.y) {
+                                const long long yo = ((long long)b * qz.C + c) * S.HW + s_hw[r];
+                                const float sq = rintf(__fsub_rn(qz.y[yo], v0));  // torch.round: half to even
+                                qz.sym[e] = (int32_t)sq;
+                                qz.buf[yo] = __fadd_rn(sq, v0);
+                            }
+                        }
+                    }
+                }
+            }
+            if (L < 3 || g + 1 < S.g1) grid_barrier(S.barrier, gridDim.x, epoch);
         }
         qz.sym += slice;
         qz.idx += slice;
+    }
+}
+
+// [N][Cin][k2] (state_dict) -> [N][k2][Cin]: a tap's input channels are contiguous (dead taps are skipped as segments)
+__global__ void k_conv_tap_major(const float *__restrict__ src, float *__restrict__ dst, int N, int Cin, int k2)
+{
+    const long long total = (long long)N * Cin * k2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e / ((long long)Cin * k2));
+        const int rem = (int)(e - (long long)n * Cin * k2);
+        const int c = rem / k2, tap = rem - c * k2;
+        dst[((size_t)n * k2 + tap) * Cin + c] = src[e];
     }
 }
 
@@ -505,6 +631,21 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
         BASIC_TRY(upload(m.b_m2, m2_b, m.c_m2, s));
         BASIC_TRY(upload_transposed(m.w_m3, m3_w, m.c_ctx, m.c_m2, 1, s));
         BASIC_TRY(upload(m.b_m3, m3_b, m.c_ctx, s));
+    }
+    m.ws_ctx.release();
+    if (m.has_conv && m.has_merger && m.G == 1) {   // N-major copies for the persistent stage kernel (k_scan_stages)
+        const size_t n_ctx = (size_t)m.c_ctx * C * m.k * m.k;
+        DevBuf tmp;
+        BASIC_TRY(tmp.reserve(n_ctx * sizeof(float)));
+        BASIC_CUDA(cudaMemcpyAsync(tmp.p, ctx_w, n_ctx * sizeof(float), cudaMemcpyDefault, s));
+        BASIC_TRY(m.ws_ctx.reserve(n_ctx * sizeof(float)));
+        k_conv_tap_major<<<256, 256, 0, s>>>(tmp.as<float>(), m.ws_ctx.as<float>(), m.c_ctx, C, m.k * m.k);
+        BASIC_LAUNCHED();
+        BASIC_CUDA(cudaStreamSynchronize(s));
+        tmp.release();
+        BASIC_TRY(upload(m.ws_m1, m1_w, (size_t)m.c_m1 * 2 * m.c_ctx, s));
+        BASIC_TRY(upload(m.ws_m2, m2_w, (size_t)m.c_m2 * m.c_m1, s));
+        BASIC_TRY(upload(m.ws_m3, m3_w, (size_t)m.c_ctx * m.c_m2, s));
     }
     BASIC_CUDA(cudaStreamSynchronize(s));
     return BASIC_OK;
@@ -890,13 +1031,21 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
 }
 
 // ---- the persistent stage kernel (k_scan_stages): when it applies and how it is launched
+static size_t scan_smem(const CtxModel &m)
+{
+    const int kmax = std::max(std::max(m.k * m.k * m.C, 2 * m.c_ctx), std::max(m.c_m1, m.c_m2));
+    return (size_t)kRowsMax * kmax * sizeof(float);
+}
+
 bool ctx_scan_supported(const CtxModel &m, int B)
 {
-    if (!m.has_conv || !m.has_merger || m.internal || m.G != 1 || m.S < 8 || !m.d_stage_cells.p) return false;
+    static const bool off = [] { const char *e = getenv("BASIC_SCAN_KERNEL"); return e && e[0] == '0'; }();  // A/B switch
+    if (off || !m.has_conv || !m.has_merger || m.internal || m.G != 1 || m.S < 8 || !m.d_stage_cells.p || !m.ws_ctx.p) return false;
     if (tc_model_eligible(m, B)) return false;
-    if ((long long)B * m.max_stage_cells > kRowsMax) return false;
-    const size_t smem = ((size_t)kRowsMax * m.k * m.k * m.C + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
-    return smem <= 200 * 1024 && m.c_m1 >= m.c_ctx && m.c_m1 >= m.c_m2;
+    if ((long long)B * m.max_stage_cells > kRowsMax || m.k > 5) return false;
+    if (m.C % 4 || m.c_m1 % 4 || m.c_m2 % 4 || (m.c_m1 | m.c_m2 | m.c_ctx) & 1) return false;   // 128-bit weight loads, channel pairs
+    if (std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) > 2 * kScanWarps * kScanCtas) return false;    // one pair per warp
+    return scan_smem(m) <= 200 * 1024;
 }
 
 // Stages [g0, g1): parameters into `params` (NCHW), scale indexes (and, with y, symbols + the y_hat write-back into buf) into
@@ -915,39 +1064,24 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     BASIC_TRY(m.scan_barrier.reserve(64));
     BASIC_CUDA(cudaMemsetAsync(m.scan_barrier.p, 0, 64, stream));
     ScanArgs S = {};
-    for (int L = 0; L < 4; ++L) {
-        LayerArgs &a = S.layer[L];
-        a.cell_hw = m.d_cell_hw.as<int32_t>();
-        a.perm = m.d_perm.as<int32_t>();
-        a.cell_tap = m.d_cell_tap.as<uint32_t>();
-        a.cell_grp = m.d_cell_grp.as<uint32_t>();
-        a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = 1;
-        a.n_begin = 0;
-    }
-    LayerArgs &c0 = S.layer[0], &l1 = S.layer[1], &l2 = S.layer[2], &l3 = S.layer[3];
-    c0.is_conv = 1; c0.ksize = m.k; c0.Cin = m.C;
-    c0.src0 = Source{buf, m.C, 1, 0};
-    c0.wt = m.w_ctx.as<float>(); c0.bias = m.b_ctx.as<float>();
-    c0.Ntot = c0.n_count = m.c_ctx; c0.out = m.a_ctx.as<float>();
-    l1.src0 = Source{m.a_ctx.as<float>(), m.c_ctx, 1, 0};
-    l1.src1 = Source{prior, m.c_ctx, 0, 0};
-    l1.wt = m.w_m1.as<float>(); l1.bias = m.b_m1.as<float>();
-    l1.Ntot = l1.n_count = m.c_m1; l1.out = m.a_m1.as<float>(); l1.lrelu = 1;
-    l2.src0 = Source{m.a_m1.as<float>(), m.c_m1, 1, 0};
-    l2.wt = m.w_m2.as<float>(); l2.bias = m.b_m2.as<float>();
-    l2.Ntot = l2.n_count = m.c_m2; l2.out = m.a_m2.as<float>(); l2.lrelu = 1;
-    l3.src0 = Source{m.a_m2.as<float>(), m.c_m2, 1, 0};
-    l3.wt = m.w_m3.as<float>(); l3.bias = m.b_m3.as<float>();
-    l3.Ntot = l3.n_count = m.c_ctx; l3.out = params; l3.out_f32 = 1;
+    S.w[0] = m.ws_ctx.as<float>(); S.w[1] = m.ws_m1.as<float>(); S.w[2] = m.ws_m2.as<float>(); S.w[3] = m.ws_m3.as<float>();
+    S.bias[0] = m.b_ctx.as<float>(); S.bias[1] = m.b_m1.as<float>(); S.bias[2] = m.b_m2.as<float>(); S.bias[3] = m.b_m3.as<float>();
+    S.N[0] = m.c_ctx; S.N[1] = m.c_m1; S.N[2] = m.c_m2; S.N[3] = m.c_ctx;
+    S.K[0] = m.k * m.k * m.C; S.K[1] = 2 * m.c_ctx; S.K[2] = m.c_m1; S.K[3] = m.c_m2;
+    S.C = m.C; S.ksize = m.k; S.HW = HW; S.W_img = m.W; S.B = B;
     S.stage_cells = m.d_stage_cells.as<int2>();
+    S.cell_hw = m.d_cell_hw.as<int32_t>();
+    S.cell_tap = m.d_cell_tap.as<uint32_t>();
+    S.cell_grp = m.d_cell_grp.as<uint32_t>();
+    S.buf = buf; S.prior = prior;
+    S.act[0] = m.a_ctx.as<float>(); S.act[1] = m.a_m1.as<float>(); S.act[2] = m.a_m2.as<float>();
+    S.params = params;
     S.g0 = g0; S.g1 = g1;
     S.qz = RowsQuant{y, buf, sym, idx, d_scale_table, n_scales, m.C};
     S.barrier = m.scan_barrier.as<unsigned>();
-    S.ctas = (m.c_m1 + 31) / 32;
-    const size_t smem = ((size_t)kRowsMax * m.k * m.k * m.C + (size_t)kGemvWarps * kRowsMax * 32) * sizeof(float);
     static PerDeviceOnce attr_once;
     if (attr_once.first()) BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_scan_stages<<<S.ctas, kGemvWarps * 32, smem, stream>>>(S);
+    k_scan_stages<<<kScanCtas, kScanWarps * 32, scan_smem(m), stream>>>(S);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }
@@ -967,7 +1101,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -47,6 +47,7 @@ struct CtxModel {
     DevBuf d_stage_cells;  // int2 [S]                first cell, cells of every stage (persistent stage kernel, G = 1)
     int max_stage_cells = 0;
     DevBuf scan_barrier;   // grid barrier counter of the persistent stage kernel
+    DevBuf ws_ctx, ws_m1, ws_m2, ws_m3;   // N-major weight copies of the persistent stage kernel (conv: [2C][tap][C])
     DevBuf d_perm;       // int32 [H*W]               position -> slot of the tensor path's activation layout (stage-major)
     DevBuf d_iperm;      // int32 [H*W]               slot -> position
     // activations (grow-only)
