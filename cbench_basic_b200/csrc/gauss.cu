@@ -33,9 +33,17 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
     __syncthreads();
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
+    const bool small = total < 0x7fffffffll && (long long)B * 2 * chw < 0x7fffffffll;   // 32-bit divisions (a 64-bit one is ~100 instructions)
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long b = e / n_pos;
-        const long long k = e - b * n_pos;
+        long long b, k;
+        if (small) {
+            const unsigned bb = (unsigned)e / (unsigned)n_pos;
+            b = bb;
+            k = (unsigned)e - bb * (unsigned)n_pos;
+        } else {
+            b = e / n_pos;
+            k = e - b * n_pos;
+        }
         const int p = positions ? positions[k] : (int)k;
         const int c = p / HW;
         float mean, sigma;
@@ -65,9 +73,17 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
 {
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
+    const bool small = total < 0x7fffffffll;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long b = e / n_pos;
-        const long long k = e - b * n_pos;
+        long long b, k;
+        if (small) {
+            const unsigned bb = (unsigned)e / (unsigned)n_pos;
+            b = bb;
+            k = (unsigned)e - bb * (unsigned)n_pos;
+        } else {
+            b = e / n_pos;
+            k = e - b * n_pos;
+        }
         const int p = positions ? positions[k] : (int)k;
         const int c = p / HW;
         const int hw = params_cl ? perm[p - c * HW] : 0;  // slot of the position

@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --c
 python tools/launch_summary.py gpurun_out/launches_$tag.csv > gpurun_out/launches_$tag.txt
 ncu --set full --clock-control none --import-source on -k regex:k_layer_tc -s 8 -c 8 -f -o gpurun_out/prof_${tag}_ctx \
     python tools/profile_step.py cfg2 2 > gpurun_out/ncu_full_ctx_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_bls_ -s 5 -c 5 -f -o gpurun_out/prof_${tag}_coder \
+ncu --set full --clock-control none --import-source on -k 'regex:k_bls_|k_pair_|k_quantize|k_dequantize|k_nchw_to_cl' -s 12 -c 14 -f -o gpurun_out/prof_${tag}_coder \
     python tools/profile_step.py cfg2 2 > gpurun_out/ncu_full_coder_$tag.log 2>&1
 for f in ctx coder; do
   ncu -i gpurun_out/prof_${tag}_$f.ncu-rep --page raw --csv > gpurun_out/ncu_full_${tag}_$f.csv 2>/dev/null
