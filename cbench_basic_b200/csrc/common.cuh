@@ -109,6 +109,9 @@ struct RansTables {
     DevBuf enc;                                // uint4 per CDF entry (same numbering as the u16 CDFs): the encoder's operands of that symbol
                                                // start' | m = ceil(2^32 / f) | f | 0  (rans_pair.cu); read through L2
     size_t blob_bytes = 0, meta_bytes = 0, cdf16_bytes = 0, lut_bytes = 0;
+    DevBuf blob_d;                             // the pair decoder's shared-memory image (rans_pair.cu): u16 d[i] = cdf[i] - 1 of every table followed by
+                                               // four 0xffff sentinels | u16 lut2 = BYTE offset of the bucket's first candidate inside the d region
+    size_t blob_d_bytes = 0, dcdf_bytes = 0;   // (blob_d_bytes = 0: the tables do not fit the 16-bit offsets)
     uint32_t total_cdf = 0, total_lut = 0;
     bool ready = false;
 };

@@ -538,6 +538,17 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
     }
 }
 
+// out[n] = b[n] + sum_k w[n][k] * v[k], k < K0 of a row of K floats (state_dict layout), FP32 in ascending k
+__global__ void k_fold_bias(const float *__restrict__ w, const float *__restrict__ b, const float *__restrict__ v, int N, int K, int K0,
+                            float *__restrict__ out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc = b[n];
+    for (int k = 0; k < K0; ++k) acc = fmaf(w[(size_t)n * K + k], v[k], acc);
+    out[n] = acc;
+}
+
 // [N][Cin][k2] (state_dict) -> [N][k2][Cin]: a tap's input channels are contiguous (dead taps are skipped as segments)
 __global__ void k_conv_tap_major(const float *__restrict__ src, float *__restrict__ dst, int N, int Cin, int k2)
 {
@@ -644,6 +655,16 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
         BASIC_CUDA(cudaStreamSynchronize(s));
         tmp.release();
         BASIC_TRY(upload(m.ws_m1, m1_w, (size_t)m.c_m1 * 2 * m.c_ctx, s));
+        // cells that see no neighbour (stage 0) have ctx == the convolution's bias: that half of the first merger layer is a
+        // constant, folded into its bias (tensor path: the stage skips the convolution launch and half of the layer's K)
+        BASIC_TRY(m.b_m1_fold.reserve((size_t)m.c_m1 * sizeof(float)));
+        if (ctx_b) {
+            k_fold_bias<<<(m.c_m1 + 127) / 128, 128, 0, s>>>(m.ws_m1.as<float>(), m.b_m1.as<float>(), m.b_ctx.as<float>(), m.c_m1,
+                                                             2 * m.c_ctx, m.c_ctx, m.b_m1_fold.as<float>());
+            BASIC_LAUNCHED();
+        } else {
+            BASIC_CUDA(cudaMemcpyAsync(m.b_m1_fold.p, m.b_m1.p, (size_t)m.c_m1 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
         BASIC_TRY(upload(m.ws_m2, m2_w, (size_t)m.c_m2 * m.c_m1, s));
         BASIC_TRY(upload(m.ws_m3, m3_w, (size_t)m.c_ctx * m.c_m2, s));
     }
@@ -952,7 +973,9 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
         a.B = B; a.HW = HW; a.W_img = m.W; a.H_img = m.H; a.G = G;
         return a;
     };
-    for (int og = 0; og < G; ++og) {
+    static const bool fold_off = [] { const char *e = getenv("BASIC_CTX_FOLD"); return e && e[0] == '0'; }();  // A/B switch
+    const bool fold0 = tc && G == 1 && m.has_merger && st.tap_or == 0 && m.b_m1_fold.p && !fold_off;
+    for (int og = 0; og < G && !fold0; ++og) {
         const int ncells = st.cell_off[og + 1] - st.cell_off[og];
         if (ncells == 0) continue;
         LayerArgs a = base_args(og, ncells);
@@ -1007,7 +1030,8 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
             if (layer == 1) {
                 a.src0 = Source{act0, m.c_ctx, G, cl};
                 a.src1 = Source{tc ? prior_cl : prior, m.c_ctx, 0, cl};
-                a.wt = m.w_m1.as<float>(); a.bias = m.b_m1.as<float>();
+                a.wt = m.w_m1.as<float>(); a.bias = fold0 ? m.b_m1_fold.as<float>() : m.b_m1.as<float>();
+                a.fold_src0 = fold0 ? 1 : 0;
                 a.Ntot = m.c_m1; a.out = act1; a.out_cl = cl; a.lrelu = 1;
             } else if (layer == 2) {
                 a.src0 = Source{act1, m.c_m1, G, cl};
@@ -1101,7 +1125,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -21,6 +21,7 @@ struct CtxModel {
     // weights, K-major ("transposed"): wt[kk][o]
     DevBuf w_ctx, b_ctx;                // conv: kk = tap * C + c
     DevBuf w_m1, b_m1, w_m2, b_m2, w_m3, b_m3;
+    DevBuf b_m1_fold;                   // G = 1: b_m1 + W_m1[:, :2C] . b_ctx -- the first merger layer's bias at cells that see no neighbour (ctx == bias)
     // the coder's INTERNAL merger (pgm_coder.py:1207-1239: 2G channel groups, the G "prior" groups with id -1): besides the
     // context branch above (widths c_m1 = c_m2 = bottleneck / 2, layers 2 and 3 also read the prior branch) a prior branch
     // prior -> p1 -> p2 of width c_p that no rule masks.  Exact FP32 kernels only.
@@ -109,6 +110,7 @@ struct LayerArgs {
     int debug;
     long long *timeline;        // optional [grid][16 tiles][8] clock64 stamps (BASIC_TC_TIMELINE), else NULL
     uint32_t vis_or[8];         // conv: OR over the launch's rows of the tap mask per input group; dense: [0] = OR of group bits
+    int fold_src0;              // tensor path, dense: src0 is constant over the launch's rows and already inside `bias` (stage 0)
 };
 
 

@@ -939,6 +939,7 @@ static void build_kb_list(const LayerArgs &a, std::vector<uint4> &out)
             shift = (tap / a.ksize - pad) * a.W_img + (tap % a.ksize - pad);
         } else {
             src = i >= a.kb_src0;
+            if (a.fold_src0 && !src) continue;   // constant source folded into the bias
             c0 = (src ? i - a.kb_src0 : i) * BK;
             const Source sc = src ? a.src1 : a.src0;
             nch = sc.channels;

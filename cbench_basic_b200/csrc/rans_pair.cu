@@ -25,8 +25,8 @@ constexpr int kPairs = 8;          // chunk slots per CTA: warps [0, kPairs) are
 constexpr int kWordUnits = 512;    // word ring per slot: u32 units of two 16-bit words (2 KB)
 constexpr int kWordGroup = 128;    // ... filled in groups of this many units
 constexpr int kDecParBlocks = 2;   // decoder operand ring: blocks of 4 steps x 32 lanes x 16 B (2 KB each)
-constexpr int kEncParBlocks = 4;   // encoder operand ring
-constexpr int kEncHelpers = 2;     // encoder: helper warps per main warp; helper h prepares the blocks with (block number) % kEncHelpers == h
+constexpr int kEncParBlocks = 6;   // encoder operand ring (two blocks per helper)
+constexpr int kEncHelpers = 3;     // encoder: helper warps per main warp (a helper is as latency-bound as a main warp); helper h prepares the blocks with (block number) % kEncHelpers == h
 constexpr int kOutBlocks = 2;      // decoder output ring: blocks of 4 steps x 32 lanes x 4 B
 constexpr int kCtrlBytes = 64;     // per slot: params_ready | out_done | stored | wp_pub | ready_w | w_epoch | pad | pad | flags of the ring's blocks [8]
 
@@ -102,7 +102,8 @@ enum { C_PARAMS = 0, C_DONE = 4, C_STORED = 8, C_WP = 12, C_READYW = 16, C_EPOCH
 // lut shift, symbols << 8, active << 31 | offset.  Everything the common case needs is straight-line predicated code: the
 // single warp of a scheduler pays the full latency of every dependent instruction and of every branch.
 __global__ void __launch_bounds__(kPairs * 64, 1)
-k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
+k_pair_decode(LaneParams P, const uint4 *__restrict__ blob_d, int blob_d_bytes, int dcdf_bytes,
+              const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
               int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
               uint32_t *__restrict__ carry_wp, int *status)
 {
@@ -116,7 +117,16 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
     const uint32_t par_s = ring_s + kWordUnits * 4;                                   // operands
     const uint32_t out_s = par_s + kDecParBlocks * 2048;                              // decoded symbols
     if (threadIdx.x < kPairs * kCtrlBytes / 4) reinterpret_cast<uint32_t *>(smem)[threadIdx.x] = 0;
-    const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kDecSlotBytes));
+    // the decoder's table image (tables.cu): d[i] = cdf[i] - 1 with sentinels | lut2 = byte offsets into the d region
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + kPairs * (kCtrlBytes + kDecSlotBytes));
+        for (int i = threadIdx.x; i < blob_d_bytes / 16; i += blockDim.x) dst[i] = blob_d[i];
+        __syncthreads();
+    }
+    uint32_t d_s = (uint32_t)__cvta_generic_to_shared(smem + kPairs * (kCtrlBytes + kDecSlotBytes));   // d region (16-byte aligned)
+    asm volatile("" : "+r"(d_s)::"memory");
+    const uint32_t lut_s = d_s + (uint32_t)dcdf_bytes;
+    const uint4 *meta_tab = reinterpret_cast<const uint4 *>(P.blob);   // 16-byte table records, read by the helper (L1 resident)
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks;
     const bool bypass = P.bypass != 0;
@@ -126,6 +136,10 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
     const uint32_t *units = reinterpret_cast<const uint32_t *>(seg + words_at);  // 2 words per unit, 4-byte aligned
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
     int st = 0;
+#ifdef PAIR_TIMING
+    long long td_wait = 0, td_work = 0, td_words = 0;
+    const long long td_start = clock64();
+#endif
     uint32_t gb = 0;     // blocks of this slot so far (all its chunks): the counters in `ctrl` count in these
     uint32_t seq = 0;    // chunks of this slot so far
     for (int k = blockIdx.x + slot * gridDim.x; k < n_chunks; k += gridDim.x * kPairs) {
@@ -149,8 +163,14 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
             auto ensure = [&]() {
                 const uint32_t need = wp + 160 < wend ? wp + 160 : wend;
                 if ((int32_t)(ready_w - need) < 0) {
+#ifdef PAIR_TIMING
+                    const long long t_e0 = clock64();
+#endif
                     if (lane == 0) st_relaxed(ctrl + C_WP, wp);
                     ready_w = wait_ge(ctrl + C_READYW, need);
+#ifdef PAIR_TIMING
+                    td_words += clock64() - t_e0;
+#endif
                 }
             };
             // one renormalisation event: the lanes below L take consecutive words in lane order
@@ -162,8 +182,15 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                 wp += __popc(nm);
             };
             for (int blk = 0; blk < nblocks; ++blk, ++gb) {
+#ifdef PAIR_TIMING
+                const long long t_w0 = clock64();
+#endif
                 wait_ge(ctrl + C_PARAMS, gb + 1);
                 if (gb >= kOutBlocks) wait_ge(ctrl + C_STORED, gb + 1 - kOutBlocks);
+#ifdef PAIR_TIMING
+                const long long t_w1 = clock64();
+                td_wait += t_w1 - t_w0;
+#endif
                 const uint32_t pbase = par_s + (gb % kDecParBlocks) * 2048 + lane * 16;
                 const uint32_t obase = out_s + (gb % kOutBlocks) * 512 + lane * 4;
                 uint4 Pq[4];
@@ -172,65 +199,60 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                 ensure();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    // operands: lut2 address of the table | address of its escape symbol's d entry | value offset (the decoded value
+                    // is (address of the symbol's d entry >> 1) + this) | lut shift, escape symbol << 8, active << 31
                     const uint4 Q = Pq[q];
-                    const bool active = (int32_t)Q.z < 0;
-                    const int maxv = (int)((Q.z >> 8) & 0xffffu) - 1;      // the escape symbol = last coded symbol
+                    const bool active = (int32_t)Q.w < 0;
                     const uint32_t cum = x & 0xffffu;
-                    int s = (int)lds16(Q.x + ((cum >> (Q.z & 31u)) << 1));
-                    const uint32_t e = Q.y + 2u * (uint32_t)s;
-                    const uint32_t c0 = lds16(e), c1 = lds16(e + 2), c2 = lds16(e + 4), c3 = lds16(e + 6);
-                    const int d = maxv - s;                                // symbols above the candidate
-                    const bool a1 = d > 0 && c1 <= cum;
-                    const bool a2 = a1 && d > 1 && c2 <= cum;
-                    const bool a3 = a2 && d > 2 && c3 <= cum;
-                    uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
-                    s += (int)a1 + (int)a2;
-                    const bool rare = active && (a3 || (bypass && s == maxv));
+                    const uint32_t e = d_s + lds16(Q.x + ((cum >> (Q.w & 31u)) << 1));   // first candidate of the bucket
+                    const uint32_t e0 = lds16(e), e1 = lds16(e + 2), e2 = lds16(e + 4), e3 = lds16(e + 6);
+                    const bool a1 = e1 < cum, a2 = e2 < cum, a3 = e3 < cum;               // (monotone; false at every sentinel)
+                    uint32_t dsel = a2 ? e2 : a1 ? e1 : e0, dnext = a2 ? e3 : a1 ? e2 : e1;
+                    uint32_t es = e + (a1 ? 2u : 0u) + (a2 ? 2u : 0u);                    // address of the decoded symbol's d entry
+                    const bool rare = active && (a3 || (bypass && es == Q.y));
+                    const uint32_t xc = ((dnext - dsel) & 0xffffu) * (x >> 16) + ((cum - 1u - dsel) & 0xffffu);   // (before the vote: off its latency)
                     if (!__any_sync(kFull, rare)) {
                         // ---- the common step
-                        const uint32_t freq = (next - start) & 0xffffu;
-                        const uint32_t xn = freq * (x >> 16) + (cum - start);
-                        x = active ? xn : x;
+                        x = active ? xc : x;
                         refill(active && x < kRansL);
-                        sts32(obase + q * 128, (uint32_t)(s + (int32_t)Q.w));
+                        sts32(obase + q * 128, (es >> 1) + Q.z);
                         continue;
                     }
                     // ---- a lane sits in a tail of narrow symbols (eight more entries per round) and / or decoded an escape
                     if (__any_sync(kFull, a3)) {
                         bool more = a3;
-                        int sc = s + 1;            // cdf[sc] <= cum is known for the lanes still searching
-                        uint32_t lo = c3;
+                        uint32_t ec = e + 6;       // d[ec] < cum is known for the lanes still searching
+                        uint32_t lo = e3;
                         while (__any_sync(kFull, more)) {
-                            const uint32_t e8 = Q.y + 2u * (uint32_t)sc;
                             uint32_t cc[9];
 #pragma unroll
-                            for (int i = 1; i <= 8; ++i) cc[i] = lds16(e8 + 2 * i);
+                            for (int i = 1; i <= 8; ++i) cc[i] = lds16(ec + 2 * i);
                             cc[0] = lo;
                             int adv = 0;
                             bool run = more;
 #pragma unroll
                             for (int i = 1; i <= 8; ++i) {
-                                run = run && sc + i <= maxv && cc[i] <= cum;
+                                run = run && cc[i] < cum;
                                 adv += (int)run;
                             }
                             uint32_t st_ = cc[0], nx_ = cc[1];
 #pragma unroll
                             for (int i = 1; i <= 7; ++i) if (adv >= i) { st_ = cc[i]; nx_ = cc[i + 1]; }
                             if (more) {
-                                sc += adv;
+                                ec += 2u * (uint32_t)adv;
                                 lo = cc[8];
-                                if (adv < 8) { s = sc; start = st_; next = nx_; more = false; }
+                                if (adv < 8) { es = ec; dsel = st_; dnext = nx_; more = false; }
                             }
                         }
                     }
                     {
-                        const uint32_t freq = (next - start) & 0xffffu;
-                        const uint32_t xn = freq * (x >> 16) + (cum - start);
+                        const uint32_t freq = (dnext - dsel) & 0xffffu;
+                        const uint32_t xn = freq * (x >> 16) + ((cum - 1u - dsel) & 0xffffu);
                         x = active ? xn : x;
                         refill(active && x < kRansL);
                     }
-                    int32_t value = s;
-                    const bool esc = active && bypass && s == maxv;
+                    uint32_t value = (es >> 1) + Q.z;
+                    const bool esc = active && bypass && es == Q.y;
                     // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count
                     // token), followed by the digits, least significant first, four tokens per unit
                     if (__any_sync(kFull, esc)) {
@@ -260,12 +282,13 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                             refill(was && x < kRansL);
                             if (wp > wend) { st |= 4; wp = wend; in = false; }   // truncated / corrupt stream
                         }
-                        if (esc) {
+                        if (esc) {   // value = maxv + offset at this point
                             const int32_t v2 = (int32_t)(raw >> 1);
-                            value = (raw & 1) ? -v2 - 1 : v2 + maxv;
+                            const int32_t maxv = (int32_t)((Q.w >> 8) & 0xffffu);
+                            value = (raw & 1) ? (uint32_t)((int32_t)value - maxv - v2 - 1) : (uint32_t)((int32_t)value + v2);
                         }
                     }
-                    sts32(obase + q * 128, (uint32_t)(value + (int32_t)Q.w));
+                    sts32(obase + q * 128, value);
                 }
                 if (wp > wend) { st |= 4; wp = wend; }   // reads past the chunk's words: truncated / corrupt stream
                 __syncwarp();
@@ -273,6 +296,9 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                     st_relaxed(ctrl + C_WP, wp);
                     st_flag(ctrl + C_DONE, gb + 1);
                 }
+#ifdef PAIR_TIMING
+                td_work += clock64() - t_w1;
+#endif
             }
             if (last_slice) {
                 if (wp != wend && lane == 0) st |= 4;
@@ -318,12 +344,14 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
                         const bool active = j0 + q < m;
                         int32_t c = ix[q];
                         if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
-                        const uint4 mt = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                        const uint4 mt = __ldg(meta_tab + c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                        const uint32_t maxv = (mt.z & 0xffffu) - 2u;                  // the escape symbol = last coded symbol
+                        const uint32_t tbase = d_s + 2u * (mt.x + 4u * (uint32_t)c);  // address of the table's d[0]
                         uint4 o;
-                        o.x = tb.lut_at(mt.y);
-                        o.y = tb.cdf_at(mt.x);
-                        o.z = ((mt.z >> 16) & 0xffu) | (((mt.z & 0xffffu) - 1u) << 8) | (active ? 0x80000000u : 0u);
-                        o.w = mt.w;
+                        o.x = lut_s + 2u * mt.y;
+                        o.y = tbase + 2u * maxv;
+                        o.z = mt.w - (tbase >> 1);
+                        o.w = ((mt.z >> 16) & 0xffu) | (maxv << 8) | (active ? 0x80000000u : 0u);
                         rec[q] = o;
                     }
 #pragma unroll
@@ -391,6 +419,11 @@ k_pair_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg
             gb += nblocks;
         }
     }
+#ifdef PAIR_TIMING
+    if (blockIdx.x == 0 && slot == 0 && lane == 0 && gb && is_main)
+        printf("[pair decode] main: blocks %u, total %lld cycles, waiting for operands / output ring %lld, for words %lld, working %lld = %lld per block\n",
+               gb, clock64() - td_start, td_wait, td_words, td_work, td_work / gb);
+#endif
     if (st) atomicOr(status, st);
 }
 
@@ -421,7 +454,10 @@ k_pair_encode(LaneParams P, const uint4 *__restrict__ enc_tab, const int32_t *__
     const uint32_t ctrl = (uint32_t)__cvta_generic_to_shared(smem + slot * kCtrlBytes);
     const uint32_t par_s = (uint32_t)__cvta_generic_to_shared(smem + kPairs * kCtrlBytes + slot * kEncSlotBytes);
     if (threadIdx.x < kPairs * kCtrlBytes / 4) reinterpret_cast<uint32_t *>(smem)[threadIdx.x] = 0;
-    const Tab<true> tb = stage_tables<true>(P.blob, P.blob_bytes, P.meta_bytes, P.cdf16_bytes, smem + kPairs * (kCtrlBytes + kEncSlotBytes));
+    // (no table image in shared memory here: the helpers need the 16-byte table records only -- 1 KB, L1 resident -- and the
+    // precomputed operand table, both read through the read-only path)
+    const uint4 *meta_tab = reinterpret_cast<const uint4 *>(P.blob);
+    __syncthreads();
     const unsigned lt_mask = (1u << lane) - 1;
     const int n_chunks = P.n_chunks_dev ? *P.n_chunks_dev : P.n_chunks;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(symbols) | reinterpret_cast<uintptr_t>(indexes)) & 15) == 0;
@@ -567,7 +603,7 @@ k_pair_encode(LaneParams P, const uint4 *__restrict__ enc_tab, const int32_t *__
                         const bool active = j0 + q < m;
                         int32_t c = ix[q];
                         if ((uint32_t)c >= (uint32_t)P.T) { if (active) st |= 1; c = 0; }
-                        const uint4 mt = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+                        const uint4 mt = __ldg(meta_tab + c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
                         const int32_t maxv = (int32_t)(mt.z & 0xffffu) - 2;
                         int32_t v = sy[q] - (int32_t)mt.w;
                         uint32_t raw = 0;
@@ -614,13 +650,14 @@ k_pair_encode(LaneParams P, const uint4 *__restrict__ enc_tab, const int32_t *__
 static constexpr int kSmemLimit = 232448;  // opt-in dynamic shared memory of one CTA on sm_100
 
 static int pair_smem(const RansTables &tb, int slot_bytes) { return kPairs * (kCtrlBytes + slot_bytes) + (int)tb.blob_bytes; }
+static int enc_smem() { return kPairs * (kCtrlBytes + kEncSlotBytes); }
+static int dec_smem(const RansTables &tb) { return kPairs * (kCtrlBytes + kDecSlotBytes) + (int)tb.blob_d_bytes; }
 
 // The pair kernels serve the default configuration: bypass_precision 4 and a table image that fits beside the rings.
 bool pair_kernels_apply(const RansTables &tb, int bypass_precision)
 {
     static const bool off = [] { const char *e = getenv("BASIC_CODER_PAIRS"); return e && e[0] == '0'; }();  // A/B switch
-    return !off && bypass_precision == 4 && tb.precision == 16 && tb.blob_bytes > 0 &&
-           pair_smem(tb, kDecSlotBytes > kEncSlotBytes ? kDecSlotBytes : kEncSlotBytes) <= kSmemLimit;
+    return !off && bypass_precision == 4 && tb.precision == 16 && tb.blob_d_bytes > 0 && dec_smem(tb) <= kSmemLimit;
 }
 
 static int pair_attrs()
@@ -643,7 +680,7 @@ int launch_pair_encode(const RansTables &tb, const LaneParams &P, const int32_t 
                        int cap_words, uint32_t *d_first, uint32_t *d_states, int *d_status, int sm_count, cudaStream_t stream)
 {
     BASIC_TRY(pair_attrs());
-    k_pair_encode<<<pair_grid(P.n_chunks, sm_count), kPairs * 32 * (1 + kEncHelpers), pair_smem(tb, kEncSlotBytes), stream>>>(
+    k_pair_encode<<<pair_grid(P.n_chunks, sm_count), kPairs * 32 * (1 + kEncHelpers), enc_smem(), stream>>>(
         P, tb.enc.as<uint4>(), d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
@@ -654,8 +691,8 @@ int launch_pair_decode(const RansTables &tb, const LaneParams &P, const unsigned
                        int sm_count, cudaStream_t stream)
 {
     BASIC_TRY(pair_attrs());
-    k_pair_decode<<<pair_grid(P.n_chunks, sm_count), kPairs * 64, pair_smem(tb, kDecSlotBytes), stream>>>(
-        P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
+    k_pair_decode<<<pair_grid(P.n_chunks, sm_count), kPairs * 64, dec_smem(tb), stream>>>(
+        P, tb.blob_d.as<uint4>(), (int)tb.blob_d_bytes, (int)tb.dcdf_bytes, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1, d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
     return BASIC_OK;
 }

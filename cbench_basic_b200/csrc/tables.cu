@@ -145,12 +145,20 @@ k_pmf_to_cdf(const float *__restrict__ pmf, int n, int precision, int32_t *__res
 __global__ void __launch_bounds__(256)
 k_pack_tables(const int32_t *__restrict__ cdfs, int stride, const TableMeta *__restrict__ meta_in,
               TableMeta *__restrict__ meta_out, uint16_t *__restrict__ cdf16, uint16_t *__restrict__ lut, int precision,
-              uint4 *__restrict__ enc)
+              uint4 *__restrict__ enc, uint16_t *__restrict__ dcdf, uint16_t *__restrict__ lut2)
 {
     const int t = blockIdx.x;
     const TableMeta m = meta_in[t];
     const int32_t *row = cdfs + (size_t)t * stride;
     if (threadIdx.x == 0) meta_out[t] = m;
+    // the pair decoder's image: d[i] = cdf[i] - 1 (mod 2^16: d[0] = 0xffff, the table's total 2^16 -> 0xffff), four 0xffff
+    // sentinels behind every table: "cdf[i] <= cum" is "d[i] < cum" and is false for every sentinel, so the search needs no
+    // end-of-table guards; start = (d + 1) & 0xffff, freq = (d[i + 1] - d[i]) & 0xffff
+    const uint32_t dbase = m.cdf_base + 4u * (uint32_t)t;
+    if (dcdf) {
+        for (int i = threadIdx.x; i < m.cdf_size + 4; i += blockDim.x)
+            dcdf[dbase + i] = i < m.cdf_size ? (uint16_t)(row[i] - 1) : (uint16_t)0xffffu;
+    }
     for (int i = threadIdx.x; i < m.cdf_size; i += blockDim.x) {
         cdf16[m.cdf_base + i] = (uint16_t)row[i];
         // the multi-lane encoder's operands of symbol i (rans_pair.cu): the state update x -> (x / f << 16) + x % f + start as
@@ -169,6 +177,7 @@ k_pack_tables(const int32_t *__restrict__ cdfs, int stride, const TableMeta *__r
             if (row[mid] <= v) lo = mid; else hi = mid - 1;
         }
         lut[m.lut_base + b] = (uint16_t)lo;
+        if (lut2) lut2[m.lut_base + b] = (uint16_t)(2u * (dbase + (uint32_t)lo));
     }
 }
 
@@ -212,6 +221,12 @@ int rans_tables_pack(RansTables &tb, cudaStream_t stream)
     tb.total_lut = lut_total;
     BASIC_TRY(tb.blob.reserve(tb.blob_bytes));
     BASIC_TRY(tb.enc.reserve((size_t)cdf_total * sizeof(uint4)));
+    tb.dcdf_bytes = pad16((size_t)(cdf_total + 4u * (uint32_t)T) * 2 + 16);
+    tb.blob_d_bytes = 2 * (size_t)(cdf_total + 4u * (uint32_t)T) < 65536 ? tb.dcdf_bytes + tb.lut_bytes : 0;   // offsets are u16
+    if (tb.blob_d_bytes) {
+        BASIC_TRY(tb.blob_d.reserve(tb.blob_d_bytes));
+        BASIC_CUDA(cudaMemsetAsync(tb.blob_d.p, 0xff, tb.blob_d_bytes, stream));
+    }
     BASIC_CUDA(cudaMemsetAsync(tb.blob.p, 0, tb.blob_bytes, stream));
     DevBuf tmp;
     BASIC_TRY(tmp.reserve(sizeof(TableMeta) * T));
@@ -221,7 +236,8 @@ int rans_tables_pack(RansTables &tb, cudaStream_t stream)
                                          reinterpret_cast<TableMeta *>(b),
                                          reinterpret_cast<uint16_t *>(b + tb.meta_bytes),
                                          reinterpret_cast<uint16_t *>(b + tb.meta_bytes + tb.cdf16_bytes), tb.precision,
-                                         tb.enc.as<uint4>());
+                                         tb.enc.as<uint4>(), tb.blob_d_bytes ? tb.blob_d.as<uint16_t>() : nullptr,
+                                         tb.blob_d_bytes ? reinterpret_cast<uint16_t *>(tb.blob_d.as<char>() + tb.dcdf_bytes) : nullptr);
     BASIC_LAUNCHED();
     BASIC_CUDA(cudaStreamSynchronize(stream));
     tmp.release();
