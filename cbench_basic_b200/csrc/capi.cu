@@ -923,7 +923,7 @@ staged:
     } else {
         uint32_t magic = 0;
         if (len >= 4) memcpy(&magic, c->host_in, 4);
-        if (magic != kMagic && magic != kMagic2) { c->stream_set = false; set_error("not a multi-lane (BLS1) container"); return BASIC_ERR_STREAM; }
+        if (magic != kMagic && magic != kMagic2 && magic != kMagic0) { c->stream_set = false; set_error("not a multi-lane (BLS) container"); return BASIC_ERR_STREAM; }
         c->stream_fp16 = magic == kMagic2;
         c->stream_pos = 4;
     }
@@ -1384,7 +1384,10 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         if (yhat_out) BASIC_CUDA(cudaMemcpyAsync(yhat_out, buf, n * 4, cudaMemcpyDefault, s));
     }
     g_trace.mark("segment coded", s);
-    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, fp16 ? &kMagic2 : &kMagic, 4, cudaMemcpyHostToDevice, s));
+    // the magic records the arithmetic of the context model: the decoder follows it (a stream written with one mode and read
+    // with another would differ in the last bits of the parameters -- garbage symbols at rounding ties, silently)
+    const uint32_t *magic = fp16 ? &kMagic2 : tc ? &kMagic : model ? &kMagic0 : &kMagic;
+    BASIC_CUDA(cudaMemcpyAsync(c->segs.p, magic, 4, cudaMemcpyHostToDevice, s));
     BASIC_TRY(copy_out(c, c->segs.p, 4 + seg_len, out, out_cap, s));
     if (out_len) *out_len = 4 + seg_len;
     g_trace.mark("copy queued", s);
@@ -1424,7 +1427,8 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
                 else memcpy(&magic, encoded, 4);
             }
             if (magic == kMagic2) prec = BASIC_CTX_FP16X3;
-            else if (prec == BASIC_CTX_FP16X3) prec = BASIC_CTX_TF32X3;
+            else if (magic == kMagic0) prec = BASIC_CTX_FP32;
+            else prec = BASIC_CTX_TF32X3;   // "BLS1" out of the y path with a context model: 3xTF32 (also the 3xFP16 range fallback)
         }
         ctx_set_run_precision(*model->m, prec);
     }

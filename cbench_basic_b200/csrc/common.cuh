@@ -186,7 +186,8 @@ template <> struct Tab<false> {
 
 static constexpr int kLanes = 32;             // lanes of one chunk = one warp
 static constexpr uint32_t kRansL = 1u << 16;  // multi-lane state lower bound
-static constexpr uint32_t kMagic = 0x31534C42u;   // "BLS1"
+static constexpr uint32_t kMagic0 = 0x30534C42u;  // "BLS0": written by the y path when its context model ran on the exact FP32 kernels
+static constexpr uint32_t kMagic = 0x31534C42u;   // "BLS1": no context model involved, or 3xTF32
 static constexpr uint32_t kMagic2 = 0x32534C42u;  // "BLS2": same container, written by the y path when its context model ran in 3xFP16
 static constexpr int kMaxSmemTables = 200 * 1024;
 

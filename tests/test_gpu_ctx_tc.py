@@ -76,6 +76,21 @@ def test_tc_round_trip(mode):
     assert float((yhat.cpu() - y).abs().max()) <= 0.5 + 1e-4
 
 
+def test_decoder_follows_the_mode_recorded_in_the_container():
+    """The magic records the arithmetic the encoder's context model ran in ("BLS0" exact FP32, "BLS1" 3xTF32, "BLS2" 3xFP16);
+    a decoder configured for ANY mode reproduces the encoder's y_hat bit for bit because it follows the stream."""
+    C_, B, H, W = 96, 2, 8, 12
+    torch.manual_seed(4)
+    y, prior = 3 * torch.randn(B, C_, H, W), torch.randn(B, 2 * C_, H, W)
+    coders = {m: build(C_, 1, "checkerboard", m, 4) for m in ("fp32", "tf32x3", "fp16x3")}
+    magic = {"fp32": b"BLS0", "tf32x3": b"BLS1", "fp16x3": b"BLS2"}
+    for wm, enc in coders.items():
+        bs, yhat_enc = enc.encode(y.cuda(), prior=prior.cuda(), return_yhat=True)
+        assert bs[:4] == magic[wm]
+        for rm, dec in coders.items():
+            assert torch.equal(dec.decode(bs, prior=prior.cuda()), yhat_enc * 1.0 + 0.0), (wm, rm)
+
+
 def test_fp16x3_range_fallback():
     """An activation of magnitude >= 4000 does not fit the 3xFP16 operand scaling: the encoder notices (device flag),
     repeats the pass in 3xTF32 and says so in the container ("BLS1"); a 3xFP16-configured decoder follows the stream.

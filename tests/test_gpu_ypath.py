@@ -364,7 +364,8 @@ def test_ypath_multilane_container_matches_cpu_spec():
     magic, n_chunks, n_slices = struct.unpack_from("<III", bs, 0)
     gmap = Y.group_of_elements(c["tg"], c["B"], c["C"]).reshape(-1)
     slice_n = [int((gmap == g).sum()) for g in range(n_slices)]
-    assert magic == 0x31534C42 and n_slices == int(c["tg"].max()) + 1 and sum(slice_n) == gsym.size
+    # "BLS0": this geometry (6 channels per group) runs the exact FP32 kernels, and the container says so
+    assert magic == 0x30534C42 and n_slices == int(c["tg"].max()) + 1 and sum(slice_n) == gsym.size
     o = Y.YPathOracle(24, 4, c["w"])
     o.update_state()
     assert bs[4:] == o.enc.encode_lanes_slices(gsym, gidx, slice_n, 3)

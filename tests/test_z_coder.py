@@ -198,7 +198,7 @@ def test_gpu_hyperprior_latent_codec_round_trip():
     data = codec.encode(y)
     (zlen,) = struct.unpack_from("I", data, 0)
     strings, shape = z_coder.read_body(data[4:4 + zlen])
-    assert len(strings) == B and tuple(shape) == (H // 2, W // 2) and data[4 + zlen:8 + zlen] in (b"BLS1", b"BLS2")
+    assert len(strings) == B and tuple(shape) == (H // 2, W // 2) and data[4 + zlen:8 + zlen] in (b"BLS0", b"BLS1", b"BLS2")
     y_hat = codec.decode(data)
     assert y_hat.shape == y.shape and float((y_hat - y).abs().max()) <= 0.5 + 1e-4
     assert torch.equal(codec.decode(data), y_hat)
