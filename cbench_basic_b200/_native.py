@@ -17,7 +17,7 @@ SYMBOLS = [
     "basic_last_error", "basic_device_count", "basic_coder_create", "basic_coder_destroy", "basic_coder_init_params",
     "basic_coder_init_cdf_params", "basic_coder_cdfs_shape", "basic_coder_get_cdfs", "basic_pmf_to_quantized_cdf",
     "basic_coder_encode_bound", "basic_coder_encode", "basic_coder_flush", "basic_coder_last_output", "basic_coder_output_size", "basic_coder_take_output", "basic_coder_decode", "basic_coder_set_stream",
-    "basic_coder_decode_stream", "basic_coder_encode_batch", "basic_coder_decode_batch", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
+    "basic_coder_decode_stream", "basic_coder_init_ar_params", "basic_coder_encode_ar", "basic_coder_decode_ar", "basic_coder_encode_batch", "basic_coder_decode_batch", "basic_coder_set_scale_table", "basic_gauss_quantize_index", "basic_gauss_dequantize",
     "basic_ctx_create", "basic_ctx_destroy", "basic_ctx_set_weights", "basic_ctx_set_weights_internal", "basic_ctx_set_map", "basic_ctx_num_stages",
     "basic_ctx_set_precision", "basic_ctx_stage_positions", "basic_ctx_stage_params", "basic_ypath_encode_bound", "basic_ypath_encode",
     "basic_ypath_decode", "basic_profile_enable", "basic_profile_read", "basic_debug_mma_bench", "basic_launch_count",
@@ -74,6 +74,9 @@ def lib():
     L.basic_coder_decode.argtypes = [vp, u8p, i64, i32p, i64, C.c_int, i32p, vp]
     L.basic_coder_set_stream.argtypes = [vp, u8p, i64, C.c_int, vp]
     L.basic_coder_decode_stream.argtypes = [vp, i32p, i64, i32p, vp]
+    L.basic_coder_init_ar_params.argtypes = [vp, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.basic_coder_encode_ar.argtypes = [vp, i32p, i32p, i64, i32p, i32p, C.c_int, u8p, i64, C.POINTER(i64), vp]
+    L.basic_coder_decode_ar.argtypes = [vp, u8p, i64, i32p, i64, i32p, i32p, C.c_int, i32p, vp]
     L.basic_coder_encode_batch.argtypes = [vp, i32p, i32p, i64, C.c_int, u8p, i64, C.POINTER(i64), vp]
     L.basic_coder_decode_batch.argtypes = [vp, u8p, C.POINTER(i64), C.c_int, i32p, i64, i32p, vp]
     L.basic_coder_set_scale_table.argtypes = [vp, f32p, C.c_int]

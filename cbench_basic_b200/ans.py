@@ -14,8 +14,9 @@ Same classes, method names, argument meaning and error behaviour as the pybind11
 Two additions: arrays may be numpy arrays OR torch CUDA tensors (then nothing crosses PCIe), and every
 class takes ``lanes=`` (1 = the reference bitstream byte for byte -- the default; 0 = multi-lane container
 sized for <= 0.5 % overhead; N > 1 = ceil(N / 32) chunks of 32 interleaved lanes) and ``device=``.
-The in-coder autoregressive index lookup (init_ar_params & co, ans_interface.hpp:58-105) is not part of the
-BaSIC path: ar_indexes / ar_offsets must be None.
+The in-coder autoregressive table lookup (``init_ar_params`` + ``ar_indexes`` / ``ar_offsets``, ans_interface.hpp:58-105,
+the table branch) is provided for the rANS coder in the reference-compatible single-stream mode (lanes = 1:
+the lookup makes every symbol depend on earlier ones).  Custom AR ops (``init_custom_ar_ops``) are not.
 """
 import ctypes as C
 
@@ -58,7 +59,7 @@ def _stream(*args):
 
 def _no_ar(ar_indexes, ar_offsets):
     if ar_indexes is not None or ar_offsets is not None:
-        raise NotImplementedError("in-coder autoregressive index lookup is outside the BaSIC hot path (SURVEY 2a)")
+        raise NotImplementedError("ar_indexes / ar_offsets need init_ar_params (rANS, lanes=1)")
 
 
 def pmf_to_quantized_cdf(pmf, precision, device=0):
@@ -101,11 +102,40 @@ class _Coder:
         N.check(N.lib().basic_coder_init_params(self._h, freqs.ctypes.data, freqs.shape[0], freqs.shape[1],
                                                 num_symbols.ctypes.data, offsets.ctypes.data))
 
-    # the AR feature exists in the reference API; it is outside the BaSIC path
-    def init_ar_params(self, *a, **k):
-        raise NotImplementedError("in-coder autoregressive tables are outside the BaSIC hot path (SURVEY 2a)")
+    # ---- in-coder autoregressive table lookup (ans_interface.cpp:75-135)
+    _ar_order = 0
 
-    init_custom_ar_ops = create_ar_ptrs = init_ar_params
+    def init_ar_params(self, ar_tables, ar_offsets):
+        tab = np.ascontiguousarray(np.asarray(ar_tables), dtype=np.int32)
+        off = np.asarray(ar_offsets)
+        norder = tab.ndim - 2
+        if off.ndim != 3 or off.shape[1] != norder or off.shape[0] != tab.shape[0]:
+            raise ValueError("ar_offset should be 3-dimensional with shape (ar_tables_size, ar_order, <=data_dims)")
+        if norder <= 0:
+            raise ValueError("ar_tables should be at least 3-dimensional with shape (ar_tables_size, index_dim, *ar_order_dims)")
+        if norder > 2:
+            raise ValueError("Too many dimensions!")
+        if self._kind != N.KIND_RANS64 or self.lanes != 1:
+            raise NotImplementedError("the AR lookup is provided for the rANS coder at lanes=1 (every symbol depends on earlier ones)")
+        N.check(N.lib().basic_coder_init_ar_params(self._h, tab.ctypes.data, tab.shape[0], tab.shape[1], tab.shape[2],
+                                                   tab.shape[3] if norder == 2 else 0))
+        self._ar_order = norder
+
+    def _ar_args(self, ar_indexes, ar_offsets, n):
+        if ar_offsets is None:
+            raise ValueError("ar_offsets is required for ar coding!")
+        off = _Arg(ar_offsets, self.device)
+        if len(off.shape) != 2 or off.shape[0] != self._ar_order or off.shape[1] != n:
+            raise ValueError("ar_offsets should have shape (ar_order, number of symbols)")
+        ai = _Arg(ar_indexes, self.device) if ar_indexes is not None else None
+        if ai is not None and ai.size != n:
+            raise ValueError("ar_indexes should have one entry per symbol")
+        return ai, off
+
+    def init_custom_ar_ops(self, *a, **k):
+        raise NotImplementedError("custom AR ops (ar_funcs.hpp) are not provided; the table lookup (init_ar_params) is")
+
+    create_ar_ptrs = init_custom_ar_ops
 
     # ---- C-ABI handle for the fused y path
     @property
@@ -140,12 +170,19 @@ class _Rans64(_Coder):
 
 class _EncoderMixin:
     def encode_with_indexes(self, symbols, indexes, ar_indexes=None, ar_offsets=None, cache=0):
-        _no_ar(ar_indexes, ar_offsets)
         sym, idx = _Arg(symbols, self.device), _Arg(indexes, self.device)
         if sym.size != idx.size:
             raise ValueError("symbols and indexes must have the same number of elements")
         n = sym.size
         out_len = C.c_int64(0)
+        if self._ar_order:   # rans64.cpp:218-228, :259-263
+            if cache:
+                raise NotImplementedError("cache=True with AR tables")
+            ai, off = self._ar_args(ar_indexes, ar_offsets, n)
+            N.check(N.lib().basic_coder_encode_ar(self._h, sym.ptr, idx.ptr, n, ai.ptr if ai else None, off.ptr, self._ar_order,
+                                                  None, 0, C.byref(out_len), _stream(sym, idx)))
+            return N.last_output(self._h)
+        _no_ar(ar_indexes, ar_offsets)
         N.check(N.lib().basic_coder_encode(self._h, sym.ptr, idx.ptr, n, self.lanes, int(bool(cache)), None, 0,
                                            C.byref(out_len), _stream(sym, idx)))
         self._cached = getattr(self, "_cached", 0) + (n if cache else 0)
@@ -167,10 +204,15 @@ class _DecoderMixin:
         return out, out.ctypes.data
 
     def decode_with_indexes(self, encoded, indexes, ar_indexes=None, ar_offsets=None):
-        _no_ar(ar_indexes, ar_offsets)
         idx = _Arg(indexes, self.device)
         enc = np.frombuffer(bytes(encoded), dtype=np.uint8)
         out, optr = self._out_like(idx, indexes)
+        if self._ar_order:   # rans64.cpp:406-416, :439-443
+            ai, off = self._ar_args(ar_indexes, ar_offsets, idx.size)
+            N.check(N.lib().basic_coder_decode_ar(self._h, enc.ctypes.data if enc.size else 0, enc.size, idx.ptr, idx.size,
+                                                  ai.ptr if ai else None, off.ptr, self._ar_order, optr, _stream(idx)))
+            return out
+        _no_ar(ar_indexes, ar_offsets)
         N.check(N.lib().basic_coder_decode(self._h, enc.ctypes.data if enc.size else 0, enc.size, idx.ptr, idx.size,
                                            self.lanes, optr, _stream(idx)))
         return out

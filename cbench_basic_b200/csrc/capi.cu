@@ -38,6 +38,11 @@ int launch_quantize_index(const float *, const float *, const int32_t *, int64_t
 int launch_dequantize(const int32_t *, const float *, const int32_t *, int64_t, int, int, int, float *, int, cudaStream_t,
                       int params_cl = 0, const int32_t *perm = nullptr);
 
+int launch_ar_effective_indexes(const int32_t *, int, int, int, int, const int32_t *, const int32_t *, const int32_t *, const int32_t *,
+                                const int32_t *, int64_t, int32_t *, int *, cudaStream_t);
+int launch_rans64_decode_ar(const RansTables &, const uint32_t *, int64_t, const int32_t *, int, int, int, int, const int32_t *,
+                            const int32_t *, const int32_t *, const int32_t *, int64_t, int, int, int32_t *, int *, cudaStream_t);
+
 struct CtxModel;
 CtxModel *ctx_new(int C, int G, int k, int device, int sm_count);
 void ctx_delete(CtxModel *);
@@ -175,6 +180,8 @@ struct basic_coder {
     // scratch
     DevBuf in_a, in_b, out_i32, words, first, states, segs, small, stream_dev, y_dev, prior_dev, buf, params, sym_all, idx_all,
         yhat_stage, slices_dev, carry_x, carry_wp, buf_cl, prior_cl, batch_first, batch_meta, batch_state;
+    DevBuf ar_table, ar_a, ar_b, ar_c, ar_eff;   // in-coder AR lookup: the table, staged ar_indexes / ar_offsets, effective indexes
+    int ar_A = 0, ar_I = 0, ar_D1 = 0, ar_D2 = 0;
     void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
     // pinned host staging (grow-only): encoded output kept for basic_coder_last_output, and the stream being decoded
     uint8_t *host_out = nullptr, *host_in = nullptr;
@@ -640,7 +647,7 @@ void basic_coder_destroy(basic_coder *c)
 {
     if (!c) return;
     DeviceGuard guard(c->device);
-    DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->rt.enc, &c->rt.blob_d, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
+    DevBuf *bufs[] = {&c->rt.cdf32, &c->rt.blob, &c->rt.enc, &c->rt.blob_d, &c->ar_table, &c->ar_a, &c->ar_b, &c->ar_c, &c->ar_eff, &c->d_scale, &c->in_a, &c->in_b, &c->out_i32, &c->words, &c->first, &c->states,
                       &c->segs, &c->small, &c->stream_dev, &c->y_dev, &c->prior_dev, &c->buf, &c->params, &c->sym_all,
                       &c->idx_all, &c->yhat_stage, &c->slices_dev, &c->carry_x, &c->carry_wp, &c->buf_cl, &c->prior_cl, &c->batch_first,
                       &c->batch_meta, &c->batch_state};
@@ -994,6 +1001,91 @@ int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, cons
     }
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
     return basic_coder_decode_stream(c, indexes, n, out, stream);
+}
+
+// ---- in-coder autoregressive table lookup (reference lanes = 1 stream only) ---------------------------------------------
+int basic_coder_init_ar_params(basic_coder *c, const int32_t *ar_tables, int A, int I, int D1, int D2)
+{
+    if (!c) return value_error("null coder");
+    if (c->kind != BASIC_KIND_RANS64) return value_error("the AR lookup is built for the rANS coder");
+    if (!ar_tables || A < 1 || I < 1 || D1 < 1 || D2 < 0)
+        return value_error("ar_tables should be at least 3-dimensional with shape (ar_tables_size, index_dim, *ar_order_dims)");
+    DeviceGuard guard(c->device);
+    const size_t count = (size_t)A * I * D1 * (D2 ? D2 : 1);
+    BASIC_TRY(c->ar_table.reserve(count * 4));
+    BASIC_CUDA(cudaMemcpy(c->ar_table.p, ar_tables, count * 4, cudaMemcpyDefault));
+    c->ar_A = A; c->ar_I = I; c->ar_D1 = D1; c->ar_D2 = D2;
+    return BASIC_OK;
+}
+
+static int ar_args(basic_coder *c, const int32_t *ar_indexes, const int32_t *ar_offsets, int order, int64_t n, cudaStream_t s,
+                   const int32_t **d_ai, const int32_t **d_o0, const int32_t **d_o1)
+{
+    if (!c->ar_A) return value_error("init_ar_params has not been called");
+    if (!ar_offsets) return value_error("ar_offsets is required for ar coding!");
+    if (order != (c->ar_D2 ? 2 : 1)) return value_error("ar_offsets should have one row per AR order of the tables");
+    *d_ai = nullptr;
+    if (ar_indexes) BASIC_TRY(to_device(ar_indexes, (size_t)n, c->ar_a, s, d_ai));
+    const int32_t *d_off;
+    BASIC_TRY(to_device(ar_offsets, (size_t)n * order, c->ar_b, s, &d_off));
+    *d_o0 = d_off;
+    *d_o1 = order == 2 ? d_off + n : nullptr;
+    return BASIC_OK;
+}
+
+int basic_coder_encode_ar(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, const int32_t *ar_indexes,
+                          const int32_t *ar_offsets, int order, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (n < 0) return value_error("negative size");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (out_len) *out_len = 0;
+    const int32_t *d_sym, *d_idx, *d_ai, *d_o0, *d_o1;
+    BASIC_TRY(ar_args(c, ar_indexes, ar_offsets, order, n, s, &d_ai, &d_o0, &d_o1));
+    BASIC_TRY(to_device(symbols, (size_t)n, c->in_a, s, &d_sym));
+    BASIC_TRY(to_device(indexes, (size_t)n, c->in_b, s, &d_idx));
+    BASIC_TRY(c->ar_eff.reserve((size_t)n * 4 + 16));
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    BASIC_CUDA(cudaMemsetAsync(c->small.p, 0, sizeof(Small), s));
+    // the encoder knows every symbol: effective table indexes in parallel, then the reference stream
+    BASIC_TRY(launch_ar_effective_indexes(c->ar_table.as<int32_t>(), c->ar_A, c->ar_I, c->ar_D1, c->ar_D2, d_ai, d_o0, d_o1, d_sym, d_idx,
+                                          n, c->ar_eff.as<int32_t>(), &ds->status, s));
+    BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    if (hs->status & 1) return value_error("AR lookup out of range of the AR tables");
+    const uint8_t *d_bytes;
+    int64_t len;
+    BASIC_TRY(encode_compat(c, d_sym, c->ar_eff.as<int32_t>(), n, s, &d_bytes, &len));
+    BASIC_TRY(copy_out(c, d_bytes, len, out, out_cap, s));
+    if (out_len) *out_len = len;
+    return BASIC_OK;
+}
+
+int basic_coder_decode_ar(basic_coder *c, const uint8_t *encoded, int64_t len, const int32_t *indexes, int64_t n,
+                          const int32_t *ar_indexes, const int32_t *ar_offsets, int order, int32_t *out, void *stream)
+{
+    BASIC_TRY(need_init(c));
+    if (n < 0 || len < 0 || (len & 3)) return value_error("a reference rANS64 stream is a whole number of 32-bit words");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int32_t *d_idx, *d_ai, *d_o0, *d_o1;
+    BASIC_TRY(ar_args(c, ar_indexes, ar_offsets, order, n, s, &d_ai, &d_o0, &d_o1));
+    BASIC_TRY(to_device(indexes, (size_t)n, c->in_b, s, &d_idx));
+    BASIC_TRY(c->stream_dev.reserve((size_t)len + 64));
+    if (len) BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyDefault, s));
+    int32_t *d_out = out;
+    const bool out_dev = is_device_ptr(out);
+    if (!out_dev) { BASIC_TRY(c->out_i32.reserve((size_t)n * 4 + 16)); d_out = c->out_i32.as<int32_t>(); }
+    Small *ds = c->small.as<Small>(), *hs = reinterpret_cast<Small *>(c->pinned);
+    BASIC_CUDA(cudaMemsetAsync(&ds->status, 0, sizeof(int), s));
+    BASIC_TRY(launch_rans64_decode_ar(c->rt, c->stream_dev.as<uint32_t>(), len / 4, c->ar_table.as<int32_t>(), c->ar_A, c->ar_I, c->ar_D1,
+                                      c->ar_D2, d_ai, d_o0, d_o1, d_idx, n, c->bypass, (int)c->bypass_precision, d_out, &ds->status, s));
+    BASIC_CUDA(cudaMemcpyAsync(&hs->status, &ds->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (!out_dev && n) BASIC_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    BASIC_CUDA(cudaStreamSynchronize(s));
+    c->stream_set = false;  // stream_dev was reused
+    return status_error(hs->status);
 }
 
 // ---- batches of independent reference streams (the z node: one lanes=1 stream per image, compressai_coder.py:233,242) --

@@ -272,7 +272,113 @@ k_rans64_decode(const uint32_t *__restrict__ words, long long nwords, const long
     if (tid == 0) { state->x = x; state->pos = pos; }
 }
 
+// ---- in-coder autoregressive table lookup (ans_interface.hpp:58-105, the table branch; rans64.cpp:259-263, :439-443) ----
+// The table an element is coded with is  ar_table[ar_index][index][v0]( [v1] )  with  v_k = off_k[i] > 0 ? symbol[i - off_k[i]] + 1 : 0:
+// it depends on up to two earlier symbols of the same array.  The encoder knows every symbol: a parallel prepass turns
+// (index, neighbours) into effective table indexes.  The decoder learns the neighbours one by one: the serial thread of the
+// lanes = 1 decoder does the lookup itself, symbol by symbol.
+struct ArParams {
+    const int32_t *table;      // [A][I][D1] or [A][I][D1][D2]
+    int A, I, D1, D2;          // D2 = 0: one neighbour
+    const int32_t *ar_indexes; // [n] or NULL (= 0)
+    const int32_t *off0, *off1;// [n] distances back (off1 NULL with one neighbour)
+};
+
+__device__ inline int32_t ar_lookup(const ArParams &P, int32_t index, long long i, const int32_t *__restrict__ symbols, int &st)
+{
+    const int32_t a = P.ar_indexes ? P.ar_indexes[i] : 0;
+    const int32_t o0 = P.off0[i];
+    int32_t v0 = o0 > 0 ? (i - o0 >= 0 ? symbols[i - o0] + 1 : (st |= 1, 0)) : 0;
+    int32_t v1 = 0;
+    if (P.D2) {
+        const int32_t o1 = P.off1[i];
+        v1 = o1 > 0 ? (i - o1 >= 0 ? symbols[i - o1] + 1 : (st |= 1, 0)) : 0;
+    }
+    // the reference indexes its nested vectors unchecked (undefined behaviour out of range): here that is an error
+    if ((uint32_t)a >= (uint32_t)P.A || (uint32_t)index >= (uint32_t)P.I || (uint32_t)v0 >= (uint32_t)P.D1 ||
+        (P.D2 && (uint32_t)v1 >= (uint32_t)P.D2)) { st |= 1; return 0; }
+    const long long at = ((long long)a * P.I + index) * P.D1 + v0;
+    return P.D2 ? P.table[at * P.D2 + v1] : P.table[at];
+}
+
+__global__ void __launch_bounds__(256)
+k_ar_effective_indexes(ArParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, long long n,
+                       int32_t *__restrict__ out, int *status)
+{
+    int st = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = ar_lookup(P, indexes[i], i, symbols, st);
+    if (st) atomicOr(status, st);
+}
+
+// lanes = 1 decoder with the lookup inside the chain: ONE thread (the dependency is symbol to symbol); tables from L2.
+__global__ void __launch_bounds__(32)
+k_rans64_decode_ar(const uint32_t *__restrict__ words, long long nwords, ArParams P, const int32_t *__restrict__ indexes, long long n,
+                   const void *__restrict__ blob, size_t meta_bytes, size_t cdf16_bytes, int T, int precision, int bypass,
+                   int bypass_precision, int32_t *__restrict__ out, int *status)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const TableView tv = make_view(blob, meta_bytes, cdf16_bytes);
+    int st = 0;
+    unsigned long long x = 0;
+    long long pos = 0;
+    if (nwords >= 2) { x = (unsigned long long)words[0] | ((unsigned long long)words[1] << 32); pos = 2; } else st |= 4;
+    uint32_t nw = pos < nwords ? words[pos] : 0u;
+    const uint32_t bp = (uint32_t)bypass_precision, maxb = (1u << bp) - 1, pmask = (1u << precision) - 1;
+    for (long long i = 0; i < n; ++i) {
+        int32_t c = ar_lookup(P, indexes[i], i, out, st);
+        if ((uint32_t)c >= (uint32_t)T) { st |= 1; c = 0; }
+        const TableMeta m = tv.meta[c];
+        const int nsyms = (int)m.cdf_size - 1, maxv = nsyms - 1;
+        const uint16_t *cdf = tv.cdf + m.cdf_base;
+        const uint32_t cum = (uint32_t)x & pmask;
+        int s2 = (int)tv.lut[m.lut_base + (cum >> m.lut_shift)];
+        while (s2 + 1 < nsyms && cdf[s2 + 1] <= cum) ++s2;   // (entries 1 .. nsyms - 1 are below 2^16; the total, stored as 0, is never probed)
+        const uint32_t start = cdf[s2], freq = (uint16_t)(cdf[s2 + 1] - start);
+        x = (unsigned long long)freq * (x >> precision) + cum - start;
+        if (x < kL64) pull_word(x, words, pos, nwords, nw, st);
+        int32_t value = s2;
+        if (bypass && s2 == maxv) {
+            uint32_t val = getbits64(x, words, pos, nwords, bp, nw, st), nb = val;
+            while (val == maxb && nb < 64) { val = getbits64(x, words, pos, nwords, bp, nw, st); nb += val; }
+            uint32_t raw = 0;
+            for (uint32_t j = 0; j < nb; ++j) {
+                val = getbits64(x, words, pos, nwords, bp, nw, st);
+                if (j * bp < 32) raw |= val << (j * bp);
+            }
+            value = (int32_t)(raw >> 1);
+            value = (raw & 1) ? -value - 1 : value + maxv;
+        }
+        out[i] = value + m.offset;
+    }
+    if (st) atomicOr(status, st);
+}
+
 }  // namespace
+
+int launch_ar_effective_indexes(const int32_t *d_table, int A, int I, int D1, int D2, const int32_t *d_ar_idx, const int32_t *d_off0,
+                                const int32_t *d_off1, const int32_t *d_sym, const int32_t *d_idx, int64_t n, int32_t *d_out,
+                                int *d_status, cudaStream_t stream)
+{
+    if (n <= 0) return BASIC_OK;
+    const ArParams P = {d_table, A, I, D1, D2, d_ar_idx, d_off0, d_off1};
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 2048) blocks = 2048;
+    k_ar_effective_indexes<<<blocks, 256, 0, stream>>>(P, d_sym, d_idx, n, d_out, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
+
+int launch_rans64_decode_ar(const RansTables &tb, const uint32_t *d_words, int64_t nwords, const int32_t *d_table, int A, int I, int D1,
+                            int D2, const int32_t *d_ar_idx, const int32_t *d_off0, const int32_t *d_off1, const int32_t *d_idx,
+                            int64_t n, int bypass, int bypass_precision, int32_t *d_out, int *d_status, cudaStream_t stream)
+{
+    const ArParams P = {d_table, A, I, D1, D2, d_ar_idx, d_off0, d_off1};
+    k_rans64_decode_ar<<<1, 32, 0, stream>>>(d_words, nwords, P, d_idx, n, tb.blob.p, tb.meta_bytes, tb.cdf16_bytes, tb.T, tb.precision,
+                                             bypass, bypass_precision, d_out, d_status);
+    BASIC_LAUNCHED();
+    return BASIC_OK;
+}
 
 // the table image goes to shared memory when it fits beside the kernel's static tiles
 static int compat_table_smem(const RansTables &tb, size_t static_bytes)

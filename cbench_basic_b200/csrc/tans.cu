@@ -105,11 +105,20 @@ struct BuildArgs {
     int *err;
 };
 
-// One CTA (one working thread) per table; table index T is the uniform bypass table.
-__global__ void k_tans_build(BuildArgs a)
+// One CTA per table (table index T is the uniform bypass table).  The count normalisation (tans.cpp:102-148, a few hundred
+// sequential operations) stays on one thread; the spread and the table fills are parallel:
+//  * spread (tans.cpp:176-190 / :288-300): position j * step mod size for j = 0, 1, ... is a permutation (step is odd), and the
+//    reference skips the positions above `high` (reserved for the low-probability symbols): the k-th symbol occurrence lands on
+//    the k-th j whose position is <= high.  A block-wide prefix sum over "position j is usable" gives every j its k, a binary
+//    search in the cumulative counts its symbol.
+//  * C- and D-table fill: the reference walks the states u in increasing order and gives each symbol's occurrences consecutive
+//    slots (stateTable[cumul[s]++], symbolNext[s]++): one thread per symbol walks the spread table and numbers its own.
+constexpr int kBuildThreads = 256;
+
+__global__ void __launch_bounds__(kBuildThreads)
+k_tans_build(BuildArgs a)
 {
-    if (threadIdx.x != 0) return;
-    const int t = blockIdx.x;
+    const int t = blockIdx.x, tid = threadIdx.x;
     const int tsz = 1 << a.tableLog;
     const int n = t < a.T ? a.nsym[t] : a.nbypass;
     if (t == a.T && !a.bypass) return;
@@ -118,68 +127,102 @@ __global__ void k_tans_build(BuildArgs a)
     uint32_t *cumul = count + a.max_nsym;
     uint32_t *tableSymbol = cumul + a.max_nsym + 2;
     short *norm = reinterpret_cast<short *>(tableSymbol + tsz);
-    for (int i = 0; i < n; ++i) count[i] = t < a.T ? (uint32_t)a.freqs[(size_t)t * a.M + i] : 1u;
-    if (normalize_count(norm, (uint32_t)a.tableLog, count, n)) { a.err[t] = 1; return; }
+    __shared__ int s_err;
+    __shared__ uint32_t s_high, s_scan[kBuildThreads];
+    for (int i = tid; i < n; i += kBuildThreads) count[i] = t < a.T ? (uint32_t)a.freqs[(size_t)t * a.M + i] : 1u;
+    if (tid == 0) s_err = 0;
+    __syncthreads();
     const uint32_t tableLog = (uint32_t)a.tableLog, tableSize = (uint32_t)tsz, tableMask = tableSize - 1;
     const uint32_t step = (tableSize >> 1) + (tableSize >> 3) + 3;
+    if (tid == 0) {
+        if (normalize_count(norm, tableLog, count, n)) s_err = 1;
+        else {
+            // cumulative counts of the spread symbols (norm > 0) and the low-probability symbols' places at the top
+            uint32_t high = tableSize - 1, run = 0;
+            for (int u = 0; u < n; ++u) {
+                cumul[u] = run;                                  // first occurrence number of symbol u
+                if (norm[u] == -1) tableSymbol[high--] = (uint32_t)u;
+                else if (norm[u] > 0) run += (uint32_t)norm[u];
+            }
+            cumul[n] = run;
+            s_high = high;
+            if (run != high + 1) s_err = 1;                      // (the reference's "pos != 0" check)
+        }
+    }
+    __syncthreads();
+    if (s_err) { if (tid == 0) a.err[t] = 1; return; }
+    const uint32_t high = s_high;
+    // ---- spread: j -> position; usable positions numbered in j order
+    const uint32_t per_thread = (tableSize + kBuildThreads - 1) / kBuildThreads;
+    const uint32_t j0 = tid * per_thread, j1 = min(j0 + per_thread, tableSize);
+    uint32_t local = 0;
+    for (uint32_t j = j0; j < j1; ++j) local += ((j * step) & tableMask) <= high;
+    s_scan[tid] = local;
+    __syncthreads();
+    if (tid == 0) { uint32_t run = 0; for (int i = 0; i < kBuildThreads; ++i) { const uint32_t v = s_scan[i]; s_scan[i] = run; run += v; } }
+    __syncthreads();
+    uint32_t k = s_scan[tid];
+    for (uint32_t j = j0; j < j1; ++j) {
+        const uint32_t pos = (j * step) & tableMask;
+        if (pos > high) continue;
+        int lo = 0, hi = n - 1;                                  // the symbol whose occurrences cover number k: last u with cumul[u] <= k, norm > 0
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (cumul[mid] <= k) lo = mid; else hi = mid - 1;
+        }
+        while (norm[lo] <= 0) --lo;                              // (symbols without spread occurrences share their successor's start)
+        tableSymbol[pos] = (uint32_t)lo;
+        ++k;
+    }
+    __syncthreads();
     if (a.build_c) {  // tans.cpp:150-228
         uint16_t *stateTable = a.ct_state + (size_t)t * tsz;
         uint32_t *nb = a.ct_nb + (size_t)t * a.max_nsym;
         int32_t *fs = a.ct_fs + (size_t)t * a.max_nsym;
-        uint32_t high = tableSize - 1;
-        cumul[0] = 0;
-        for (int u = 1; u <= n; u++) {
-            if (norm[u - 1] == -1) { cumul[u] = cumul[u - 1] + 1; tableSymbol[high--] = (uint32_t)(u - 1); }
-            else cumul[u] = cumul[u - 1] + (uint32_t)norm[u - 1];
+        // slot of a symbol's first state = states of all symbols before it (a low-probability symbol has one)
+        if (tid == 0) {
+            uint32_t total = 0;
+            for (int s2 = 0; s2 < n; s2++) {
+                count[s2] = total;                               // (count is free now: first stateTable slot of the symbol)
+                if (norm[s2] == 0) { nb[s2] = 0; fs[s2] = 0; }
+                else if (norm[s2] == -1 || norm[s2] == 1) { nb[s2] = (tableLog << 16) - (1u << tableLog); fs[s2] = (int32_t)total - 1; total++; }
+                else {
+                    const uint32_t maxBitsOut = tableLog - hb32((uint32_t)(norm[s2] - 1));
+                    const uint32_t minStatePlus = (uint32_t)norm[s2] << maxBitsOut;
+                    nb[s2] = (maxBitsOut << 16) - minStatePlus;
+                    fs[s2] = (int32_t)total - norm[s2];
+                    total += (uint32_t)norm[s2];
+                }
+            }
         }
-        cumul[n] = tableSize + 1;
-        uint32_t pos = 0;
-        for (int s = 0; s < n; s++)
-            for (int k = 0; k < norm[s]; k++) {
-                tableSymbol[pos] = (uint32_t)s;
-                pos = (pos + step) & tableMask;
-                while (pos > high) pos = (pos + step) & tableMask;
-            }
-        if (pos != 0) { a.err[t] = 1; return; }
-        for (uint32_t u = 0; u < tableSize; u++) { const uint32_t s = tableSymbol[u]; stateTable[cumul[s]++] = (uint16_t)(tableSize + u); }
-        uint32_t total = 0;
-        for (int s = 0; s < n; s++) {
-            if (norm[s] == 0) { nb[s] = 0; fs[s] = 0; }
-            else if (norm[s] == -1 || norm[s] == 1) { nb[s] = (tableLog << 16) - (1u << tableLog); fs[s] = (int32_t)total - 1; total++; }
-            else {
-                const uint32_t maxBitsOut = tableLog - hb32((uint32_t)(norm[s] - 1));
-                const uint32_t minStatePlus = (uint32_t)norm[s] << maxBitsOut;
-                nb[s] = (maxBitsOut << 16) - minStatePlus;
-                fs[s] = (int32_t)total - norm[s];
-                total += (uint32_t)norm[s];
-            }
+        __syncthreads();
+        for (int s2 = tid; s2 < n; s2 += kBuildThreads) {
+            if (norm[s2] == 0) continue;
+            uint32_t slot = count[s2];
+            for (uint32_t u = 0; u < tableSize; u++)
+                if (tableSymbol[u] == (uint32_t)s2) stateTable[slot++] = (uint16_t)(tableSize + u);
         }
     }
     if (a.build_d) {  // tans.cpp:262-318
         TansDEntry *table = a.dt + (size_t)t * tsz;
-        uint32_t *symbolNext = count;  // count is no longer needed
-        uint32_t high = tableSize - 1;
-        int fast = 1;
-        const short largeLimit = (short)(1 << (tableLog - 1));
-        for (int s = 0; s < n; s++) {
-            if (norm[s] == -1) { table[high--].symbol = (uint16_t)s; symbolNext[s] = 1; }
-            else { if (norm[s] >= largeLimit) fast = 0; symbolNext[s] = (uint32_t)(uint16_t)norm[s]; }
+        if (tid == 0) {
+            int fast = 1;
+            const short largeLimit = (short)(1 << (tableLog - 1));
+            for (int s2 = 0; s2 < n; s2++) if (norm[s2] >= largeLimit) fast = 0;
+            a.dt_fast[t] = fast;
         }
-        uint32_t pos = 0;
-        for (int s = 0; s < n; s++)
-            for (int k = 0; k < norm[s]; k++) {
-                table[pos].symbol = (uint16_t)s;
-                pos = (pos + step) & tableMask;
-                while (pos > high) pos = (pos + step) & tableMask;
+        for (int s2 = tid; s2 < n; s2 += kBuildThreads) {
+            if (norm[s2] == 0) continue;
+            uint32_t next = norm[s2] == -1 ? 1u : (uint32_t)(uint16_t)norm[s2];
+            for (uint32_t u = 0; u < tableSize; u++) {
+                if (tableSymbol[u] != (uint32_t)s2) continue;
+                const uint32_t nbBits = tableLog - hb32(next);
+                table[u].symbol = (uint16_t)s2;
+                table[u].nbBits = (uint16_t)(uint8_t)nbBits;
+                table[u].newState = (uint32_t)((uint16_t)next << nbBits) - tableSize;
+                ++next;
             }
-        if (pos != 0) { a.err[t] = 1; return; }
-        for (uint32_t u = 0; u < tableSize; u++) {
-            const uint16_t sym = table[u].symbol;
-            const uint16_t next = (uint16_t)symbolNext[sym]++;
-            table[u].nbBits = (uint8_t)(tableLog - hb32(next));
-            table[u].newState = (uint32_t)((next << table[u].nbBits) - tableSize);
         }
-        a.dt_fast[t] = fast;
     }
 }
 
@@ -424,7 +467,7 @@ int tans_init(TansTables &t, const int32_t *freqs, int T, int M, const int32_t *
     a.bypass = bypass; a.nbypass = 1 << bypass_precision; a.build_c = t.has_c; a.build_d = t.has_d;
     a.ct_state = t.ct_state.as<uint16_t>(); a.ct_nb = t.ct_nb.as<uint32_t>(); a.ct_fs = t.ct_fs.as<int32_t>();
     a.dt = t.dt.as<TansDEntry>(); a.dt_fast = t.dt_fast.as<int32_t>(); a.scratch = t.scratch.as<uint32_t>(); a.err = t.err.as<int>();
-    k_tans_build<<<(unsigned)TT, 32, 0, s>>>(a);
+    k_tans_build<<<(unsigned)TT, kBuildThreads, 0, s>>>(a);
     BASIC_LAUNCHED();
     std::vector<int> err(TT);
     BASIC_CUDA(cudaMemcpyAsync(err.data(), t.err.p, TT * 4, cudaMemcpyDeviceToHost, s));

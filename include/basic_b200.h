@@ -92,6 +92,20 @@ int basic_coder_decode(basic_coder *c, const uint8_t *encoded, int64_t len, cons
 int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, int lanes, void *stream);
 int basic_coder_decode_stream(basic_coder *c, const int32_t *indexes, int64_t n, int32_t *out, void *stream);
 
+/* ---- in-coder autoregressive table lookup (ans_interface.hpp:58-105 table branch, ans_interface.cpp:75-135 init_ar_params;
+ * used by the reference's lossless coders, entropy_coder/ans.py:78-158) -------------------------------------------------
+ * basic_coder_init_ar_params: ar_tables int32 [A, I, D1] (one neighbour) or [A, I, D1, D2] (two; D2 = 0 otherwise), host or
+ * device.  With AR tables set, an element is coded with table  ar_tables[ar_index][index][v0]([v1]),
+ * v_k = ar_offsets[k][i] > 0 ? symbol[i - ar_offsets[k][i]] + 1 : 0  (rans64.cpp:259-263, :439-443).
+ * basic_coder_encode_ar / _decode_ar: ar_indexes int32 [n] or NULL (= 0), ar_offsets int32 [order, n] (order = 1 or 2 as
+ * initialised); the reference (lanes = 1) stream only -- the lookup makes every symbol depend on earlier ones.  Out-of-range
+ * lookups, undefined behaviour in the reference, are BASIC_ERR_VALUE here. */
+int basic_coder_init_ar_params(basic_coder *c, const int32_t *ar_tables, int A, int I, int D1, int D2);
+int basic_coder_encode_ar(basic_coder *c, const int32_t *symbols, const int32_t *indexes, int64_t n, const int32_t *ar_indexes,
+                          const int32_t *ar_offsets, int order, uint8_t *out, int64_t out_cap, int64_t *out_len, void *stream);
+int basic_coder_decode_ar(basic_coder *c, const uint8_t *encoded, int64_t len, const int32_t *indexes, int64_t n,
+                          const int32_t *ar_indexes, const int32_t *ar_offsets, int order, int32_t *out, void *stream);
+
 /* ---- batches of independent reference streams (the z node: compressai_coder.py:233,242 code one stream per image) --
  * n_streams runs of n symbols each ([n_streams, n] row-major, host or device) become n_streams lanes=1 rANS64 streams in
  * ONE launch (one CTA per stream), delivered back to back into `out` (or, with out == NULL, into the coder's pinned

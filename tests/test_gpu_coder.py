@@ -331,3 +331,44 @@ def test_coders_on_two_devices_in_one_process(A, gauss):
             assert np.array_equal(dec.decode_with_indexes(bs, idx), sym)
             out.append(bs)
     assert out[0] == out[2] and out[1] == out[3]
+
+
+# ----------------------------------------------------------------------------------------------- in-coder AR lookup (row f3)
+@pytest.mark.parametrize("order", [1, 2])
+def test_ar_table_lookup_matches_reference(A, cv, order):
+    """ans_interface.hpp:58-105 (table branch): the table of element i is ar_tables[ar_index][index][v0]([v1]) with
+    v_k = off_k[i] > 0 ? symbol[i - off_k[i]] + 1 : 0.  Stream byte-identical to the unmodified reference coder's (oracle/_ref),
+    both directions, and each side decodes the other's stream."""
+    from oracle import ref_loader
+    R = ref_loader.load("ans")
+    if R is None:
+        pytest.skip("oracle/_ref/ans not built")
+    rng = np.random.default_rng(11 + order)
+    n, T, hi = 20000, 8, 40
+    sym = rng.integers(0, hi, n).astype(np.int32)
+    idx = rng.integers(0, T, n).astype(np.int32)
+    ar_idx = rng.integers(0, 2, n).astype(np.int32)
+    shape = (2, T) + (hi + 1,) * order
+    ar_tables = rng.integers(0, T, shape).astype(np.int32)
+    off = np.stack([np.minimum(rng.choice([0, 1, 2, 7], n), np.arange(n)) for _ in range(order)]).astype(np.int32)
+    ar_offsets_init = np.zeros((2, order, 2), dtype=np.int32)     # stored, never read by the reference's coding calls
+    renc, rdec = R.Rans64Encoder(16, True, 4), R.Rans64Decoder(16, True, 4)
+    enc, dec = A.Rans64Encoder(lanes=1), A.Rans64Decoder(lanes=1)
+    for c in (renc, rdec, enc, dec):
+        c.init_params(cv["a_freqs"], cv["a_nsym"], cv["a_offsets"])
+        c.init_ar_params(ar_tables, ar_offsets_init)
+    ref_bytes = renc.encode_with_indexes(sym, idx, ar_idx, off, False)
+    got = enc.encode_with_indexes(sym, idx, ar_idx, off)
+    assert got == ref_bytes
+    assert np.array_equal(dec.decode_with_indexes(ref_bytes, idx, ar_idx, off), sym)
+    assert np.array_equal(rdec.decode_with_indexes(got, idx, ar_idx, off), sym)
+    # device-resident operands, no ar_indexes (= table set 0)
+    ts, ti, to = torch.from_numpy(sym).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(off).cuda()
+    assert enc.encode_with_indexes(ts, ti, None, to) == renc.encode_with_indexes(sym, idx, None, off, False)
+    with pytest.raises(ValueError):
+        enc.encode_with_indexes(sym, idx, ar_idx, None)           # "ar_offsets is required for ar coding!"
+    bad = ar_tables.copy()
+    bad[0, 0, 0] = T + 3                                          # a table entry past the coder's tables: an error, not UB
+    enc.init_ar_params(bad, ar_offsets_init)
+    with pytest.raises(ValueError):
+        enc.encode_with_indexes(sym, idx, np.zeros(n, np.int32), off)
