@@ -156,13 +156,13 @@ def test_tc_vs_oracle_c192_teacher_forced(mode):
     order = torch.cat([torch.nonzero(gmap == g).reshape(-1) for g in range(2)])
     mean_ref, scale_ref = (t.reshape(-1)[order].double() for t in Y.split_mean_scale(params_ref))
     bad_s = np.nonzero(gsym != sym)[0]
-    assert bad_s.size <= 8
+    assert bad_s.size <= 2     # observed on B200: 1 (3xTF32) / 0 (3xFP16), profiles/r2_tie_counts.txt; each must sit on a tie (below)
     if bad_s.size:
         d = (c["y"].reshape(-1)[order][bad_s].double() - mean_ref[bad_s])
         assert np.all(np.abs(gsym[bad_s] - sym[bad_s]) == 1)
         assert float(((d - d.floor()) - 0.5).abs().max()) <= 2 * REL_TOL, "symbol disagreement away from a .5 tie"
     bad_i = np.nonzero(gidx != idx)[0]
-    assert bad_i.size <= 8
+    assert bad_i.size <= 2     # observed on B200: 0 / 0
     if bad_i.size:
         lo = np.minimum(gidx[bad_i], idx[bad_i])
         assert np.all(np.abs(gidx[bad_i] - idx[bad_i]) == 1)

@@ -328,7 +328,7 @@ def test_ypath_vs_oracle_c192_checkerboard():
     assert rel_err(gparams, params_ref) <= REL_TOL
     assert np.array_equal(gsym, sym), f"{int((gsym != sym).sum())} symbols differ from the oracle"
     bad = np.nonzero(gidx != idx)[0]
-    assert bad.size <= 4, f"{bad.size} scale indexes differ"
+    assert bad.size <= 1, f"{bad.size} scale indexes differ"   # observed on B200: 0 (profiles/r2_tie_counts.txt); a tie is checked below
     if bad.size:
         # stream order -> element: stage-major, then (c, h, w) of the stage's mask
         gmap = Y.group_of_elements(c["tg"], 1, 192).reshape(-1)
