@@ -1,6 +1,7 @@
 // Gaussian-conditional quantisation + scale index (reference: pgm_coder.py:802-821 _select_best_indexes,
 // torch_ans.py:105-159 _data_preprocess "uniform" quantiser, pgm_coder.py:927-941 / :965-978 the per-group
-// gather / scatter).  Elementwise, HBM-bound: one thread per coded element, coalesced along the position list.
+// gather / scatter).  Elementwise: a thread takes four consecutive elements of the stream -- position list, symbols and
+// indexes move with 128-bit accesses, one division per quad -- and gathers their parameters / latents.
 #include "common.cuh"
 
 namespace basic {
@@ -22,6 +23,33 @@ __device__ inline int scale_index(float sigma, const float *__restrict__ tab, in
     return d0 <= d1 ? lo - 1 : lo;
 }
 
+// One coded element: where its parameters and its latent live.  Streams (symbols / indexes, and the position list) are
+// contiguous: a thread takes FOUR consecutive elements and moves them with 128-bit accesses when they belong to one image.
+struct ElemAddr {
+    long long yo;     // offset of the latent in y / y_hat
+    float mean, sigma;
+};
+
+__device__ inline ElemAddr elem_addr(const float *__restrict__ params, long long b, int p, int C, int HW, long long chw, int params_cl,
+                                     const int32_t *__restrict__ perm, bool want_sigma)
+{
+    ElemAddr r;
+    const int c = p / HW;
+    r.yo = b * chw + p;
+    if (params_cl) {  // blocked channels-last parameters of the tensor path (ctx.cuh): (mean, scale) are neighbours
+        const int hw = perm[p - c * HW];  // slot of the position
+        const float2 ms = *reinterpret_cast<const float2 *>(
+            params + ((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2);
+        r.mean = ms.x;
+        r.sigma = ms.y;
+    } else {
+        const long long po = b * 2 * chw + p + (long long)c * HW;  // channel 2c (mean); scale is HW further
+        r.mean = params[po];
+        r.sigma = want_sigma ? params[po + HW] : 0.f;
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(256)
 k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, const int32_t *__restrict__ positions,
                  long long n_pos, int B, int C, int HW, const float *__restrict__ scale_table, int n_scales,
@@ -33,36 +61,44 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
     __syncthreads();
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
-    const bool small = total < 0x7fffffffll && (long long)B * 2 * chw < 0x7fffffffll;   // 32-bit divisions (a 64-bit one is ~100 instructions)
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        long long b, k;
-        if (small) {
-            const unsigned bb = (unsigned)e / (unsigned)n_pos;
-            b = bb;
-            k = (unsigned)e - bb * (unsigned)n_pos;
+    // quads never straddle two images when n_pos is a multiple of 4; the streams must be 16-byte aligned
+    const bool vec = (n_pos & 3) == 0 && positions &&
+                     ((reinterpret_cast<uintptr_t>(positions) | reinterpret_cast<uintptr_t>(indexes) | reinterpret_cast<uintptr_t>(symbols)) & 15) == 0;
+    const long long quads = (total + 3) >> 2;
+    const bool small = total < 0x7fffffffll;
+    for (long long qd = blockIdx.x * (long long)blockDim.x + threadIdx.x; qd < quads; qd += (long long)gridDim.x * blockDim.x) {
+        const long long e0 = qd << 2;
+        const long long b = small ? (long long)((unsigned)e0 / (unsigned)n_pos) : e0 / n_pos;  // a 64-bit division is ~100 instructions
+        const long long k0 = e0 - b * n_pos;
+        int p[4];
+        int32_t ix[4], sy[4];
+        if (vec) {
+            const int4 pp = __ldg(reinterpret_cast<const int4 *>(positions + k0));
+            p[0] = pp.x; p[1] = pp.y; p[2] = pp.z; p[3] = pp.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, true);
+                ix[j] = scale_index(a.sigma, tab, n_scales);
+                if (y) {
+                    const float s = rintf(__fsub_rn(y[a.yo], a.mean));  // torch.round: half to even
+                    sy[j] = (int32_t)s;
+                    if (yhat) yhat[a.yo] = __fadd_rn(s, a.mean);
+                }
+            }
+            *reinterpret_cast<int4 *>(indexes + e0) = make_int4(ix[0], ix[1], ix[2], ix[3]);
+            if (y) *reinterpret_cast<int4 *>(symbols + e0) = make_int4(sy[0], sy[1], sy[2], sy[3]);
         } else {
-            b = e / n_pos;
-            k = e - b * n_pos;
-        }
-        const int p = positions ? positions[k] : (int)k;
-        const int c = p / HW;
-        float mean, sigma;
-        if (params_cl) {  // blocked channels-last parameters of the tensor path (ctx.cuh): (mean, scale) are neighbours
-            const int hw = perm[p - c * HW];  // slot of the position
-            const float2 ms = *reinterpret_cast<const float2 *>(
-                params + ((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2);
-            mean = ms.x;
-            sigma = ms.y;
-        } else {
-            const long long po = b * 2 * chw + p + (long long)c * HW;  // channel 2c (mean); scale is HW further
-            mean = params[po];
-            sigma = params[po + HW];
-        }
-        indexes[e] = scale_index(sigma, tab, n_scales);
-        if (y) {
-            const float s = rintf(__fsub_rn(y[b * chw + p], mean));  // torch.round: half to even
-            symbols[e] = (int32_t)s;
-            if (yhat) yhat[b * chw + p] = __fadd_rn(s, mean);
+            for (int j = 0; j < 4 && e0 + j < total; ++j) {
+                const long long e = e0 + j, bb = e / n_pos, k = e - bb * n_pos;
+                const int pj = positions ? positions[k] : (int)k;
+                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, true);
+                indexes[e] = scale_index(a.sigma, tab, n_scales);
+                if (y) {
+                    const float s = rintf(__fsub_rn(y[a.yo], a.mean));
+                    symbols[e] = (int32_t)s;
+                    if (yhat) yhat[a.yo] = __fadd_rn(s, a.mean);
+                }
+            }
         }
     }
 }
@@ -73,24 +109,30 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
 {
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
-    const bool small = total < 0x7fffffffll;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        long long b, k;
-        if (small) {
-            const unsigned bb = (unsigned)e / (unsigned)n_pos;
-            b = bb;
-            k = (unsigned)e - bb * (unsigned)n_pos;
+    const bool vec = (n_pos & 3) == 0 && positions &&
+                     ((reinterpret_cast<uintptr_t>(positions) | reinterpret_cast<uintptr_t>(symbols)) & 15) == 0;
+    const long long quads = (total + 3) >> 2;
+    for (long long qd = blockIdx.x * (long long)blockDim.x + threadIdx.x; qd < quads; qd += (long long)gridDim.x * blockDim.x) {
+        const long long e0 = qd << 2;
+        if (vec) {
+            const long long b = total < 0x7fffffffll ? (long long)((unsigned)e0 / (unsigned)n_pos) : e0 / n_pos, k0 = e0 - b * n_pos;
+            const int4 pp = __ldg(reinterpret_cast<const int4 *>(positions + k0));
+            const int4 ss = *reinterpret_cast<const int4 *>(symbols + e0);
+            const int p[4] = {pp.x, pp.y, pp.z, pp.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, false);
+                // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
+                yhat[a.yo] = __fadd_rn(__fadd_rn((float)sv[j], a.mean), 0.0f);
+            }
         } else {
-            b = e / n_pos;
-            k = e - b * n_pos;
+            for (int j = 0; j < 4 && e0 + j < total; ++j) {
+                const long long e = e0 + j, bb = e / n_pos, k = e - bb * n_pos;
+                const int pj = positions ? positions[k] : (int)k;
+                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, false);
+                yhat[a.yo] = __fadd_rn(__fadd_rn((float)symbols[e], a.mean), 0.0f);
+            }
         }
-        const int p = positions ? positions[k] : (int)k;
-        const int c = p / HW;
-        const int hw = params_cl ? perm[p - c * HW] : 0;  // slot of the position
-        const float mean = params_cl ? params[((((long long)b * ((HW + 31) >> 5) + (hw >> 5)) * (C >> 1) + (c >> 1)) * 32 + (hw & 31)) * 4 + (c & 1) * 2]
-                                     : params[b * 2 * chw + p + (long long)c * HW];
-        // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
-        yhat[b * chw + p] = __fadd_rn(__fadd_rn((float)symbols[e], mean), 0.0f);
     }
 }
 
@@ -102,7 +144,7 @@ int launch_quantize_index(const float *y, const float *params, const int32_t *po
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
-    long long blocks = (total + 255) / 256;
+    long long blocks = ((total + 3) / 4 + 255) / 256;   // four elements per thread
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
     k_quantize_index<<<(int)blocks, 256, 0, stream>>>(y, params, positions, n_pos, B, C, HW, d_scale_table, n_scales, symbols,
                                                       indexes, yhat, params_cl, perm);
@@ -115,7 +157,7 @@ int launch_dequantize(const int32_t *symbols, const float *params, const int32_t
 {
     const long long total = (long long)B * n_pos;
     if (total == 0) return BASIC_OK;
-    long long blocks = (total + 255) / 256;
+    long long blocks = ((total + 3) / 4 + 255) / 256;   // four elements per thread
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
     k_dequantize<<<(int)blocks, 256, 0, stream>>>(symbols, params, positions, n_pos, B, C, HW, yhat, params_cl, perm);
     BASIC_LAUNCHED();

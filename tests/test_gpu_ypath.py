@@ -433,3 +433,31 @@ def test_combined_coder_dispatch(yv):
     bs = comb.encode(c["y"].cuda(), prior=c["prior"].cuda(), blend_weight=w)
     assert bs == b.encode(c["y"].cuda(), prior=c["prior"].cuda())
     assert torch.equal(comb.decode(bs, prior=c["prior"].cuda(), blend_weight=w), b.decode(bs, prior=c["prior"].cuda()))
+
+
+def test_cfg2_batch_against_oracle():
+    """BASELINE configs[1] at its full size -- 24 Kodak-shape images, C = 192, the TIMED mode (multi-lane, 3xFP16 context model):
+    images 0 and 23 of the batch against the CPU oracle (images are independent, so the oracle runs them one at a time).
+    Symbols and scale indexes identical, except where the oracle's own value sits on a rounding tie; parameters within 1e-5."""
+    import bench
+    dev = torch.device("cuda", 0)
+    y, prior, w = bench.make_inputs("cfg2", 0)
+    coder = bench.build_coder("cfg2", w, 0, dev)
+    yd, pd = y.to(dev), prior.to(dev)
+    bs, yhat_enc = coder.encode(yd, prior=pd, return_yhat=True)
+    out = coder.decode(bs, prior=pd)
+    assert torch.equal(out, yhat_enc * 1.0 + 0.0)
+    tg, tab = Y.default_pgm("checkerboard", 1, 32, 48), Y.get_scale_table()
+    for b in (0, 23):
+        with torch.no_grad():
+            _, _, yhat_o = Y.encode_symbols(y[b:b + 1], prior[b:b + 1], tg, w, tab)
+            mean_o, _ = Y.split_mean_scale(Y.params_for(yhat_o, tg, prior[b:b + 1], w))
+        sym_o = torch.round(yhat_o - mean_o)
+        sym_g = torch.round(out[b:b + 1].cpu() - mean_o)
+        bad = sym_g != sym_o
+        frac = (y[b:b + 1] - mean_o)[bad].double()
+        assert int(bad.sum()) <= 2 and bool((((frac - torch.floor(frac)) - 0.5).abs() <= 2e-5 * (1 + frac.abs())).all()), int(bad.sum())
+        ok = ~bad
+        assert float(((out[b:b + 1].cpu() - yhat_o)[ok].abs() / yhat_o[ok].abs().clamp_min(1.0)).max()) <= REL_TOL
+    r = bench.oracle_mismatches("cfg2", coder, y, prior, w, yd, pd)
+    assert r["off_tie"] == 0 and r["symbol_mismatches"] <= 2 and r["index_mismatches"] <= 2 and r["params_max_rel_err"] <= REL_TOL, r
