@@ -59,6 +59,7 @@ size_t ctx_cl_elems(int B, int channels, int HW);
 int ctx_num_stages(const CtxModel &);
 int ctx_set_precision(CtxModel &, int, int);
 int ctx_precision(const CtxModel &);
+int ctx_run_precision(const CtxModel &);
 const int32_t *ctx_perm(const CtxModel &);
 int mma_bench(int mode, int ts, int n_cols, int iters, int same_acc, long long *cycles);
 void ctx_set_run_precision(CtxModel &, int);
@@ -69,7 +70,7 @@ int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
 bool ctx_scan_supported(const CtxModel &, int B);
 int ctx_scan_run(CtxModel &, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
-                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t);
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t, const int32_t *dq_sym = nullptr);
 
 struct TansTables;
 TansTables *tans_new();
@@ -1361,8 +1362,9 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     // tensor-core context model: it reads channels-last copies of the prior (made once) and of the y_hat buffer
     // (refreshed after every group's write-back)
     if (model) ctx_set_run_precision(*model->m, ctx_precision(*model->m));
-    const bool tc = model && ctx_uses_tc(*model->m, B);
+    // few-row stages (scanline-like maps) take the persistent stage kernel -- exact FP32, whatever precision is configured
     const bool scan = model && ctx_scan_supported(*model->m, B);
+    const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1524,8 +1526,10 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         }
         ctx_set_run_precision(*model->m, prec);
     }
-    const bool tc = model && ctx_uses_tc(*model->m, B);
-    const bool scan = model && ctx_scan_supported(*model->m, B);   // many-stage map: one fused launch per stage (ctx.cu k_scan_stages)
+    // many-stage map: one fused launch per stage (ctx.cu k_scan_stages) -- what the encoder used when the stream says exact FP32
+    const bool scan = model && ctx_scan_supported(*model->m, B) &&
+                      (lanes == BASIC_LANES_REFERENCE || ctx_run_precision(*model->m) == BASIC_CTX_FP32);
+    const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1565,7 +1569,9 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         if (model) {
             if (g > 0) {
                 ProfScope ps(PROF_CTX, s);
-                if (scan) BASIC_TRY(ctx_scan_run(*model->m, g, g + 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s));
+                // (the fused stage launch starts by turning the previous stage's symbols into y_hat)
+                if (scan) BASIC_TRY(ctx_scan_run(*model->m, g, g + 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s,
+                                                 slice_n[g - 1] > 0 ? sym : nullptr));
                 else BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
             }
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));
@@ -1591,7 +1597,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
                                         si.len, idx, cnt, si.cs[g], si.n_chunks, S, g, c->carry_x.as<uint32_t>(),
                                         c->carry_wp.as<uint32_t>(), sym, &ds->status, c->sm_count, s));
         }
-        if (cnt > 0) {
+        if (cnt > 0 && !(scan && g + 1 < S)) {
             ProfScope ps(PROF_GAUSS, s);
             BASIC_TRY(launch_dequantize(sym, params_src, pos, n_pos, B, C, HW, buf, c->sm_count, s, tc ? 1 : 0,
                                         tc ? ctx_perm(*model->m) : nullptr));

@@ -357,185 +357,333 @@ k_layer_rows(LayerArgs a)
 }
 
 // ---- many-stage maps (scanline: one position per stage, 1536 stages for a Kodak-shape image; the serial JointAR coder):
-// one PERSISTENT kernel walks the stages.  Per stage the four layers of the context model are matrix-vector products
-// (rows = batch x cells of the stage <= 4): every CTA gathers the layer's input vectors into shared memory, every warp
-// owns two neighbouring output channels and streams their weight rows (N-major copies of the matrices, 128-bit loads, L2
-// resident) against them, lanes striding over K, then a butterfly sum -- about two instructions per multiply-add (the
-// 32-channel GEMV of k_layer_rows needs ~15: its CTAs drew 5 bytes per cycle).  The last layer's pair is (mean, scale) of
-// one latent channel, so the quantiser runs in its epilogue.  A grid-wide barrier separates the layers.  The encoder knows
-// y: its whole pass is ONE launch; the decoder launches the kernel once per stage (the coder sits between two stages).
-// Deterministic (fixed summation order); one channel group only (G = 1).
-constexpr int kScanWarps = 8, kScanCtas = 40, kScanInFlight = 6;   // (6 x 2 x 512-byte weight loads in flight per warp)
-//   // 320 warps = channel pairs of the widest layer at C = 192
+// one PERSISTENT kernel walks the stages.  Per stage the four layers of the context model are matrix-vector products over
+// a handful of rows (rows = batch x cells of the stage), so what a stage costs is latency, not arithmetic:
+//  * every weight the kernel needs stays resident in shared memory for its whole life -- CTA c of the grid owns the
+//    output-channel pairs c, c + grid, c + 2 grid, ... of every layer (N-major rows, the convolution only with the taps some
+//    stage of the map can see): 113 KB at C = 192 on 148 CTAs;
+//  * what CTAs exchange -- the layer outputs of the current stage and y_hat -- travels as {value, tag} words (8 bytes, written
+//    and read as one access, so a matching tag IS the value's arrival: the "LL" protocol of collective libraries).  Layer
+//    outputs carry a tag that counts (stage, layer) steps, y_hat the id of the coding call.  A consumer polls the words it
+//    gathers until their tags match: no grid barrier, no fence, and a CTA never waits for more than the data it reads.  (A
+//    grid barrier per layer cost 2.4 k cycles of the 5.4 k a layer took.)  Buffers are reused every stage; a producer cannot
+//    overwrite a word a consumer still needs because its own next input depends on that consumer's output (a CTA that owns
+//    no channel of a layer does not gather for it);
+//  * vectors are contiguous (per-stage [row][N] outputs, position-major y_hat and prior): a gather is a few 128-bit loads
+//    per thread, where the NCHW gather asked L2 for one sector per float from 148 CTAs at once.
+// The multiply itself: a warp per channel pair, lanes striding over K, four partial sums per output, butterfly.  The last
+// layer's pair is (mean, scale) of one latent channel, so the quantiser runs in its epilogue.  The encoder knows y: its
+// whole pass is ONE launch; the decoder launches the kernel once per stage (the coder sits between two stages) and the
+// launch first turns the previous stage's symbols into y_hat.  Deterministic (fixed summation order); one channel group (G = 1).
+constexpr int kScanWarps = 8, kScanRows = 4, kScanMaxRows = 32;   // (more rows per stage: every CTA gathers every row -- the tiled kernels win)
 
 struct ScanArgs {
     const float *w[4];           // N-major: conv [2C][k2][C], dense [N][K]
     const float *bias[4];
-    int N[4], K[4];              // K[0] = k2 * C
+    int N[4], K[4];              // K[0] = ntaps * C: the convolution's K is compact (only the taps of `taps`, in that order)
+    int pairs[4];                // channel pairs a CTA owns per layer = ceil(N / 2 / gridDim.x) <= kScanWarps
+    int ntaps;
+    unsigned char taps[25];
+    int shift[25];               // offset of tap taps[t] relative to the centre: dy * W + dx
     int C, ksize, HW, W_img, B;
     const int2 *stage_cells;     // per stage: first cell, cells
     const int32_t *cell_hw;
     const uint32_t *cell_tap, *cell_grp;
     float *buf;                  // y_hat [B, C, HW]
-    const float *prior;          // [B, 2C, HW]
-    float *act[3];               // ctx, m1, m2 outputs [B, N, HW]
+    uint2 *yhat_pm;              // ... and its position-major copy [B, HW, C] of {value, call tag}: a tap is C contiguous words
+    const float *prior_pm;       // prior, position-major [B, HW, 2C]
+    uint2 *vec[4];               // outputs of the four layers for the rows of the CURRENT stage, [row][N] of {value, step tag}
+                                 // (one channel group: a layer only reads its own cell's previous layer)
     float *params;               // [B, 2C, HW]
     int g0, g1;                  // stages [g0, g1)
     RowsQuant qz;                // sym / idx point at the slice of stage g0
-    unsigned *barrier;           // zeroed before the launch
+    const int32_t *dq_sym;       // decoder: the symbols of stage g0 - 1, dequantised into buf before anything else; else NULL
+    uint32_t step0;              // tag of (stage g, layer L) = step0 + 4 (g - g0) + L + 1: monotonic over launches
+    uint32_t call_tag;           // tag of every y_hat word of this coding call
+    long long *timing;           // SCAN_TIMING builds
 };
 
-__device__ inline void grid_barrier(unsigned *counter, unsigned nblocks, unsigned &epoch)
+// One 16-byte load of two {value, tag} words (L2, never L1).  A gather issues a batch of these and only then looks at the tags,
+// re-reading the words that have not arrived yet: the loads of a batch overlap instead of costing an L2 round trip each.
+__device__ __forceinline__ uint4 ll_ld(const uint2 *p)
 {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ++epoch;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        const unsigned target = epoch * nblocks;
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < target);
+    uint4 q;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+    return q;
+}
+
+__device__ __forceinline__ float2 ll_wait(uint4 q, const uint2 *p, uint32_t tag)
+{
+    int spins = 0;
+    while (q.y != tag || q.w != tag) {
+        q = ll_ld(p);
+        if (++spins > (1 << 24)) asm volatile("trap;");   // a producer died: fail the launch instead of hanging the GPU
     }
-    __syncthreads();
+    return make_float2(__uint_as_float(q.x), __uint_as_float(q.z));
+}
+
+constexpr int kScanBatch = 5;   // 16-byte loads in flight per thread (12 taps x 96 channel pairs / 256 threads = 4.5)
+
+// Two neighbouring output channels (weight rows w, w + K in shared memory) against R input vectors A[r][K], one of kScanSplit
+// interleaved parts of K: lanes stride over the part in 128-bit steps, four partial sums per output (x, y, z, w components),
+// then a butterfly; lane 0 leaves the 2 R sums in part[r][0 / 1].  The order of the additions depends on nothing but K.
+constexpr int kScanSplit = 4;
+
+template <int R>
+__device__ __forceinline__ void scan_pair_part(const float *__restrict__ wrow, const float *__restrict__ A, int K, int q, int lane, float *part)
+{
+    const int K4 = K >> 2;
+    const float4 *w0 = reinterpret_cast<const float4 *>(wrow), *w1 = w0 + K4;
+    const float4 *A4 = reinterpret_cast<const float4 *>(A);
+    float4 a0[R], a1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a0[r] = a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = q * 32 + lane; i < K4; i += 32 * kScanSplit) {
+        const float4 x0 = w0[i], x1 = w1[i];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 av = A4[r * K4 + i];
+            a0[r].x = fmaf(av.x, x0.x, a0[r].x); a0[r].y = fmaf(av.y, x0.y, a0[r].y);
+            a0[r].z = fmaf(av.z, x0.z, a0[r].z); a0[r].w = fmaf(av.w, x0.w, a0[r].w);
+            a1[r].x = fmaf(av.x, x1.x, a1[r].x); a1[r].y = fmaf(av.y, x1.y, a1[r].y);
+            a1[r].z = fmaf(av.z, x1.z, a1[r].z); a1[r].w = fmaf(av.w, x1.w, a1[r].w);
+        }
+    }
+    float v0[R], v1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        v0[r] = (a0[r].x + a0[r].y) + (a0[r].z + a0[r].w);
+        v1[r] = (a1[r].x + a1[r].y) + (a1[r].z + a1[r].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v0[r] += __shfl_xor_sync(0xffffffffu, v0[r], o);
+            v1[r] += __shfl_xor_sync(0xffffffffu, v1[r], o);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { part[2 * r] = v0[r]; part[2 * r + 1] = v1[r]; }
+    }
 }
 
 __global__ void __launch_bounds__(kScanWarps * 32)
 k_scan_stages(const __grid_constant__ ScanArgs S)
 {
-    extern __shared__ __align__(16) float A[];   // [rows][K] of the current layer
-    __shared__ int s_b[kRowsMax], s_hw[kRowsMax];
-    __shared__ uint32_t s_tap[kRowsMax], s_grp[kRowsMax];
+    extern __shared__ __align__(16) float smem[];   // resident weights of the four layers | A [kScanRows][Kmax]
+    __shared__ int sr_b[2][kScanMaxRows], sr_hw[2][kScanMaxRows], sr_i[2][kScanMaxRows];   // the rows of the current / next stage
+    __shared__ uint32_t sr_tap[2][kScanMaxRows], sr_grp[2][kScanMaxRows];
+    __shared__ float s_part[kScanWarps * kScanSplit][kScanRows][2];   // partial sums of (owned pair, K part)
+    __shared__ float s_tab[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gw = blockIdx.x * kScanWarps + warp;          // this warp's channel pair in every layer
-    const int k2 = S.ksize * S.ksize, pad = S.ksize / 2, C = S.C;
-    unsigned epoch = 0;
-    RowsQuant qz = S.qz;
-    for (int g = S.g0; g < S.g1; ++g) {
-        const int2 sc = S.stage_cells[g];
-        const int rows = S.B * sc.y;                         // <= kRowsMax
-        const long long slice = (long long)S.B * qz.C * sc.y;
-        if (tid < rows) {
-            const int b = tid / sc.y, cell = sc.x + (tid - b * sc.y);
-            s_b[tid] = b; s_hw[tid] = S.cell_hw[cell]; s_tap[tid] = S.cell_tap[cell]; s_grp[tid] = S.cell_grp[cell];
-        }
-        __syncthreads();
-        uint32_t tap_or = 0;
-        for (int r = 0; r < rows; ++r) tap_or |= s_tap[r];
+    const int cta = blockIdx.x, nctas = gridDim.x;
+    const int k2 = S.ksize * S.ksize, C = S.C;
+    int woff[5];
+    woff[0] = 0;
+#pragma unroll
+    for (int L = 0; L < 4; ++L) woff[L + 1] = woff[L] + S.pairs[L] * 2 * S.K[L];
+    float *A = smem + woff[4];
+    for (int i = tid; i < S.qz.n_scales && i < 256; i += blockDim.x) s_tab[i] = S.qz.scale_table[i];
+    // ---- this CTA's weight rows
 #pragma unroll 1
-        for (int L = 0; L < 4; ++L) {
-            const int K = S.K[L], N = S.N[L];
-            // ---- gather the input vectors (other CTAs wrote them during this launch: L2 loads, never L1)
+    for (int L = 0; L < 4; ++L) {
+        const int K4 = S.K[L] >> 2, C4 = C >> 2;
+        for (int j = 0; j < S.pairs[L]; ++j) {
+            const int n0 = 2 * (j * nctas + cta);
+            if (n0 >= S.N[L]) continue;
+            float4 *dst = reinterpret_cast<float4 *>(smem + woff[L] + j * 2 * S.K[L]);
             if (L == 0) {
-                for (int r = 0; r < rows; ++r) {
-                    const float *src = S.buf + (long long)s_b[r] * C * S.HW + s_hw[r];
-                    const uint32_t vis = s_tap[r];
-                    for (int c = tid; c < C; c += blockDim.x) {
-                        float v[25];
-#pragma unroll
-                        for (int t = 0; t < 25; ++t) {   // all taps of a channel in flight at once
-                            const int shift = (t / S.ksize - pad) * S.W_img + (t % S.ksize - pad);
-                            v[t] = (t < k2 && ((vis >> t) & 1u)) ? __ldcg(src + (long long)c * S.HW + shift) : 0.f;
-                        }
-#pragma unroll
-                        for (int t = 0; t < 25; ++t) if (t < k2) A[(size_t)r * K + t * C + c] = v[t];
-                    }
+                const float4 *src = reinterpret_cast<const float4 *>(S.w[0] + (size_t)n0 * k2 * C);
+                for (int i = tid; i < 2 * K4; i += blockDim.x) {
+                    const int o = i >= K4, q = i - o * K4, slot = q / C4, c4 = q - slot * C4;
+                    dst[i] = __ldg(src + (size_t)(o * k2 + S.taps[slot]) * C4 + c4);
                 }
             } else {
-                const float *src0 = S.act[L - 1];
-                const int c0n = S.N[L - 1];
-                for (int r = 0; r < rows; ++r) {
-                    const bool vis = s_grp[r] & 1u;
-                    const long long at = (long long)s_b[r] * c0n * S.HW + s_hw[r];
-                    for (int c = tid; c < c0n; c += blockDim.x) A[(size_t)r * K + c] = vis ? __ldcg(src0 + at + (long long)c * S.HW) : 0.f;
-                    if (L == 1) {   // the prior: always visible
-                        const long long ap = (long long)s_b[r] * (K - c0n) * S.HW + s_hw[r];
-                        for (int c = tid; c < K - c0n; c += blockDim.x) A[(size_t)r * K + c0n + c] = __ldcg(S.prior + ap + (long long)c * S.HW);
-                    }
-                }
+                const float4 *src = reinterpret_cast<const float4 *>(S.w[L] + (size_t)n0 * S.K[L]);
+                for (int i = tid; i < 2 * K4; i += blockDim.x) dst[i] = __ldg(src + i);
             }
-            __syncthreads();
-            // ---- two output channels per warp
-            if (2 * gw < N && rows > 0) {
-                const int n0 = 2 * gw;
-                const float4 *w0 = reinterpret_cast<const float4 *>(S.w[L] + (size_t)n0 * K);
-                const float4 *w1 = reinterpret_cast<const float4 *>(S.w[L] + (size_t)(n0 + 1) * K);
-                float acc0[kRowsMax], acc1[kRowsMax];
+        }
+    }
+    RowsQuant qz = S.qz;
+#ifdef SCAN_TIMING
+    long long tk[5] = {0, 0, 0, 0, 0}, t_a = clock64(), t_b;   // (unused), gather, multiply, chunk sync, stage sync
+#define SCAN_T(i) do { t_b = clock64(); tk[i] += t_b - t_a; t_a = t_b; } while (0)
+#else
+#define SCAN_T(i) do { } while (0)
+#endif
+    if (S.dq_sym) {   // decoder: y_hat of the previous stage (every CTA writes the same words and reads its own back)
+        const int2 pc = S.stage_cells[S.g0 - 1];
+        const int per_b = C * pc.y;
+        for (int e = tid; e < S.B * per_b; e += blockDim.x) {
+            const int row = e / C, c = e - row * C, b = row / pc.y, i = row - b * pc.y;
+            const int hw = S.cell_hw[pc.x + i];
+            const float mean = __uint_as_float(__ldcg(&S.vec[3][(size_t)row * 2 * C + 2 * c].x));   // (the previous launch left its parameters there)
+            // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
+            const float v = __fadd_rn(__fadd_rn((float)S.dq_sym[(size_t)b * per_b + (size_t)c * pc.y + i], mean), 0.0f);
+            S.buf[((long long)b * C + c) * S.HW + hw] = v;
+            S.yhat_pm[((long long)b * S.HW + hw) * C + c] = make_uint2(__float_as_uint(v), S.call_tag);
+        }
+    }
+    __syncthreads();
+    SCAN_T(0);
+    uint32_t step = S.step0;
+    // the rows of a stage: image, cell, position, visibility -- loaded one stage ahead
+    auto load_rows = [&](int g, int slot) {
+        const int2 sc = S.stage_cells[g];
+        for (int row = tid; row < S.B * sc.y; row += blockDim.x) {
+            const int b = row / sc.y, i = row - b * sc.y, cell = sc.x + i;
+            sr_b[slot][row] = b; sr_i[slot][row] = i; sr_hw[slot][row] = S.cell_hw[cell]; sr_tap[slot][row] = S.cell_tap[cell];
+            sr_grp[slot][row] = S.cell_grp[cell];
+        }
+    };
+    load_rows(S.g0, S.g0 & 1);
+    __syncthreads();
+    for (int g = S.g0; g < S.g1; ++g) {
+        const int2 sc = S.stage_cells[g];
+        const int rows_total = S.B * sc.y;
+        const long long slice = (long long)S.B * qz.C * sc.y;
+        const int *s_b = sr_b[g & 1], *s_hw = sr_hw[g & 1], *s_i = sr_i[g & 1];
+        const uint32_t *s_tap = sr_tap[g & 1], *s_grp = sr_grp[g & 1];
+        if (g + 1 < S.g1) load_rows(g + 1, (g + 1) & 1);   // (its last readers passed the barrier that ended stage g - 1)
+#pragma unroll 1
+        for (int L = 0; L < 4; ++L) {
+            ++step;
+            const int K = S.K[L], N = S.N[L];
+            if (2 * cta >= N) continue;   // this CTA owns no channel of the layer: it neither gathers nor waits (CTA-uniform)
+            const int owned = min(S.pairs[L], (N / 2 - cta + nctas - 1) / nctas);   // pairs cta, cta + nctas, ... < N / 2
+            const int n0 = 2 * (warp * nctas + cta);
+            const bool mine = warp < owned;
+            float bias0 = 0.f, bias1 = 0.f, yv = 0.f;
+            if (mine) { bias0 = S.bias[L][n0]; bias1 = S.bias[L][n0 + 1]; }
+            if (L == 3 && mine && qz.y && lane < rows_total && rows_total <= kScanRows)   // (off the chain: it waits in DRAM while the layer runs)
+                yv = qz.y[((long long)s_b[lane] * qz.C + (n0 >> 1)) * S.HW + s_hw[lane]];
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows_total; r0 += kScanRows) {
+                const int rows = min(kScanRows, rows_total - r0);
+                // ---- gather the input vectors: contiguous 128-bit loads out of L2, polled until the tags match
+                {
+                    float2 *A2 = reinterpret_cast<float2 *>(A);
+                    const int C2 = C >> 1, K2 = K >> 1;
+                    for (int r = 0; r < rows; ++r) {
+                        const int b = s_b[r0 + r], hw = s_hw[r0 + r];
+                        if (L == 0) {
+                            const uint32_t vis = s_tap[r0 + r];
+                            const uint2 *src = S.yhat_pm + ((long long)b * S.HW + hw) * C;
+                            for (int base = tid; base < K2; base += blockDim.x * kScanBatch) {
+                                uint4 q[kScanBatch];
+                                const uint2 *ptr[kScanBatch];
 #pragma unroll
-                for (int r = 0; r < kRowsMax; ++r) acc0[r] = acc1[r] = 0.f;
-                const int nseg = L == 0 ? k2 : 1, seg4 = (L == 0 ? C : K) >> 2;   // conv: one segment per tap, dead taps skipped
-                for (int seg = 0; seg < nseg; ++seg) {
-                    if (L == 0 && !((tap_or >> seg) & 1u)) continue;
-                    const int base4 = seg * seg4;
-                    for (int i0 = lane; i0 < seg4; i0 += 32 * kScanInFlight) {
-                        float4 x0[kScanInFlight], x1[kScanInFlight];
-#pragma unroll
-                        for (int u = 0; u < kScanInFlight; ++u) {
-                            const int i = i0 + 32 * u;
-                            const bool ok = i < seg4;
-                            x0[u] = ok ? __ldg(w0 + base4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            x1[u] = ok ? __ldg(w1 + base4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < kScanInFlight; ++u) {
-                            const int i = i0 + 32 * u;
-                            if (i < seg4) {
-#pragma unroll
-                                for (int r = 0; r < kRowsMax; ++r) {
-                                    if (r < rows) {
-                                        const float4 av = *reinterpret_cast<const float4 *>(A + (size_t)r * K + 4 * (base4 + i));
-                                        acc0[r] = fmaf(av.x, x0[u].x, acc0[r]); acc0[r] = fmaf(av.y, x0[u].y, acc0[r]);
-                                        acc0[r] = fmaf(av.z, x0[u].z, acc0[r]); acc0[r] = fmaf(av.w, x0[u].w, acc0[r]);
-                                        acc1[r] = fmaf(av.x, x1[u].x, acc1[r]); acc1[r] = fmaf(av.y, x1[u].y, acc1[r]);
-                                        acc1[r] = fmaf(av.z, x1[u].z, acc1[r]); acc1[r] = fmaf(av.w, x1[u].w, acc1[r]);
+                                for (int u = 0; u < kScanBatch; ++u) {
+                                    const int i = base + u * blockDim.x, t = i / C2, c2 = i - t * C2;
+                                    ptr[u] = nullptr;
+                                    if (i < K2 && ((vis >> S.taps[t]) & 1u)) {
+                                        ptr[u] = src + (long long)S.shift[t] * C + 2 * c2;
+                                        q[u] = ll_ld(ptr[u]);
                                     }
                                 }
+#pragma unroll
+                                for (int u = 0; u < kScanBatch; ++u) {
+                                    const int i = base + u * blockDim.x;
+                                    if (i < K2) A2[r * K2 + i] = ptr[u] ? ll_wait(q[u], ptr[u], S.call_tag) : make_float2(0.f, 0.f);
+                                }
+                            }
+                        } else {
+                            const int c0n2 = S.N[L - 1] >> 1;
+                            const bool vis = s_grp[r0 + r] & 1u;
+                            const uint2 *src0 = S.vec[L - 1] + (size_t)(r0 + r) * S.N[L - 1];
+                            const float2 *src1 = reinterpret_cast<const float2 *>(S.prior_pm + ((long long)b * S.HW + hw) * (K - S.N[L - 1]));
+                            // (K2 <= 2 x 256 at C = 192; i >= c0n2 only at L == 1: the prior, always visible)
+                            for (int base = tid; base < K2; base += blockDim.x * 2) {
+                                const int i0 = base, i1 = base + blockDim.x;
+                                const bool t0 = vis && i0 < c0n2, t1 = vis && i1 < c0n2;
+                                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+                                float2 p0 = make_float2(0.f, 0.f), p1 = p0;
+                                if (t0) q0 = ll_ld(src0 + 2 * i0);
+                                if (t1) q1 = ll_ld(src0 + 2 * i1);
+                                if (i0 >= c0n2 && i0 < K2) p0 = __ldg(src1 + (i0 - c0n2));
+                                if (i1 >= c0n2 && i1 < K2) p1 = __ldg(src1 + (i1 - c0n2));
+                                if (i0 < K2) A2[r * K2 + i0] = t0 ? ll_wait(q0, src0 + 2 * i0, step - 1) : p0;
+                                if (i1 < K2) A2[r * K2 + i1] = t1 ? ll_wait(q1, src0 + 2 * i1, step - 1) : p1;
                             }
                         }
                     }
                 }
-#pragma unroll
-                for (int r = 0; r < kRowsMax; ++r) {
-                    if (r < rows) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
-                            acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
-                        }
+                __syncthreads();
+                SCAN_T(1);
+                // ---- (owned pair, K part) items over the warps
+                for (int item = warp; item < owned * kScanSplit; item += kScanWarps) {
+                    const int j = item / kScanSplit, q = item - j * kScanSplit;
+                    const float *wrow = smem + woff[L] + j * 2 * K;
+                    float *part = &s_part[item][0][0];
+                    switch (rows) {
+                    case 1: scan_pair_part<1>(wrow, A, K, q, lane, part); break;
+                    case 2: scan_pair_part<2>(wrow, A, K, q, lane, part); break;
+                    case 3: scan_pair_part<3>(wrow, A, K, q, lane, part); break;
+                    default: scan_pair_part<4>(wrow, A, K, q, lane, part); break;
                     }
                 }
-                if (lane == 0) {
-                    const float b0 = S.bias[L][n0], b1 = S.bias[L][n0 + 1];
-                    float *out = L < 3 ? S.act[L] : S.params;
-                    for (int r = 0; r < rows; ++r) {
-                        float v0 = acc0[r] + b0, v1 = acc1[r] + b1;
-                        if (L == 1 || L == 2) {
-                            v0 = v0 > 0.f ? v0 : v0 * kSlope;
-                            v1 = v1 > 0.f ? v1 : v1 * kSlope;
+                SCAN_T(2);
+                __syncthreads();
+                SCAN_T(3);
+                // ---- warp j, lane r finishes row r of pair j
+                if (mine && lane < rows) {
+                    const int row = r0 + lane;
+                    const float(*pp)[kScanRows][2] = &s_part[warp * kScanSplit];
+                    float m0 = (pp[0][lane][0] + pp[1][lane][0]) + (pp[2][lane][0] + pp[3][lane][0]);
+                    float m1 = (pp[0][lane][1] + pp[1][lane][1]) + (pp[2][lane][1] + pp[3][lane][1]);
+                    m0 += bias0;
+                    m1 += bias1;
+                    if (L == 1 || L == 2) {
+                        m0 = m0 > 0.f ? m0 : m0 * kSlope;
+                        m1 = m1 > 0.f ? m1 : m1 * kSlope;
+                    }
+                    *reinterpret_cast<uint4 *>(S.vec[L] + (size_t)row * N + n0) = make_uint4(__float_as_uint(m0), step, __float_as_uint(m1), step);
+                    if (L == 3) {   // (mean, scale) of latent channel n0 / 2: scale index, symbol, y_hat
+                        const int c = n0 >> 1, b = s_b[row];
+                        const long long e = (long long)b * qz.C * sc.y + (long long)c * sc.y + s_i[row];
+                        const long long yo = ((long long)b * qz.C + c) * S.HW + s_hw[row];
+                        if (qz.y) {
+                            if (rows_total > kScanRows) yv = qz.y[yo];
+                            const float sq = rintf(__fsub_rn(yv, m0));  // torch.round: half to even
+                            const float yh = __fadd_rn(sq, m0);
+                            S.yhat_pm[((long long)b * S.HW + s_hw[row]) * qz.C + c] = make_uint2(__float_as_uint(yh), S.call_tag);   // (first: the next stage waits for it)
+                            qz.sym[e] = (int32_t)sq;
+                            qz.buf[yo] = yh;
                         }
-                        const long long oo = ((long long)s_b[r] * N + n0) * S.HW + s_hw[r];
-                        out[oo] = v0;
-                        out[oo + S.HW] = v1;
-                        if (L == 3) {   // (mean, scale) of latent channel gw: scale index, symbol, y_hat
-                            const int c = gw, b = s_b[r], i = r - b * sc.y;
-                            const long long e = (long long)b * qz.C * sc.y + (long long)c * sc.y + i;
-                            qz.idx[e] = scale_index_dev(v1, qz.scale_table, qz.n_scales);
-                            if (qz.y) {
-                                const long long yo = ((long long)b * qz.C + c) * S.HW + s_hw[r];
-                                const float sq = rintf(__fsub_rn(qz.y[yo], v0));  // torch.round: half to even
-                                qz.sym[e] = (int32_t)sq;
-                                qz.buf[yo] = __fadd_rn(sq, v0);
-                            }
-                        }
+                        qz.idx[e] = scale_index_dev(m1, s_tab, qz.n_scales);
+                        const long long oo = ((long long)b * N + n0) * S.HW + s_hw[row];
+                        S.params[oo] = m0;
+                        S.params[oo + S.HW] = m1;
                     }
                 }
+                SCAN_T(4);
             }
-            if (L < 3 || g + 1 < S.g1) grid_barrier(S.barrier, gridDim.x, epoch);
         }
+        __syncthreads();   // the row records of stage g + 1 are complete, those of stage g free
+        SCAN_T(0);
         qz.sym += slice;
         qz.idx += slice;
     }
+#ifdef SCAN_TIMING
+    if (tid == 0 && cta == 0)
+        for (int i = 0; i < 5; ++i) S.timing[i] = tk[i];
+#endif
+}
+
+// [B][channels][HW] -> [B][HW][channels] (the stage kernel's position-major copy of the prior)
+__global__ void __launch_bounds__(256)
+k_to_position_major(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8)
+        tile[j][tx] = (c0 + j < channels && p0 + tx < HW) ? src[((size_t)b * channels + c0 + j) * HW + p0 + tx] : 0.f;
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+        if (p0 + j < HW && c0 + tx < channels) dst[((size_t)b * HW + p0 + j) * channels + c0 + tx] = tile[tx][j];
 }
 
 // out[n] = b[n] + sum_k w[n][k] * v[k], k < K0 of a row of K floats (state_dict layout), FP32 in ascending k
@@ -858,6 +1006,7 @@ static int launch_layer(CtxModel &m, LayerArgs a, const PackedW &pw, const Packe
 
 bool ctx_uses_tc(const CtxModel &m, int B) { return tc_model_eligible(m, B); }
 int ctx_precision(const CtxModel &m) { return m.precision; }
+int ctx_run_precision(const CtxModel &m) { return m.run_precision; }
 const int32_t *ctx_perm(const CtxModel &m) { return m.d_perm.as<int32_t>(); }
 // blocked channels-last copy in the operand format of the mode the next stage calls run in (floats, or split16)
 int ctx_to_cl(CtxModel &m, const float *src, float *dst, int B, int channels, cudaStream_t s)
@@ -1055,58 +1204,121 @@ int ctx_stage_params(CtxModel &m, int g, const float *buf, const float *prior, i
 }
 
 // ---- the persistent stage kernel (k_scan_stages): when it applies and how it is launched
-static size_t scan_smem(const CtxModel &m)
+static int scan_ctas(const CtxModel &m)
 {
-    const int kmax = std::max(std::max(m.k * m.k * m.C, 2 * m.c_ctx), std::max(m.c_m1, m.c_m2));
-    return (size_t)kRowsMax * kmax * sizeof(float);
+    static const int forced = [] { const char *e = getenv("BASIC_SCAN_CTAS"); return e ? atoi(e) : 0; }();  // sweeps
+    return forced > 0 ? std::min(forced, m.sm_count) : m.sm_count;   // one CTA per SM: all of them must be resident (grid barrier)
+}
+
+static size_t scan_smem(const CtxModel &m, int ntaps)
+{
+    const int nctas = scan_ctas(m);
+    const int K[4] = {ntaps * m.C, 2 * m.c_ctx, m.c_m1, m.c_m2}, N[4] = {m.c_ctx, m.c_m1, m.c_m2, m.c_ctx};
+    size_t fl = 0;
+    int kmax = 0;
+    for (int L = 0; L < 4; ++L) {
+        fl += (size_t)((N[L] / 2 + nctas - 1) / nctas) * 2 * K[L];
+        kmax = std::max(kmax, K[L]);
+    }
+    return (fl + (size_t)kScanRows * kmax) * sizeof(float);
 }
 
 bool ctx_scan_supported(const CtxModel &m, int B)
 {
     static const bool off = [] { const char *e = getenv("BASIC_SCAN_KERNEL"); return e && e[0] == '0'; }();  // A/B switch
     if (off || !m.has_conv || !m.has_merger || m.internal || m.G != 1 || m.S < 8 || !m.d_stage_cells.p || !m.ws_ctx.p) return false;
-    if (tc_model_eligible(m, B)) return false;
-    if ((long long)B * m.max_stage_cells > kRowsMax || m.k > 5) return false;
+    // (up to kScanMaxRows rows per stage the tensor path would run 128-row tiles that are mostly empty, four launches per stage;
+    // measured at 64 rows per stage: 258 us here against 160 us there)
+    if ((long long)B * m.max_stage_cells > kScanMaxRows || m.k > 5) return false;
     if (m.C % 4 || m.c_m1 % 4 || m.c_m2 % 4 || (m.c_m1 | m.c_m2 | m.c_ctx) & 1) return false;   // 128-bit weight loads, channel pairs
-    if (std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) > 2 * kScanWarps * kScanCtas) return false;    // one pair per warp
-    return scan_smem(m) <= 200 * 1024;
+    const int nctas = scan_ctas(m);
+    if ((std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) / 2 + nctas - 1) / nctas > kScanWarps) return false;   // a warp per owned pair
+    return scan_smem(m, m.k * m.k) <= 216 * 1024;   // (+ 8 KB of static shared memory: 227 KB per CTA)
 }
 
 // Stages [g0, g1): parameters into `params` (NCHW), scale indexes (and, with y, symbols + the y_hat write-back into buf) into
-// the stream slices starting at idx / sym.  One launch.
+// the stream slices starting at idx / sym.  One launch.  dq_sym (decoder): symbols of stage g0 - 1, dequantised into buf first.
 int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
-                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t stream)
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t stream, const int32_t *dq_sym)
 {
     if (g0 < 0 || g1 > m.S || g0 >= g1) return value_error("stage range out of bounds");
+    if (dq_sym && g0 == 0) return value_error("no stage precedes stage 0");
     const int HW = m.H * m.W;
-    if (m.act_B < B || !m.a_ctx.p) {
-        BASIC_TRY(m.a_ctx.reserve(cl_elems(B, m.c_ctx, HW) * sizeof(float)));
-        BASIC_TRY(m.a_m1.reserve(cl_elems(B, m.c_m1, HW) * sizeof(float)));
-        BASIC_TRY(m.a_m2.reserve(cl_elems(B, m.c_m2, HW) * sizeof(float)));
-        m.act_B = B;
+    // workspace: tagged layer outputs [kScanMaxRows][N] x 4 | tagged position-major y_hat [B][HW][C] | position-major prior
+    const size_t vec_w = (size_t)kScanMaxRows * (2 * m.c_ctx + m.c_m1 + m.c_m2), yh_w = (size_t)B * HW * m.C;
+    const size_t ws_bytes = (vec_w + yh_w) * sizeof(uint2) + (size_t)B * HW * 2 * m.C * sizeof(float) + 64;
+    const int nctas = scan_ctas(m);
+    const uint32_t steps = 4u * (uint32_t)(g1 - g0);
+    if (ws_bytes > m.scan_ws.cap || m.scan_nctas != nctas || m.scan_step > 0x7fff0000u - steps || m.scan_call > 0x7fff0000u) {
+        // (re)allocated, or the tags are about to wrap: every tag back to "never written"
+        if (g0 != 0) return value_error("stage kernel: workspace changed in the middle of a coding call");
+        BASIC_TRY(m.scan_ws.reserve(ws_bytes));
+        BASIC_CUDA(cudaMemsetAsync(m.scan_ws.p, 0, m.scan_ws.cap, stream));
+        m.scan_step = 0;
+        m.scan_call = 0;
+        m.scan_nctas = nctas;
     }
-    BASIC_TRY(m.scan_barrier.reserve(64));
-    BASIC_CUDA(cudaMemsetAsync(m.scan_barrier.p, 0, 64, stream));
+    uint2 *vec = m.scan_ws.as<uint2>(), *yhat_pm = vec + vec_w;
+    float *prior_pm = reinterpret_cast<float *>(yhat_pm + yh_w);
+    if (g0 == 0) {   // a new coding call (both the encoder's one launch and the decoder's first start here)
+        ++m.scan_call;
+        const dim3 grid((HW + 31) / 32, (2 * m.C + 31) / 32, B);
+        k_to_position_major<<<grid, 256, 0, stream>>>(prior, prior_pm, 2 * m.C, HW);
+        BASIC_LAUNCHED();
+    }
     ScanArgs S = {};
+    // the taps ANY stage of the map can see, whatever [g0, g1) is: the compact K order -- and with it the order of the
+    // additions -- must be the same in the encoder's one launch and the decoder's per-stage launches (masked taps add +0)
+    uint32_t tap_union = 0;
+    for (const auto &st : m.stages) tap_union |= st.tap_or;
+    for (int t = 0; t < m.k * m.k; ++t)
+        if ((tap_union >> t) & 1u) {
+            S.shift[S.ntaps] = (t / m.k - m.k / 2) * m.W + (t % m.k - m.k / 2);
+            S.taps[S.ntaps++] = (unsigned char)t;
+        }
     S.w[0] = m.ws_ctx.as<float>(); S.w[1] = m.ws_m1.as<float>(); S.w[2] = m.ws_m2.as<float>(); S.w[3] = m.ws_m3.as<float>();
     S.bias[0] = m.b_ctx.as<float>(); S.bias[1] = m.b_m1.as<float>(); S.bias[2] = m.b_m2.as<float>(); S.bias[3] = m.b_m3.as<float>();
     S.N[0] = m.c_ctx; S.N[1] = m.c_m1; S.N[2] = m.c_m2; S.N[3] = m.c_ctx;
-    S.K[0] = m.k * m.k * m.C; S.K[1] = 2 * m.c_ctx; S.K[2] = m.c_m1; S.K[3] = m.c_m2;
+    S.K[0] = S.ntaps * m.C; S.K[1] = 2 * m.c_ctx; S.K[2] = m.c_m1; S.K[3] = m.c_m2;
+    for (int L = 0; L < 4; ++L) S.pairs[L] = (S.N[L] / 2 + nctas - 1) / nctas;
     S.C = m.C; S.ksize = m.k; S.HW = HW; S.W_img = m.W; S.B = B;
     S.stage_cells = m.d_stage_cells.as<int2>();
     S.cell_hw = m.d_cell_hw.as<int32_t>();
     S.cell_tap = m.d_cell_tap.as<uint32_t>();
     S.cell_grp = m.d_cell_grp.as<uint32_t>();
-    S.buf = buf; S.prior = prior;
-    S.act[0] = m.a_ctx.as<float>(); S.act[1] = m.a_m1.as<float>(); S.act[2] = m.a_m2.as<float>();
+    S.buf = buf; S.yhat_pm = yhat_pm; S.prior_pm = prior_pm;
+    S.vec[0] = vec;
+    S.vec[1] = S.vec[0] + (size_t)kScanMaxRows * m.c_ctx;
+    S.vec[2] = S.vec[1] + (size_t)kScanMaxRows * m.c_m1;
+    S.vec[3] = S.vec[2] + (size_t)kScanMaxRows * m.c_m2;
     S.params = params;
     S.g0 = g0; S.g1 = g1;
     S.qz = RowsQuant{y, buf, sym, idx, d_scale_table, n_scales, m.C};
-    S.barrier = m.scan_barrier.as<unsigned>();
+    S.dq_sym = dq_sym;
+    S.step0 = m.scan_step;
+    S.call_tag = m.scan_call;
+#ifdef SCAN_TIMING
+    BASIC_TRY(m.scan_barrier.reserve(256));
+    S.timing = m.scan_barrier.as<long long>();
+#endif
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_scan_stages<<<kScanCtas, kScanWarps * 32, scan_smem(m), stream>>>(S);
+    if (attr_once.first()) BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    k_scan_stages<<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
+    m.scan_step += steps;
+#ifdef SCAN_TIMING
+    if (g1 - g0 > 4) {
+        long long tk[5];
+        BASIC_CUDA(cudaStreamSynchronize(stream));
+        BASIC_CUDA(cudaMemcpy(tk, m.scan_barrier.as<long long>(), sizeof(tk), cudaMemcpyDeviceToHost));
+        const long long ns = g1 - g0;
+        FILE *tf = fopen("gpurun_out/scan_timing.txt", "a");
+        if (!tf) tf = stderr;
+        fprintf(tf, "scan cta 0: %lld stages, rows %d; cycles per stage: stage sync %lld  gather + wait %lld  multiply %lld  sync %lld  epilogue %lld\n",
+                ns, B * m.max_stage_cells, tk[0] / ns, tk[1] / ns, tk[2] / ns, tk[3] / ns, tk[4] / ns);
+        if (tf != stderr) fclose(tf);
+    }
+#endif
     return BASIC_OK;
 }
 
@@ -1125,7 +1337,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->scan_ws, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

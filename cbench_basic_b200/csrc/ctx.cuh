@@ -47,7 +47,10 @@ struct CtxModel {
     DevBuf d_positions;  // int32 [C*H*W]             coded element offsets, stage-major
     DevBuf d_stage_cells;  // int2 [S]                first cell, cells of every stage (persistent stage kernel, G = 1)
     int max_stage_cells = 0;
-    DevBuf scan_barrier;   // grid barrier counter of the persistent stage kernel
+    DevBuf scan_barrier;   // (SCAN_TIMING builds: cycle counters of the persistent stage kernel)
+    uint32_t scan_step = 0, scan_call = 0;   // tags of the stage kernel's exchanged words: (stage, layer) steps and coding calls so far
+    DevBuf scan_ws;        // ... its tagged per-stage layer outputs [row][N], tagged position-major y_hat, position-major prior
+    int scan_nctas = 0;
     DevBuf ws_ctx, ws_m1, ws_m2, ws_m3;   // N-major weight copies of the persistent stage kernel (conv: [2C][tap][C])
     DevBuf d_perm;       // int32 [H*W]               position -> slot of the tensor path's activation layout (stage-major)
     DevBuf d_iperm;      // int32 [H*W]               slot -> position
