@@ -69,8 +69,19 @@ int ctx_range_flag_copy(CtxModel &, cudaStream_t, int *);
 int ctx_stage_positions(const CtxModel &, int, const int32_t **, int64_t *);
 int ctx_dims(const CtxModel &, int *C, int *G, int *H, int *W);
 bool ctx_scan_supported(const CtxModel &, int B);
+struct ScanDecodeHost {   // (ctx.cuh)
+    const RansTables *tables;
+    int bypass;
+    const unsigned char *seg;
+    long long seg_cap;
+    int n_chunks;
+    const int32_t *chunk_syms;
+    int *status;
+};
 int ctx_scan_run(CtxModel &, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
-                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t, const int32_t *dq_sym = nullptr);
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t, const int32_t *dq_sym = nullptr,
+                 const ScanDecodeHost *dec = nullptr);
+bool ctx_scan_decode_supported(const CtxModel &, int n_chunks, int bypass_precision, int freq_precision);
 
 struct TansTables;
 TansTables *tans_new();
@@ -1541,10 +1552,13 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
     // memory and upload it while the GPU is busy
-    if (model) {
+    // (a multi-lane stream on the stage kernel may be decoded inside ONE launch: decided once the segment is parsed)
+    bool g0_done = false;
+    if (model && !(scan && lanes != BASIC_LANES_REFERENCE)) {
         ProfScope ps(PROF_CTX, s);
         if (scan) BASIC_TRY(ctx_scan_run(*model->m, 0, 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s));
         else BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
+        g0_done = true;
     }
     g_trace.mark("g0 queued", s);
     BASIC_TRY(basic_coder_set_stream(c, encoded, len, lanes, stream));
@@ -1563,15 +1577,24 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         BASIC_TRY(c->carry_x.reserve((size_t)si.n_chunks * 128 + 16));
         BASIC_TRY(c->carry_wp.reserve((size_t)si.n_chunks * 4 + 16));
     }
-    for (int g = 0; g < S; ++g) {
+    bool fused = false;
+    if (scan && lanes != BASIC_LANES_REFERENCE && ctx_scan_decode_supported(*model->m, si.n_chunks, (int)c->bypass_precision, c->rt.precision)) {
+        // the whole decode in one launch: context model, scale indexes, the coder's chunk warps and the write-back (ctx.cu)
+        ProfScope ps(PROF_CTX, s);
+        ScanDecodeHost dh = {&c->rt, c->bypass, c->stream_dev.as<unsigned char>() + c->stream_pos, si.len, si.n_chunks, si.cs.data(), &ds->status};
+        BASIC_TRY(ctx_scan_run(*model->m, 0, S, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s,
+                               nullptr, &dh));
+        fused = true;
+    }
+    for (int g = 0; g < S && !fused; ++g) {
         const int32_t *pos = nullptr;
         int64_t n_pos = (int64_t)C * HW;
         if (model) {
-            if (g > 0) {
+            if (g > 0 || !g0_done) {
                 ProfScope ps(PROF_CTX, s);
                 // (the fused stage launch starts by turning the previous stage's symbols into y_hat)
                 if (scan) BASIC_TRY(ctx_scan_run(*model->m, g, g + 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s,
-                                                 slice_n[g - 1] > 0 ? sym : nullptr));
+                                                 g > 0 && slice_n[g - 1] > 0 ? sym : nullptr));
                 else BASIC_TRY(ctx_stage_params(*model->m, g, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
             }
             BASIC_TRY(ctx_stage_positions(*model->m, g, &pos, &n_pos));

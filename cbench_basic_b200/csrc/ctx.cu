@@ -16,6 +16,7 @@
 #include <cstdio>
 
 #include "ctx.cuh"
+#include "rans_lanes.cuh"
 
 namespace basic {
 
@@ -377,6 +378,23 @@ k_layer_rows(LayerArgs a)
 // launch first turns the previous stage's symbols into y_hat.  Deterministic (fixed summation order); one channel group (G = 1).
 constexpr int kScanWarps = 8, kScanRows = 4, kScanMaxRows = 32;   // (more rows per stage: every CTA gathers every row -- the tiled kernels win)
 
+// The decoder's single launch: the multi-lane coder's chunk warps live inside the stage kernel.  Chunk k belongs to warp
+// 7 - k / grid of CTA k % grid; it keeps its 32 lane states and its word position in registers from stage to stage, takes
+// the scale indexes (and means) of its share of the stage's slice as tagged words from the CTAs that computed them, decodes,
+// and publishes y_hat = symbol + mean as tagged words -- which is what the next stage's convolution waits for.
+constexpr int kScanDecSlots = 4;   // warps 7 .. 4 of a CTA
+struct ScanDecode {
+    const unsigned char *blob;   // coder tables (rans tables blob in global memory, read through the read-only path)
+    size_t meta_bytes, cdf16_bytes;
+    int T, precision, bypass;
+    const unsigned char *seg;    // the segment (device)
+    long long seg_cap;
+    int seg_slices, n_chunks;
+    const int32_t *chunk_syms;   // per slice
+    uint4 *idx_t;                // [slice element] {scale index, tag, mean, tag} of the current stage
+    int *status;
+};
+
 struct ScanArgs {
     const float *w[4];           // N-major: conv [2C][k2][C], dense [N][K]
     const float *bias[4];
@@ -401,6 +419,7 @@ struct ScanArgs {
     uint32_t step0;              // tag of (stage g, layer L) = step0 + 4 (g - g0) + L + 1: monotonic over launches
     uint32_t call_tag;           // tag of every y_hat word of this coding call
     long long *timing;           // SCAN_TIMING builds
+    ScanDecode dec;              // n_chunks > 0: the decoder's single launch
 };
 
 // One 16-byte load of two {value, tag} words (L2, never L1).  A gather issues a batch of these and only then looks at the tags,
@@ -470,6 +489,118 @@ __device__ __forceinline__ void scan_pair_part(const float *__restrict__ wrow, c
     }
 }
 
+// One chunk's share [dbase, dbase + m) of the current stage's slice, decoded by its warp: the coding steps of k_bls_decode
+// (rans_lanes.cu: local symbol j -> lane (j % 128) / 4, step (j / 128) * 4 + j % 4; renormalising lanes take consecutive words in
+// lane order; bypass_precision 4 escapes), operands arriving as tagged words, stream words out of a 128-word window in
+// shared memory (beyond it: global), tables through the read-only path.
+__device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<false> &tb, const uint32_t *__restrict__ units, const uint32_t *win,
+                                               uint32_t wbase, uint32_t wend, uint32_t &x, uint32_t &wp, int &st, long long dbase, int m,
+                                               int lane, uint32_t tag, int cells, const int *s_hw)
+{
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int prec = S.dec.precision;
+    const uint32_t pmask = (1u << prec) - 1;
+    const uint16_t *win16 = reinterpret_cast<const uint16_t *>(win);
+    const uint16_t *words16 = reinterpret_cast<const uint16_t *>(units);
+    auto word_at = [&](uint32_t at) -> uint32_t {
+        const uint32_t off = at - wbase;
+        return off < 128u ? win16[off] : __ldg(words16 + at);
+    };
+    auto refill = [&](bool need) {
+        const unsigned nm = __ballot_sync(0xffffffffu, need);
+        if (need) {
+            const uint32_t at = wp + __popc(nm & lt_mask);
+            uint32_t word = 0;
+            if (at < wend) word = word_at(at); else st |= 4;
+            x = (x << 16) | word;
+        }
+        wp += __popc(nm);
+    };
+    const int C = S.C, per_b = C * cells;
+    const int nblocks = (m + 127) >> 7;
+    for (int blk = 0; blk < nblocks; ++blk) {
+        const int j0 = blk * 128 + lane * 4;
+        // operands of the block's four symbols: {scale index, tag, mean, tag}, all loads first
+        uint4 op[4];
+        uint4 mt[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (j0 + q < m) op[q] = ll_ld(reinterpret_cast<const uint2 *>(S.dec.idx_t + dbase + j0 + q));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int c = 0;
+            if (j0 + q < m) {
+                int spins = 0;
+                while (op[q].y != tag || op[q].w != tag) {
+                    op[q] = ll_ld(reinterpret_cast<const uint2 *>(S.dec.idx_t + dbase + j0 + q));
+                    if (++spins > (1 << 24)) asm volatile("trap;");
+                }
+                c = (int)op[q].x;
+                if ((uint32_t)c >= (uint32_t)S.dec.T) { st |= 1; c = 0; }
+            }
+            mt[q] = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool active = j0 + q < m;
+            const Tab<false>::addr_t cd = tb.cdf_at(mt[q].x);
+            const int nsyms = (int)(mt[q].z & 0xffffu) - 1, maxv = nsyms - 1;
+            const uint32_t cum = x & pmask;
+            int s = (int)Tab<false>::ld16<0>(tb.lut_at(mt[q].y + (cum >> ((mt[q].z >> 16) & 0xffu))));
+            while (s + 1 < nsyms && Tab<false>::ld16<2>(cd + 2 * s) <= cum) ++s;   // (the 16-bit CDF stores 2^16 as 0: guarded by nsyms)
+            const uint32_t start = Tab<false>::ld16<0>(cd + 2 * s), next = Tab<false>::ld16<2>(cd + 2 * s);
+            const uint32_t freq = (uint16_t)(next - start);
+            if (active) x = freq * (x >> prec) + cum - start;
+            refill(active && x < kRansL);
+            int32_t value = s;
+            const bool esc = active && S.dec.bypass && s == maxv;
+            // bypass_precision 4: the first unit starts with the digit count nb (<= 8 for a 32-bit payload, one count token),
+            // followed by the digits, least significant first, four tokens per unit
+            if (__any_sync(0xffffffffu, esc)) {
+                bool in = esc, first = true;
+                uint32_t nb = 0, raw = 0, jj = 0;
+                while (__any_sync(0xffffffffu, in)) {
+                    const bool was = in;
+                    if (in) {
+                        uint32_t cnt, used, bits = x;
+                        if (first) {
+                            nb = x & 15u;
+                            if (nb > 8) { st |= 4; nb = 0; }  // no encoder writes this
+                            cnt = min(3u, nb);
+                            used = cnt + 1;
+                            bits = x >> 4;
+                            first = false;
+                        } else {
+                            cnt = min(4u, nb - jj);
+                            used = cnt;
+                        }
+                        raw |= (bits & ((1u << (4 * cnt)) - 1)) << (4 * jj);
+                        jj += cnt;
+                        x >>= 4 * used;
+                        in = jj < nb;
+                    }
+                    refill(was && x < kRansL);
+                }
+                if (esc) {
+                    const int32_t v2 = (int32_t)(raw >> 1);
+                    value = (raw & 1) ? -v2 - 1 : v2 + maxv;
+                }
+            }
+            if (active) {
+                const int32_t sym = value + (int32_t)mt[q].w;
+                // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
+                const float v = __fadd_rn(__fadd_rn((float)sym, __uint_as_float(op[q].z)), 0.0f);
+                const long long e = dbase + j0 + q;
+                const int b = (int)(e / per_b), r2 = (int)(e - (long long)b * per_b), c = r2 / cells, i = r2 - c * cells;
+                const int hw = s_hw[b * cells + i];
+                S.yhat_pm[((long long)b * S.HW + hw) * C + c] = make_uint2(__float_as_uint(v), S.call_tag);
+                S.buf[((long long)b * C + c) * S.HW + hw] = v;
+            }
+        }
+    }
+}
+
+template <bool DEC>   // DEC: the decoder's single launch (chunk warps inside the kernel)
 __global__ void __launch_bounds__(kScanWarps * 32)
 k_scan_stages(const __grid_constant__ ScanArgs S)
 {
@@ -477,6 +608,7 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
     __shared__ int sr_b[2][kScanMaxRows], sr_hw[2][kScanMaxRows], sr_i[2][kScanMaxRows];   // the rows of the current / next stage
     __shared__ uint32_t sr_tap[2][kScanMaxRows], sr_grp[2][kScanMaxRows];
     __shared__ float s_part[kScanWarps * kScanSplit][kScanRows][2];   // partial sums of (owned pair, K part)
+    __shared__ uint32_t s_win[kScanDecSlots][64];   // decoder warps: the next 128 stream words of their chunk
     __shared__ float s_tab[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x, nctas = gridDim.x;
@@ -529,6 +661,25 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
     }
     __syncthreads();
     SCAN_T(0);
+    // ---- decoder warps (single-launch decoding)
+    const int dslot = kScanWarps - 1 - warp;
+    const int dk = dslot * nctas + cta;                       // this warp's chunk
+    const bool dec_warp = DEC && dslot < kScanDecSlots && dk < S.dec.n_chunks;
+    uint32_t dx = 0, dwp = 0, dwend = 0, dwbase = 0;
+    int dst = 0;
+    const uint32_t *d_units = nullptr;
+    Tab<false> dtb;
+    if (DEC && dec_warp) {
+        const uint32_t *end_word = reinterpret_cast<const uint32_t *>(S.dec.seg) + 2 + S.dec.seg_slices;
+        const uint32_t *states = end_word + S.dec.n_chunks;
+        const long long words_at = kSegHdr + 4ll * S.dec.seg_slices + 4ll * S.dec.n_chunks + 128ll * S.dec.n_chunks;
+        d_units = reinterpret_cast<const uint32_t *>(S.dec.seg + words_at);
+        dwend = end_word[dk];
+        dwp = dk ? end_word[dk - 1] : 0;
+        if (dwend < dwp || words_at + 2ll * dwend > S.dec.seg_cap) { dst |= 4; dwend = dwp = 0; }  // corrupt directory
+        dx = states[(size_t)dk * 32 + lane];
+        dtb.init(S.dec.blob, nullptr, S.dec.meta_bytes, S.dec.cdf16_bytes);
+    }
     uint32_t step = S.step0;
     // the rows of a stage: image, cell, position, visibility -- loaded one stage ahead
     auto load_rows = [&](int g, int slot) {
@@ -548,6 +699,13 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
         const int *s_b = sr_b[g & 1], *s_hw = sr_hw[g & 1], *s_i = sr_i[g & 1];
         const uint32_t *s_tap = sr_tap[g & 1], *s_grp = sr_grp[g & 1];
         if (g + 1 < S.g1) load_rows(g + 1, (g + 1) & 1);   // (its last readers passed the barrier that ended stage g - 1)
+        if (DEC && dec_warp) {   // the next 128 words of the chunk: in shared memory long before the stage's indexes arrive
+            dwbase = dwp & ~1u;
+            const uint32_t u0 = dwbase >> 1, u_lim = (dwend + 1) >> 1;
+            s_win[dslot][lane] = u0 + lane < u_lim ? __ldg(d_units + u0 + lane) : 0u;
+            s_win[dslot][lane + 32] = u0 + 32 + lane < u_lim ? __ldg(d_units + u0 + 32 + lane) : 0u;
+            __syncwarp();
+        }
 #pragma unroll 1
         for (int L = 0; L < 4; ++L) {
             ++step;
@@ -653,7 +811,9 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
                             qz.sym[e] = (int32_t)sq;
                             qz.buf[yo] = yh;
                         }
-                        qz.idx[e] = scale_index_dev(m1, s_tab, qz.n_scales);
+                        const int si = scale_index_dev(m1, s_tab, qz.n_scales);
+                        if (DEC) S.dec.idx_t[e] = make_uint4((uint32_t)si, step, __float_as_uint(m0), step);   // (first: a chunk warp waits for it)
+                        qz.idx[e] = si;
                         const long long oo = ((long long)b * N + n0) * S.HW + s_hw[row];
                         S.params[oo] = m0;
                         S.params[oo + S.HW] = m1;
@@ -662,10 +822,20 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
                 SCAN_T(4);
             }
         }
+        if (DEC && dec_warp) {
+            const long long n = slice, cs = S.dec.chunk_syms[g], dbase = (long long)dk * cs, rem = n - dbase;
+            const int m = (int)(rem <= 0 ? 0 : rem < cs ? rem : cs);
+            if (m > 0)
+                scan_decode_share(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
+        }
         __syncthreads();   // the row records of stage g + 1 are complete, those of stage g free
         SCAN_T(0);
         qz.sym += slice;
         qz.idx += slice;
+    }
+    if (DEC && dec_warp) {
+        if (dwp != dwend && lane == 0) dst |= 4;   // the chunk's words must be used up exactly
+        if (dst) atomicOr(S.dec.status, dst);
     }
 #ifdef SCAN_TIMING
     if (tid == 0 && cta == 0)
@@ -1238,15 +1408,23 @@ bool ctx_scan_supported(const CtxModel &m, int B)
 
 // Stages [g0, g1): parameters into `params` (NCHW), scale indexes (and, with y, symbols + the y_hat write-back into buf) into
 // the stream slices starting at idx / sym.  One launch.  dq_sym (decoder): symbols of stage g0 - 1, dequantised into buf first.
+bool ctx_scan_decode_supported(const CtxModel &m, int n_chunks, int bypass_precision, int freq_precision)
+{
+    static const bool off = [] { const char *e = getenv("BASIC_SCAN_DECODE"); return e && e[0] == '0'; }();  // A/B switch
+    return !off && n_chunks > 0 && n_chunks <= kScanDecSlots * scan_ctas(m) && bypass_precision == 4 && freq_precision <= 16;
+}
+
 int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
-                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t stream, const int32_t *dq_sym)
+                 int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t stream, const int32_t *dq_sym,
+                 const ScanDecodeHost *dec)
 {
     if (g0 < 0 || g1 > m.S || g0 >= g1) return value_error("stage range out of bounds");
     if (dq_sym && g0 == 0) return value_error("no stage precedes stage 0");
     const int HW = m.H * m.W;
     // workspace: tagged layer outputs [kScanMaxRows][N] x 4 | tagged position-major y_hat [B][HW][C] | position-major prior
     const size_t vec_w = (size_t)kScanMaxRows * (2 * m.c_ctx + m.c_m1 + m.c_m2), yh_w = (size_t)B * HW * m.C;
-    const size_t ws_bytes = (vec_w + yh_w) * sizeof(uint2) + (size_t)B * HW * 2 * m.C * sizeof(float) + 64;
+    const size_t idx_w = (size_t)kScanMaxRows * m.C;   // {scale index, tag, mean, tag} per element of a stage's slice
+    const size_t ws_bytes = (vec_w + yh_w) * sizeof(uint2) + idx_w * sizeof(uint4) + (size_t)B * HW * 2 * m.C * sizeof(float) + 64;
     const int nctas = scan_ctas(m);
     const uint32_t steps = 4u * (uint32_t)(g1 - g0);
     if (ws_bytes > m.scan_ws.cap || m.scan_nctas != nctas || m.scan_step > 0x7fff0000u - steps || m.scan_call > 0x7fff0000u) {
@@ -1259,7 +1437,8 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
         m.scan_nctas = nctas;
     }
     uint2 *vec = m.scan_ws.as<uint2>(), *yhat_pm = vec + vec_w;
-    float *prior_pm = reinterpret_cast<float *>(yhat_pm + yh_w);
+    uint4 *idx_t = reinterpret_cast<uint4 *>(yhat_pm + yh_w);
+    float *prior_pm = reinterpret_cast<float *>(idx_t + idx_w);
     if (g0 == 0) {   // a new coding call (both the encoder's one launch and the decoder's first start here)
         ++m.scan_call;
         const dim3 grid((HW + 31) / 32, (2 * m.C + 31) / 32, B);
@@ -1297,13 +1476,36 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     S.dq_sym = dq_sym;
     S.step0 = m.scan_step;
     S.call_tag = m.scan_call;
+    if (dec) {   // single-launch decoding: the coder's chunk warps run inside the kernel
+        if (g0 != 0 || g1 != m.S || y || dq_sym) return value_error("in-kernel decoding covers the whole map in one launch");
+        BASIC_TRY(m.scan_cs.reserve((size_t)m.S * sizeof(int32_t)));
+        BASIC_CUDA(cudaMemcpyAsync(m.scan_cs.p, dec->chunk_syms, (size_t)m.S * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        const RansTables &tb = *dec->tables;
+        S.dec.blob = tb.blob.as<unsigned char>();
+        S.dec.meta_bytes = tb.meta_bytes;
+        S.dec.cdf16_bytes = tb.cdf16_bytes;
+        S.dec.T = tb.T;
+        S.dec.precision = tb.precision;
+        S.dec.bypass = dec->bypass;
+        S.dec.seg = dec->seg;
+        S.dec.seg_cap = dec->seg_cap;
+        S.dec.seg_slices = m.S;
+        S.dec.n_chunks = dec->n_chunks;
+        S.dec.chunk_syms = m.scan_cs.as<int32_t>();
+        S.dec.idx_t = idx_t;
+        S.dec.status = dec->status;
+    }
 #ifdef SCAN_TIMING
     BASIC_TRY(m.scan_barrier.reserve(256));
     S.timing = m.scan_barrier.as<long long>();
 #endif
     static PerDeviceOnce attr_once;
-    if (attr_once.first()) BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-    k_scan_stages<<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
+    if (attr_once.first()) {
+        BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    }
+    if (dec) k_scan_stages<true><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
+    else k_scan_stages<false><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
     m.scan_step += steps;
 #ifdef SCAN_TIMING
@@ -1337,7 +1539,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->scan_ws, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->scan_ws, &m->scan_cs, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

@@ -49,6 +49,7 @@ struct CtxModel {
     int max_stage_cells = 0;
     DevBuf scan_barrier;   // (SCAN_TIMING builds: cycle counters of the persistent stage kernel)
     uint32_t scan_step = 0, scan_call = 0;   // tags of the stage kernel's exchanged words: (stage, layer) steps and coding calls so far
+    DevBuf scan_cs;        // ... single-launch decoding: chunk_syms of every slice
     DevBuf scan_ws;        // ... its tagged per-stage layer outputs [row][N], tagged position-major y_hat, position-major prior
     int scan_nctas = 0;
     DevBuf ws_ctx, ws_m1, ws_m2, ws_m3;   // N-major weight copies of the persistent stage kernel (conv: [2C][tap][C])
@@ -72,6 +73,17 @@ struct CtxModel {
     DevBuf cl_params;                 // ... and the blocked channels-last parameters behind its NCHW result
 };
 
+
+// What the stage kernel needs to decode inside its one launch (ctx.cu k_scan_stages / scan_decode_share)
+struct ScanDecodeHost {
+    const RansTables *tables;
+    int bypass;
+    const unsigned char *seg;     // device: the segment
+    long long seg_cap;
+    int n_chunks;
+    const int32_t *chunk_syms;    // host: per slice (pageable memory is fine: copied before the call returns)
+    int *status;                  // device: coder status flags (atomicOr)
+};
 
 struct Source {          // one block of K coming from an NCHW activation tensor
     const float *ptr;    // [B, channels, H, W]
