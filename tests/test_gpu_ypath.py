@@ -461,3 +461,24 @@ def test_cfg2_batch_against_oracle():
         assert float(((out[b:b + 1].cpu() - yhat_o)[ok].abs() / yhat_o[ok].abs().clamp_min(1.0)).max()) <= REL_TOL
     r = bench.oracle_mismatches("cfg2", coder, y, prior, w, yd, pd)
     assert r["off_tie"] == 0 and r["symbol_mismatches"] <= 2 and r["index_mismatches"] <= 2 and r["params_max_rel_err"] <= REL_TOL, r
+
+
+@pytest.mark.parametrize("B", [1, 3, 6, 9])
+def test_scanline_stage_kernel_rows_against_oracle(B):
+    """The persistent stage kernel (ctx.cu k_scan_stages) with 1 .. 9 rows per stage (<= 4: one row chunk; 6, 9: two and three
+    chunks): y_hat of encoder and both decoders (lanes = 0: chunk warps inside the one launch; lanes = 1: a launch per stage
+    that first dequantises the previous stage) against the CPU oracle -- same symbols, means within 1e-5."""
+    c = _random_case(12, 1, B, 6, 7, 40 + B, method="scanline")
+    tab = Y.get_scale_table()
+    with torch.no_grad():
+        _, _, yhat_o = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    sizes = {}
+    for lanes in (0, 1):
+        coder = make_coder(c, lanes, method="scanline")
+        bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+        out = coder.decode(bs, prior=prior)
+        assert torch.equal(out, yhat_enc * 1.0 + 0.0)          # lossless, bit for bit
+        assert_latents_match(out.cpu(), yhat_o)
+        sizes[lanes] = len(bs)
+    assert sizes[0] >= sizes[1]
