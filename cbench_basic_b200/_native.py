@@ -141,14 +141,19 @@ _bytes_ptr.restype = C.c_void_p
 _bytes_ptr.argtypes = [C.py_object]
 
 
-def last_output(handle):
-    """The stream of the last encoding call made with out == NULL, as a bytes object.  The object is allocated at
-    its final size and the library copies into it directly (chunk by chunk while the rest is still in flight)."""
+def last_output(handle, prefix=b""):
+    """The stream of the last encoding call made with out == NULL, as a bytes object, behind `prefix` (a framing header).
+    The object is allocated at its final size and the library copies into it directly (chunk by chunk while the rest is
+    still in flight): no second pass over a multi-megabyte stream to prepend a few header bytes."""
     n = int(lib().basic_coder_output_size(handle))
     if n == 0:
-        return b""
-    out = _new_bytes(None, n)
-    check(lib().basic_coder_take_output(handle, _bytes_ptr(out), n))
+        return bytes(prefix)
+    k = len(prefix)
+    out = _new_bytes(None, k + n)
+    base = _bytes_ptr(out)
+    if k:
+        C.memmove(base, prefix, k)
+    check(lib().basic_coder_take_output(handle, base + k, n))
     return out
 
 

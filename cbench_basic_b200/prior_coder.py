@@ -380,23 +380,24 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
         with self.profiler.start_time_profile("time_prior_preprocess_encode"):
             y, p = self._operand(self._transform(input, quantizer_params)), self._operand(prior)
             self._set_map(self._get_pgm(input.shape, pgm))
-        with self.profiler.start_time_profile("time_ans_encode"):
-            h = self.ans_encoder.handle
-            out_len = C.c_int64(0)
-            yhat = torch.empty(y.shape, dtype=torch.float32, device=self.device) if return_yhat else None
-            # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object
-            N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
-                                               C.byref(out_len), yhat.data_ptr() if return_yhat else None,
-                                               self._stream()))
-            byte_string = N.last_output(h)
         head = b""
         if self.fixed_input_shape is not None:
             assert B == self.fixed_input_shape[0] and tuple(input.shape[2:]) == tuple(self.fixed_input_shape[1:])
         elif not self.force_input_prior_shape_aligned:
             head = struct.pack("B", 3) + struct.pack("<H", B) + struct.pack("<H", H) + struct.pack("<H", W)  # :581-597
+        with self.profiler.start_time_profile("time_ans_encode"):
+            h = self.ans_encoder.handle
+            out_len = C.c_int64(0)
+            yhat = torch.empty(y.shape, dtype=torch.float32, device=self.device) if return_yhat else None
+            # out = NULL: the stream lands in the coder's pinned host buffer; one copy makes the bytes object -- header and
+            # stream in ONE object filled in place (prepending seven bytes to a 16 MB stream would copy it again)
+            N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
+                                               C.byref(out_len), yhat.data_ptr() if return_yhat else None,
+                                               self._stream()))
+            byte_string = N.last_output(h, prefix=head)
         if return_yhat:
-            return head + byte_string, self._inverse_transform(yhat, quantizer_params)
-        return head + byte_string
+            return byte_string, self._inverse_transform(yhat, quantizer_params)
+        return byte_string
 
     def decode(self, byte_string: bytes, *args, prior=None, pgm=None, quantizer_params=None, **kwargs) -> torch.Tensor:
         assert hasattr(self, "ans_decoder"), "Not Initialized! Should call self.update_state() before coding!"
