@@ -721,50 +721,60 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
 #pragma unroll 1
             for (int r0 = 0; r0 < rows_total; r0 += kScanRows) {
                 const int rows = min(kScanRows, rows_total - r0);
-                // ---- gather the input vectors: contiguous 128-bit loads out of L2, polled until the tags match
+                // ---- gather the input vectors: contiguous 128-bit loads out of L2, polled until the tags match.  The rows of the
+                // chunk form ONE index space (row-major pairs of floats), so that a thread's loads of all rows are in flight together
                 {
                     float2 *A2 = reinterpret_cast<float2 *>(A);
-                    const int C2 = C >> 1, K2 = K >> 1;
-                    for (int r = 0; r < rows; ++r) {
-                        const int b = s_b[r0 + r], hw = s_hw[r0 + r];
-                        if (L == 0) {
-                            const uint32_t vis = s_tap[r0 + r];
-                            const uint2 *src = S.yhat_pm + ((long long)b * S.HW + hw) * C;
-                            for (int base = tid; base < K2; base += blockDim.x * kScanBatch) {
-                                uint4 q[kScanBatch];
-                                const uint2 *ptr[kScanBatch];
+                    const int C2 = C >> 1, K2 = K >> 1, total = rows * K2;
+                    if (L == 0) {
+                        for (int base = tid; base < total; base += blockDim.x * kScanBatch) {
+                            uint4 q[kScanBatch];
+                            const uint2 *ptr[kScanBatch];
 #pragma unroll
-                                for (int u = 0; u < kScanBatch; ++u) {
-                                    const int i = base + u * blockDim.x, t = i / C2, c2 = i - t * C2;
-                                    ptr[u] = nullptr;
-                                    if (i < K2 && ((vis >> S.taps[t]) & 1u)) {
-                                        ptr[u] = src + (long long)S.shift[t] * C + 2 * c2;
+                            for (int u = 0; u < kScanBatch; ++u) {
+                                const int o = base + u * blockDim.x;
+                                ptr[u] = nullptr;
+                                if (o < total) {
+                                    const int r = o / K2, i = o - r * K2, t = i / C2, c2 = i - t * C2;
+                                    if ((s_tap[r0 + r] >> S.taps[t]) & 1u) {
+                                        ptr[u] = S.yhat_pm + ((long long)s_b[r0 + r] * S.HW + s_hw[r0 + r] + S.shift[t]) * C + 2 * c2;
                                         q[u] = ll_ld(ptr[u]);
                                     }
                                 }
+                            }
 #pragma unroll
-                                for (int u = 0; u < kScanBatch; ++u) {
-                                    const int i = base + u * blockDim.x;
-                                    if (i < K2) A2[r * K2 + i] = ptr[u] ? ll_wait(q[u], ptr[u], S.call_tag) : make_float2(0.f, 0.f);
+                            for (int u = 0; u < kScanBatch; ++u) {
+                                const int o = base + u * blockDim.x;
+                                if (o < total) A2[o] = ptr[u] ? ll_wait(q[u], ptr[u], S.call_tag) : make_float2(0.f, 0.f);
+                            }
+                        }
+                    } else {
+                        const int c0n2 = S.N[L - 1] >> 1, p2 = K2 - c0n2;   // (p2 > 0 only at L == 1: the prior, always visible)
+                        for (int base = tid; base < total; base += blockDim.x * 2) {
+                            uint4 q[2];
+                            float2 pv[2];
+                            const uint2 *ptr[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int o = base + u * blockDim.x;
+                                ptr[u] = nullptr;
+                                pv[u] = make_float2(0.f, 0.f);
+                                if (o < total) {
+                                    const int r = o / K2, i = o - r * K2;
+                                    if (i < c0n2) {
+                                        if (s_grp[r0 + r] & 1u) {
+                                            ptr[u] = S.vec[L - 1] + (size_t)(r0 + r) * S.N[L - 1] + 2 * i;
+                                            q[u] = ll_ld(ptr[u]);
+                                        }
+                                    } else {
+                                        pv[u] = __ldg(reinterpret_cast<const float2 *>(S.prior_pm + ((long long)s_b[r0 + r] * S.HW + s_hw[r0 + r]) * (2 * p2)) + (i - c0n2));
+                                    }
                                 }
                             }
-                        } else {
-                            const int c0n2 = S.N[L - 1] >> 1;
-                            const bool vis = s_grp[r0 + r] & 1u;
-                            const uint2 *src0 = S.vec[L - 1] + (size_t)(r0 + r) * S.N[L - 1];
-                            const float2 *src1 = reinterpret_cast<const float2 *>(S.prior_pm + ((long long)b * S.HW + hw) * (K - S.N[L - 1]));
-                            // (K2 <= 2 x 256 at C = 192; i >= c0n2 only at L == 1: the prior, always visible)
-                            for (int base = tid; base < K2; base += blockDim.x * 2) {
-                                const int i0 = base, i1 = base + blockDim.x;
-                                const bool t0 = vis && i0 < c0n2, t1 = vis && i1 < c0n2;
-                                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-                                float2 p0 = make_float2(0.f, 0.f), p1 = p0;
-                                if (t0) q0 = ll_ld(src0 + 2 * i0);
-                                if (t1) q1 = ll_ld(src0 + 2 * i1);
-                                if (i0 >= c0n2 && i0 < K2) p0 = __ldg(src1 + (i0 - c0n2));
-                                if (i1 >= c0n2 && i1 < K2) p1 = __ldg(src1 + (i1 - c0n2));
-                                if (i0 < K2) A2[r * K2 + i0] = t0 ? ll_wait(q0, src0 + 2 * i0, step - 1) : p0;
-                                if (i1 < K2) A2[r * K2 + i1] = t1 ? ll_wait(q1, src0 + 2 * i1, step - 1) : p1;
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int o = base + u * blockDim.x;
+                                if (o < total) A2[o] = ptr[u] ? ll_wait(q[u], ptr[u], step - 1) : pv[u];
                             }
                         }
                     }

@@ -482,3 +482,26 @@ def test_scanline_stage_kernel_rows_against_oracle(B):
         assert_latents_match(out.cpu(), yhat_o)
         sizes[lanes] = len(bs)
     assert sizes[0] >= sizes[1]
+
+
+def test_scanline_one_launch_decoder_on_damaged_streams():
+    """The in-kernel chunk decoder (lanes = 0 on the stage kernel) must come back on damaged input: a truncated container is
+    refused before anything is launched, flipped stream words decode to different latents or raise -- neither hangs."""
+    from cbench_basic_b200._native import StreamError
+    c = _random_case(12, 1, 2, 6, 7, 77, method="scanline")
+    coder = make_coder(c, 0, method="scanline")
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+    assert torch.equal(coder.decode(bs, prior=prior), yhat_enc * 1.0 + 0.0)
+    with pytest.raises((StreamError, ValueError)):
+        coder.decode(bs[:len(bs) // 2], prior=prior)
+    bad = bytearray(bs)
+    for at in range(len(bad) - 40, len(bad) - 8):   # the tail of the word region
+        bad[at] ^= 0x5A
+    try:
+        out = coder.decode(bytes(bad), prior=prior)
+    except (StreamError, ValueError):
+        out = None
+    assert out is None or not torch.equal(out, yhat_enc * 1.0 + 0.0)
+    # the coder is still usable afterwards
+    assert torch.equal(coder.decode(bs, prior=prior), yhat_enc * 1.0 + 0.0)
