@@ -489,6 +489,14 @@ def run_ours(args, rank, world, local_rank):
                 outs.append((bs, coder.decode(bs, prior=up, **kw(level))))
         return outs
 
+    def step_zero_copy():   # the opt-in hand-over: encode returns a view of its page-locked buffer, decode uploads out of it
+        outs = []
+        for level in levels:
+            for uy, up in res_units:
+                view = coder.encode(uy, prior=up, zero_copy=True, **kw(level))
+                outs.append(coder.decode(view, prior=up, **kw(level)))
+        return outs
+
     out_host = torch.empty(B, C_, H, W, dtype=torch.float32).pin_memory()
     if tiles is not None:
         host_units = [(yp[:, :, a:b].contiguous().pin_memory(), pp[:, :, a:b].contiguous().pin_memory()) for a, b in tiles]
@@ -550,6 +558,12 @@ def run_ours(args, rank, world, local_rank):
         ms, enc_ms = timed(step_resident, args.steps, args.warmup, split=single)
         launches = N.launch_count() // (args.steps + args.warmup)
     ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 2)
+    ms_zc = None
+    if method != "combined":
+        try:
+            ms_zc, _ = timed(step_zero_copy, max(2, args.steps // 2), 2)
+        except (ValueError, TypeError):
+            ms_zc = None
 
     # sizes gather: the one collective of the path
     sizes = sharding.gather_sizes([stream_bytes], device=dev)
@@ -701,6 +715,10 @@ def run_ours(args, rank, world, local_rank):
                                            "reference API), y_hat left on the device"},
             "e2e": {"value": pix_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "zero_copy": None if ms_zc is None else {
+                "ms_per_step": ms_zc, "value": pix_total / (ms_zc * 1e-3) / 1e6, "unit": "Mpixel/s", "rank": 0,
+                "what": "same step through the opt-in hand-over: encode(zero_copy=True) returns a memoryview of the coder's page-locked "
+                        "buffer instead of a bytes object, decode() uploads straight out of it (no host copy of the stream in either call)"},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_coder": coder_roof, "phases": phases,
             "coder_lane_sweep": sweep, "cpu_baseline": cpu, "delta_bpp": dbpp, "stream_bytes_per_rank": [s[0] for s in sizes],
             "bpp": sum(s[0] for s in sizes) * 8 / pix_total,

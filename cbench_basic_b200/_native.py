@@ -157,6 +157,17 @@ def last_output(handle, prefix=b""):
     return out
 
 
+def last_output_view(handle):
+    """Zero-copy form of last_output(): a read-only memoryview over the coder's page-locked staging buffer (the device-to-host
+    copy is awaited, nothing else moves).  Valid until the next encoding call on the same coder; a decoder given this view
+    uploads straight out of it (no staging copy either: the library recognises page-locked memory)."""
+    ptr, n = C.c_void_p(), C.c_int64()
+    check(lib().basic_coder_last_output(handle, C.byref(ptr), C.byref(n)))
+    if not n.value:
+        return memoryview(b"")
+    return memoryview((C.c_uint8 * n.value).from_address(ptr.value)).toreadonly()
+
+
 PHASES = ("context_model", "quantise", "coder_encode", "coder_decode", "host_set_stream", "host_staging")
 
 

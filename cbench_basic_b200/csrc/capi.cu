@@ -197,6 +197,7 @@ struct basic_coder {
     void *pinned = nullptr;  // 256 B of pinned host memory for status / length read-back
     // pinned host staging (grow-only): encoded output kept for basic_coder_last_output, and the stream being decoded
     uint8_t *host_out = nullptr, *host_in = nullptr;
+    const uint8_t *host_src = nullptr;  // where the current stream's bytes can be read on the host: host_in, or the caller's page-locked buffer
     size_t host_out_cap = 0, host_in_cap = 0;
     int64_t last_len = 0;
     std::vector<cudaEvent_t> out_events;  // one per chunk of the last device-to-host delivery into host_out
@@ -871,7 +872,22 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
     BASIC_TRY(reserve_pinned(&c->host_in, &c->host_in_cap, (size_t)len + 64));
     if ((size_t)len + 64 > c->stream_dev.cap) BASIC_CUDA(cudaStreamSynchronize(s));
     BASIC_TRY(c->stream_dev.reserve((size_t)len + 64));
-    if (len && is_device_ptr(encoded)) {
+    c->host_src = c->host_in;
+    if (len && is_pinned_host_ptr(encoded)) {
+        // page-locked input (e.g. the zero-copy view an encoder hands out): no staging copy -- one upload on the copy stream,
+        // directories parsed where the bytes are.  The caller keeps the buffer alive while this stream is being decoded.
+        if (!c->in_event) BASIC_CUDA(cudaEventCreateWithFlags(&c->in_event, cudaEventDisableTiming));
+        if (!c->copy_stream) BASIC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
+        BASIC_CUDA(cudaMemsetAsync(c->stream_dev.as<uint8_t>() + len, 0, 64, c->copy_stream));
+        BASIC_CUDA(cudaEventRecord(c->in_event, c->copy_stream));
+        BASIC_CUDA(cudaStreamWaitEvent(s, c->in_event, 0));
+        c->host_src = encoded;
+        c->stream_len = len;
+        c->stream_lanes = lanes;
+        c->stream_set = true;
+        goto staged;
+    } else if (len && is_device_ptr(encoded)) {
         BASIC_CUDA(cudaMemcpyAsync(c->host_in, encoded, (size_t)len, cudaMemcpyDeviceToHost, s));
         BASIC_CUDA(cudaMemcpyAsync(c->stream_dev.p, encoded, (size_t)len, cudaMemcpyDeviceToDevice, s));
         BASIC_CUDA(cudaStreamSynchronize(s));
@@ -941,7 +957,7 @@ staged:
         c->stream_pos = -1;  // state is initialised by the first decode_stream launch
     } else {
         uint32_t magic = 0;
-        if (len >= 4) memcpy(&magic, c->host_in, 4);
+        if (len >= 4) memcpy(&magic, c->host_src, 4);
         if (magic != kMagic && magic != kMagic2 && magic != kMagic0) { c->stream_set = false; set_error("not a multi-lane (BLS) container"); return BASIC_ERR_STREAM; }
         c->stream_fp16 = magic == kMagic2;
         c->stream_pos = 4;
@@ -972,7 +988,7 @@ int basic_coder_decode_stream(basic_coder *c, const int32_t *indexes, int64_t n,
     } else {
         if (n > 0 || c->stream_pos < c->stream_len) {
             SegInfo si;
-            BASIC_TRY(parse_segment(c->host_in + c->stream_pos, c->stream_len - c->stream_pos, 1, &n, &si));
+            BASIC_TRY(parse_segment(c->host_src + c->stream_pos, c->stream_len - c->stream_pos, 1, &n, &si));
             ProfScope ps(PROF_DECODE, s);
             BASIC_TRY(launch_bls_decode(c->rt, c->bypass, (int)c->bypass_precision, c->stream_dev.as<unsigned char>() + c->stream_pos,
                                         si.len, d_idx, n, si.cs[0], si.n_chunks, 1, 0, nullptr, nullptr, d_out, &ds->status,
@@ -1573,7 +1589,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     }
     SegInfo si;
     if (lanes != BASIC_LANES_REFERENCE) {
-        BASIC_TRY(parse_segment(c->host_in + c->stream_pos, c->stream_len - c->stream_pos, S, slice_n.data(), &si));
+        BASIC_TRY(parse_segment(c->host_src + c->stream_pos, c->stream_len - c->stream_pos, S, slice_n.data(), &si));
         BASIC_TRY(c->carry_x.reserve((size_t)si.n_chunks * 128 + 16));
         BASIC_TRY(c->carry_wp.reserve((size_t)si.n_chunks * 4 + 16));
     }

@@ -90,6 +90,18 @@ inline bool is_device_ptr(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Page-locked (cudaHostAlloc / cudaHostRegister) host memory: the DMA engines read it directly, no staging copy needed.
+inline bool is_pinned_host_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 // Per-table metadata, one 16-byte record (a single LDS.128 / LDG.128 in the kernels).
 struct __align__(16) TableMeta {
     uint32_t cdf_base;  // first entry of this table inside the packed u16 CDF array

@@ -368,7 +368,10 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
         with self.profiler.start_time_profile("time_data_preprocess_encode"):
             return self._inverse_transform(torch.round(self._transform(input, quantizer_params)), quantizer_params)
 
-    def encode(self, input, *args, prior=None, pgm=None, quantizer_params=None, return_yhat=False, **kwargs) -> bytes:
+    def encode(self, input, *args, prior=None, pgm=None, quantizer_params=None, return_yhat=False, zero_copy=False, **kwargs) -> bytes:
+        """pgm_coder.py:912-951 + the framing of :581-597.  zero_copy=True (ours, opt-in; needs a configuration that writes no
+        framing header): instead of `bytes` a read-only memoryview over the coder's page-locked output buffer, valid until the
+        next encode() of this object -- decode() takes it as it is and uploads straight from it."""
         assert hasattr(self, "ans_encoder"), "Not Initialized! Should call self.update_state() before coding!"
         if prior is None:
             raise ValueError("prior should not be None!")
@@ -394,7 +397,9 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
             N.check(N.lib().basic_ypath_encode(h, self._ctx, y.data_ptr(), p.data_ptr(), B, Cc, H, W, self.lanes, None, 0,
                                                C.byref(out_len), yhat.data_ptr() if return_yhat else None,
                                                self._stream()))
-            byte_string = N.last_output(h, prefix=head)
+            if zero_copy and head:
+                raise ValueError("zero_copy needs force_input_prior_shape_aligned=True or fixed_input_shape (no framing header)")
+            byte_string = N.last_output_view(h) if zero_copy else N.last_output(h, prefix=head)
         if return_yhat:
             return byte_string, self._inverse_transform(yhat, quantizer_params)
         return byte_string

@@ -505,3 +505,21 @@ def test_scanline_one_launch_decoder_on_damaged_streams():
     assert out is None or not torch.equal(out, yhat_enc * 1.0 + 0.0)
     # the coder is still usable afterwards
     assert torch.equal(coder.decode(bs, prior=prior), yhat_enc * 1.0 + 0.0)
+
+
+def test_zero_copy_view_equals_bytes():
+    """encode(zero_copy=True): a read-only view of the coder's page-locked buffer with the bytes of the plain call; decode() takes
+    the view (uploading straight out of page-locked memory) and a bytes copy of it alike."""
+    c = _random_case(12, 1, 2, 8, 8, 5)
+    coder = make_coder(c, 0, method="checkerboard")
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+    view = coder.encode(y, prior=prior, zero_copy=True)
+    assert isinstance(view, memoryview) and view.readonly and bytes(view) == bs
+    out_v = coder.decode(view, prior=prior)
+    out_b = coder.decode(bs, prior=prior)
+    assert torch.equal(out_v, out_b) and torch.equal(out_v, yhat_enc * 1.0 + 0.0)
+    coder_h = make_coder(c, 0, method="checkerboard")
+    coder_h.force_input_prior_shape_aligned = False          # a framing header cannot be prepended without a copy
+    with pytest.raises(ValueError):
+        coder_h.encode(y, prior=prior, zero_copy=True)
