@@ -205,6 +205,7 @@ struct basic_coder {
     cudaEvent_t in_event = nullptr;  // completion of the last upload out of host_in
     cudaStream_t copy_stream = nullptr;  // the upload runs beside whatever is already queued on the caller's stream
     cudaEvent_t ev_start = nullptr, ev_prior = nullptr, ev_y = nullptr;  // host inputs of the y path uploaded on copy_stream
+    cudaEvent_t ev_sub[4] = {nullptr, nullptr, nullptr, nullptr};       // ... in image sub-batches: one event per sub-batch
     // cache for cache=1 / flush()
     std::vector<int32_t> cache_sym, cache_idx;         // lanes = 1: concatenated operands (device copies made at flush)
     std::vector<std::vector<uint8_t>> cache_segments;  // multi-lane: encoded segments
@@ -244,8 +245,26 @@ int to_device(const T *p, size_t count, DevBuf &staging, cudaStream_t s, const T
 // Host inputs of the y path: uploaded on the coder's copy stream (prior first, then y), so that the caller's stream only
 // waits for what the next kernel needs -- the first group's context model runs while y is still on the bus, and in the
 // decoder the stream's staging copy runs while the prior is.  Device inputs pass through.
+// Images are independent, so a large batch is uploaded in sub-batches (plan->n > 1: prior and y of sub-batch 0, then of
+// sub-batch 1, ... with one event each) and the caller runs the groups of a sub-batch while the next one is on the bus.
+struct SubPlan {
+    int n = 1;
+    int b0[5] = {0, 0, 0, 0, 0};   // sub-batch i = images [b0[i], b0[i + 1])
+    bool host = false;             // events ev_sub[i] were recorded: the caller's stream waits for them itself
+};
+
+SubPlan plan_subs(int B, bool host_inputs, bool eligible)
+{
+    static const int forced = [] { const char *e = getenv("BASIC_SUB_BATCHES"); return e ? atoi(e) : 0; }();   // A/B switch (1 = off)
+    SubPlan p;
+    p.n = !host_inputs || !eligible || B < 8 ? 1 : (B >= 16 ? 4 : 2);
+    if (forced > 0 && host_inputs && eligible) p.n = std::max(1, std::min(std::min(forced, 4), B));
+    for (int i = 0; i <= p.n; ++i) p.b0[i] = (int)((long long)i * B / p.n);
+    return p;
+}
+
 int upload_inputs(basic_coder *c, const float *y, size_t n_y, const float *prior, size_t n_prior, cudaStream_t s,
-                  const float **d_y, const float **d_prior, bool *y_pending)
+                  const float **d_y, const float **d_prior, bool *y_pending, SubPlan *plan = nullptr, int B = 1)
 {
     *y_pending = false;
     const bool y_host = y && !is_device_ptr(y), p_host = prior && !is_device_ptr(prior);
@@ -253,23 +272,36 @@ int upload_inputs(basic_coder *c, const float *y, size_t n_y, const float *prior
     *d_prior = prior;
     if (!y_host && !p_host) return BASIC_OK;
     if (!c->copy_stream) BASIC_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t *e : {&c->ev_start, &c->ev_prior, &c->ev_y})
+    for (cudaEvent_t *e : {&c->ev_start, &c->ev_prior, &c->ev_y, &c->ev_sub[0], &c->ev_sub[1], &c->ev_sub[2], &c->ev_sub[3]})
         if (!*e) BASIC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (p_host) BASIC_TRY(c->prior_dev.reserve(n_prior * sizeof(float) + 16));
     if (y_host) BASIC_TRY(c->y_dev.reserve(n_y * sizeof(float) + 16));
     // the staging buffers may still be read by what an earlier call queued on `s`
     BASIC_CUDA(cudaEventRecord(c->ev_start, s));
     BASIC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_start, 0));
+    if (p_host) *d_prior = c->prior_dev.as<float>();
+    if (y_host) *d_y = c->y_dev.as<float>();
+    if (plan && plan->n > 1) {
+        const size_t yi = n_y / (size_t)B, pi = n_prior / (size_t)B;   // floats per image
+        for (int i = 0; i < plan->n; ++i) {
+            const size_t b0 = (size_t)plan->b0[i], nb = (size_t)(plan->b0[i + 1] - plan->b0[i]);
+            if (p_host)
+                BASIC_CUDA(cudaMemcpyAsync(c->prior_dev.as<float>() + b0 * pi, prior + b0 * pi, nb * pi * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+            if (y_host)
+                BASIC_CUDA(cudaMemcpyAsync(c->y_dev.as<float>() + b0 * yi, y + b0 * yi, nb * yi * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+            BASIC_CUDA(cudaEventRecord(c->ev_sub[i], c->copy_stream));
+        }
+        plan->host = true;
+        return BASIC_OK;
+    }
     if (p_host) {
         BASIC_CUDA(cudaMemcpyAsync(c->prior_dev.p, prior, n_prior * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
         BASIC_CUDA(cudaEventRecord(c->ev_prior, c->copy_stream));
         BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_prior, 0));
-        *d_prior = c->prior_dev.as<float>();
     }
     if (y_host) {
         BASIC_CUDA(cudaMemcpyAsync(c->y_dev.p, y, n_y * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
         BASIC_CUDA(cudaEventRecord(c->ev_y, c->copy_stream));
-        *d_y = c->y_dev.as<float>();
         *y_pending = true;  // the caller makes `s` wait for ev_y before the first kernel that reads y
     }
     return BASIC_OK;
@@ -1381,17 +1413,19 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
     const float *d_y, *d_prior;
     bool y_pending = false;
     g_trace.mark("enter", s);
-    BASIC_TRY(upload_inputs(c, y, n, prior, 2 * n, s, &d_y, &d_prior, &y_pending));
-    g_trace.mark("uploaded", s);
-    float *buf = c->buf.as<float>(), *params = c->params.as<float>();
-    int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
-    const float *params_src = params;
     // tensor-core context model: it reads channels-last copies of the prior (made once) and of the y_hat buffer
     // (refreshed after every group's write-back)
     if (model) ctx_set_run_precision(*model->m, ctx_precision(*model->m));
     // few-row stages (scanline-like maps) take the persistent stage kernel -- exact FP32, whatever precision is configured
     const bool scan = model && ctx_scan_supported(*model->m, B);
     const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
+    // host inputs of a large batch arrive in image sub-batches; the groups of a sub-batch run while the next one is on the bus
+    SubPlan subs = plan_subs(B, (y && !is_device_ptr(y)) || (prior && !is_device_ptr(prior)), model && !scan);
+    BASIC_TRY(upload_inputs(c, y, n, prior, 2 * n, s, &d_y, &d_prior, &y_pending, &subs, B));
+    g_trace.mark("uploaded", s);
+    float *buf = c->buf.as<float>(), *params = c->params.as<float>();
+    int32_t *sym = c->sym_all.as<int32_t>(), *idx = c->idx_all.as<int32_t>();
+    const float *params_src = params;
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1409,7 +1443,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         BASIC_CUDA(cudaMemsetAsync(buf, 0, n * 4, s));
         if (tc) {  // (in the operand format of the current mode: redone by the 3xTF32 fallback)
             BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
-            BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
+            if (subs.n == 1) BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
         }
         if (scan) {
             // many-stage map (scanline, the serial JointAR coder): ONE persistent launch walks every stage -- context model,
@@ -1427,6 +1461,44 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
             }
             ProfScope ps(PROF_CTX, s);
             return ctx_scan_run(*model->m, 0, S, buf, d_prior, B, params, d_y, sym, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s);
+        }
+        if (subs.n > 1) {
+            // sub-batch by sub-batch (images are independent; the stream order -- group-major, image-major inside a group -- is
+            // kept by where the symbols are written)
+            const size_t img = (size_t)C * HW, pimg = tc ? ctx_cl_elems(1, 2 * C, HW) : 2 * img;
+            const size_t cl_y = tc ? ctx_cl_elems(1, C, HW) : 0, cl_p = tc ? ctx_cl_elems(1, 2 * C, HW) : 0;
+            std::vector<int64_t> npos((size_t)S);
+            std::vector<const int32_t *> posv((size_t)S);
+            for (int g = 0; g < S; ++g) {
+                BASIC_TRY(ctx_stage_positions(*model->m, g, &posv[(size_t)g], &npos[(size_t)g]));
+                slice_n.push_back((int64_t)B * npos[(size_t)g]);
+            }
+            for (int i = 0; i < subs.n; ++i) {
+                const int b0 = subs.b0[i], nb = subs.b0[i + 1] - b0;
+                if (nb <= 0) continue;
+                if (subs.host) BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_sub[i], 0));
+                if (tc) BASIC_TRY(ctx_to_cl(*model->m, d_prior + b0 * 2 * img, prior_cl + b0 * cl_p, nb, 2 * C, s));
+                size_t at = 0;
+                for (int g = 0; g < S; ++g) {
+                    {
+                        ProfScope ps(PROF_CTX, s);
+                        BASIC_TRY(ctx_stage_params(*model->m, g, buf + b0 * img, d_prior + b0 * 2 * img, nb, params + b0 * pimg, s,
+                                                   tc ? buf_cl + b0 * cl_y : nullptr, tc ? prior_cl + b0 * cl_p : nullptr, tc));
+                    }
+                    const int64_t n_pos = npos[(size_t)g];
+                    if (n_pos > 0) {
+                        ProfScope ps(PROF_GAUSS, s);
+                        const size_t o = at + (size_t)b0 * n_pos;
+                        BASIC_TRY(launch_quantize_index(d_y + b0 * img, params_src + b0 * pimg, posv[(size_t)g], n_pos, nb, C, HW, c->d_scale.as<float>(),
+                                                        (int)c->h_scale.size(), sym + o, idx + o, buf + b0 * img, c->sm_count, s, tc ? 1 : 0,
+                                                        tc ? ctx_perm(*model->m) : nullptr));
+                        if (tc && g + 1 < S) BASIC_TRY(ctx_to_cl(*model->m, buf + b0 * img, buf_cl + b0 * cl_y, nb, C, s));
+                    }
+                    at += (size_t)B * n_pos;
+                }
+                done = at;
+            }
+            return BASIC_OK;
         }
         for (int g = 0; g < S; ++g) {
             const int32_t *pos = nullptr;
@@ -1528,7 +1600,6 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const float *d_prior, *d_none;
     bool none_pending = false;
     g_trace.mark("enter", s);
-    BASIC_TRY(upload_inputs(c, nullptr, 0, prior, 2 * n, s, &d_none, &d_prior, &none_pending));
     // the reconstruction is built in place when the caller's output lives on the device
     const bool direct = is_device_ptr(yhat_out) && (reinterpret_cast<uintptr_t>(yhat_out) & 255) == 0;
     float *buf = direct ? yhat_out : c->buf.as<float>(), *params = c->params.as<float>();
@@ -1557,6 +1628,10 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const bool scan = model && ctx_scan_supported(*model->m, B) &&
                       (lanes == BASIC_LANES_REFERENCE || ctx_run_precision(*model->m) == BASIC_CTX_FP32);
     const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
+    // a host prior of a large batch arrives in image sub-batches: the first group's context model of a sub-batch runs while
+    // the next one is on the bus
+    SubPlan subs = plan_subs(B, prior && !is_device_ptr(prior), model && !scan);
+    BASIC_TRY(upload_inputs(c, nullptr, 0, prior, 2 * n, s, &d_none, &d_prior, &none_pending, &subs, B));
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)
         BASIC_TRY(c->buf_cl.reserve(ctx_cl_elems(B, C, HW) * 4));
@@ -1564,13 +1639,26 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         buf_cl = c->buf_cl.as<float>();
         prior_cl = c->prior_cl.as<float>();
         BASIC_CUDA(cudaMemsetAsync(buf_cl, 0, ctx_cl_elems(B, C, HW) * 4, s));
-        BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
+        if (subs.n == 1) BASIC_TRY(ctx_to_cl(*model->m, d_prior, prior_cl, B, 2 * C, s));
     }
     // the first group's parameters do not depend on the stream: queue them, then stage the stream into pinned
     // memory and upload it while the GPU is busy
     // (a multi-lane stream on the stage kernel may be decoded inside ONE launch: decided once the segment is parsed)
     bool g0_done = false;
-    if (model && !(scan && lanes != BASIC_LANES_REFERENCE)) {
+    if (model && subs.n > 1) {
+        const size_t img = (size_t)C * HW, pimg = tc ? ctx_cl_elems(1, 2 * C, HW) : 2 * img;
+        const size_t cl_y = tc ? ctx_cl_elems(1, C, HW) : 0, cl_p = tc ? ctx_cl_elems(1, 2 * C, HW) : 0;
+        ProfScope ps(PROF_CTX, s);
+        for (int i = 0; i < subs.n; ++i) {
+            const int b0 = subs.b0[i], nb = subs.b0[i + 1] - b0;
+            if (nb <= 0) continue;
+            if (subs.host) BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_sub[i], 0));
+            if (tc) BASIC_TRY(ctx_to_cl(*model->m, d_prior + b0 * 2 * img, prior_cl + b0 * cl_p, nb, 2 * C, s));
+            BASIC_TRY(ctx_stage_params(*model->m, 0, buf + b0 * img, d_prior + b0 * 2 * img, nb, params + b0 * pimg, s,
+                                       tc ? buf_cl + b0 * cl_y : nullptr, tc ? prior_cl + b0 * cl_p : nullptr, tc));
+        }
+        g0_done = true;
+    } else if (model && !(scan && lanes != BASIC_LANES_REFERENCE)) {
         ProfScope ps(PROF_CTX, s);
         if (scan) BASIC_TRY(ctx_scan_run(*model->m, 0, 1, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s));
         else BASIC_TRY(ctx_stage_params(*model->m, 0, buf, d_prior, B, params, s, buf_cl, prior_cl, tc));
