@@ -546,9 +546,22 @@ __device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<f
             const Tab<false>::addr_t cd = tb.cdf_at(mt[q].x);
             const int nsyms = (int)(mt[q].z & 0xffffu) - 1, maxv = nsyms - 1;
             const uint32_t cum = x & pmask;
+            // bucket LUT -> four CDF entries at once (one round trip; the 16-bit CDF stores 2^16 as 0: guarded by nsyms) -> select;
+            // further probes only in tails of width-1 symbols
             int s = (int)Tab<false>::ld16<0>(tb.lut_at(mt[q].y + (cum >> ((mt[q].z >> 16) & 0xffu))));
-            while (s + 1 < nsyms && Tab<false>::ld16<2>(cd + 2 * s) <= cum) ++s;   // (the 16-bit CDF stores 2^16 as 0: guarded by nsyms)
-            const uint32_t start = Tab<false>::ld16<0>(cd + 2 * s), next = Tab<false>::ld16<2>(cd + 2 * s);
+            const Tab<false>::addr_t e = cd + 2 * s;
+            const uint32_t c0 = Tab<false>::ld16<0>(e), c1 = Tab<false>::ld16<2>(e), c2 = Tab<false>::ld16<4>(e), c3 = Tab<false>::ld16<6>(e);
+            const bool a1 = s + 1 < nsyms && c1 <= cum;
+            const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
+            const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
+            uint32_t start = a2 ? c2 : a1 ? c1 : c0, next = a2 ? c3 : a1 ? c2 : c1;
+            s += (int)a1 + (int)a2;
+            if (a3) {
+                ++s;
+                while (s + 1 < nsyms && Tab<false>::ld16<2>(cd + 2 * s) <= cum) ++s;
+                start = Tab<false>::ld16<0>(cd + 2 * s);
+                next = Tab<false>::ld16<2>(cd + 2 * s);
+            }
             const uint32_t freq = (uint16_t)(next - start);
             if (active) x = freq * (x >> prec) + cum - start;
             refill(active && x < kRansL);
