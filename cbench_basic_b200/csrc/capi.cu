@@ -81,7 +81,7 @@ struct ScanDecodeHost {   // (ctx.cuh)
 int ctx_scan_run(CtxModel &, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
                  int32_t *idx, const float *d_scale_table, int n_scales, cudaStream_t, const int32_t *dq_sym = nullptr,
                  const ScanDecodeHost *dec = nullptr);
-bool ctx_scan_decode_supported(const CtxModel &, int n_chunks, int bypass_precision, int freq_precision);
+bool ctx_scan_decode_supported(const CtxModel &, int B, int n_chunks, int bypass_precision, int freq_precision);
 
 struct TansTables;
 TansTables *tans_new();
@@ -1682,7 +1682,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         BASIC_TRY(c->carry_wp.reserve((size_t)si.n_chunks * 4 + 16));
     }
     bool fused = false;
-    if (scan && lanes != BASIC_LANES_REFERENCE && ctx_scan_decode_supported(*model->m, si.n_chunks, (int)c->bypass_precision, c->rt.precision)) {
+    if (scan && lanes != BASIC_LANES_REFERENCE && ctx_scan_decode_supported(*model->m, B, si.n_chunks, (int)c->bypass_precision, c->rt.precision)) {
         // the whole decode in one launch: context model, scale indexes, the coder's chunk warps and the write-back (ctx.cu)
         ProfScope ps(PROF_CTX, s);
         ScanDecodeHost dh = {&c->rt, c->bypass, c->stream_dev.as<unsigned char>() + c->stream_pos, si.len, si.n_chunks, si.cs.data(), &ds->status};

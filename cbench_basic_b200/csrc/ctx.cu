@@ -420,6 +420,8 @@ struct ScanArgs {
     uint32_t call_tag;           // tag of every y_hat word of this coding call
     long long *timing;           // SCAN_TIMING builds
     ScanDecode dec;              // n_chunks > 0: the decoder's single launch
+    int CB;                      // k_scan_blocks: channel blocks per row block (grid = row blocks x CB)
+    const float *wc;             // k_scan_blocks: the convolution's weights with only the visible taps, N-major [2C][ntaps * C]
 };
 
 // One 16-byte load of two {value, tag} words (L2, never L1).  A gather issues a batch of these and only then looks at the tags,
@@ -866,6 +868,270 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
 #endif
 }
 
+// ---- the same walk for stages of 5 .. 128 rows (a batch of scanline images: configs[3]'s scanline level codes 64 crops at
+// once): a 2-D decomposition.  The rows of a stage are cut into blocks of kBlkRows; CTA (rb, cb) of a row-blocks x CB grid
+// computes, for the rows of block rb, the channel pairs cb, cb + CB, ... of every layer.  A CTA owns 1 / CB of the weights -- too
+// much to keep resident -- so each warp streams the two weight rows of a pair from L2 once per stage against all rows of the
+// block held in shared memory (k_scan_stages with R rows would gather every row in every CTA: 322 MB of L2 traffic per stage at
+// 64 rows; here: weights x row blocks + vectors x CB = ~100 MB).  Exchange, tags, quantiser and the in-kernel chunk decoder are
+// those of k_scan_stages; vectors only travel inside a row block.
+constexpr int kBlkRows = 8, kBlkMaxRows = 128, kBlkInFlight = 4;
+
+template <int R>
+__device__ __forceinline__ void blk_pair(const float *__restrict__ w0g, const float *__restrict__ w1g, const float *__restrict__ A, int K,
+                                         int lane, float &m0, float &m1)
+{
+    const int K4 = K >> 2;
+    const float4 *w0 = reinterpret_cast<const float4 *>(w0g), *w1 = reinterpret_cast<const float4 *>(w1g);
+    const float4 *A4 = reinterpret_cast<const float4 *>(A);
+    float a0[R], a1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a0[r] = a1[r] = 0.f;
+    for (int i0 = lane; i0 < K4; i0 += 32 * kBlkInFlight) {
+        float4 x0[kBlkInFlight], x1[kBlkInFlight];
+#pragma unroll
+        for (int u = 0; u < kBlkInFlight; ++u) {
+            const int i = i0 + 32 * u;
+            const bool ok = i < K4;
+            x0[u] = ok ? __ldg(w0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x1[u] = ok ? __ldg(w1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kBlkInFlight; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < K4) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 av = A4[r * K4 + i];
+                    a0[r] = fmaf(av.x, x0[u].x, a0[r]); a0[r] = fmaf(av.y, x0[u].y, a0[r]);
+                    a0[r] = fmaf(av.z, x0[u].z, a0[r]); a0[r] = fmaf(av.w, x0[u].w, a0[r]);
+                    a1[r] = fmaf(av.x, x1[u].x, a1[r]); a1[r] = fmaf(av.y, x1[u].y, a1[r]);
+                    a1[r] = fmaf(av.z, x1[u].z, a1[r]); a1[r] = fmaf(av.w, x1[u].w, a1[r]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            a0[r] += __shfl_xor_sync(0xffffffffu, a0[r], o);
+            a1[r] += __shfl_xor_sync(0xffffffffu, a1[r], o);
+        }
+    }
+    m0 = a0[0];
+    m1 = a1[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) if (lane == r) { m0 = a0[r]; m1 = a1[r]; }
+}
+
+template <bool DEC>
+__global__ void __launch_bounds__(kScanWarps * 32)
+k_scan_blocks(const __grid_constant__ ScanArgs S)
+{
+    extern __shared__ __align__(16) float A[];   // [kBlkRows][Kmax]
+    __shared__ int sr_b[2][kBlkMaxRows], sr_hw[2][kBlkMaxRows], sr_i[2][kBlkMaxRows];   // the rows of the current / next stage (all of them: the chunk decoder needs any)
+    __shared__ uint32_t sr_tap[2][kBlkMaxRows], sr_grp[2][kBlkMaxRows];
+    __shared__ uint32_t s_win[kScanDecSlots][64];
+    __shared__ float s_tab[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x, nctas = gridDim.x, CB = S.CB, rb = cta / CB, cb = cta - rb * CB;
+    const int C = S.C;
+    for (int i = tid; i < S.qz.n_scales && i < 256; i += blockDim.x) s_tab[i] = S.qz.scale_table[i];
+    RowsQuant qz = S.qz;
+    // ---- decoder warps (single-launch decoding), as in k_scan_stages
+    const int dslot = kScanWarps - 1 - warp;
+    const int dk = dslot * nctas + cta;
+    const bool dec_warp = DEC && dslot < kScanDecSlots && dk < S.dec.n_chunks;
+    uint32_t dx = 0, dwp = 0, dwend = 0, dwbase = 0;
+    int dst = 0;
+    const uint32_t *d_units = nullptr;
+    Tab<false> dtb;
+    if (DEC && dec_warp) {
+        const uint32_t *end_word = reinterpret_cast<const uint32_t *>(S.dec.seg) + 2 + S.dec.seg_slices;
+        const uint32_t *states = end_word + S.dec.n_chunks;
+        const long long words_at = kSegHdr + 4ll * S.dec.seg_slices + 4ll * S.dec.n_chunks + 128ll * S.dec.n_chunks;
+        d_units = reinterpret_cast<const uint32_t *>(S.dec.seg + words_at);
+        dwend = end_word[dk];
+        dwp = dk ? end_word[dk - 1] : 0;
+        if (dwend < dwp || words_at + 2ll * dwend > S.dec.seg_cap) { dst |= 4; dwend = dwp = 0; }
+        dx = states[(size_t)dk * 32 + lane];
+        dtb.init(S.dec.blob, nullptr, S.dec.meta_bytes, S.dec.cdf16_bytes);
+    }
+    if (S.dq_sym) {   // decoder launched stage by stage: y_hat of the previous stage first (every CTA writes the same words)
+        const int2 pc = S.stage_cells[S.g0 - 1];
+        const int per_b = C * pc.y;
+        for (int e = tid; e < S.B * per_b; e += blockDim.x) {
+            const int row = e / C, c = e - row * C, b = row / pc.y, i = row - b * pc.y;
+            const int hw = S.cell_hw[pc.x + i];
+            const float mean = __uint_as_float(__ldcg(&S.vec[3][(size_t)row * 2 * C + 2 * c].x));
+            const float v = __fadd_rn(__fadd_rn((float)S.dq_sym[(size_t)b * per_b + (size_t)c * pc.y + i], mean), 0.0f);
+            S.buf[((long long)b * C + c) * S.HW + hw] = v;
+            S.yhat_pm[((long long)b * S.HW + hw) * C + c] = make_uint2(__float_as_uint(v), S.call_tag);
+        }
+        __syncthreads();
+    }
+    uint32_t step = S.step0;
+    auto load_rows = [&](int g, int slot) {
+        const int2 sc = S.stage_cells[g];
+        for (int row = tid; row < S.B * sc.y; row += blockDim.x) {
+            const int b = row / sc.y, i = row - b * sc.y, cell = sc.x + i;
+            sr_b[slot][row] = b; sr_i[slot][row] = i; sr_hw[slot][row] = S.cell_hw[cell]; sr_tap[slot][row] = S.cell_tap[cell];
+            sr_grp[slot][row] = S.cell_grp[cell];
+        }
+    };
+    load_rows(S.g0, S.g0 & 1);
+    __syncthreads();
+    for (int g = S.g0; g < S.g1; ++g) {
+        const int2 sc = S.stage_cells[g];
+        const int rows_total = S.B * sc.y;
+        const long long slice = (long long)S.B * qz.C * sc.y;
+        const int *s_b = sr_b[g & 1], *s_hw = sr_hw[g & 1], *s_i = sr_i[g & 1];
+        const uint32_t *s_tap = sr_tap[g & 1], *s_grp = sr_grp[g & 1];
+        if (g + 1 < S.g1) load_rows(g + 1, (g + 1) & 1);
+        if (DEC && dec_warp) {
+            dwbase = dwp & ~1u;
+            const uint32_t u0 = dwbase >> 1, u_lim = (dwend + 1) >> 1;
+            s_win[dslot][lane] = u0 + lane < u_lim ? __ldg(d_units + u0 + lane) : 0u;
+            s_win[dslot][lane + 32] = u0 + 32 + lane < u_lim ? __ldg(d_units + u0 + 32 + lane) : 0u;
+            __syncwarp();
+        }
+        const int r0 = rb * kBlkRows, rows = min(kBlkRows, rows_total - r0);   // this CTA's rows of the stage (<= 0: none)
+#pragma unroll 1
+        for (int L = 0; L < 4; ++L) {
+            ++step;
+            const int K = S.K[L], N = S.N[L], npairs = N >> 1;
+            if (rows <= 0 || cb >= npairs) continue;   // nothing of this layer is computed here: neither gather nor wait (CTA-uniform)
+            // ---- gather the rows of the block (as k_scan_stages: one index space, loads of a batch in flight together)
+            {
+                float2 *A2 = reinterpret_cast<float2 *>(A);
+                const int C2 = C >> 1, K2 = K >> 1, total = rows * K2;
+                if (L == 0) {
+                    for (int base = tid; base < total; base += blockDim.x * kScanBatch) {
+                        uint4 q[kScanBatch];
+                        const uint2 *ptr[kScanBatch];
+#pragma unroll
+                        for (int u = 0; u < kScanBatch; ++u) {
+                            const int o = base + u * blockDim.x;
+                            ptr[u] = nullptr;
+                            if (o < total) {
+                                const int r = o / K2, i = o - r * K2, t = i / C2, c2 = i - t * C2;
+                                if ((s_tap[r0 + r] >> S.taps[t]) & 1u) {
+                                    ptr[u] = S.yhat_pm + ((long long)s_b[r0 + r] * S.HW + s_hw[r0 + r] + S.shift[t]) * C + 2 * c2;
+                                    q[u] = ll_ld(ptr[u]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kScanBatch; ++u) {
+                            const int o = base + u * blockDim.x;
+                            if (o < total) A2[o] = ptr[u] ? ll_wait(q[u], ptr[u], S.call_tag) : make_float2(0.f, 0.f);
+                        }
+                    }
+                } else {
+                    const int c0n2 = S.N[L - 1] >> 1, p2 = K2 - c0n2;
+                    for (int base = tid; base < total; base += blockDim.x * 4) {
+                        uint4 q[4];
+                        float2 pv[4];
+                        const uint2 *ptr[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int o = base + u * blockDim.x;
+                            ptr[u] = nullptr;
+                            pv[u] = make_float2(0.f, 0.f);
+                            if (o < total) {
+                                const int r = o / K2, i = o - r * K2;
+                                if (i < c0n2) {
+                                    if (s_grp[r0 + r] & 1u) {
+                                        ptr[u] = S.vec[L - 1] + (size_t)(r0 + r) * S.N[L - 1] + 2 * i;
+                                        q[u] = ll_ld(ptr[u]);
+                                    }
+                                } else {
+                                    pv[u] = __ldg(reinterpret_cast<const float2 *>(S.prior_pm + ((long long)s_b[r0 + r] * S.HW + s_hw[r0 + r]) * (2 * p2)) + (i - c0n2));
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int o = base + u * blockDim.x;
+                            if (o < total) A2[o] = ptr[u] ? ll_wait(q[u], ptr[u], step - 1) : pv[u];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- a warp per owned channel pair, all rows of the block at once (rows past `rows` hold stale values: computed, never used)
+            const float *wl = L == 0 ? S.wc : S.w[L];
+            for (int p = cb + warp * CB; p < npairs; p += kScanWarps * CB) {
+                const int n0 = 2 * p;
+                float m0, m1;
+                if (rows > 4) blk_pair<8>(wl + (size_t)n0 * K, wl + (size_t)(n0 + 1) * K, A, K, lane, m0, m1);
+                else blk_pair<4>(wl + (size_t)n0 * K, wl + (size_t)(n0 + 1) * K, A, K, lane, m0, m1);
+                if (lane < rows) {   // lane r finishes row r
+                    const int row = r0 + lane;
+                    m0 += S.bias[L][n0];
+                    m1 += S.bias[L][n0 + 1];
+                    if (L == 1 || L == 2) {
+                        m0 = m0 > 0.f ? m0 : m0 * kSlope;
+                        m1 = m1 > 0.f ? m1 : m1 * kSlope;
+                    }
+                    *reinterpret_cast<uint4 *>(S.vec[L] + (size_t)row * N + n0) = make_uint4(__float_as_uint(m0), step, __float_as_uint(m1), step);
+                    if (L == 3) {   // (mean, scale) of latent channel p: scale index, symbol, y_hat
+                        const int c = p, b = s_b[row];
+                        const long long e = (long long)b * qz.C * sc.y + (long long)c * sc.y + s_i[row];
+                        const long long yo = ((long long)b * qz.C + c) * S.HW + s_hw[row];
+                        if (qz.y) {
+                            const float sq = rintf(__fsub_rn(qz.y[yo], m0));  // torch.round: half to even
+                            const float yh = __fadd_rn(sq, m0);
+                            S.yhat_pm[((long long)b * S.HW + s_hw[row]) * qz.C + c] = make_uint2(__float_as_uint(yh), S.call_tag);
+                            qz.sym[e] = (int32_t)sq;
+                            qz.buf[yo] = yh;
+                        }
+                        const int si = scale_index_dev(m1, s_tab, qz.n_scales);
+                        if (DEC) S.dec.idx_t[e] = make_uint4((uint32_t)si, step, __float_as_uint(m0), step);
+                        qz.idx[e] = si;
+                        const long long oo = ((long long)b * N + n0) * S.HW + s_hw[row];
+                        S.params[oo] = m0;
+                        S.params[oo + S.HW] = m1;
+                    }
+                }
+            }
+            __syncthreads();   // A is rewritten by the next layer's gather
+        }
+        if (DEC && dec_warp) {
+            const long long n = slice, cs = S.dec.chunk_syms[g], dbase = (long long)dk * cs, rem = n - dbase;
+            const int m = (int)(rem <= 0 ? 0 : rem < cs ? rem : cs);
+            if (m > 0)
+                scan_decode_share(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
+        }
+        __syncthreads();   // the row records of stage g + 1 are complete, those of stage g free
+        qz.sym += slice;
+        qz.idx += slice;
+    }
+    if (DEC && dec_warp) {
+        if (dwp != dwend && lane == 0) dst |= 4;
+        if (dst) atomicOr(S.dec.status, dst);
+    }
+}
+
+// the visible taps of the N-major convolution weights, packed: dst[n][t * C + c] = src[n][taps[t] * C + c]
+__global__ void k_compact_taps(const float *__restrict__ src, float *__restrict__ dst, int N, int C, int k2, int ntaps, uint32_t tap_union)
+{
+    __shared__ int taps[32];
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int t = 0; t < k2; ++t) if ((tap_union >> t) & 1u) taps[n++] = t;
+    }
+    __syncthreads();
+    const long long total = (long long)N * ntaps * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        const int t = (int)(r % ntaps), n = (int)(r / ntaps);
+        dst[i] = src[((size_t)n * k2 + taps[t]) * C + c];
+    }
+}
+
 // [B][channels][HW] -> [B][HW][channels] (the stage kernel's position-major copy of the prior)
 __global__ void __launch_bounds__(256)
 k_to_position_major(const float *__restrict__ src, float *__restrict__ dst, int channels, int HW)
@@ -985,6 +1251,7 @@ int ctx_set_weights(CtxModel &m, const float *ctx_w, const float *ctx_b, const f
         BASIC_TRY(upload(m.b_m3, m3_b, m.c_ctx, s));
     }
     m.ws_ctx.release();
+    m.ws_ctxc_key = 0xffffffffu;
     if (m.has_conv && m.has_merger && m.G == 1) {   // N-major copies for the persistent stage kernel (k_scan_stages)
         const size_t n_ctx = (size_t)m.c_ctx * C * m.k * m.k;
         DevBuf tmp;
@@ -1416,14 +1683,22 @@ static size_t scan_smem(const CtxModel &m, int ntaps)
     return (fl + (size_t)kScanRows * kmax) * sizeof(float);
 }
 
+static size_t blk_smem(const CtxModel &m, int ntaps)
+{
+    const int kmax = std::max(std::max(ntaps * m.C, 2 * m.c_ctx), std::max(m.c_m1, m.c_m2));
+    return (size_t)kBlkRows * kmax * sizeof(float);
+}
+
 bool ctx_scan_supported(const CtxModel &m, int B)
 {
     static const bool off = [] { const char *e = getenv("BASIC_SCAN_KERNEL"); return e && e[0] == '0'; }();  // A/B switch
     if (off || !m.has_conv || !m.has_merger || m.internal || m.G != 1 || m.S < 8 || !m.d_stage_cells.p || !m.ws_ctx.p) return false;
     // (up to kScanMaxRows rows per stage the tensor path would run 128-row tiles that are mostly empty, four launches per stage;
     // measured at 64 rows per stage: 258 us here against 160 us there)
-    if ((long long)B * m.max_stage_cells > kScanMaxRows || m.k > 5) return false;
+    if ((long long)B * m.max_stage_cells > kBlkMaxRows || m.k > 5) return false;
     if (m.C % 4 || m.c_m1 % 4 || m.c_m2 % 4 || (m.c_m1 | m.c_m2 | m.c_ctx) & 1) return false;   // 128-bit weight loads, channel pairs
+    if ((long long)B * m.max_stage_cells > kScanRows)   // row blocks (k_scan_blocks): only the rows of a block live in shared memory
+        return blk_smem(m, m.k * m.k) <= 216 * 1024;
     const int nctas = scan_ctas(m);
     if ((std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) / 2 + nctas - 1) / nctas > kScanWarps) return false;   // a warp per owned pair
     return scan_smem(m, m.k * m.k) <= 216 * 1024;   // (+ 8 KB of static shared memory: 227 KB per CTA)
@@ -1431,10 +1706,22 @@ bool ctx_scan_supported(const CtxModel &m, int B)
 
 // Stages [g0, g1): parameters into `params` (NCHW), scale indexes (and, with y, symbols + the y_hat write-back into buf) into
 // the stream slices starting at idx / sym.  One launch.  dq_sym (decoder): symbols of stage g0 - 1, dequantised into buf first.
-bool ctx_scan_decode_supported(const CtxModel &m, int n_chunks, int bypass_precision, int freq_precision)
+// grid of the stage kernels for `rows` rows per stage: k_scan_stages (one CTA per SM) up to kScanRows rows, else k_scan_blocks
+// (row blocks x channel blocks)
+static void scan_grid(const CtxModel &m, int rows, int *nctas, int *CB)
+{
+    if (rows <= kScanRows) { *nctas = scan_ctas(m); *CB = 0; return; }
+    const int RB = (rows + kBlkRows - 1) / kBlkRows;
+    *CB = std::max(1, std::min(scan_ctas(m) / RB, std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) / 2));
+    *nctas = RB * *CB;
+}
+
+bool ctx_scan_decode_supported(const CtxModel &m, int B, int n_chunks, int bypass_precision, int freq_precision)
 {
     static const bool off = [] { const char *e = getenv("BASIC_SCAN_DECODE"); return e && e[0] == '0'; }();  // A/B switch
-    return !off && n_chunks > 0 && n_chunks <= kScanDecSlots * scan_ctas(m) && bypass_precision == 4 && freq_precision <= 16;
+    int nctas, CB;
+    scan_grid(m, B * m.max_stage_cells, &nctas, &CB);
+    return !off && n_chunks > 0 && n_chunks <= kScanDecSlots * nctas && bypass_precision == 4 && freq_precision <= 16;
 }
 
 int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, int B, float *params, const float *y, int32_t *sym,
@@ -1445,10 +1732,12 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     if (dq_sym && g0 == 0) return value_error("no stage precedes stage 0");
     const int HW = m.H * m.W;
     // workspace: tagged layer outputs [kScanMaxRows][N] x 4 | tagged position-major y_hat [B][HW][C] | position-major prior
-    const size_t vec_w = (size_t)kScanMaxRows * (2 * m.c_ctx + m.c_m1 + m.c_m2), yh_w = (size_t)B * HW * m.C;
-    const size_t idx_w = (size_t)kScanMaxRows * m.C;   // {scale index, tag, mean, tag} per element of a stage's slice
+    const size_t vec_w = (size_t)kBlkMaxRows * (2 * m.c_ctx + m.c_m1 + m.c_m2), yh_w = (size_t)B * HW * m.C;
+    const size_t idx_w = (size_t)kBlkMaxRows * m.C;   // {scale index, tag, mean, tag} per element of a stage's slice
     const size_t ws_bytes = (vec_w + yh_w) * sizeof(uint2) + idx_w * sizeof(uint4) + (size_t)B * HW * 2 * m.C * sizeof(float) + 64;
-    const int nctas = scan_ctas(m);
+    int nctas, CB;
+    scan_grid(m, B * m.max_stage_cells, &nctas, &CB);
+    if (nctas > m.sm_count) return value_error("stage kernel: more rows per stage than the grid can hold");
     const uint32_t steps = 4u * (uint32_t)(g1 - g0);
     if (ws_bytes > m.scan_ws.cap || m.scan_nctas != nctas || m.scan_step > 0x7fff0000u - steps || m.scan_call > 0x7fff0000u) {
         // (re)allocated, or the tags are about to wrap: every tag back to "never written"
@@ -1490,9 +1779,9 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     S.cell_grp = m.d_cell_grp.as<uint32_t>();
     S.buf = buf; S.yhat_pm = yhat_pm; S.prior_pm = prior_pm;
     S.vec[0] = vec;
-    S.vec[1] = S.vec[0] + (size_t)kScanMaxRows * m.c_ctx;
-    S.vec[2] = S.vec[1] + (size_t)kScanMaxRows * m.c_m1;
-    S.vec[3] = S.vec[2] + (size_t)kScanMaxRows * m.c_m2;
+    S.vec[1] = S.vec[0] + (size_t)kBlkMaxRows * m.c_ctx;
+    S.vec[2] = S.vec[1] + (size_t)kBlkMaxRows * m.c_m1;
+    S.vec[3] = S.vec[2] + (size_t)kBlkMaxRows * m.c_m2;
     S.params = params;
     S.g0 = g0; S.g1 = g1;
     S.qz = RowsQuant{y, buf, sym, idx, d_scale_table, n_scales, m.C};
@@ -1526,8 +1815,21 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     if (attr_once.first()) {
         BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
         BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        BASIC_CUDA(cudaFuncSetAttribute(k_scan_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+        BASIC_CUDA(cudaFuncSetAttribute(k_scan_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     }
-    if (dec) k_scan_stages<true><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
+    if (CB > 0) {   // row blocks: the convolution's visible taps packed once per (weights, map)
+        if (m.ws_ctxc_key != tap_union || !m.ws_ctxc.p) {
+            BASIC_TRY(m.ws_ctxc.reserve((size_t)m.c_ctx * S.ntaps * m.C * sizeof(float) + 16));
+            k_compact_taps<<<256, 256, 0, stream>>>(m.ws_ctx.as<float>(), m.ws_ctxc.as<float>(), m.c_ctx, m.C, m.k * m.k, S.ntaps, tap_union);
+            BASIC_LAUNCHED();
+            m.ws_ctxc_key = tap_union;
+        }
+        S.CB = CB;
+        S.wc = m.ws_ctxc.as<float>();
+        if (dec) k_scan_blocks<true><<<nctas, kScanWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
+        else k_scan_blocks<false><<<nctas, kScanWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
+    } else if (dec) k_scan_stages<true><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     else k_scan_stages<false><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
     m.scan_step += steps;
@@ -1562,7 +1864,7 @@ void ctx_delete(CtxModel *m)
                       &m->d_cell_tap, &m->d_cell_grp, &m->d_positions, &m->a_ctx, &m->a_m1, &m->a_m2,
                       &m->p_ctx.buf, &m->p_m1.buf, &m->p_m2.buf, &m->p_m3.buf, &m->cl_ctx, &m->cl_m1, &m->cl_m2, &m->cl_buf,
                       &m->cl_prior, &m->q_ctx.buf, &m->q_m1.buf, &m->q_m2.buf, &m->q_m3.buf, &m->range_flag, &m->kb_pool, &m->d_perm, &m->d_iperm, &m->cl_params,
-                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->scan_ws, &m->scan_cs, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
+                      &m->w_p1, &m->b_p1, &m->w_p2, &m->b_p2, &m->a_p1, &m->a_p2, &m->d_stage_cells, &m->scan_barrier, &m->scan_ws, &m->scan_cs, &m->ws_ctxc, &m->ws_ctx, &m->ws_m1, &m->ws_m2, &m->ws_m3, &m->b_m1_fold};
     for (DevBuf *b : bufs) b->release();
     delete m;
 }

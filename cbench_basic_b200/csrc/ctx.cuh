@@ -49,6 +49,8 @@ struct CtxModel {
     int max_stage_cells = 0;
     DevBuf scan_barrier;   // (SCAN_TIMING builds: cycle counters of the persistent stage kernel)
     uint32_t scan_step = 0, scan_call = 0;   // tags of the stage kernel's exchanged words: (stage, layer) steps and coding calls so far
+    DevBuf ws_ctxc;        // ... k_scan_blocks: convolution weights with only the visible taps, N-major [2C][ntaps * C]
+    uint32_t ws_ctxc_key = 0xffffffffu;   // the tap set they were packed for
     DevBuf scan_cs;        // ... single-launch decoding: chunk_syms of every slice
     DevBuf scan_ws;        // ... its tagged per-stage layer outputs [row][N], tagged position-major y_hat, position-major prior
     int scan_nctas = 0;

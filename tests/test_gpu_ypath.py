@@ -463,11 +463,12 @@ def test_cfg2_batch_against_oracle():
     assert r["off_tie"] == 0 and r["symbol_mismatches"] <= 2 and r["index_mismatches"] <= 2 and r["params_max_rel_err"] <= REL_TOL, r
 
 
-@pytest.mark.parametrize("B", [1, 3, 6, 9])
+@pytest.mark.parametrize("B", [1, 3, 6, 9, 20])
 def test_scanline_stage_kernel_rows_against_oracle(B):
-    """The persistent stage kernel (ctx.cu k_scan_stages) with 1 .. 9 rows per stage (<= 4: one row chunk; 6, 9: two and three
-    chunks): y_hat of encoder and both decoders (lanes = 0: chunk warps inside the one launch; lanes = 1: a launch per stage
-    that first dequantises the previous stage) against the CPU oracle -- same symbols, means within 1e-5."""
+    """The persistent stage kernels (ctx.cu) with 1 .. 20 rows per stage (<= 4: k_scan_stages, weights resident; 6, 9, 20:
+    k_scan_blocks with one, two and three row blocks): y_hat of encoder and both decoders (lanes = 0: chunk warps inside the one
+    launch; lanes = 1: a launch per stage that first dequantises the previous stage) against the CPU oracle -- same symbols,
+    means within 1e-5."""
     c = _random_case(12, 1, B, 6, 7, 40 + B, method="scanline")
     tab = Y.get_scale_table()
     with torch.no_grad():
