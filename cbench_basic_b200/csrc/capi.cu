@@ -1630,7 +1630,10 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
     // a host prior of a large batch arrives in image sub-batches: the first group's context model of a sub-batch runs while
     // the next one is on the bus
-    SubPlan subs = plan_subs(B, prior && !is_device_ptr(prior), model && !scan);
+    // (one channel group only: with several, later stages read activations an earlier stage cached per image of the WHOLE batch)
+    int m_c = 0, m_g = 1, m_h = 0, m_w = 0;
+    if (model) ctx_dims(*model->m, &m_c, &m_g, &m_h, &m_w);
+    SubPlan subs = plan_subs(B, prior && !is_device_ptr(prior), model && !scan && m_g == 1);
     BASIC_TRY(upload_inputs(c, nullptr, 0, prior, 2 * n, s, &d_none, &d_prior, &none_pending, &subs, B));
     float *buf_cl = nullptr, *prior_cl = nullptr;
     if (tc) {  // channels-last views for the tensor-core context model (see basic_ypath_encode)

@@ -524,3 +524,18 @@ def test_zero_copy_view_equals_bytes():
     coder_h.force_input_prior_shape_aligned = False          # a framing header cannot be prepended without a copy
     with pytest.raises(ValueError):
         coder_h.encode(y, prior=prior, zero_copy=True)
+
+
+@pytest.mark.parametrize("G,method", [(1, "checkerboard"), (2, "channelwise-checkerboard")])
+def test_host_inputs_in_sub_batches(G, method):
+    """Host tensors of a batch of >= 8 images are uploaded in image sub-batches (capi.cu plan_subs): same bytes and the same
+    latents as device inputs, also with two channel groups (later stages read activations cached by earlier ones)."""
+    c = _random_case(12, G, 16, 6, 8, 91 + G, method=method)
+    coder = make_coder(c, 0, method=method, ctx_precision="auto")
+    y, prior = c["y"], c["prior"]
+    bs_d, yhat_d = coder.encode(y.cuda(), prior=prior.cuda(), return_yhat=True)
+    bs_h = coder.encode(y.pin_memory(), prior=prior.pin_memory())
+    assert bs_h == bs_d
+    out_h = coder.decode(bs_h, prior=prior.pin_memory())
+    out_d = coder.decode(bs_d, prior=prior.cuda())
+    assert torch.equal(out_h, out_d) and torch.equal(out_d, yhat_d * 1.0 + 0.0)
