@@ -875,7 +875,7 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
 // block held in shared memory (k_scan_stages with R rows would gather every row in every CTA: 322 MB of L2 traffic per stage at
 // 64 rows; here: weights x row blocks + vectors x CB = ~100 MB).  Exchange, tags, quantiser and the in-kernel chunk decoder are
 // those of k_scan_stages; vectors only travel inside a row block.
-constexpr int kBlkRows = 8, kBlkMaxRows = 128, kBlkInFlight = 4;
+constexpr int kBlkRows = 8, kBlkMaxRows = 128, kBlkInFlight = 4, kBlkWarps = 16;   // (16 rows per block: 9.3 -> 13.9 ms on configs[3]'s scanline level)
 
 template <int R>
 __device__ __forceinline__ void blk_pair(const float *__restrict__ w0g, const float *__restrict__ w1g, const float *__restrict__ A, int K,
@@ -926,7 +926,7 @@ __device__ __forceinline__ void blk_pair(const float *__restrict__ w0g, const fl
 }
 
 template <bool DEC>
-__global__ void __launch_bounds__(kScanWarps * 32)
+__global__ void __launch_bounds__(kBlkWarps * 32)
 k_scan_blocks(const __grid_constant__ ScanArgs S)
 {
     extern __shared__ __align__(16) float A[];   // [kBlkRows][Kmax]
@@ -940,7 +940,7 @@ k_scan_blocks(const __grid_constant__ ScanArgs S)
     for (int i = tid; i < S.qz.n_scales && i < 256; i += blockDim.x) s_tab[i] = S.qz.scale_table[i];
     RowsQuant qz = S.qz;
     // ---- decoder warps (single-launch decoding), as in k_scan_stages
-    const int dslot = kScanWarps - 1 - warp;
+    const int dslot = kBlkWarps - 1 - warp;
     const int dk = dslot * nctas + cta;
     const bool dec_warp = DEC && dslot < kScanDecSlots && dk < S.dec.n_chunks;
     uint32_t dx = 0, dwp = 0, dwend = 0, dwbase = 0;
@@ -1062,7 +1062,7 @@ k_scan_blocks(const __grid_constant__ ScanArgs S)
             __syncthreads();
             // ---- a warp per owned channel pair, all rows of the block at once (rows past `rows` hold stale values: computed, never used)
             const float *wl = L == 0 ? S.wc : S.w[L];
-            for (int p = cb + warp * CB; p < npairs; p += kScanWarps * CB) {
+            for (int p = cb + warp * CB; p < npairs; p += kBlkWarps * CB) {
                 const int n0 = 2 * p;
                 float m0, m1;
                 if (rows > 4) blk_pair<8>(wl + (size_t)n0 * K, wl + (size_t)(n0 + 1) * K, A, K, lane, m0, m1);
@@ -1683,6 +1683,15 @@ static size_t scan_smem(const CtxModel &m, int ntaps)
     return (fl + (size_t)kScanRows * kmax) * sizeof(float);
 }
 
+static int scan_ntaps(const CtxModel &m)   // taps some stage of the current map can see
+{
+    uint32_t u = 0;
+    for (const auto &st : m.stages) u |= st.tap_or;
+    int n = 0;
+    for (; u; u &= u - 1) ++n;
+    return std::max(n, 1);
+}
+
 static size_t blk_smem(const CtxModel &m, int ntaps)
 {
     const int kmax = std::max(std::max(ntaps * m.C, 2 * m.c_ctx), std::max(m.c_m1, m.c_m2));
@@ -1698,7 +1707,7 @@ bool ctx_scan_supported(const CtxModel &m, int B)
     if ((long long)B * m.max_stage_cells > kBlkMaxRows || m.k > 5) return false;
     if (m.C % 4 || m.c_m1 % 4 || m.c_m2 % 4 || (m.c_m1 | m.c_m2 | m.c_ctx) & 1) return false;   // 128-bit weight loads, channel pairs
     if ((long long)B * m.max_stage_cells > kScanRows)   // row blocks (k_scan_blocks): only the rows of a block live in shared memory
-        return blk_smem(m, m.k * m.k) <= 216 * 1024;
+        return blk_smem(m, scan_ntaps(m)) <= 216 * 1024;
     const int nctas = scan_ctas(m);
     if ((std::max(m.c_m1, std::max(m.c_m2, m.c_ctx)) / 2 + nctas - 1) / nctas > kScanWarps) return false;   // a warp per owned pair
     return scan_smem(m, m.k * m.k) <= 216 * 1024;   // (+ 8 KB of static shared memory: 227 KB per CTA)
@@ -1827,8 +1836,8 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
         }
         S.CB = CB;
         S.wc = m.ws_ctxc.as<float>();
-        if (dec) k_scan_blocks<true><<<nctas, kScanWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
-        else k_scan_blocks<false><<<nctas, kScanWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
+        if (dec) k_scan_blocks<true><<<nctas, kBlkWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
+        else k_scan_blocks<false><<<nctas, kBlkWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
     } else if (dec) k_scan_stages<true><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     else k_scan_stages<false><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
