@@ -838,6 +838,16 @@ int basic_coder_last_output(basic_coder *c, const uint8_t **ptr, int64_t *len)
 
 int64_t basic_coder_output_size(basic_coder *c) { return c ? c->last_len : 0; }
 
+// delivery of a stream into the caller's bytes object with non-temporal stores: measured (cfg2 bench step) 3 % slower with one
+// rank per node -- the decoder that follows reads the bytes out of DRAM instead of the cache -- and 10 % faster with eight, where
+// the ranks compete for host memory bandwidth (no read-for-ownership: a third less traffic).  BASIC_NT_DELIVERY=0 / 1 overrides.
+static const bool kNtDelivery = [] {
+    const char *e = getenv("BASIC_NT_DELIVERY");
+    if (e) return e[0] == '1';
+    const char *l = getenv("LOCAL_WORLD_SIZE");
+    return l && atoi(l) >= 4;
+}();
+
 int basic_coder_take_output(basic_coder *c, uint8_t *dst, int64_t cap)
 {
     if (!c || (!dst && c->last_len)) return value_error("null argument");
@@ -852,7 +862,8 @@ int basic_coder_take_output(basic_coder *c, uint8_t *dst, int64_t cap)
         for (int k = t; k < chunks; k += nt) {
             if (k < pending) cudaEventSynchronize(c->out_events[k]);
             const int64_t at = (int64_t)k * kHostChunk;
-            memcpy(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
+            if (kNtDelivery) copy_streaming(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
+            else memcpy(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
         }
     };
     if (nt <= 1) work(0);
