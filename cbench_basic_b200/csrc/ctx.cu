@@ -385,7 +385,7 @@ constexpr int kScanWarps = 16, kScanRows = 4, kScanMaxRows = 32;   // (more rows
 constexpr int kScanDecSlots = 4;   // warps 7 .. 4 of a CTA
 struct ScanDecode {
     const unsigned char *blob;   // coder tables (rans tables blob in global memory, read through the read-only path)
-    size_t meta_bytes, cdf16_bytes;
+    size_t blob_bytes, meta_bytes, cdf16_bytes;
     int T, precision, bypass;
     const unsigned char *seg;    // the segment (device)
     long long seg_cap;
@@ -420,6 +420,7 @@ struct ScanArgs {
     uint32_t call_tag;           // tag of every y_hat word of this coding call
     long long *timing;           // SCAN_TIMING builds
     ScanDecode dec;              // n_chunks > 0: the decoder's single launch
+    int dctas;                   // k_scan_stages<DEC>: the last dctas CTAs of the grid only decode (tables in their shared memory)
     int CB;                      // k_scan_blocks: channel blocks per row block (grid = row blocks x CB)
     const float *wc;             // k_scan_blocks: the convolution's weights with only the visible taps, N-major [2C][ntaps * C]
 };
@@ -495,7 +496,8 @@ __device__ __forceinline__ void scan_pair_part(const float *__restrict__ wrow, c
 // (rans_lanes.cu: local symbol j -> lane (j % 128) / 4, step (j / 128) * 4 + j % 4; renormalising lanes take consecutive words in
 // lane order; bypass_precision 4 escapes), operands arriving as tagged words, stream words out of a 128-word window in
 // shared memory (beyond it: global), tables through the read-only path.
-__device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<false> &tb, const uint32_t *__restrict__ units, const uint32_t *win,
+template <bool SM>
+__device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<SM> &tb, const uint32_t *__restrict__ units, const uint32_t *win,
                                                uint32_t wbase, uint32_t wend, uint32_t &x, uint32_t &wp, int &st, long long dbase, int m,
                                                int lane, uint32_t tag, int cells, const int *s_hw)
 {
@@ -525,6 +527,9 @@ __device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<f
         // operands of the block's four symbols: {scale index, tag, mean, tag}, all loads first
         uint4 op[4];
         uint4 mt[4];
+#ifdef SCAN_TIMING
+        const long long tw0 = clock64();
+#endif
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             if (j0 + q < m) op[q] = ll_ld(reinterpret_cast<const uint2 *>(S.dec.idx_t + dbase + j0 + q));
@@ -542,17 +547,21 @@ __device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<f
             }
             mt[q] = tb.meta_at(c);  // cdf_base | lut_base | cdf_size, lut_shift | offset
         }
+#ifdef SCAN_TIMING
+        __syncwarp();
+        if (dbase == 0 && lane == 0) S.timing[9] += clock64() - tw0;   // chunk 0: waiting for its operands
+#endif
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const bool active = j0 + q < m;
-            const Tab<false>::addr_t cd = tb.cdf_at(mt[q].x);
+            const typename Tab<SM>::addr_t cd = tb.cdf_at(mt[q].x);
             const int nsyms = (int)(mt[q].z & 0xffffu) - 1, maxv = nsyms - 1;
             const uint32_t cum = x & pmask;
             // bucket LUT -> four CDF entries at once (one round trip; the 16-bit CDF stores 2^16 as 0: guarded by nsyms) -> select;
             // further probes only in tails of width-1 symbols
-            int s = (int)Tab<false>::ld16<0>(tb.lut_at(mt[q].y + (cum >> ((mt[q].z >> 16) & 0xffu))));
-            const Tab<false>::addr_t e = cd + 2 * s;
-            const uint32_t c0 = Tab<false>::ld16<0>(e), c1 = Tab<false>::ld16<2>(e), c2 = Tab<false>::ld16<4>(e), c3 = Tab<false>::ld16<6>(e);
+            int s = (int)Tab<SM>::template ld16<0>(tb.lut_at(mt[q].y + (cum >> ((mt[q].z >> 16) & 0xffu))));
+            const typename Tab<SM>::addr_t e = cd + 2 * s;
+            const uint32_t c0 = Tab<SM>::template ld16<0>(e), c1 = Tab<SM>::template ld16<2>(e), c2 = Tab<SM>::template ld16<4>(e), c3 = Tab<SM>::template ld16<6>(e);
             const bool a1 = s + 1 < nsyms && c1 <= cum;
             const bool a2 = a1 && s + 2 < nsyms && c2 <= cum;
             const bool a3 = a2 && s + 3 < nsyms && c3 <= cum;
@@ -560,9 +569,9 @@ __device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<f
             s += (int)a1 + (int)a2;
             if (a3) {
                 ++s;
-                while (s + 1 < nsyms && Tab<false>::ld16<2>(cd + 2 * s) <= cum) ++s;
-                start = Tab<false>::ld16<0>(cd + 2 * s);
-                next = Tab<false>::ld16<2>(cd + 2 * s);
+                while (s + 1 < nsyms && Tab<SM>::template ld16<2>(cd + 2 * s) <= cum) ++s;
+                start = Tab<SM>::template ld16<0>(cd + 2 * s);
+                next = Tab<SM>::template ld16<2>(cd + 2 * s);
             }
             const uint32_t freq = (uint16_t)(next - start);
             if (active) x = freq * (x >> prec) + cum - start;
@@ -605,8 +614,9 @@ __device__ __forceinline__ void scan_decode_share(const ScanArgs &S, const Tab<f
                 const int32_t sym = value + (int32_t)mt[q].w;
                 // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
                 const float v = __fadd_rn(__fadd_rn((float)sym, __uint_as_float(op[q].z)), 0.0f);
-                const long long e = dbase + j0 + q;
-                const int b = (int)(e / per_b), r2 = (int)(e - (long long)b * per_b), c = r2 / cells, i = r2 - c * cells;
+                const unsigned e = (unsigned)dbase + (unsigned)(j0 + q);   // (a slice holds < 2^31 elements: 32-bit divisions)
+                const unsigned b = e / (unsigned)per_b, r2 = e - b * (unsigned)per_b;
+                const unsigned c = cells == 1 ? r2 : r2 / (unsigned)cells, i = cells == 1 ? 0u : r2 - c * (unsigned)cells;
                 const int hw = s_hw[b * cells + i];
                 S.yhat_pm[((long long)b * S.HW + hw) * C + c] = make_uint2(__float_as_uint(v), S.call_tag);
                 S.buf[((long long)b * C + c) * S.HW + hw] = v;
@@ -626,8 +636,61 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
     __shared__ uint32_t s_win[kScanDecSlots][64];   // decoder warps: the next 128 stream words of their chunk
     __shared__ float s_tab[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cta = blockIdx.x, nctas = gridDim.x;
+    const int cta = blockIdx.x, nctas = gridDim.x - (DEC ? S.dctas : 0);   // nctas: the CTAs that own weights
     const int k2 = S.ksize * S.ksize, C = S.C;
+    if (DEC && cta >= nctas) {
+        // ---- a decoder CTA: the coder tables in ITS shared memory (the 113 KB of weights leave no room for them beside a weight
+        // CTA's, and table lookups out of L2 made a coding step 2.5 k cycles), one chunk per warp, nothing else to do
+        unsigned char *sm8 = reinterpret_cast<unsigned char *>(smem);
+        const Tab<true> tb = stage_tables<true>(S.dec.blob, S.dec.blob_bytes, S.dec.meta_bytes, S.dec.cdf16_bytes, sm8);
+        uint32_t *win = reinterpret_cast<uint32_t *>(sm8 + ((S.dec.blob_bytes + 15) & ~(size_t)15)) + warp * 64;
+        const int dk = (cta - nctas) + warp * S.dctas;
+        const bool on = dk < S.dec.n_chunks;
+        uint32_t dx = 0, dwp = 0, dwend = 0, dwbase = 0;
+        int dst = 0;
+        const uint32_t *d_units = nullptr;
+        if (on) {
+            const uint32_t *end_word = reinterpret_cast<const uint32_t *>(S.dec.seg) + 2 + S.dec.seg_slices;
+            const uint32_t *states = end_word + S.dec.n_chunks;
+            const long long words_at = kSegHdr + 4ll * S.dec.seg_slices + 4ll * S.dec.n_chunks + 128ll * S.dec.n_chunks;
+            d_units = reinterpret_cast<const uint32_t *>(S.dec.seg + words_at);
+            dwend = end_word[dk];
+            dwp = dk ? end_word[dk - 1] : 0;
+            if (dwend < dwp || words_at + 2ll * dwend > S.dec.seg_cap) { dst |= 4; dwend = dwp = 0; }  // corrupt directory
+            dx = states[(size_t)dk * 32 + lane];
+        }
+        uint32_t step = S.step0;
+        for (int g = S.g0; g < S.g1; ++g) {
+            const int2 sc = S.stage_cells[g];
+            for (int row = tid; row < S.B * sc.y; row += blockDim.x) sr_hw[0][row] = S.cell_hw[sc.x + (row % sc.y)];
+            __syncthreads();
+            step += 4;
+            if (on) {
+                const long long n = (long long)S.B * C * sc.y, cs = S.dec.chunk_syms[g], dbase = (long long)dk * cs, rem = n - dbase;
+                const int m = (int)(rem <= 0 ? 0 : rem < cs ? rem : cs);
+                if (m > 0) {
+                    dwbase = dwp & ~1u;
+                    const uint32_t u0 = dwbase >> 1, u_lim = (dwend + 1) >> 1;
+                    win[lane] = u0 + lane < u_lim ? __ldg(d_units + u0 + lane) : 0u;
+                    win[lane + 32] = u0 + 32 + lane < u_lim ? __ldg(d_units + u0 + 32 + lane) : 0u;
+                    __syncwarp();
+#ifdef SCAN_TIMING
+                    const long long td0 = clock64();
+#endif
+                    scan_decode_share<true>(S, tb, d_units, win, dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, sr_hw[0]);
+#ifdef SCAN_TIMING
+                    if (dk == 0 && lane == 0) S.timing[8] += clock64() - td0;
+#endif
+                }
+            }
+            __syncthreads();
+        }
+        if (on) {
+            if (dwp != dwend && lane == 0) dst |= 4;
+            if (dst) atomicOr(S.dec.status, dst);
+        }
+        return;
+    }
     int woff[5];
     woff[0] = 0;
 #pragma unroll
@@ -679,7 +742,7 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
     // ---- decoder warps (single-launch decoding)
     const int dslot = kScanWarps - 1 - warp;
     const int dk = dslot * nctas + cta;                       // this warp's chunk
-    const bool dec_warp = DEC && dslot < kScanDecSlots && dk < S.dec.n_chunks;
+    const bool dec_warp = DEC && S.dctas == 0 && dslot < kScanDecSlots && dk < S.dec.n_chunks;   // (no decoder CTAs: chunk warps beside the weights)
     uint32_t dx = 0, dwp = 0, dwend = 0, dwbase = 0;
     int dst = 0;
     const uint32_t *d_units = nullptr;
@@ -850,8 +913,14 @@ k_scan_stages(const __grid_constant__ ScanArgs S)
         if (DEC && dec_warp) {
             const long long n = slice, cs = S.dec.chunk_syms[g], dbase = (long long)dk * cs, rem = n - dbase;
             const int m = (int)(rem <= 0 ? 0 : rem < cs ? rem : cs);
+#ifdef SCAN_TIMING
+            const long long td0 = clock64();
+#endif
             if (m > 0)
-                scan_decode_share(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
+                scan_decode_share<false>(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
+#ifdef SCAN_TIMING
+            if (dk == 0 && lane == 0) S.timing[8] += clock64() - td0;   // chunk 0: operand wait + decode of its share, all stages
+#endif
         }
         __syncthreads();   // the row records of stage g + 1 are complete, those of stage g free
         SCAN_T(0);
@@ -1102,7 +1171,7 @@ k_scan_blocks(const __grid_constant__ ScanArgs S)
             const long long n = slice, cs = S.dec.chunk_syms[g], dbase = (long long)dk * cs, rem = n - dbase;
             const int m = (int)(rem <= 0 ? 0 : rem < cs ? rem : cs);
             if (m > 0)
-                scan_decode_share(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
+                scan_decode_share<false>(S, dtb, d_units, s_win[dslot], dwbase, dwend, dx, dwp, dst, dbase, m, lane, step, sc.y, s_hw);
         }
         __syncthreads();   // the row records of stage g + 1 are complete, those of stage g free
         qz.sym += slice;
@@ -1780,7 +1849,22 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     S.bias[0] = m.b_ctx.as<float>(); S.bias[1] = m.b_m1.as<float>(); S.bias[2] = m.b_m2.as<float>(); S.bias[3] = m.b_m3.as<float>();
     S.N[0] = m.c_ctx; S.N[1] = m.c_m1; S.N[2] = m.c_m2; S.N[3] = m.c_ctx;
     S.K[0] = S.ntaps * m.C; S.K[1] = 2 * m.c_ctx; S.K[2] = m.c_m1; S.K[3] = m.c_m2;
-    for (int L = 0; L < 4; ++L) S.pairs[L] = (S.N[L] / 2 + nctas - 1) / nctas;
+    // single-launch decoding on k_scan_stages: a few CTAs of the grid hold the coder tables instead of weights and do nothing
+    // but decode (one chunk per warp), when the chunks fit them and the weights still fit the remaining CTAs
+    constexpr int kDecCtas = 4;
+    int wctas = nctas;
+    size_t dec_smem = 0;
+    if (dec && CB == 0 && dec->n_chunks <= kDecCtas * kScanWarps && nctas > 4 * kDecCtas) {
+        static const bool off = [] { const char *e = getenv("BASIC_SCAN_DEC_CTAS"); return e && e[0] == '0'; }();  // A/B switch
+        const size_t need = ((dec->tables->blob_bytes + 15) & ~(size_t)15) + (size_t)kScanWarps * 256 + 16;
+        int worst = 0;
+        for (int L = 0; L < 4; ++L) worst = std::max(worst, (S.N[L] / 2 + (nctas - kDecCtas) - 1) / (nctas - kDecCtas));
+        if (!off && need <= 216 * 1024 && worst <= kScanWarps) {
+            wctas = nctas - kDecCtas;
+            dec_smem = need;
+        }
+    }
+    for (int L = 0; L < 4; ++L) S.pairs[L] = (S.N[L] / 2 + wctas - 1) / wctas;
     S.C = m.C; S.ksize = m.k; S.HW = HW; S.W_img = m.W; S.B = B;
     S.stage_cells = m.d_stage_cells.as<int2>();
     S.cell_hw = m.d_cell_hw.as<int32_t>();
@@ -1803,7 +1887,9 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
         BASIC_CUDA(cudaMemcpyAsync(m.scan_cs.p, dec->chunk_syms, (size_t)m.S * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
         const RansTables &tb = *dec->tables;
         S.dec.blob = tb.blob.as<unsigned char>();
+        S.dec.blob_bytes = tb.blob_bytes;
         S.dec.meta_bytes = tb.meta_bytes;
+        S.dctas = nctas - wctas;
         S.dec.cdf16_bytes = tb.cdf16_bytes;
         S.dec.T = tb.T;
         S.dec.precision = tb.precision;
@@ -1817,7 +1903,10 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
         S.dec.status = dec->status;
     }
 #ifdef SCAN_TIMING
-    BASIC_TRY(m.scan_barrier.reserve(256));
+    if (!m.scan_barrier.p) {
+        BASIC_TRY(m.scan_barrier.reserve(256));
+        BASIC_CUDA(cudaMemset(m.scan_barrier.p, 0, 256));
+    }
     S.timing = m.scan_barrier.as<long long>();
 #endif
     static PerDeviceOnce attr_once;
@@ -1838,20 +1927,30 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
         S.wc = m.ws_ctxc.as<float>();
         if (dec) k_scan_blocks<true><<<nctas, kBlkWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
         else k_scan_blocks<false><<<nctas, kBlkWarps * 32, blk_smem(m, S.ntaps), stream>>>(S);
-    } else if (dec) k_scan_stages<true><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
+    } else if (dec) {
+        // (resident weights laid out for wctas owners)
+        size_t fl = 0;
+        int kmax = 0;
+        for (int L = 0; L < 4; ++L) { fl += (size_t)S.pairs[L] * 2 * S.K[L]; kmax = std::max(kmax, S.K[L]); }
+        const size_t w_smem = (fl + (size_t)kScanRows * kmax) * sizeof(float);
+        if (std::max(w_smem, dec_smem) > 216 * 1024) return value_error("stage kernel: shared memory");
+        k_scan_stages<true><<<nctas, kScanWarps * 32, std::max(w_smem, dec_smem), stream>>>(S);
+    }
     else k_scan_stages<false><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
     m.scan_step += steps;
 #ifdef SCAN_TIMING
     if (g1 - g0 > 4) {
-        long long tk[5];
+        long long tk[10];
         BASIC_CUDA(cudaStreamSynchronize(stream));
         BASIC_CUDA(cudaMemcpy(tk, m.scan_barrier.as<long long>(), sizeof(tk), cudaMemcpyDeviceToHost));
+        BASIC_CUDA(cudaMemset(m.scan_barrier.p, 0, 256));
         const long long ns = g1 - g0;
         FILE *tf = fopen("gpurun_out/scan_timing.txt", "a");
         if (!tf) tf = stderr;
         fprintf(tf, "scan cta 0: %lld stages, rows %d; cycles per stage: stage sync %lld  gather + wait %lld  multiply %lld  sync %lld  epilogue %lld\n",
                 ns, B * m.max_stage_cells, tk[0] / ns, tk[1] / ns, tk[2] / ns, tk[3] / ns, tk[4] / ns);
+        fprintf(tf, "   chunk 0's warp: operand wait + decode %lld cycles per stage, of which waiting for operands %lld\n", tk[8] / ns, tk[9] / ns);
         if (tf != stderr) fclose(tf);
     }
 #endif
