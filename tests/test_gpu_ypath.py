@@ -539,3 +539,21 @@ def test_host_inputs_in_sub_batches(G, method):
     out_h = coder.decode(bs_h, prior=prior.pin_memory())
     out_d = coder.decode(bs_d, prior=prior.cuda())
     assert torch.equal(out_h, out_d) and torch.equal(out_d, yhat_d * 1.0 + 0.0)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 5, 6), (3, 6, 7), (7, 4, 9), (13, 9, 8)])
+def test_stage_kernels_on_zigzag_maps(B, H, W):
+    """Anti-diagonal stages: several cells per stage and a different number in every stage (rows = B x cells: 1 .. 104 here, so
+    both stage kernels and several row blocks are exercised, with partly filled blocks).  Encoder and both decoders against the
+    CPU oracle."""
+    c = _random_case(12, 1, B, H, W, 300 + B, method="zigzag")
+    tab = Y.get_scale_table()
+    with torch.no_grad():
+        _, _, yhat_o = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    for lanes in (0, 1):
+        coder = make_coder(c, lanes, method="zigzag")
+        bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+        out = coder.decode(bs, prior=prior)
+        assert torch.equal(out, yhat_enc * 1.0 + 0.0)
+        assert_latents_match(out.cpu(), yhat_o)
