@@ -376,7 +376,8 @@ k_layer_rows(LayerArgs a)
 // layer's pair is (mean, scale) of one latent channel, so the quantiser runs in its epilogue.  The encoder knows y: its
 // whole pass is ONE launch; the decoder launches the kernel once per stage (the coder sits between two stages) and the
 // launch first turns the previous stage's symbols into y_hat.  Deterministic (fixed summation order); one channel group (G = 1).
-constexpr int kScanWarps = 16, kScanRows = 4, kScanMaxRows = 32;   // (more rows per stage: every CTA gathers every row -- the tiled kernels win)
+constexpr int kScanWarps = 16, kScanRows = 4, kScanMaxRows = 32;   // (launched for <= kScanRows rows per stage; more rows go to k_scan_blocks:
+                                                                   // here every CTA would gather every row)
 
 // The decoder's single launch: the multi-lane coder's chunk warps live inside the stage kernel.  Chunk k belongs to warp
 // 7 - k / grid of CTA k % grid; it keeps its 32 lane states and its word position in registers from stage to stage, takes
