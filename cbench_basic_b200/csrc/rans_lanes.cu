@@ -261,7 +261,22 @@ k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, int n_slices, const uint
         if (threadIdx.x < 32) out_states[(size_t)k * 32 + threadIdx.x] = states[(size_t)k * 32 + threadIdx.x];
         const uint32_t end = end_word[k], beg = k ? end_word[k - 1] : 0;
         const uint16_t *src = scratch + (size_t)k * cap_words + first_word[k];
-        for (uint32_t i = threadIdx.x; i < end - beg; i += blockDim.x) out_words[beg + i] = src[i];
+        // 32-bit stores (the destination is 4-byte aligned from its first even word on; the source has whatever parity the
+        // chunk's first word had): half the store instructions of a word-by-word copy
+        uint16_t *dst = out_words + beg;
+        const uint32_t n = end - beg;
+        const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 1) & 1u) < n ? (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 1) & 1u) : n;
+        if (threadIdx.x == 0 && head) dst[0] = src[0];
+        const uint32_t pairs = (n - head) >> 1;
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+        const uint16_t *s2 = src + head;
+        if ((reinterpret_cast<uintptr_t>(s2) & 3) == 0) {
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(s2);
+            for (uint32_t i = threadIdx.x; i < pairs; i += blockDim.x) dst32[i] = s32[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < pairs; i += blockDim.x) dst32[i] = (uint32_t)s2[2 * i] | ((uint32_t)s2[2 * i + 1] << 16);
+        }
+        if (threadIdx.x == 32 && ((n - head) & 1)) dst[n - 1] = src[n - 1];
         if (k == n_chunks - 1 && threadIdx.x == 0 && (end & 1)) out_words[end] = 0;  // pad to 4 bytes
     }
 }
