@@ -324,7 +324,7 @@ def coder_lane_sweep(coder, device_index, hbm_peak, n_sym=1 << 24):
         ref_enc = ans.Rans64Encoder(lanes=1, device=device_index)
         ref_enc.init_params(freqs, nsym, offs)
         lanes1_bytes = len(ref_enc.encode_with_indexes(ts, ti))
-        for lanes in (0, 148 * 8 * 32, 148 * 16 * 32, 4 * 148 * 16 * 32):
+        for lanes in (0, 148 * 8 * 32, 148 * 16 * 32, 148 * 32 * 32, 4 * 148 * 16 * 32):
             enc = ans.Rans64Encoder(lanes=lanes, device=device_index)
             dec = ans.Rans64Decoder(lanes=lanes, device=device_index)
             for c in (enc, dec):

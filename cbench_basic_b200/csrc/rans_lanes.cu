@@ -287,8 +287,12 @@ k_bls_gather(const int *n_chunks_dev, int n_chunks_arg, int n_slices, const uint
 // waits on a global load.  Ring = kRingUnits u32 units (2 words each), filled in groups of kGroupUnits.
 constexpr int kRingUnits = 512, kGroupUnits = 128;
 
-template <bool SM, bool BP4>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+// MAXW: warps per CTA the instantiation is compiled for (registers per thread follow: 32 warps = 64 registers).  Thirty-two
+// state-carrying warps per SM hide twice the chain latency of sixteen -- for streams with more than 16 chunks per SM.
+constexpr int kHugeWarps = 32;
+
+template <bool SM, bool BP4, int MAXW = kMaxWarps>
+__global__ void __launch_bounds__(MAXW * 32, 1)
 k_bls_decode(LaneParams P, const unsigned char *__restrict__ seg, long long seg_cap, const int32_t *__restrict__ indexes,
              int32_t *__restrict__ out, int seg_slices, int first_slice, int last_slice, uint32_t *__restrict__ carry_x,
              uint32_t *__restrict__ carry_wp, int *status)
@@ -620,6 +624,7 @@ static int set_attrs()
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, true, kHugeWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     }
     return BASIC_OK;
 }
@@ -671,10 +676,17 @@ int launch_bls_decode(const RansTables &tb, int bypass, int bypass_precision, co
     if (smem > 0 && n_chunks <= 8 * sm_count && pair_kernels_apply(tb, bypass_precision))
         return launch_pair_decode(tb, P, d_seg, seg_cap, d_idx, seg_slices, slice, d_carry_x, d_carry_wp, d_out, d_status, sm_count, stream);
     BASIC_TRY(set_attrs());
-    const int nw = warps_for(n_chunks, sm_count, smem);
-    const dim3 grid(grid_for(n_chunks, sm_count)), block(nw * 32);
+    int nw = warps_for(n_chunks, sm_count, smem);
+    const dim3 grid(grid_for(n_chunks, sm_count));
     auto kern = smem > 0 ? (bypass_precision == 4 ? k_bls_decode<true, true> : k_bls_decode<true, false>)
                          : (bypass_precision == 4 ? k_bls_decode<false, true> : k_bls_decode<false, false>);
+    static const bool huge_off = [] { const char *e = getenv("BASIC_CODER_WARPS32"); return e && e[0] == '0'; }();   // A/B switch
+    if (!huge_off && smem > 0 && bypass_precision == 4 && n_chunks > kMaxWarps * sm_count &&
+        smem + kHugeWarps * kRingUnits * 4 <= kSmemLimit) {   // more than 16 chunks per SM: 32 warps per CTA
+        nw = kHugeWarps;
+        kern = k_bls_decode<true, true, kHugeWarps>;
+    }
+    const dim3 block(nw * 32);
     kern<<<grid, block, smem + nw * kRingUnits * 4, stream>>>(P, d_seg, seg_cap, d_idx, d_out, seg_slices, slice == 0, slice == seg_slices - 1,
                                                               d_carry_x, d_carry_wp, d_status);
     BASIC_LAUNCHED();
