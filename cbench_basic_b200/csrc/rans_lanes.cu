@@ -29,8 +29,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------ encode
 // scratch layout: chunk k owns words [k * cap_words, (k + 1) * cap_words), filled back to front.
 // Outputs per chunk: first_word[k] (index inside the chunk's scratch), states[k * 32 + lane].
-template <bool SM, bool BP4>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+template <bool SM, bool BP4, int MAXW = kMaxWarps>   // (MAXW = 32: see k_bls_decode)
+__global__ void __launch_bounds__(MAXW * 32, 1)
 k_bls_encode(LaneParams P, const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes,
              uint16_t *__restrict__ scratch, int cap_words, uint32_t *__restrict__ first_word,
              uint32_t *__restrict__ states, int *status)
@@ -620,6 +620,7 @@ static int set_attrs()
         const int dec_smem = kMaxSmemTables + kRingBytes < kSmemLimit ? kMaxSmemTables + kRingBytes : kSmemLimit;
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
+        BASIC_CUDA(cudaFuncSetAttribute(k_bls_encode<true, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTables));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
         BASIC_CUDA(cudaFuncSetAttribute(k_bls_decode<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_smem));
@@ -640,7 +641,13 @@ int launch_bls_encode(const RansTables &tb, int bypass, int bypass_precision, co
     const LaneParams P = make_params(tb, bypass, bypass_precision, 0, 128, n_chunks, n_slices, sl);
     const int smem = smem_for(tb);
     BASIC_TRY(set_attrs());
-    if (n_chunks > 0 && smem > 0 && pair_kernels_apply(tb, bypass_precision)) {
+    static const bool huge_off = [] { const char *e = getenv("BASIC_CODER_WARPS32"); return e && e[0] == '0'; }();   // A/B switch
+    if (!huge_off && n_chunks > kMaxWarps * sm_count && smem > 0 && bypass_precision == 4) {
+        // more than 16 chunks per SM (lanes chosen freely): 32 state-carrying warps per SM beat eight main / helper groups
+        k_bls_encode<true, true, 32><<<grid_for(n_chunks, sm_count), 32 * 32, smem, stream>>>(P, d_sym, d_idx, d_scratch, cap_words, d_first,
+                                                                                                d_states, d_status);
+        BASIC_LAUNCHED();
+    } else if (n_chunks > 0 && smem > 0 && pair_kernels_apply(tb, bypass_precision)) {
         BASIC_TRY(launch_pair_encode(tb, P, d_sym, d_idx, d_scratch, cap_words, d_first, d_states, d_status, sm_count, stream));
     } else if (n_chunks > 0) {
         const dim3 grid(grid_for(n_chunks, sm_count)), block(warps_for(n_chunks, sm_count, smem) * 32);
