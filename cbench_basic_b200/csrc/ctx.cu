@@ -1910,6 +1910,15 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     }
     S.timing = m.scan_barrier.as<long long>();
 #endif
+    // The stage kernels need their whole grid resident (CTAs wait for each other's words).  Two of them from two streams could
+    // each get a part of the SMs and wait forever, so launches on one device are chained through an event: the next one starts
+    // when the previous one has finished, whatever streams they are on.
+    static cudaEvent_t scan_done[64] = {};
+    int cur_dev = 0;
+    BASIC_CUDA(cudaGetDevice(&cur_dev));
+    cudaEvent_t &ev_done = scan_done[cur_dev & 63];
+    if (!ev_done) BASIC_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    else BASIC_CUDA(cudaStreamWaitEvent(stream, ev_done, 0));
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
         BASIC_CUDA(cudaFuncSetAttribute(k_scan_stages<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
@@ -1939,6 +1948,7 @@ int ctx_scan_run(CtxModel &m, int g0, int g1, float *buf, const float *prior, in
     }
     else k_scan_stages<false><<<nctas, kScanWarps * 32, scan_smem(m, S.ntaps), stream>>>(S);
     BASIC_LAUNCHED();
+    BASIC_CUDA(cudaEventRecord(ev_done, stream));
     m.scan_step += steps;
 #ifdef SCAN_TIMING
     if (g1 - g0 > 4) {
