@@ -8,14 +8,34 @@ namespace basic {
 
 namespace {
 
+// Where a scale sits in a log-spaced table, as a guess: index ~ (log2(sigma) - lg_min) * inv_step.  The search below starts there
+// and walks to the exact answer, so a table that is not log-spaced only costs steps (inv_step = 0: a linear scan).
+struct TableGuess {
+    float lg_min, inv_step;
+};
+
+__device__ inline TableGuess table_guess(const float *__restrict__ tab, int n)
+{
+    TableGuess g = {0.f, 0.f};
+    if (n >= 2 && tab[0] > 0.f && tab[n - 1] > tab[0]) {
+        g.lg_min = __log2f(tab[0]);
+        g.inv_step = (float)(n - 1) / (__log2f(tab[n - 1]) - g.lg_min);
+    }
+    return g;
+}
+
 // argmin_t |sigma - table[t]| in float32, first minimum (torch.argmin on CPU returns the first).
-__device__ inline int scale_index(float sigma, const float *__restrict__ tab, int n)
+__device__ inline int scale_index(float sigma, const float *__restrict__ tab, int n, TableGuess tg)
 {
     if (!(fabsf(sigma) <= 3.402823466e38f)) return 0;  // NaN / inf: every distance is NaN / inf -> index 0
-    int lo = 0, hi = n;                                // first t with tab[t] >= sigma
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (tab[mid] < sigma) lo = mid + 1; else hi = mid;
+    // lo = first t with tab[t] >= sigma (what a binary search returns): guessed, then corrected -- zero or one step each way
+    // on the reference's table, six dependent probes saved
+    int lo = 0;
+    if (sigma > tab[0]) {
+        lo = (int)((__log2f(sigma) - tg.lg_min) * tg.inv_step) + 1;
+        lo = lo < 1 ? 1 : lo > n ? n : lo;
+        while (lo > 0 && tab[lo - 1] >= sigma) --lo;
+        while (lo < n && tab[lo] < sigma) ++lo;
     }
     if (lo == 0) return 0;
     if (lo == n) return n - 1;
@@ -30,11 +50,19 @@ struct ElemAddr {
     float mean, sigma;
 };
 
+// p / HW for 0 <= p < 2^31 with m = ceil(2^32 / HW): the high word of p * m overshoots by at most one
+__device__ inline int div_hw(int p, int HW, unsigned m)
+{
+    unsigned q = __umulhi((unsigned)p, m);
+    if (q * (unsigned)HW > (unsigned)p) --q;
+    return (int)q;
+}
+
 __device__ inline ElemAddr elem_addr(const float *__restrict__ params, long long b, int p, int C, int HW, long long chw, int params_cl,
-                                     const int32_t *__restrict__ perm, bool want_sigma)
+                                     const int32_t *__restrict__ perm, bool want_sigma, unsigned hw_magic)
 {
     ElemAddr r;
-    const int c = p / HW;
+    const int c = HW == 1 ? p : div_hw(p, HW, hw_magic);
     r.yo = b * chw + p;
     if (params_cl) {  // blocked channels-last parameters of the tensor path (ctx.cuh): (mean, scale) are neighbours
         const int hw = perm[p - c * HW];  // slot of the position
@@ -59,6 +87,8 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
     __shared__ float tab[256];
     for (int i = threadIdx.x; i < n_scales; i += blockDim.x) tab[i] = scale_table[i];
     __syncthreads();
+    const TableGuess tg = table_guess(tab, n_scales);
+    const unsigned hw_magic = HW > 1 ? (unsigned)((0x100000000ull + (unsigned)HW - 1) / (unsigned)HW) : 0u;
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
     // quads never straddle two images when n_pos is a multiple of 4; the streams must be 16-byte aligned
@@ -77,8 +107,8 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
             p[0] = pp.x; p[1] = pp.y; p[2] = pp.z; p[3] = pp.w;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, true);
-                ix[j] = scale_index(a.sigma, tab, n_scales);
+                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, true, hw_magic);
+                ix[j] = scale_index(a.sigma, tab, n_scales, tg);
                 if (y) {
                     const float s = rintf(__fsub_rn(y[a.yo], a.mean));  // torch.round: half to even
                     sy[j] = (int32_t)s;
@@ -91,8 +121,8 @@ k_quantize_index(const float *__restrict__ y, const float *__restrict__ params, 
             for (int j = 0; j < 4 && e0 + j < total; ++j) {
                 const long long e = e0 + j, bb = e / n_pos, k = e - bb * n_pos;
                 const int pj = positions ? positions[k] : (int)k;
-                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, true);
-                indexes[e] = scale_index(a.sigma, tab, n_scales);
+                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, true, hw_magic);
+                indexes[e] = scale_index(a.sigma, tab, n_scales, tg);
                 if (y) {
                     const float s = rintf(__fsub_rn(y[a.yo], a.mean));
                     symbols[e] = (int32_t)s;
@@ -109,6 +139,7 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
 {
     const long long total = (long long)B * n_pos;
     const long long chw = (long long)C * HW;
+    const unsigned hw_magic = HW > 1 ? (unsigned)((0x100000000ull + (unsigned)HW - 1) / (unsigned)HW) : 0u;
     const bool vec = (n_pos & 3) == 0 && positions &&
                      ((reinterpret_cast<uintptr_t>(positions) | reinterpret_cast<uintptr_t>(symbols)) & 15) == 0;
     const long long quads = (total + 3) >> 2;
@@ -121,7 +152,7 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
             const int p[4] = {pp.x, pp.y, pp.z, pp.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, false);
+                const ElemAddr a = elem_addr(params, b, p[j], C, HW, chw, params_cl, perm, false, hw_magic);
                 // pgm_coder.py:973-975 (sym + mean), then _data_postprocess x * 1 + 0 (turns -0.0 into +0.0)
                 yhat[a.yo] = __fadd_rn(__fadd_rn((float)sv[j], a.mean), 0.0f);
             }
@@ -129,7 +160,7 @@ k_dequantize(const int32_t *__restrict__ symbols, const float *__restrict__ para
             for (int j = 0; j < 4 && e0 + j < total; ++j) {
                 const long long e = e0 + j, bb = e / n_pos, k = e - bb * n_pos;
                 const int pj = positions ? positions[k] : (int)k;
-                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, false);
+                const ElemAddr a = elem_addr(params, bb, pj, C, HW, chw, params_cl, perm, false, hw_magic);
                 yhat[a.yo] = __fadd_rn(__fadd_rn((float)symbols[e], a.mean), 0.0f);
             }
         }
