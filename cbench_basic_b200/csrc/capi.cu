@@ -465,7 +465,12 @@ int reserve_pinned(uint8_t **buf, size_t *cap, size_t bytes)
 // Delivers `len` encoded bytes that live on the device: into the caller's buffer, or (out == NULL) into the
 // coder's pinned staging buffer, from where basic_coder_last_output hands them out without another device trip.
 int finish_out(basic_coder *c);
-constexpr int64_t kHostChunk = 1 << 20;  // granularity of the pipelined host copies
+// granularity of the pipelined host copies (BASIC_HOST_CHUNK_KB overrides)
+static const int64_t kHostChunk = [] {
+    const char *e = getenv("BASIC_HOST_CHUNK_KB");
+    const int64_t kb = e ? atoll(e) : 1024;
+    return (kb < 64 ? 64 : kb > 16384 ? 16384 : kb) << 10;
+}();
 constexpr int kHostThreadsMax = 8;
 // host threads of the staging copies: BASIC_HOST_THREADS, else up to 4 but no more than this rank's share of the cores
 // (LOCAL_WORLD_SIZE ranks per node under torchrun); 1 = the calling thread only
