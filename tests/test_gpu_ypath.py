@@ -557,3 +557,27 @@ def test_stage_kernels_on_zigzag_maps(B, H, W):
         out = coder.decode(bs, prior=prior)
         assert torch.equal(out, yhat_enc * 1.0 + 0.0)
         assert_latents_match(out.cpu(), yhat_o)
+
+
+@pytest.mark.parametrize("B", [1, 6])
+def test_stage_kernels_c192_against_oracle(B):
+    """The stage kernels at the channel count of the BASELINE configurations (C = 192: 148 CTAs with two or three channel pairs
+    each, the dedicated decoder CTAs; B = 6: row blocks with streamed weights) on a small scanline image, against the CPU oracle."""
+    c = _random_case(192, 1, B, 4, 6, 500 + B, method="scanline")
+    tab = Y.get_scale_table()
+    with torch.no_grad():
+        _, _, yhat_o = Y.encode_symbols(c["y"], c["prior"], c["tg"], c["w"], tab)
+        mean_o, _ = Y.split_mean_scale(Y.params_for(yhat_o, c["tg"], c["prior"], c["w"]))
+    y, prior = c["y"].cuda(), c["prior"].cuda()
+    for lanes in (0, 1):
+        coder = make_coder(c, lanes, method="scanline")
+        bs, yhat_enc = coder.encode(y, prior=prior, return_yhat=True)
+        out = coder.decode(bs, prior=prior)
+        assert torch.equal(out, yhat_enc * 1.0 + 0.0)
+        # same symbols except where the oracle's own value sits on a rounding tie (4800-deep sums), means within 1e-5
+        sym_o, sym_g = torch.round(yhat_o - mean_o), torch.round(out.cpu() - mean_o)
+        bad = sym_g != sym_o
+        frac = (c["y"] - mean_o)[bad].double()
+        assert int(bad.sum()) <= 2 and bool((((frac - torch.floor(frac)) - 0.5).abs() <= 2e-5 * (1 + frac.abs())).all()), int(bad.sum())
+        ok = ~bad
+        assert float(((out.cpu() - yhat_o)[ok].abs() / yhat_o[ok].abs().clamp_min(1.0)).max()) <= REL_TOL
