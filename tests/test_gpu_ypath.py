@@ -526,11 +526,12 @@ def test_zero_copy_view_equals_bytes():
         coder_h.encode(y, prior=prior, zero_copy=True)
 
 
-@pytest.mark.parametrize("G,method", [(1, "checkerboard"), (2, "channelwise-checkerboard")])
-def test_host_inputs_in_sub_batches(G, method):
+@pytest.mark.parametrize("C_,G,method", [(12, 1, "checkerboard"), (12, 2, "channelwise-checkerboard"), (192, 1, "checkerboard")])
+def test_host_inputs_in_sub_batches(C_, G, method):
     """Host tensors of a batch of >= 8 images are uploaded in image sub-batches (capi.cu plan_subs): same bytes and the same
-    latents as device inputs, also with two channel groups (later stages read activations cached by earlier ones)."""
-    c = _random_case(12, G, 16, 6, 8, 91 + G, method=method)
+    latents as device inputs, also with two channel groups (later stages read activations cached by earlier ones) and at
+    C = 192 (the 3xFP16 tensor-core kernels on sub-batches)."""
+    c = _random_case(C_, G, 16, 6, 8, 91 + G, method=method)
     coder = make_coder(c, 0, method=method, ctx_precision="auto")
     y, prior = c["y"], c["prior"]
     bs_d, yhat_d = coder.encode(y.cuda(), prior=prior.cuda(), return_yhat=True)
