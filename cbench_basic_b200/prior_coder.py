@@ -306,20 +306,28 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
             return topo_groups.default_map("scanline", 1, H, W)
         if pgm is None and self.topo_group_predictor is not None:
             pgm = self.topo_group_predictor_cache
-        if pgm is None:
-            return topo_groups.default_map(self.default_topo_group_method, self.channel_groups, H, W)
+        if pgm is None:   # (the default map of a shape is built once: ~30 us of host time per call otherwise)
+            cache = self.__dict__.setdefault("_default_maps", {})
+            key = (self.default_topo_group_method, self.channel_groups, H, W)
+            if key not in cache:
+                if len(cache) > 64:
+                    cache.clear()
+                cache[key] = topo_groups.default_map(self.default_topo_group_method, self.channel_groups, H, W)
+            return cache[key]
         return topo_groups.tile_map(pgm, self.channel_groups, H, W)
 
     def _set_map(self, tg):
         """Hands the group map to the library -- once per (H, W, map): the cell lists, tap masks and position lists it derives
         stay on the device between calls."""
+        if self._map_key is not None and tg is self.__dict__.get("_map_obj"):
+            return   # the very tensor of the last call (a cached default map)
         tg32 = np.ascontiguousarray(tg[0].numpy(), dtype=np.int32)
         key = (tg32.shape, tg32.tobytes())
-        if key == self._map_key:
-            return
-        self._map_key = None
-        N.check(N.lib().basic_ctx_set_map(self._ctx, tg32.ctypes.data, tg32.shape[1], tg32.shape[2]))
-        self._map_key = key
+        if key != self._map_key:
+            self._map_key = None
+            N.check(N.lib().basic_ctx_set_map(self._ctx, tg32.ctypes.data, tg32.shape[1], tg32.shape[2]))
+            self._map_key = key
+        self.__dict__["_map_obj"] = tg
 
     def _operand(self, t):
         """float32, contiguous; a CPU tensor stays where it is: the C ABI takes host pointers and uploads them on its own
