@@ -339,12 +339,22 @@ class GaussianChannelGroupMaskConv2DTopoGroupPGMPriorCoder(CoderModuleBase):
 
     # ------------------------------------------------------------------------------------------ quantiser (torch_ans.py:105-180)
     def _qparams(self, quantizer_params):
-        q = self.quantizer_params if quantizer_params is None else torch.as_tensor(quantizer_params, dtype=torch.float32)
+        if quantizer_params is None:
+            # the module's own buffer lives on the device: read it once per (storage, version), not with a device
+            # synchronisation in every call
+            q = self.quantizer_params
+            key = (q.data_ptr(), q._version, str(q.device))
+            cached = self.__dict__.get("_q_host")
+            if cached is None or cached[0] != key:
+                cached = (key, self._zero_step(torch.as_tensor(q.detach().cpu().tolist(), dtype=torch.float32)))
+                self.__dict__["_q_host"] = cached
+            return cached[1]
+        return self._zero_step(torch.as_tensor(quantizer_params, dtype=torch.float32))
+
+    def _zero_step(self, q):
         if self.quantizer_type == "uniform":
-            zero, step = float(q[0]), float(q[2])
-        else:
-            zero, step = 0.0, float(q.reshape(-1)[0])
-        return zero, step
+            return float(q[0]), float(q[2])
+        return 0.0, float(q.reshape(-1)[0])
 
     def _transform(self, x, quantizer_params=None):
         zero, step = self._qparams(quantizer_params)
