@@ -862,13 +862,19 @@ int basic_coder_take_output(basic_coder *c, uint8_t *dst, int64_t cap)
     const int chunks = (int)((len + kHostChunk - 1) / kHostChunk);
     const int pending = c->out_chunks;  // chunks [0, pending) still have an event to wait for
     const int nt = std::max(1, std::min(kHostThreads, chunks));
+    // slices of a chunk (an eighth) are handed out dynamically: every thread works on the chunk that has just arrived, so what is
+    // left to copy after the LAST chunk lands is one slice per thread, not one chunk on one thread
+    const int64_t slice = std::max<int64_t>(kHostChunk / 8, 64 << 10);
+    const int slices = (int)((len + slice - 1) / slice), per_chunk = (int)(kHostChunk / slice);
+    std::atomic<int> next{0};
     const std::function<void(int)> work = [&](int t) {
         if (t > 0) cudaSetDevice(c->device);
-        for (int k = t; k < chunks; k += nt) {
+        for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < slices;) {
+            const int k = i / per_chunk;
             if (k < pending) cudaEventSynchronize(c->out_events[k]);
-            const int64_t at = (int64_t)k * kHostChunk;
-            if (kNtDelivery) copy_streaming(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
-            else memcpy(dst + at, c->host_out + at, (size_t)std::min(kHostChunk, len - at));
+            const int64_t at = (int64_t)i * slice;
+            if (kNtDelivery) copy_streaming(dst + at, c->host_out + at, (size_t)std::min(slice, len - at));
+            else memcpy(dst + at, c->host_out + at, (size_t)std::min(slice, len - at));
         }
     };
     if (nt <= 1) work(0);
@@ -952,12 +958,24 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
         cudaStream_t up = c->copy_stream;
         // workers only copy; the calling thread issues the uploads in chunk order as they become ready (CUDA calls from
         // several threads on one stream serialise in the driver and cost more than they save)
-        std::vector<std::atomic<int>> ready((size_t)chunks);
-        for (auto &r : ready) r.store(0, std::memory_order_relaxed);
-        auto copy_chunk = [&](int k) {
-            const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
+        // The unit of the host copies is a SLICE (an eighth of a chunk): all threads work on the first chunk first, so its upload
+        // starts after one slice time instead of one chunk time (with whole chunks per thread the first eight chunks became
+        // ready together, 125 us in, and the bus idled until then).
+        const int64_t slice = std::max<int64_t>(kHostChunk / 8, 64 << 10);
+        const int slices = (int)((len + slice - 1) / slice), per_chunk = (int)(kHostChunk / slice);
+        std::vector<std::atomic<int>> ready((size_t)chunks), left((size_t)chunks);
+        for (int k = 0; k < chunks; ++k) {
+            ready[(size_t)k].store(0, std::memory_order_relaxed);
+            left[(size_t)k].store(std::min(per_chunk, slices - k * per_chunk), std::memory_order_relaxed);
+        }
+        auto copy_slice = [&](int i) {
+            const int64_t at = (int64_t)i * slice, nb = std::min(slice, len - at);
             copy_streaming(c->host_in + at, encoded + at, (size_t)nb);
-            ready[(size_t)k].store(1, std::memory_order_release);
+            const int k = i / per_chunk;
+            if (left[(size_t)k].fetch_sub(1, std::memory_order_acq_rel) == 1) ready[(size_t)k].store(1, std::memory_order_release);
+        };
+        auto copy_chunk = [&](int k) {
+            for (int i = k * per_chunk; i < std::min(slices, (k + 1) * per_chunk); ++i) copy_slice(i);
         };
         auto upload_chunk = [&](int k) {
             const int64_t at = (int64_t)k * kHostChunk, nb = std::min(kHostChunk, len - at);
@@ -973,15 +991,15 @@ int basic_coder_set_stream(basic_coder *c, const uint8_t *encoded, int64_t len, 
             std::atomic<int> next{0};
             const std::function<void(int)> work = [&](int t) {
                 if (t > 0) {
-                    for (int k; (k = next.fetch_add(1, std::memory_order_relaxed)) < chunks;) copy_chunk(k);
+                    for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < slices;) copy_slice(i);
                     return;
                 }
                 int issued = 0;
                 while (issued < chunks) {
-                    const int k = next.load(std::memory_order_relaxed) < chunks ? next.fetch_add(1, std::memory_order_relaxed) : chunks;
-                    if (k < chunks) copy_chunk(k);
+                    const int i = next.load(std::memory_order_relaxed) < slices ? next.fetch_add(1, std::memory_order_relaxed) : slices;
+                    if (i < slices) copy_slice(i);
                     while (issued < chunks && ready[(size_t)issued].load(std::memory_order_acquire)) upload_chunk(issued++);
-                    if (k >= chunks && issued < chunks && !ready[(size_t)issued].load(std::memory_order_acquire)) std::this_thread::yield();
+                    if (i >= slices && issued < chunks && !ready[(size_t)issued].load(std::memory_order_acquire)) std::this_thread::yield();
                 }
             };
             HostPool::get().run(nt, work);
