@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libbasic_b200.so")
-SOURCES = ["capi.cu", "tables.cu", "rans_compat.cu", "rans_lanes.cu", "rans_pair.cu", "gauss.cu", "ctx.cu", "ctx_tc.cu", "tans.cu"]
+SOURCES = ["capi.cu", "tables.cu", "rans_compat.cu", "rans_lanes.cu", "rans_pair.cu", "gauss.cu", "ctx.cu", "ctx_scan.cu", "ctx_tc.cu", "tans.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-cudart", "static"] + \
              [f"-D{d}" for d in os.environ.get("BASIC_NVCC_DEFS", "").split(",") if d]   # debug builds (kernel timing switches)

@@ -1481,7 +1481,7 @@ int basic_ypath_encode(basic_coder *c, basic_ctx *model, const float *y, const f
         }
         if (scan) {
             // many-stage map (scanline, the serial JointAR coder): ONE persistent launch walks every stage -- context model,
-            // scale indexes, quantisation and the y_hat write-back (ctx.cu k_scan_stages)
+            // scale indexes, quantisation and the y_hat write-back (ctx_scan.cu k_scan_stages)
             if (y_pending) {
                 BASIC_CUDA(cudaStreamWaitEvent(s, c->ev_y, 0));
                 y_pending = false;
@@ -1658,7 +1658,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
         }
         ctx_set_run_precision(*model->m, prec);
     }
-    // many-stage map: one fused launch per stage (ctx.cu k_scan_stages) -- what the encoder used when the stream says exact FP32
+    // many-stage map: one fused launch per stage (ctx_scan.cu k_scan_stages) -- what the encoder used when the stream says exact FP32
     const bool scan = model && ctx_scan_supported(*model->m, B) &&
                       (lanes == BASIC_LANES_REFERENCE || ctx_run_precision(*model->m) == BASIC_CTX_FP32);
     const bool tc = model && !scan && ctx_uses_tc(*model->m, B);
@@ -1720,7 +1720,7 @@ int basic_ypath_decode(basic_coder *c, basic_ctx *model, const uint8_t *encoded,
     }
     bool fused = false;
     if (scan && lanes != BASIC_LANES_REFERENCE && ctx_scan_decode_supported(*model->m, B, si.n_chunks, (int)c->bypass_precision, c->rt.precision)) {
-        // the whole decode in one launch: context model, scale indexes, the coder's chunk warps and the write-back (ctx.cu)
+        // the whole decode in one launch: context model, scale indexes, the coder's chunk warps and the write-back (ctx_scan.cu)
         ProfScope ps(PROF_CTX, s);
         ScanDecodeHost dh = {&c->rt, c->bypass, c->stream_dev.as<unsigned char>() + c->stream_pos, si.len, si.n_chunks, si.cs.data(), &ds->status};
         BASIC_TRY(ctx_scan_run(*model->m, 0, S, buf, d_prior, B, params, nullptr, nullptr, idx, c->d_scale.as<float>(), (int)c->h_scale.size(), s,

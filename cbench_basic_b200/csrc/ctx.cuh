@@ -76,7 +76,7 @@ struct CtxModel {
 };
 
 
-// What the stage kernel needs to decode inside its one launch (ctx.cu k_scan_stages / scan_decode_share)
+// What the stage kernel needs to decode inside its one launch (ctx_scan.cu k_scan_stages / scan_decode_share)
 struct ScanDecodeHost {
     const RansTables *tables;
     int bypass;

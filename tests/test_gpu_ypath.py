@@ -465,7 +465,7 @@ def test_cfg2_batch_against_oracle():
 
 @pytest.mark.parametrize("B", [1, 3, 6, 9, 20])
 def test_scanline_stage_kernel_rows_against_oracle(B):
-    """The persistent stage kernels (ctx.cu) with 1 .. 20 rows per stage (<= 4: k_scan_stages, weights resident; 6, 9, 20:
+    """The persistent stage kernels (ctx_scan.cu) with 1 .. 20 rows per stage (<= 4: k_scan_stages, weights resident; 6, 9, 20:
     k_scan_blocks with one, two and three row blocks): y_hat of encoder and both decoders (lanes = 0: chunk warps inside the one
     launch; lanes = 1: a launch per stage that first dequantises the previous stage) against the CPU oracle -- same symbols,
     means within 1e-5."""
